@@ -1,0 +1,252 @@
+"""Writer for the reference ACIR wire format + the synthetic benchmark circuits.
+
+`Circuit::write` = gzip(bincode(circuit)) (acir/src/circuit/mod.rs:145-152); field elements are
+serialised as 64-char lowercase hex strings (acir_field/src/generic_ark.rs:114-121).  The solver
+itself only READS this format (C++ decoder in csrc/acir.cpp); the writer exists so tests, the
+bench and users can hand the library the same bytes the reference would consume.
+
+The synthetic generator follows SURVEY.md 8(d) / BASELINE.md 4: splitmix64 stream, width-3 PLONK
+gates  q_M*w_a*w_b + q_l*w_a + q_r*w_b + q_o*w_new + q_c = 0, operands from the previous 64
+witnesses ("local") or from all earlier witnesses ("global"), every 16th opcode re-emits an earlier
+gate as an all-known check.
+"""
+import gzip
+import struct
+
+P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+MASK64 = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & MASK64
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & MASK64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK64
+        return z ^ (z >> 31)
+
+    def field(self):
+        v = self.next() | (self.next() << 64) | (self.next() << 128) | (self.next() << 192)
+        return v % P
+
+    def nonzero_field(self):
+        while True:
+            v = self.field()
+            if v:
+                return v
+
+    def below(self, n):
+        return self.next() % n
+
+
+class Writer:
+    def __init__(self):
+        self.parts = []
+
+    def u8(self, v):
+        self.parts.append(struct.pack("<B", v))
+
+    def u32(self, v):
+        self.parts.append(struct.pack("<I", v))
+
+    def u64(self, v):
+        self.parts.append(struct.pack("<Q", v))
+
+    def fe(self, v):
+        self.parts.append(_FE_PREFIX)
+        self.parts.append(b"%064x" % (v % P))
+
+    def string(self, s):
+        b = s.encode()
+        self.u64(len(b))
+        self.parts.append(b)
+
+    def bytes(self):
+        return b"".join(self.parts)
+
+
+_FE_PREFIX = struct.pack("<Q", 64)
+
+
+def w_expression(w, mul_terms, lin, q_c):
+    w.u64(len(mul_terms))
+    for (c, a, b) in mul_terms:
+        w.fe(c)
+        w.u32(a)
+        w.u32(b)
+    w.u64(len(lin))
+    for (c, x) in lin:
+        w.fe(c)
+        w.u32(x)
+    w.fe(q_c)
+
+
+BLACKBOX_TAGS = {"AND": 0, "XOR": 1, "RANGE": 2, "SHA256": 3, "Blake2s": 4, "SchnorrVerify": 5, "Pedersen": 6,
+                 "HashToField128Security": 7, "EcdsaSecp256k1": 8, "EcdsaSecp256r1": 9, "FixedBaseScalarMul": 10,
+                 "Keccak256": 11, "Keccak256VariableLength": 12, "RecursiveAggregation": 13}
+
+
+class CircuitBuilder:
+    """Append opcodes, then `to_bytes()` gives gzip(bincode(Circuit))."""
+
+    def __init__(self):
+        self.w = Writer()
+        self.n_opcodes = 0
+        self.max_witness = 0
+        self.private_parameters = []
+        self.public_parameters = []
+        self.return_values = []
+
+    def _see(self, *ws):
+        for x in ws:
+            if x > self.max_witness:
+                self.max_witness = x
+
+    def arithmetic(self, mul_terms, lin, q_c=0):
+        self.w.u32(0)
+        w_expression(self.w, mul_terms, lin, q_c)
+        self.n_opcodes += 1
+        for (_, a, b) in mul_terms:
+            self._see(a, b)
+        for (_, x) in lin:
+            self._see(x)
+
+    def _fi(self, fi):
+        self.w.u32(fi[0])
+        self.w.u32(fi[1])
+        self._see(fi[0])
+
+    def _vfi(self, v):
+        self.w.u64(len(v))
+        for fi in v:
+            self._fi(fi)
+
+    def _vw(self, v):
+        self.w.u64(len(v))
+        for x in v:
+            self.w.u32(x)
+            self._see(x)
+
+    def logic(self, name, lhs, rhs, output):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS[name])
+        self._fi(lhs)
+        self._fi(rhs)
+        self.w.u32(output)
+        self._see(output)
+        self.n_opcodes += 1
+
+    def range(self, inp):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["RANGE"])
+        self._fi(inp)
+        self.n_opcodes += 1
+
+    def hash256(self, name, inputs, outputs):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS[name])
+        self._vfi(inputs)
+        self._vw(outputs)
+        self.n_opcodes += 1
+
+    def keccak_var(self, inputs, var_message_size, outputs):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["Keccak256VariableLength"])
+        self._vfi(inputs)
+        self._fi(var_message_size)
+        self._vw(outputs)
+        self.n_opcodes += 1
+
+    def pedersen(self, inputs, domain_separator, outputs):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["Pedersen"])
+        self._vfi(inputs)
+        self.w.u32(domain_separator)
+        self.w.u32(outputs[0])
+        self.w.u32(outputs[1])
+        self._see(*outputs)
+        self.n_opcodes += 1
+
+    def fixed_base_scalar_mul(self, low, high, outputs):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["FixedBaseScalarMul"])
+        self._fi(low)
+        self._fi(high)
+        self.w.u32(outputs[0])
+        self.w.u32(outputs[1])
+        self._see(*outputs)
+        self.n_opcodes += 1
+
+    def to_raw(self, current_witness_index=None):
+        head = Writer()
+        head.u32(self.max_witness + 1 if current_witness_index is None else current_witness_index)
+        head.u64(self.n_opcodes)
+        tail = Writer()
+        for s in (self.private_parameters, self.public_parameters, self.return_values):
+            tail.u64(len(s))
+            for x in sorted(set(s)):
+                tail.u32(x)
+        tail.u64(0)  # assert_messages
+        return head.bytes() + self.w.bytes() + tail.bytes()
+
+    def to_bytes(self, current_witness_index=None, level=1):
+        return gzip.compress(self.to_raw(current_witness_index), compresslevel=level, mtime=0)
+
+
+SEED_BASE = 0xAC1DB20000000000
+N_INPUTS = 8
+
+
+def synthetic_arith_circuit(n_gates, seed_id=1, mode="local", coeffs="dense", window=64, check_every=16):
+    """SURVEY 8(d) generator.  Returns (acir_bytes, input_witnesses, n_witnesses).
+
+    Witnesses 0..7 are the per-instance inputs; opcode i either defines a new witness from two
+    earlier ones or (every `check_every`-th opcode) re-emits an earlier gate verbatim."""
+    rng = SplitMix64(SEED_BASE + seed_id)
+    b = CircuitBuilder()
+    gates = []
+    n_defined = N_INPUTS
+    pow2 = [pow(2, j, P) for j in range(0, 64)]
+    for i in range(n_gates):
+        if check_every and i % check_every == check_every - 1 and gates:
+            g = gates[rng.below(len(gates))]
+            b.arithmetic(*g)
+            continue
+        lo = max(0, n_defined - window) if mode == "local" else 0
+        a = lo + rng.below(n_defined - lo)
+        c = lo + rng.below(n_defined - lo)
+        out = n_defined
+        if coeffs == "dense":
+            qm, ql, qr, qo, qc = (rng.nonzero_field() for _ in range(5))
+        else:  # "noir-like": q_o = -1, q_M in {0,1}, q_l,q_r in {0,+-1,2^j}
+            def small():
+                k = rng.below(4)
+                if k == 0:
+                    return 0
+                if k == 1:
+                    return 1
+                if k == 2:
+                    return P - 1
+                return pow2[rng.below(64)]
+            qm, ql, qr, qo, qc = rng.below(2), small(), small(), P - 1, (rng.below(2) and small())
+        mul = [(qm, a, c)] if qm else []
+        lin = [(q, w) for (q, w) in ((ql, a), (qr, c), (qo, out)) if q]
+        g = (mul, lin, qc)
+        b.arithmetic(*g)
+        gates.append(g)
+        n_defined += 1
+    b.private_parameters = list(range(N_INPUTS))
+    return b.to_bytes(current_witness_index=n_defined - 1 if n_defined else 0), list(range(N_INPUTS)), n_defined
+
+
+def synthetic_inputs(batch, n_inputs=N_INPUTS, seed_id=1, first_instance=0):
+    """Per-instance inputs, uniform Fr, as [batch][n_inputs][32] big-endian bytes (instance-indexed stream)."""
+    out = bytearray(batch * n_inputs * 32)
+    for i in range(batch):
+        rng = SplitMix64((SEED_BASE + seed_id) ^ (0x9E3779B97F4A7C15 * (first_instance + i + 1) & MASK64))
+        for k in range(n_inputs):
+            out[(i * n_inputs + k) * 32:(i * n_inputs + k + 1) * 32] = rng.field().to_bytes(32, "big")
+    return bytes(out)

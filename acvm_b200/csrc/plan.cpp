@@ -1,0 +1,545 @@
+// Plan compiler (see plan.hpp).  Static restatement of the reference's per-opcode decisions:
+//   which witnesses are known when an opcode is reached   acvm/src/pwg/arithmetic.rs:212-239 (evaluate)
+//   solvable / check / too-many-unknowns classification    acvm/src/pwg/arithmetic.rs:27-127,176-209
+//   blackbox input pre-check + output insert_value          acvm/src/pwg/blackbox/mod.rs:32-62, pwg/mod.rs:338-357
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+namespace acvmb {
+
+namespace {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t ASSIGN_NEVER = 0xFFFFFFFFu;
+constexpr uint32_t ASSIGN_INPUT = 0xFFFFFFFEu;
+
+struct Prod {
+    U256 c;
+    uint32_t a, b;
+};
+struct Lin {
+    U256 c;
+    uint32_t w;
+};
+
+class Scheduler {
+   public:
+    Scheduler(uint32_t S, uint32_t n_slots) : S_(S), ready_(n_slots, 0), war_(n_slots, 0) {}
+
+    void grow_slots(uint32_t n) {
+        if (n > ready_.size()) {
+            ready_.resize(n, 0);
+            war_.resize(n, 0);
+        }
+    }
+
+    void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
+        uint32_t e = 0;
+        for (size_t i = 0; i < nr; ++i) e = std::max(e, ready_[reads[i]]);
+        for (size_t i = 0; i < nw; ++i) e = std::max(e, std::max(ready_[writes[i]], war_[writes[i]]));
+        uint32_t s = find(e);
+        if (++fill_[s] == S_) next_[s] = s + 1;
+        steps_.push_back(s);
+        ops_.push_back(rec);
+        for (size_t i = 0; i < nw; ++i) ready_[writes[i]] = s + 1;
+        for (size_t i = 0; i < nr; ++i) war_[reads[i]] = std::max(war_[reads[i]], s + 1);
+        n_steps_ = std::max(n_steps_, s + 1);
+    }
+
+    uint32_t n_steps() const { return n_steps_; }
+    size_t n_ops() const { return ops_.size(); }
+
+    // emit the dense [n_steps_padded][S] record array
+    void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps) const {
+        n_steps_padded = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
+        if (n_steps_padded == 0) n_steps_padded = chunk_steps;
+        stream.assign((size_t)n_steps_padded * S_, OpRec{});
+        std::vector<uint32_t> cursor(n_steps_padded, 0);
+        for (size_t i = 0; i < ops_.size(); ++i) {
+            uint32_t s = steps_[i];
+            stream[(size_t)s * S_ + cursor[s]++] = ops_[i];
+        }
+    }
+
+   private:
+    uint32_t find(uint32_t s) {
+        ensure(s);
+        uint32_t r = s;
+        while (true) {
+            ensure(r);
+            if (next_[r] == r) break;
+            r = next_[r];
+        }
+        // path compression
+        while (next_[s] != r && next_[s] != s) {
+            uint32_t n = next_[s];
+            next_[s] = r;
+            s = n;
+        }
+        return r;
+    }
+    void ensure(uint32_t s) {
+        while (fill_.size() <= s) {
+            next_.push_back((uint32_t)fill_.size());
+            fill_.push_back(0);
+        }
+    }
+    uint32_t S_;
+    std::vector<uint32_t> ready_, war_;
+    std::vector<uint32_t> fill_, next_;
+    std::vector<uint32_t> steps_;
+    std::vector<OpRec> ops_;
+    uint32_t n_steps_ = 0;
+};
+
+struct Compiler {
+    const Circuit& c;
+    PlanOptions opt;
+    Plan plan;
+    std::vector<uint8_t> known;
+    Scheduler sched;
+    uint32_t temp_base, temp_next = 0;
+
+    Compiler(const Circuit& circ, const PlanOptions& o, uint32_t nw)
+        : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw) {}
+
+    uint32_t new_temp() {
+        uint32_t t = temp_base + (temp_next % opt.temp_pool);
+        ++temp_next;
+        return t;
+    }
+
+    static void put(uint32_t dst[8], const U256& v) { hf::to_limbs32(v, dst); }
+
+    void fail_static(uint32_t opcode, uint32_t kind, uint32_t aux, const std::string& detail) {
+        plan.static_fail.present = true;
+        plan.static_fail.opcode = opcode;
+        plan.static_fail.kind = kind;
+        plan.static_fail.aux = aux;
+        plan.static_fail.detail = detail;
+    }
+
+    void mark_assigned(uint32_t w, uint32_t opcode) {
+        known[w] = 1;
+        plan.assign_opcode[w] = opcode;
+    }
+
+    // Lower  sum(products) + sum(linears) + constant  into chained micro-gates.
+    // assign: write the value to `out`; otherwise CHECK it is zero.
+    // out_check: `out` is already assigned -> compare instead of store (insert_value semantics).
+    void lower_sum(std::vector<Prod> prods, std::vector<Lin> lins, const U256& constant, bool assign, uint32_t out,
+                   uint32_t opcode, bool out_check) {
+        uint32_t acc = NONE;
+        const U256 one = hf::from_u64(1);
+        bool first_gate = true;
+        while (first_gate || !prods.empty() || !lins.empty()) {
+            first_gate = false;
+            OpRec r{};
+            uint32_t flags = 0;
+            uint32_t x = NONE, y = NONE, w1 = NONE, w2 = NONE;
+            U256 cM, cY, c1, c2;
+            uint32_t reads[4];
+            size_t nr = 0;
+            uint64_t imad = 0;
+            if (!prods.empty()) {
+                Prod p = prods.back();
+                prods.pop_back();
+                flags |= GF_MUL | GF_Y;
+                x = p.a;
+                y = p.b;
+                cM = p.c;
+                for (size_t i = 0; i < lins.size(); ++i)
+                    if (lins[i].w == y) {
+                        cY = lins[i].c;
+                        lins.erase(lins.begin() + i);
+                        break;
+                    }
+                imad += 136;
+            } else if (acc != NONE) {
+                flags |= GF_Y;
+                y = acc;
+                cY = one;
+                acc = NONE;
+            } else if (!lins.empty()) {
+                flags |= GF_Y;
+                y = lins.back().w;
+                cY = lins.back().c;
+                lins.pop_back();
+            }
+            uint32_t nlin = 0;
+            auto push_lin = [&](const U256& cc, uint32_t w) {
+                if (nlin == 0) {
+                    c1 = cc;
+                    w1 = w;
+                } else {
+                    c2 = cc;
+                    w2 = w;
+                }
+                ++nlin;
+            };
+            if (flags & GF_MUL) {
+                // prefer the x-term in w1 so the kernel reuses the registers it already holds
+                for (size_t i = 0; i < lins.size(); ++i)
+                    if (lins[i].w == x) {
+                        push_lin(lins[i].c, x);
+                        flags |= GF_W1_IS_X;
+                        lins.erase(lins.begin() + i);
+                        break;
+                    }
+            }
+            if (acc != NONE && nlin < 2) {
+                push_lin(one, acc);
+                acc = NONE;
+            }
+            while (nlin < 2 && !lins.empty() && acc == NONE) {
+                push_lin(lins.back().c, lins.back().w);
+                lins.pop_back();
+            }
+            bool final_gate = prods.empty() && lins.empty() && acc == NONE;
+            flags |= nlin << GF_NLIN_SHIFT;
+            uint32_t kind;
+            uint32_t dst = NONE;
+            if (final_gate) {
+                kind = assign ? MK_GATE_ASSIGN : MK_GATE_CHECK;
+                if (assign) {
+                    dst = out;
+                    if (out_check) flags |= GF_OUT_CHECK;
+                }
+                put(r.c[4], constant);
+            } else {
+                kind = MK_GATE_ASSIGN;
+                dst = new_temp();
+                ++plan.stats.n_temps;
+            }
+            r.w[0] = kind | (flags << 8);
+            r.w[1] = opcode;
+            r.w[2] = dst;
+            r.w[3] = x;
+            r.w[4] = y;
+            r.w[5] = w1;
+            r.w[6] = w2;
+            r.w[7] = 0;
+            put(r.c[0], hf::to_mont2(cM));
+            put(r.c[1], hf::to_mont(cY));
+            put(r.c[2], hf::to_mont(c1));
+            put(r.c[3], hf::to_mont(c2));
+            if (flags & GF_MUL) reads[nr++] = x;
+            if (flags & GF_Y) reads[nr++] = y;
+            if (nlin >= 1 && !(flags & GF_W1_IS_X)) reads[nr++] = w1;
+            if (nlin >= 2) reads[nr++] = w2;
+            uint32_t K = ((flags & GF_Y) ? 1 : 0) + nlin;
+            if (K) imad += 64 * K + 72;
+            plan.stats.dev_imad += imad;
+            // distinct operand reads
+            {
+                uint32_t tmp[4];
+                size_t nd = 0;
+                for (size_t i = 0; i < nr; ++i) {
+                    bool dup = false;
+                    for (size_t j = 0; j < nd; ++j) dup |= tmp[j] == reads[i];
+                    if (!dup) tmp[nd++] = reads[i];
+                }
+                plan.stats.alg_bytes += 32 * nd;
+            }
+            uint32_t writes[1];
+            size_t nw = 0;
+            if (dst != NONE) {
+                if (flags & GF_OUT_CHECK) {
+                    reads[nr++] = dst;
+                    plan.stats.alg_bytes += 32;
+                } else {
+                    writes[nw++] = dst;
+                    plan.stats.alg_bytes += 32;
+                }
+            }
+            sched.place(r, reads, nr, writes, nw);
+            ++plan.stats.n_micro;
+            if (kind == MK_GATE_ASSIGN) ++plan.stats.n_gate_assign; else ++plan.stats.n_gate_check;
+            if (!final_gate) acc = dst;
+        }
+    }
+
+    // returns false when compilation must stop (static failure)
+    bool arithmetic(uint32_t idx, const Expression& e) {
+        std::vector<Prod> prods;
+        std::vector<Lin> lins;
+        // unknown linear entries after the reference's evaluate()
+        std::vector<Lin> unknown;
+        uint32_t n_both_unknown = 0;
+        bool value_dependent = false;
+        for (auto& t : e.mul_terms) {
+            bool ka = known[t.a], kb = known[t.b];
+            if (ka && kb) {
+                plan.stats.ref_fr_mul += 2;
+                if (!t.c.is_zero()) prods.push_back({t.c, t.a, t.b});
+            } else if (!ka && !kb) {
+                if (!t.c.is_zero()) ++n_both_unknown;
+            } else {
+                plan.stats.ref_fr_mul += 1;
+                if (!t.c.is_zero()) value_dependent = true;  // coefficient q_M*w_known is per-instance
+            }
+        }
+        for (auto& t : e.linear_combinations) {
+            if (known[t.w]) {
+                plan.stats.ref_fr_mul += 1;
+                if (!t.c.is_zero()) lins.push_back({t.c, t.w});
+            } else if (!t.c.is_zero()) {
+                unknown.push_back({t.c, t.w});
+            }
+        }
+        if (value_dependent)
+            throw std::runtime_error("opcode " + std::to_string(idx) +
+                                     ": arithmetic gate whose unknown is a multiplication operand (value-dependent "
+                                     "coefficient) is not supported by the device plan yet");
+        if (n_both_unknown > 1) {
+            fail_static(idx, EK_REFERENCE_PANIC, 0, "Mul term in the arithmetic opcode must contain either zero or one term");
+            return false;
+        }
+        if (n_both_unknown == 1 || unknown.size() > 1) {
+            fail_static(idx, EK_TOO_MANY_UNKNOWNS, 0, "expression has too many unknowns");
+            return false;
+        }
+        if (unknown.empty()) {
+            lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/false, NONE, idx, false);
+            return true;
+        }
+        // exactly one unknown (coeff != 0): w := -(sum)/coeff ; fold k = -1/coeff into every term
+        U256 k = hf::neg(hf::inverse(unknown[0].c));
+        plan.stats.ref_fr_mul += 1;
+        plan.stats.ref_fr_inv += 1;
+        for (auto& p : prods) p.c = hf::mul(p.c, k);
+        for (auto& l : lins) l.c = hf::mul(l.c, k);
+        U256 qc = hf::mul(e.q_c, k);
+        uint32_t w = unknown[0].w;
+        lower_sum(std::move(prods), std::move(lins), qc, /*assign=*/true, w, idx, false);
+        mark_assigned(w, idx);
+        return true;
+    }
+
+    bool blackbox(uint32_t idx, const BlackBoxCall& b) {
+        for (auto& in : b.inputs)
+            if (!known[in.witness]) {  // blackbox/mod.rs:55-62
+                fail_static(idx, EK_MISSING_ASSIGNMENT, in.witness, "missing assignment for witness index " + std::to_string(in.witness));
+                return false;
+            }
+        OpRec r{};
+        uint32_t reads[3];
+        size_t nr = 0;
+        uint32_t writes[2];
+        size_t nw = 0;
+        switch (b.func) {
+            case BB_AND:
+            case BB_XOR: {
+                if (b.inputs[0].num_bits != b.inputs[1].num_bits) {
+                    fail_static(idx, EK_REFERENCE_PANIC, 0, "number of bits specified for each input must be the same");
+                    return false;
+                }
+                uint32_t out = b.outputs[0];
+                uint32_t flags = 0;
+                reads[nr++] = b.inputs[0].witness;
+                reads[nr++] = b.inputs[1].witness;
+                if (known[out]) {
+                    flags |= GF_OUT_CHECK;
+                    reads[nr++] = out;
+                } else {
+                    writes[nw++] = out;
+                }
+                r.w[0] = (b.func == BB_AND ? MK_AND : MK_XOR) | (flags << 8);
+                r.w[1] = idx;
+                r.w[2] = out;
+                r.w[3] = b.inputs[0].witness;
+                r.w[4] = b.inputs[1].witness;
+                r.w[5] = r.w[6] = NONE;
+                r.w[7] = b.inputs[0].num_bits;
+                sched.place(r, reads, nr, writes, nw);
+                if (!known[out]) mark_assigned(out, idx);
+                ++plan.stats.n_micro;
+                ++plan.stats.n_logic;
+                plan.stats.alg_bytes += 96;
+                return true;
+            }
+            case BB_RANGE: {
+                reads[nr++] = b.inputs[0].witness;
+                r.w[0] = MK_RANGE;
+                r.w[1] = idx;
+                r.w[2] = NONE;
+                r.w[3] = b.inputs[0].witness;
+                r.w[4] = r.w[5] = r.w[6] = NONE;
+                r.w[7] = b.inputs[0].num_bits;
+                sched.place(r, reads, nr, writes, nw);
+                ++plan.stats.n_micro;
+                ++plan.stats.n_range;
+                plan.stats.alg_bytes += 32;
+                return true;
+            }
+            default:
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": blackbox function " + blackbox_name(b.func) +
+                                         " is not supported by the device plan yet");
+        }
+    }
+
+    void run(const std::vector<uint32_t>& inputs) {
+        plan.S = opt.S;
+        plan.chunk_steps = opt.chunk_steps;
+        plan.num_witnesses = (uint32_t)known.size();
+        plan.n_opcodes = (uint32_t)c.opcodes.size();
+        plan.input_witnesses = inputs;
+        plan.assign_opcode.assign(known.size(), ASSIGN_NEVER);
+        for (uint32_t w : inputs) {
+            known[w] = 1;
+            plan.assign_opcode[w] = ASSIGN_INPUT;
+        }
+        for (uint32_t i = 0; i < c.opcodes.size(); ++i) {
+            const Opcode& op = c.opcodes[i];
+            bool ok = true;
+            switch (op.kind) {
+                case OP_Arithmetic:
+                    ok = arithmetic(i, op.expr);
+                    break;
+                case OP_BlackBox:
+                    ok = blackbox(i, op.bb);
+                    break;
+                default:
+                    throw std::runtime_error("opcode " + std::to_string(i) + ": opcode kind " + std::to_string(op.kind) +
+                                             " (Directive/Brillig/Memory) is not supported by the device plan yet");
+            }
+            if (!ok) break;
+        }
+        sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
+        plan.n_slots = temp_base + opt.temp_pool;
+        plan.stats.n_opcodes = c.opcodes.size();
+        plan.stats.n_steps = sched.n_steps();
+        plan.stats.n_slots_filled = sched.n_ops();
+    }
+};
+
+uint32_t witness_span(const Circuit& c, const std::vector<uint32_t>& inputs) {
+    uint32_t m = c.current_witness_index;
+    auto upd = [&](uint32_t w) { m = std::max(m, w); };
+    auto expr = [&](const Expression& e) {
+        for (auto& t : e.mul_terms) {
+            upd(t.a);
+            upd(t.b);
+        }
+        for (auto& t : e.linear_combinations) upd(t.w);
+    };
+    for (uint32_t w : inputs) upd(w);
+    for (auto& op : c.opcodes) {
+        switch (op.kind) {
+            case OP_Arithmetic:
+                expr(op.expr);
+                break;
+            case OP_BlackBox:
+                for (auto& in : op.bb.inputs) upd(in.witness);
+                for (uint32_t w : op.bb.outputs) upd(w);
+                break;
+            default:
+                break;
+        }
+    }
+    return m + 1;
+}
+
+}  // namespace
+
+Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt) {
+    if (opt.S == 0 || opt.S > 64) throw std::runtime_error("plan: S must be in 1..64");
+    uint32_t nw = witness_span(c, input_witnesses);
+    Compiler comp(c, opt, nw);
+    comp.run(input_witnesses);
+    return std::move(comp.plan);
+}
+
+// ---- (de)serialisation: one flat blob for the multi-GPU broadcast -----------------------------
+namespace {
+template <typename T>
+void put_pod(std::vector<uint8_t>& b, const T& v) {
+    const uint8_t* p = (const uint8_t*)&v;
+    b.insert(b.end(), p, p + sizeof(T));
+}
+template <typename T>
+void put_vec(std::vector<uint8_t>& b, const std::vector<T>& v) {
+    put_pod<uint64_t>(b, v.size());
+    const uint8_t* p = (const uint8_t*)v.data();
+    b.insert(b.end(), p, p + v.size() * sizeof(T));
+    while (b.size() % 16) b.push_back(0);
+}
+struct Cursor {
+    const uint8_t* d;
+    size_t n, o = 0;
+    template <typename T>
+    T pod() {
+        if (o + sizeof(T) > n) throw std::runtime_error("plan blob truncated");
+        T v;
+        memcpy(&v, d + o, sizeof(T));
+        o += sizeof(T);
+        return v;
+    }
+    template <typename T>
+    std::vector<T> vec() {
+        uint64_t k = pod<uint64_t>();
+        if (o + k * sizeof(T) > n) throw std::runtime_error("plan blob truncated");
+        std::vector<T> v(k);
+        memcpy(v.data(), d + o, k * sizeof(T));
+        o += k * sizeof(T);
+        while (o % 16) ++o;
+        return v;
+    }
+};
+constexpr uint64_t kPlanMagic = 0x3130304e414c5042ULL;  // "BPLAN001"
+}  // namespace
+
+std::vector<uint8_t> serialize_plan(const Plan& p) {
+    std::vector<uint8_t> b;
+    put_pod<uint64_t>(b, kPlanMagic);
+    put_pod<uint32_t>(b, p.S);
+    put_pod<uint32_t>(b, p.num_witnesses);
+    put_pod<uint32_t>(b, p.n_slots);
+    put_pod<uint32_t>(b, p.n_opcodes);
+    put_pod<uint32_t>(b, p.chunk_steps);
+    put_pod<uint32_t>(b, p.needs_full_kernel ? 1u : 0u);
+    put_pod<uint32_t>(b, p.n_steps);
+    put_pod<uint32_t>(b, p.static_fail.present ? 1u : 0u);
+    put_pod<uint32_t>(b, p.static_fail.opcode);
+    put_pod<uint32_t>(b, p.static_fail.kind);
+    put_pod<uint32_t>(b, p.static_fail.aux);
+    put_pod<uint32_t>(b, 0u);
+    put_pod<PlanStats>(b, p.stats);
+    while (b.size() % 16) b.push_back(0);
+    put_vec(b, p.input_witnesses);
+    put_vec(b, p.assign_opcode);
+    put_vec(b, p.payload);
+    put_vec(b, p.stream);
+    return b;
+}
+
+Plan deserialize_plan(const uint8_t* data, size_t len) {
+    Cursor c{data, len};
+    if (c.pod<uint64_t>() != kPlanMagic) throw std::runtime_error("not a plan blob");
+    Plan p;
+    p.S = c.pod<uint32_t>();
+    p.num_witnesses = c.pod<uint32_t>();
+    p.n_slots = c.pod<uint32_t>();
+    p.n_opcodes = c.pod<uint32_t>();
+    p.chunk_steps = c.pod<uint32_t>();
+    p.needs_full_kernel = c.pod<uint32_t>() != 0;
+    p.n_steps = c.pod<uint32_t>();
+    p.static_fail.present = c.pod<uint32_t>() != 0;
+    p.static_fail.opcode = c.pod<uint32_t>();
+    p.static_fail.kind = c.pod<uint32_t>();
+    p.static_fail.aux = c.pod<uint32_t>();
+    c.pod<uint32_t>();
+    p.stats = c.pod<PlanStats>();
+    while (c.o % 16) ++c.o;
+    p.input_witnesses = c.vec<uint32_t>();
+    p.assign_opcode = c.vec<uint32_t>();
+    p.payload = c.vec<uint32_t>();
+    p.stream = c.vec<OpRec>();
+    if (p.stream.size() != (size_t)p.n_steps * p.S) throw std::runtime_error("plan blob: stream size mismatch");
+    return p;
+}
+
+}  // namespace acvmb

@@ -1,0 +1,113 @@
+// Plan compiler: ACIR opcodes -> a statically scheduled stream of fixed-size device records.
+//
+// The reference solves opcodes strictly in order, one instance at a time, discovering which
+// witnesses are known as it goes (acvm/src/pwg/mod.rs:236-303, arithmetic.rs:27-239).  For a batch
+// of instances of the SAME circuit the known-set after opcode i is a static property of the
+// circuit, so it is resolved ONCE here on the host:
+//   * every Arithmetic opcode becomes ASSIGN / CHECK micro-gates with the unknown's coefficient
+//     inverted at plan time (the reference inverts per gate per instance),
+//   * micro-ops are list-scheduled into "steps" of S independent slots (dependencies from the
+//     witness dataflow), so one CTA = one tile of T instances executes S*T lanes per step,
+//   * the record stream is what the kernel stages through shared memory with TMA bulk copies.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "acir.hpp"
+
+namespace acvmb {
+
+// ---- device record (192 B, 16 B aligned) ------------------------------------------------------
+struct OpRec {
+    uint32_t w[8];      // [0]=kind|flags<<8  [1]=acir opcode index  [2]=out slot  [3]=x  [4]=y  [5]=w1  [6]=w2  [7]=aux
+    uint32_t c[5][8];   // gate: cM*R^2, cY*R, c1*R, c2*R, cC (canonical)   (8 x u32 little-endian limbs)
+};
+static_assert(sizeof(OpRec) == 192, "OpRec layout");
+
+enum MicroKind : uint32_t {
+    MK_NOP = 0,
+    MK_GATE_ASSIGN = 1,   // out := cM*x*y + cY*y + c1*w1 + c2*w2 + cC
+    MK_GATE_CHECK = 2,    // same expression must be 0 else UnsatisfiedConstrain@opcode
+    MK_AND = 3,           // out := (x & y) masked to aux bits, mod p       (logic.rs:11-56)
+    MK_XOR = 4,
+    MK_RANGE = 5,         // num_bits(x) > aux  => UnsatisfiedConstrain     (range.rs:7-18)
+    MK_SHA256 = 6,        // payload[aux..]: n_in, (witness,num_bits)*, 32 outputs
+    MK_KECCAK256 = 7,
+    MK_FIXED_BASE = 8,    // x=low y=high out=x-coord w1=y-coord slot
+    MK_PEDERSEN = 9,      // payload[aux..]: n_in, domain_separator, witness*, out_x, out_y
+    MK_GATE_GENERAL = 10, // value-dependent arithmetic gate (unknown is a mul operand)
+    MK_COPY_CHECK = 11,   // insert_value on an already assigned witness: x must equal y
+};
+
+// flags (w[0] >> 8)
+enum : uint32_t {
+    GF_MUL = 1u << 0,        // cM term present (x and y loaded)
+    GF_Y = 1u << 1,          // y term present (always set when GF_MUL)
+    GF_NLIN_SHIFT = 2,       // bits 2..3: number of extra linear terms (0..2) -> w1, w2
+    GF_W1_IS_X = 1u << 4,    // w1 is the same slot as x (saves a reload)
+    GF_OUT_CHECK = 1u << 5,  // output slot already holds a value: compare instead of store (insert_value, mod.rs:338-357)
+    GF_HEAVY = 1u << 6,      // needs the FULL kernel variant
+};
+
+// error kinds mirrored from OpcodeResolutionError (acvm/src/pwg/mod.rs:100-114) + reference panics
+enum ErrKind : uint32_t {
+    EK_NONE = 0,
+    EK_MISSING_ASSIGNMENT = 1,        // OpcodeNotSolvable(MissingAssignment(w)); aux = witness
+    EK_TOO_MANY_UNKNOWNS = 2,         // OpcodeNotSolvable(ExpressionHasTooManyUnknowns)
+    EK_UNSUPPORTED_BLACKBOX = 3,      // UnsupportedBlackBoxFunc; aux = func
+    EK_UNSATISFIED_CONSTRAIN = 4,     // opcode_location = Resolved(Acir(opcode_index))
+    EK_INDEX_OUT_OF_BOUNDS = 5,       // aux = index (array_size via acvmb_status.aux2)
+    EK_BLACKBOX_FAILED = 6,           // aux = func
+    EK_BRILLIG_FAILED = 7,
+    EK_REFERENCE_PANIC = 8,           // the reference would panic!() here (malformed circuit / API misuse)
+};
+
+enum StatusCode : uint32_t { ST_SOLVED = 0, ST_IN_PROGRESS = 1, ST_FAILURE = 2, ST_REQUIRES_FOREIGN_CALL = 3 };
+
+struct StaticFail {
+    bool present = false;
+    uint32_t opcode = 0, kind = 0, aux = 0;
+    std::string detail;
+};
+
+struct PlanStats {
+    uint64_t n_opcodes = 0, n_micro = 0, n_steps = 0, n_slots_filled = 0;
+    uint64_t n_gate_assign = 0, n_gate_check = 0, n_logic = 0, n_range = 0, n_hash = 0, n_curve = 0;
+    uint64_t ref_fr_mul = 0;       // Fr multiplications the reference performs per instance (SURVEY 8d accounting)
+    uint64_t ref_fr_inv = 0;       // field inversions the reference performs per instance
+    uint64_t dev_imad = 0;         // 32x32 multiply-accumulates the device executes per instance (gate ops)
+    uint64_t alg_bytes = 0;        // algorithmic HBM bytes per instance: 32 B per operand read + 32 B per witness written
+    uint64_t n_temps = 0;
+};
+
+struct Plan {
+    uint32_t S = 16;                   // slots per step
+    uint32_t num_witnesses = 0;        // current_witness_index + 1 (dense output width)
+    uint32_t n_slots = 0;              // witnesses + temporaries
+    uint32_t n_opcodes = 0;
+    uint32_t chunk_steps = 2;          // steps per TMA stage
+    bool needs_full_kernel = false;
+    std::vector<uint32_t> input_witnesses;  // order of the per-instance input columns
+    std::vector<OpRec> stream;         // n_steps_padded * S records
+    uint32_t n_steps = 0;              // padded to a multiple of chunk_steps
+    std::vector<uint32_t> payload;     // variable-length operand lists (hash inputs ...)
+    std::vector<uint32_t> assign_opcode;  // per witness: opcode index that assigns it, 0xFFFFFFFF = never, 0xFFFFFFFE = input
+    StaticFail static_fail;            // the whole batch fails here (unless an instance failed earlier)
+    PlanStats stats;
+};
+
+struct PlanOptions {
+    uint32_t S = 16;
+    uint32_t chunk_steps = 2;
+    uint32_t temp_pool = 2048;
+};
+
+// Throws std::runtime_error for opcodes outside the device scope.
+Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt);
+
+// flat byte blob (host metadata + stream) used for the one-time multi-GPU broadcast
+std::vector<uint8_t> serialize_plan(const Plan& p);
+Plan deserialize_plan(const uint8_t* data, size_t len);
+
+}  // namespace acvmb

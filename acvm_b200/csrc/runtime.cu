@@ -1,0 +1,733 @@
+// Host runtime behind the C ABI (include/acvm_b200.h): context, compiled circuit, device-resident
+// batch, sub-batching, I/O staging.  Mirrors the ownership model of the reference's ACVM struct
+// (acvm/src/pwg/mod.rs:129-181): the circuit owns the opcodes/plan, a batch owns the witness columns.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/acvm_b200.h"
+#include "acir.hpp"
+#include "plan.hpp"
+#include "vm_kernel.cuh"
+
+using namespace acvmb;
+
+static thread_local std::string g_last_error;
+static int set_err(int rc, const std::string& msg) {
+    g_last_error = msg;
+    return rc;
+}
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return set_err(_e == cudaErrorMemoryAllocation ? ACVMB_ERR_OOM : ACVMB_ERR_CUDA,       \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+    } while (0)
+
+struct acvmb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaDeviceProp prop{};
+    uint32_t opt_T = 0;   // 0 = auto
+    uint32_t opt_S = 16;
+    uint32_t opt_chunk_steps = 2;
+    uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
+    uint64_t staging_bytes = 512ull << 20;
+};
+
+struct acvmb_circuit {
+    acvmb_ctx* ctx = nullptr;
+    Plan plan;
+    uint8_t* d_stream = nullptr;
+    uint32_t* d_payload = nullptr;
+    uint32_t* d_assign = nullptr;
+    uint32_t* d_input_slots = nullptr;
+    acvmb_run_info run{};
+    ~acvmb_circuit() {
+        if (d_stream) cudaFree(d_stream);
+        if (d_payload) cudaFree(d_payload);
+        if (d_assign) cudaFree(d_assign);
+        if (d_input_slots) cudaFree(d_input_slots);
+    }
+};
+
+struct acvmb_batch {
+    acvmb_circuit* c = nullptr;
+    uint32_t n_inst = 0, T = 0, n_tiles = 0;
+    uint4* d_cols = nullptr;
+    unsigned long long* d_fail = nullptr;
+    uint8_t* d_in = nullptr;
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    uint32_t* d_out_ids = nullptr;
+    size_t out_ids_cap = 0;
+    size_t stage_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_gather[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    ~acvmb_batch() {
+        if (d_cols) cudaFree(d_cols);
+        if (d_fail) cudaFree(d_fail);
+        if (d_in) cudaFree(d_in);
+        if (d_stage[0]) cudaFree(d_stage[0]);
+        if (d_stage[1]) cudaFree(d_stage[1]);
+        if (d_out_ids) cudaFree(d_out_ids);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_gather[i]) cudaEventDestroy(ev_gather[i]);
+            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+        }
+    }
+};
+
+struct acvmb_vm {
+    acvmb_circuit* c = nullptr;
+    acvmb_batch* b = nullptr;
+    std::vector<uint8_t> inputs;      // [n_initial][32]
+    acvmb_status status{ACVMB_IN_PROGRESS, 0, 0, 0};
+    std::vector<uint8_t> witness;     // dense [num_witnesses][32] after solve
+    std::vector<uint32_t> assign;
+    bool solved_once = false;
+};
+
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* acvmb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int acvmb_ctx_create(int device, acvmb_ctx** out) {
+    if (!out) return set_err(ACVMB_ERR_INVALID_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(ACVMB_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                                "); acvm_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return set_err(ACVMB_ERR_INVALID_ARG, "device index out of range");
+    auto ctx = std::make_unique<acvmb_ctx>();
+    ctx->device = device;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaGetDeviceProperties(&ctx->prop, device));
+    if (ctx->prop.major < 10)
+        return set_err(ACVMB_ERR_NO_DEVICE, std::string("device ") + ctx->prop.name + " is sm_" + std::to_string(ctx->prop.major) +
+                                                std::to_string(ctx->prop.minor) + "; kernels are built for sm_100a only");
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    return ACVMB_OK;
+}
+
+extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" int acvmb_device_name(acvmb_ctx* ctx, char* buf, size_t len) {
+    if (!ctx || !buf || !len) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    snprintf(buf, len, "%s", ctx->prop.name);
+    return ACVMB_OK;
+}
+
+extern "C" void* acvmb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void acvmb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value) {
+    if (!ctx || !key) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    std::string k(key);
+    if (k == "T") ctx->opt_T = (uint32_t)value;
+    else if (k == "S") ctx->opt_S = (uint32_t)value;
+    else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
+    else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
+    else if (k == "staging_bytes") ctx->staging_bytes = value;
+    else return set_err(ACVMB_ERR_INVALID_ARG, "unknown option " + k);
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int upload_plan(acvmb_circuit* c) {
+    const Plan& p = c->plan;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    size_t sb = p.stream.size() * sizeof(OpRec);
+    CUDA_TRY(cudaMalloc(&c->d_stream, std::max<size_t>(sb, 16)));
+    CUDA_TRY(cudaMemcpy(c->d_stream, p.stream.data(), sb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_payload, std::max<size_t>(p.payload.size() * 4, 16)));
+    if (!p.payload.empty()) CUDA_TRY(cudaMemcpy(c->d_payload, p.payload.data(), p.payload.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_assign, std::max<size_t>(p.assign_opcode.size() * 4, 16)));
+    CUDA_TRY(cudaMemcpy(c->d_assign, p.assign_opcode.data(), p.assign_opcode.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_input_slots, std::max<size_t>(p.input_witnesses.size() * 4, 16)));
+    if (!p.input_witnesses.empty())
+        CUDA_TRY(cudaMemcpy(c->d_input_slots, p.input_witnesses.data(), p.input_witnesses.size() * 4, cudaMemcpyHostToDevice));
+    return ACVMB_OK;
+}
+
+static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32_t* input_witnesses, uint32_t n_inputs,
+                               acvmb_circuit** out) {
+    auto c = std::make_unique<acvmb_circuit>();
+    c->ctx = ctx;
+    PlanOptions opt;
+    opt.S = ctx->opt_S;
+    opt.chunk_steps = ctx->opt_chunk_steps;
+    std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
+    try {
+        c->plan = compile_plan(circ, inputs, opt);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_UNSUPPORTED, e.what());
+    }
+    int rc = upload_plan(c.get());
+    if (rc) return rc;
+    *out = c.release();
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_circuit_from_acir(acvmb_ctx* ctx, const uint8_t* gz, size_t len, const uint32_t* input_witnesses,
+                                       uint32_t n_inputs, acvmb_circuit** out) {
+    if (!ctx || !gz || !out || (n_inputs && !input_witnesses)) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Circuit circ;
+    try {
+        circ = decode_circuit(gz, len);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    return circuit_from_struct(ctx, circ, input_witnesses, n_inputs, out);
+}
+
+extern "C" void acvmb_circuit_destroy(acvmb_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    delete c;
+}
+
+extern "C" int acvmb_circuit_info(const acvmb_circuit* c, acvmb_plan_info* o) {
+    if (!c || !o) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    const Plan& p = c->plan;
+    memset(o, 0, sizeof(*o));
+    o->n_opcodes = p.stats.n_opcodes;
+    o->n_micro_ops = p.stats.n_micro;
+    o->n_steps = p.stats.n_steps;
+    o->n_slots_filled = p.stats.n_slots_filled;
+    o->n_gate_assign = p.stats.n_gate_assign;
+    o->n_gate_check = p.stats.n_gate_check;
+    o->n_logic = p.stats.n_logic;
+    o->n_range = p.stats.n_range;
+    o->n_hash = p.stats.n_hash;
+    o->n_curve = p.stats.n_curve;
+    o->ref_fr_mul = p.stats.ref_fr_mul;
+    o->ref_fr_inv = p.stats.ref_fr_inv;
+    o->dev_imad = p.stats.dev_imad;
+    o->alg_bytes = p.stats.alg_bytes;
+    o->n_temps = p.stats.n_temps;
+    o->num_witnesses = p.num_witnesses;
+    o->n_slots = p.n_slots;
+    o->S = p.S;
+    o->needs_full_kernel = p.needs_full_kernel;
+    o->static_fail_present = p.static_fail.present;
+    o->static_fail_opcode = p.static_fail.opcode;
+    o->static_fail_kind = p.static_fail.kind;
+    o->static_fail_aux = p.static_fail.aux;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_circuit_assign_opcodes(const acvmb_circuit* c, uint32_t* out, uint32_t n) {
+    if (!c || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (n != c->plan.num_witnesses) return set_err(ACVMB_ERR_INVALID_ARG, "n must equal num_witnesses");
+    memcpy(out, c->plan.assign_opcode.data(), (size_t)n * 4);
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_circuit_serialize(const acvmb_circuit* c, uint8_t* buf, size_t cap, size_t* needed) {
+    if (!c || !needed) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    std::vector<uint8_t> blob = serialize_plan(c->plan);
+    *needed = blob.size();
+    if (!buf) return ACVMB_OK;
+    if (cap < blob.size()) return set_err(ACVMB_ERR_INVALID_ARG, "buffer too small");
+    memcpy(buf, blob.data(), blob.size());
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, size_t len, acvmb_circuit** out) {
+    if (!ctx || !blob || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    auto c = std::make_unique<acvmb_circuit>();
+    c->ctx = ctx;
+    try {
+        c->plan = deserialize_plan(blob, len);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    int rc = upload_plan(c.get());
+    if (rc) return rc;
+    *out = c.release();
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static uint32_t pick_T(const acvmb_ctx* ctx, const Plan& p) {
+    uint32_t T = ctx->opt_T ? ctx->opt_T : std::max(1u, 128u / p.S);
+    if (T > 32) T = 32;
+    while (T > 1 && !vm_config_supported((int)T, (int)p.S)) T /= 2;
+    return T;
+}
+
+extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_batch** out) {
+    if (!c || !out || n_instances == 0) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    auto b = std::make_unique<acvmb_batch>();
+    b->c = c;
+    b->n_inst = n_instances;
+    b->T = pick_T(c->ctx, c->plan);
+    if (!vm_config_supported((int)b->T, (int)c->plan.S))
+        return set_err(ACVMB_ERR_INVALID_ARG, "no kernel instantiation for T=" + std::to_string(b->T) + " S=" + std::to_string(c->plan.S));
+    b->n_tiles = (n_instances + b->T - 1) / b->T;
+    size_t col_bytes = (size_t)b->n_tiles * b->T * c->plan.n_slots * 32;
+    CUDA_TRY(cudaMalloc(&b->d_cols, col_bytes));
+    CUDA_TRY(cudaMalloc(&b->d_fail, (size_t)b->n_tiles * b->T * 8));
+    size_t in_bytes = (size_t)n_instances * c->plan.input_witnesses.size() * 32;
+    CUDA_TRY(cudaMalloc(&b->d_in, std::max<size_t>(in_bytes, 16)));
+    CUDA_TRY(cudaEventCreate(&b->ev0));
+    CUDA_TRY(cudaEventCreate(&b->ev1));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&b->ev_gather[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming));
+    }
+    *out = b.release();
+    return ACVMB_OK;
+}
+
+extern "C" void acvmb_batch_destroy(acvmb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->c->ctx->device);
+    delete b;
+}
+
+extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
+    if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    acvmb_circuit* c = b->c;
+    cudaStream_t s = c->ctx->stream;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    uint32_t n_in = (uint32_t)c->plan.input_witnesses.size();
+    size_t in_bytes = (size_t)b->n_inst * n_in * 32;
+    if (in_bytes && !inputs_be32) return set_err(ACVMB_ERR_INVALID_ARG, "inputs are NULL");
+    CUDA_TRY(cudaEventRecord(b->ev0, s));
+    if (in_bytes) CUDA_TRY(cudaMemcpyAsync(b->d_in, inputs_be32, in_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_fill_u64(b->d_fail, (size_t)b->n_tiles * b->T, ~0ull, s));
+    CUDA_TRY(launch_scatter_inputs(b->d_in, c->d_input_slots, n_in, b->d_cols, c->plan.n_slots, (int)b->T, b->n_inst, s));
+    CUDA_TRY(cudaEventRecord(b->ev1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    c->run.scatter_ms += ms;
+    c->run.kernel_launches += 2;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
+    if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    acvmb_circuit* c = b->c;
+    cudaStream_t s = c->ctx->stream;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    VmArgs a{};
+    a.stream = c->d_stream;
+    a.payload = c->d_payload;
+    a.cols = b->d_cols;
+    a.fail = b->d_fail;
+    a.n_steps = c->plan.n_steps;
+    a.chunk_steps = c->plan.chunk_steps;
+    a.n_slots = c->plan.n_slots;
+    a.n_tiles = b->n_tiles;
+    KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel};
+    CUDA_TRY(cudaEventRecord(b->ev0, s));
+    CUDA_TRY(launch_vm(cfg, a, s));
+    CUDA_TRY(cudaEventRecord(b->ev1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    if (kernel_ms) *kernel_ms = ms;
+    c->run.kernel_ms += ms;
+    c->run.kernel_launches += 1;
+    c->run.T = b->T;
+    c->run.S = c->plan.S;
+    c->run.n_tiles = b->n_tiles;
+    c->run.threads_per_cta = b->T * c->plan.S;
+    return ACVMB_OK;
+}
+
+static void decode_status(const Plan& p, unsigned long long word, acvmb_status* st) {
+    uint32_t fop = (uint32_t)(word >> 32);
+    if (p.static_fail.present && p.static_fail.opcode <= fop) {
+        // a per-instance failure at the same opcode cannot exist: the static failure stops the plan there
+        st->code = ACVMB_FAILURE;
+        st->err_kind = p.static_fail.kind;
+        st->opcode_index = p.static_fail.opcode;
+        st->aux = p.static_fail.aux;
+    } else if (word == ~0ull) {
+        st->code = ACVMB_SOLVED;
+        st->err_kind = ACVMB_E_NONE;
+        st->opcode_index = p.n_opcodes;
+        st->aux = 0;
+    } else {
+        st->code = ACVMB_FAILURE;
+        st->err_kind = (uint32_t)((word >> 28) & 0xF);
+        st->opcode_index = fop;
+        st->aux = (uint32_t)(word & 0x0FFFFFFFu);
+    }
+}
+
+extern "C" int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status) {
+    if (!b || !out_status) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(b->c->ctx->device));
+    std::vector<unsigned long long> words(b->n_inst);
+    CUDA_TRY(cudaMemcpy(words.data(), b->d_fail, (size_t)b->n_inst * 8, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < b->n_inst; ++i) decode_status(b->c->plan, words[i], &out_status[i]);
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids,
+                                    uint8_t* out) {
+    if (!b || !out || first + n > b->n_inst) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    acvmb_circuit* c = b->c;
+    acvmb_ctx* ctx = c->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t n_out = out_ids ? n_out_ids : c->plan.num_witnesses;
+    if (n == 0 || n_out == 0) return ACVMB_OK;
+    if (out_ids) {
+        for (uint32_t i = 0; i < n_out_ids; ++i)
+            if (out_ids[i] >= c->plan.num_witnesses) return set_err(ACVMB_ERR_INVALID_ARG, "witness index out of range");
+        if (b->out_ids_cap < n_out_ids) {
+            cudaFree(b->d_out_ids);
+            b->d_out_ids = nullptr;
+            CUDA_TRY(cudaMalloc(&b->d_out_ids, (size_t)n_out_ids * 4));
+            b->out_ids_cap = n_out_ids;
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->d_out_ids, out_ids, (size_t)n_out_ids * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    size_t row = (size_t)n_out * 32;
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n, ctx->staging_bytes / row));
+    size_t need = (size_t)chunk * row;
+    if (b->stage_bytes < need) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(b->d_stage[i]);
+            b->d_stage[i] = nullptr;
+        }
+        b->stage_bytes = 0;
+        CUDA_TRY(cudaMalloc(&b->d_stage[0], need));
+        CUDA_TRY(cudaMalloc(&b->d_stage[1], need));
+        b->stage_bytes = need;
+    }
+    uint32_t sf = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
+    CUDA_TRY(cudaEventRecord(b->ev0, ctx->stream));
+    uint32_t k = 0;
+    for (uint32_t off = 0; off < n; off += chunk, ++k) {
+        uint32_t cnt = std::min(chunk, n - off);
+        int buf = k & 1;
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, b->ev_copy[buf], 0));  // staging buffer is free again
+        CUDA_TRY(launch_gather_outputs(b->d_cols, c->plan.n_slots, (int)b->T, out_ids ? b->d_out_ids : nullptr, n_out, first + off,
+                                       cnt, b->d_fail, c->d_assign, sf, b->d_stage[buf], ctx->stream));
+        CUDA_TRY(cudaEventRecord(b->ev_gather[buf], ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev_gather[buf], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)off * row, b->d_stage[buf], (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(b->ev_copy[buf], ctx->copy_stream));
+        c->run.kernel_launches += 1;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    c->run.gather_ms += ms;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out) {
+    (void)b;
+    (void)out;
+    return set_err(ACVMB_ERR_UNSUPPORTED, "acvmb_batch_checksum: not implemented yet");
+}
+
+// ---------------------------------------------------------------------------------------------
+static uint32_t resident_instances(acvmb_circuit* c, uint32_t batch, uint32_t T, uint32_t n_out) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint64_t budget = c->ctx->max_resident_bytes ? c->ctx->max_resident_bytes : (uint64_t)(free_b * 0.90);
+    uint64_t fixed = 2 * std::min<uint64_t>(c->ctx->staging_bytes, (uint64_t)batch * n_out * 32) + (64ull << 20);
+    uint64_t per_inst = (uint64_t)c->plan.n_slots * 32 + 8 + c->plan.input_witnesses.size() * 32;
+    uint64_t fit = budget > fixed ? (budget - fixed) / per_inst : 0;
+    fit = (fit / T) * T;
+    if (fit < T) fit = T;
+    return (uint32_t)std::min<uint64_t>(fit, batch);
+}
+
+extern "C" int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                                 uint32_t n_out_ids, uint8_t* out_witness, acvmb_status* out_status) {
+    if (!c) return set_err(ACVMB_ERR_INVALID_ARG, "circuit is NULL");
+    if (batch == 0) return ACVMB_OK;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    memset(&c->run, 0, sizeof(c->run));
+    uint32_t T = pick_T(c->ctx, c->plan);
+    uint32_t n_out = out_ids ? n_out_ids : c->plan.num_witnesses;
+    uint32_t resident = resident_instances(c, batch, T, out_witness ? n_out : 0);
+    size_t n_in = c->plan.input_witnesses.size();
+    acvmb_batch* b = nullptr;
+    uint32_t cap = 0;
+    int rc = ACVMB_OK;
+    uint32_t n_sub = 0;
+    for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += resident, ++n_sub) {
+        uint32_t cnt = std::min(resident, batch - off);
+        if (!b || cnt != cap) {
+            if (b) acvmb_batch_destroy(b);
+            b = nullptr;
+            rc = acvmb_batch_create(c, cnt, &b);
+            if (rc) break;
+            cap = cnt;
+        }
+        rc = acvmb_batch_upload(b, inputs_be32 ? inputs_be32 + (size_t)off * n_in * 32 : nullptr);
+        if (rc) break;
+        rc = acvmb_batch_run(b, nullptr);
+        if (rc) break;
+        if (out_status) {
+            rc = acvmb_batch_status(b, out_status + off);
+            if (rc) break;
+        }
+        if (out_witness) rc = acvmb_batch_download(b, 0, cnt, out_ids, n_out_ids, out_witness + (size_t)off * n_out * 32);
+    }
+    if (b) acvmb_batch_destroy(b);
+    c->run.resident_instances = resident;
+    c->run.n_subbatches = n_sub;
+    return rc;
+}
+
+extern "C" int acvmb_last_run_info(const acvmb_circuit* c, acvmb_run_info* out) {
+    if (!c || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    *out = c->run;
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-instance ACVM mirror (batch of 1)
+// ---------------------------------------------------------------------------------------------
+extern "C" int acvmb_vm_new(acvmb_ctx* ctx, const uint8_t* gz, size_t len, const uint32_t* widx, const uint8_t* wval,
+                            uint32_t n_initial, acvmb_vm** out) {
+    if (!ctx || !gz || !out || (n_initial && (!widx || !wval))) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    auto vm = std::make_unique<acvmb_vm>();
+    int rc = acvmb_circuit_from_acir(ctx, gz, len, widx, n_initial, &vm->c);
+    if (rc) return rc;
+    vm->inputs.assign(wval, wval + (size_t)n_initial * 32);
+    vm->assign = vm->c->plan.assign_opcode;
+    // ACVM::new: Solved when there are no opcodes (mod.rs:147)
+    vm->status.code = vm->c->plan.n_opcodes == 0 ? ACVMB_SOLVED : ACVMB_IN_PROGRESS;
+    *out = vm.release();
+    return ACVMB_OK;
+}
+
+extern "C" void acvmb_vm_destroy(acvmb_vm* vm) {
+    if (!vm) return;
+    if (vm->b) acvmb_batch_destroy(vm->b);
+    if (vm->c) acvmb_circuit_destroy(vm->c);
+    delete vm;
+}
+
+extern "C" int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out) {
+    if (!vm) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (!vm->solved_once) {
+        vm->witness.assign((size_t)vm->c->plan.num_witnesses * 32, 0);
+        int rc = acvmb_solve_batch(vm->c, 1, vm->inputs.data(), nullptr, 0, vm->witness.data(), &vm->status);
+        if (rc) return rc;
+        vm->solved_once = true;
+    }
+    if (out) *out = vm->status;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_vm_status(const acvmb_vm* vm, acvmb_status* out) {
+    if (!vm || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    *out = vm->status;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_vm_instruction_pointer(const acvmb_vm* vm, uint32_t* out) {
+    if (!vm || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    *out = vm->solved_once ? vm->status.opcode_index : 0;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_vm_num_witnesses(const acvmb_vm* vm, uint32_t* out) {
+    if (!vm || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    *out = vm->c->plan.num_witnesses;
+    return ACVMB_OK;
+}
+
+static bool vm_present(const acvmb_vm* vm, uint32_t w) {
+    uint32_t ao = vm->assign[w];
+    if (ao == 0xFFFFFFFEu) return true;
+    if (!vm->solved_once || ao == 0xFFFFFFFFu) return false;
+    uint32_t limit = vm->status.code == ACVMB_SOLVED ? 0xFFFFFFFFu : vm->status.opcode_index;
+    return ao < limit;
+}
+
+extern "C" int acvmb_vm_witness(const acvmb_vm* vm, uint32_t w, uint8_t out[32], int* present) {
+    if (!vm || !out || !present) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (w >= vm->c->plan.num_witnesses) {
+        *present = 0;
+        memset(out, 0, 32);
+        return ACVMB_OK;
+    }
+    *present = vm_present(vm, w) ? 1 : 0;
+    if (*present && !vm->solved_once) {
+        // initial witness before solve(): answer from the inputs
+        const auto& in = vm->c->plan.input_witnesses;
+        for (size_t i = 0; i < in.size(); ++i)
+            if (in[i] == w) memcpy(out, vm->inputs.data() + i * 32, 32);
+        return ACVMB_OK;
+    }
+    if (*present) memcpy(out, vm->witness.data() + (size_t)w * 32, 32); else memset(out, 0, 32);
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_vm_finalize(acvmb_vm* vm, uint8_t* out, uint8_t* present, uint32_t n) {
+    if (!vm || !out || !present) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (vm->status.code != ACVMB_SOLVED) return set_err(ACVMB_ERR_STATE, "ACVM is not ready to be finalized");  // mod.rs:177-179
+    if (n != vm->c->plan.num_witnesses) return set_err(ACVMB_ERR_INVALID_ARG, "n must equal num_witnesses");
+    if (!vm->solved_once) {  // no opcodes: the map is the initial witness
+        vm->witness.assign((size_t)n * 32, 0);
+        const auto& in = vm->c->plan.input_witnesses;
+        for (size_t i = 0; i < in.size(); ++i) memcpy(vm->witness.data() + (size_t)in[i] * 32, vm->inputs.data() + i * 32, 32);
+        vm->solved_once = true;
+    }
+    memcpy(out, vm->witness.data(), (size_t)n * 32);
+    for (uint32_t w = 0; w < n; ++w) present[w] = vm_present(vm, w) ? 1 : 0;
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BlackBoxFunctionSolver trait, batched: thin wrappers that build a one-opcode circuit
+// ---------------------------------------------------------------------------------------------
+static int run_single_opcode(acvmb_ctx* ctx, const Opcode& op, uint32_t n_witnesses, const std::vector<uint32_t>& inputs,
+                             const std::vector<uint32_t>& outs, const uint8_t* in_be, uint32_t batch, uint8_t* out_be,
+                             acvmb_status* st) {
+    Circuit circ;
+    circ.current_witness_index = n_witnesses - 1;
+    circ.opcodes.push_back(op);
+    acvmb_circuit* c = nullptr;
+    int rc = circuit_from_struct(ctx, circ, inputs.data(), (uint32_t)inputs.size(), &c);
+    if (rc) return rc;
+    rc = acvmb_solve_batch(c, batch, in_be, outs.data(), (uint32_t)outs.size(), out_be, st);
+    acvmb_circuit_destroy(c);
+    return rc;
+}
+
+extern "C" int acvmb_fixed_base_scalar_mul(acvmb_ctx* ctx, const uint8_t* low, const uint8_t* high, uint32_t batch, uint8_t* out_xy,
+                                           acvmb_status* st) {
+    if (!ctx || !low || !high || !out_xy) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Opcode op;
+    op.kind = OP_BlackBox;
+    op.bb.func = BB_FixedBaseScalarMul;
+    op.bb.inputs = {{1, 128}, {2, 128}};
+    op.bb.outputs = {3, 4};
+    std::vector<uint8_t> in((size_t)batch * 64);
+    for (uint32_t i = 0; i < batch; ++i) {
+        memcpy(&in[(size_t)i * 64], low + (size_t)i * 32, 32);
+        memcpy(&in[(size_t)i * 64 + 32], high + (size_t)i * 32, 32);
+    }
+    return run_single_opcode(ctx, op, 5, {1, 2}, {3, 4}, in.data(), batch, out_xy, st);
+}
+
+extern "C" int acvmb_pedersen(acvmb_ctx* ctx, const uint8_t* inputs, uint32_t n_inputs, uint32_t batch, uint32_t domain_separator,
+                              uint8_t* out_xy, acvmb_status* st) {
+    if (!ctx || (!inputs && n_inputs) || !out_xy) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Opcode op;
+    op.kind = OP_BlackBox;
+    op.bb.func = BB_Pedersen;
+    std::vector<uint32_t> in_ids;
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+        op.bb.inputs.push_back({i + 1, 254});
+        in_ids.push_back(i + 1);
+    }
+    op.bb.n_message_inputs = n_inputs;
+    op.bb.domain_separator = domain_separator;
+    op.bb.outputs = {n_inputs + 1, n_inputs + 2};
+    return run_single_opcode(ctx, op, n_inputs + 3, in_ids, {n_inputs + 1, n_inputs + 2}, inputs, batch, out_xy, st);
+}
+
+static int hash_bytes(acvmb_ctx* ctx, uint32_t func, const uint8_t* msgs, uint32_t msg_len, uint32_t batch, uint8_t* digests) {
+    if (!ctx || (!msgs && msg_len) || !digests) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Opcode op;
+    op.kind = OP_BlackBox;
+    op.bb.func = func;
+    std::vector<uint32_t> in_ids, out_ids;
+    for (uint32_t i = 0; i < msg_len; ++i) {
+        op.bb.inputs.push_back({i + 1, 8});
+        in_ids.push_back(i + 1);
+    }
+    op.bb.n_message_inputs = msg_len;
+    for (uint32_t i = 0; i < 32; ++i) {
+        op.bb.outputs.push_back(msg_len + 1 + i);
+        out_ids.push_back(msg_len + 1 + i);
+    }
+    // one byte per witness, like the ACIR opcode (hash.rs:51-66)
+    std::vector<uint8_t> in((size_t)batch * msg_len * 32, 0);
+    for (size_t i = 0; i < (size_t)batch * msg_len; ++i) in[i * 32 + 31] = msgs[i];
+    std::vector<uint8_t> out((size_t)batch * 32 * 32);
+    std::vector<acvmb_status> st(batch);
+    int rc = run_single_opcode(ctx, op, msg_len + 33, in_ids, out_ids, in.data(), batch, out.data(), st.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)batch * 32; ++i) digests[i] = out[i * 32 + 31];
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_sha256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint32_t batch, uint8_t* digests) {
+    return hash_bytes(ctx, BB_SHA256, msgs, msg_len, batch, digests);
+}
+extern "C" int acvmb_keccak256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint32_t batch, uint8_t* digests) {
+    return hash_bytes(ctx, BB_Keccak256, msgs, msg_len, batch, digests);
+}
+
+extern "C" int acvmb_imad_microbench(acvmb_ctx* ctx, double* a, double* b, double* c, double* mhz) {
+    if (!ctx) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(imad_microbench(a, b, c, mhz));
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-only entry point (no device needed): decode + compile, return info and the plan blob.
+// Used by the CPU test-suite to check the decoder and the plan compiler without a GPU.
+// ---------------------------------------------------------------------------------------------
+extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
+                                       acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed) {
+    if (!gz || (n_inputs && !input_witnesses)) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Circuit circ;
+    try {
+        circ = decode_circuit(gz, len);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    acvmb_circuit tmp;
+    PlanOptions opt;
+    opt.S = S ? S : 16;
+    try {
+        tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_UNSUPPORTED, e.what());
+    }
+    if (info) acvmb_circuit_info(&tmp, info);
+    if (needed || blob) {
+        std::vector<uint8_t> b = serialize_plan(tmp.plan);
+        if (needed) *needed = b.size();
+        if (blob) {
+            if (cap < b.size()) return set_err(ACVMB_ERR_INVALID_ARG, "buffer too small");
+            memcpy(blob, b.data(), b.size());
+        }
+    }
+    return ACVMB_OK;
+}

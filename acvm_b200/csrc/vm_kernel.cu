@@ -1,0 +1,469 @@
+// Step-VM kernels for sm_100a: one CTA = one tile of T witness instances, S micro-op slots per step.
+//
+// Replaces the reference's serial interpreter loop (acvm/src/pwg/mod.rs:236-303) and the opcode
+// solvers it dispatches to (arithmetic.rs:27-239, blackbox/logic.rs, blackbox/range.rs, ...).
+//
+//  * thread (slot, lane) executes micro-op `slot` of the current step for instance `tile*T + lane`;
+//    lanes of the same slot read the SAME record -> shared-memory broadcast, zero divergence.
+//  * the record stream is shared by every CTA: it is staged global -> shared with TMA bulk copies
+//    (cp.async.bulk + mbarrier complete_tx) through a 4-deep ring, one elected thread issuing.
+//  * witness columns are tile-major in HBM: each operand load is T*16 contiguous bytes per plane.
+//  * one __syncthreads() per step orders the CTA's own global stores/loads (the plan guarantees a
+//    slot never reads a column written in the same step).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fr.cuh"
+#include "plan.hpp"
+#include "vm_kernel.cuh"
+#ifdef ACVMB_HEAVY_OPS
+#include "heavy_ops.cuh"
+#endif
+
+namespace acvmb {
+
+using fr::Fe;
+
+constexpr int NSTAGE = 4;
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (inline PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// ---------------------------------------------------------------------------------------------
+// column access
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void load_w(Fe& v, const uint4* cb, uint32_t w) {
+    const uint4* p = cb + (size_t)w * (2 * T);
+    uint4 lo = p[0], hi = p[T];
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+}
+template <int T>
+__device__ __forceinline__ void store_w(uint4* cb, uint32_t w, const Fe& v) {
+    uint4* p = cb + (size_t)w * (2 * T);
+    p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ void lds_fe(Fe& v, const uint32_t* c) {
+    const uint4* p = reinterpret_cast<const uint4*>(c);
+    uint4 lo = p[0], hi = p[1];
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+}
+
+__device__ __forceinline__ void record_fail(unsigned long long* fail, uint32_t opcode, uint32_t kind, uint32_t aux) {
+    unsigned long long key = ((unsigned long long)opcode << 32) | ((unsigned long long)(kind & 0xF) << 28) | (aux & 0x0FFFFFFFu);
+    atomicMin(fail, key);
+}
+
+// b-limb source for the gate dot product: term 0 lives in registers, terms 1,2 are plan constants in smem
+struct GateLimbs {
+    const Fe& first;
+    const uint32_t* c1;
+    const uint32_t* c2;
+    __device__ __forceinline__ uint32_t operator()(int k, int i) const {
+        return k == 0 ? first.l[i] : (k == 1 ? c1[i] : c2[i]);
+    }
+};
+struct SmemLimbs {
+    const uint32_t* c;
+    __device__ __forceinline__ uint32_t operator()(int, int i) const { return c[i]; }
+};
+
+// out = cM*x*y + cY*y + c1*w1 + c2*w2 + cC  -- evaluated as ((cM*x + cY)*y + c1*w1 + c2*w2) + cC with
+// one Montgomery reduction for the bracket and one for cM*x (see fr.cuh / DESIGN.md for the bounds).
+template <int T>
+__device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    Fe res;
+    if (flags & GF_Y) {
+        Fe x, y, first;
+        load_w<T>(y, cb, r->w[4]);
+        if (flags & GF_MUL) {
+            load_w<T>(x, cb, r->w[3]);
+            const Fe* a1[1] = {&x};
+            fr::mont_dot_fn<1>(first, a1, SmemLimbs{r->c[0]});  // cM*R^2 * x / R = cM*x*R  (< 1.19p)
+            Fe cY;
+            lds_fe(cY, r->c[1]);
+            fr::add_raw(first, first, cY);
+            fr::cond_sub_p(first);                               // < 1.19p
+        } else {
+            lds_fe(first, r->c[1]);
+        }
+        const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
+        if (nlin == 0) {
+            const Fe* a[1] = {&y};
+            fr::mont_dot_fn<1>(res, a, GateLimbs{first, nullptr, nullptr});
+        } else {
+            Fe w1;
+            if (flags & GF_W1_IS_X) w1 = x; else load_w<T>(w1, cb, r->w[5]);
+            if (nlin == 1) {
+                const Fe* a[2] = {&y, &w1};
+                fr::mont_dot_fn<2>(res, a, GateLimbs{first, r->c[2], nullptr});
+            } else {
+                Fe w2;
+                load_w<T>(w2, cb, r->w[6]);
+                const Fe* a[3] = {&y, &w1, &w2};
+                fr::mont_dot_fn<3>(res, a, GateLimbs{first, r->c[2], r->c[3]});
+            }
+        }
+        fr::cond_sub_p(res);
+        Fe cC;
+        lds_fe(cC, r->c[4]);
+        fr::add_raw(res, res, cC);
+        fr::cond_sub_p(res);
+    } else {
+        lds_fe(res, r->c[4]);
+    }
+    if (kind == MK_GATE_ASSIGN) {
+        if (flags & GF_OUT_CHECK) {
+            Fe old;
+            load_w<T>(old, cb, r->w[2]);
+            if (!fr::eq(old, res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        } else {
+            store_w<T>(cb, r->w[2], res);
+        }
+    } else {
+        if (!fr::is_zero(res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+    }
+}
+
+// AND / XOR on the low `nb` bits of the canonical values (acir_field/src/generic_ark.rs:322-354,446-473)
+template <int T>
+__device__ __forceinline__ void exec_logic(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    Fe x, y, res;
+    load_w<T>(x, cb, r->w[3]);
+    load_w<T>(y, cb, r->w[4]);
+    const uint32_t nb = r->w[7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t m;
+        if (nb >= 32u * (i + 1)) m = 0xFFFFFFFFu;
+        else if (nb <= 32u * i) m = 0u;
+        else m = (1u << (nb - 32u * i)) - 1u;
+        uint32_t a = x.l[i] & m, b = y.l[i] & m;
+        res.l[i] = (kind == MK_AND) ? (a & b) : (a ^ b);
+    }
+    if (nb >= 254) fr::reduce_256(res);
+    if (flags & GF_OUT_CHECK) {
+        Fe old;
+        load_w<T>(old, cb, r->w[2]);
+        if (!fr::eq(old, res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+    } else {
+        store_w<T>(cb, r->w[2], res);
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned long long* fail) {
+    Fe x;
+    load_w<T>(x, cb, r->w[3]);
+    if (fr::num_bits(x) > r->w[7]) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+}
+
+template <int T, int S, bool FULL>
+__global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGE * chunk_bytes);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t slot = tid / T;
+    const uint32_t lane = tid % T;
+    const uint32_t tile = blockIdx.x;
+    uint4* cb = a.cols + (size_t)tile * a.n_slots * (2 * T) + lane;
+    unsigned long long* fail = a.fail + (size_t)tile * T + lane;
+
+    const uint32_t n_chunks = a.n_steps / a.chunk_steps;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t pre = n_chunks < (uint32_t)NSTAGE ? n_chunks : (uint32_t)NSTAGE;
+        for (uint32_t c = 0; c < pre; ++c) {
+            mbar_expect_tx(&bars[c], chunk_bytes);
+            tma_bulk_g2s(smem + (size_t)c * chunk_bytes, a.stream + (size_t)c * chunk_bytes, chunk_bytes, &bars[c]);
+        }
+    }
+
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t st = c % NSTAGE;
+        mbar_wait(&bars[st], (c / NSTAGE) & 1);
+        const OpRec* recs = reinterpret_cast<const OpRec*>(smem + (size_t)st * chunk_bytes);
+        for (uint32_t s = 0; s < a.chunk_steps; ++s) {
+            const OpRec* r = recs + s * S + slot;
+            const uint32_t hdr = r->w[0];
+            const uint32_t kind = hdr & 0xFF, flags = hdr >> 8;
+            switch (kind) {
+                case MK_NOP:
+                    break;
+                case MK_GATE_ASSIGN:
+                case MK_GATE_CHECK:
+                    exec_gate<T>(r, kind, flags, cb, fail);
+                    break;
+                case MK_AND:
+                case MK_XOR:
+                    exec_logic<T>(r, kind, flags, cb, fail);
+                    break;
+                case MK_RANGE:
+                    exec_range<T>(r, cb, fail);
+                    break;
+                default:
+#ifdef ACVMB_HEAVY_OPS
+                    if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload);
+#endif
+                    break;
+            }
+            __syncthreads();
+        }
+        // every thread is past the last read of this stage: refill it
+        if (tid == 0 && c + NSTAGE < n_chunks) {
+            mbar_expect_tx(&bars[st], chunk_bytes);
+            tma_bulk_g2s(smem + (size_t)st * chunk_bytes, a.stream + (size_t)(c + NSTAGE) * chunk_bytes, chunk_bytes, &bars[st]);
+        }
+    }
+}
+
+template <int T, int S, bool FULL>
+static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
+    size_t smem = (size_t)NSTAGE * args.chunk_steps * S * sizeof(OpRec) + NSTAGE * sizeof(uint64_t);
+    auto k = vm_kernel<T, S, FULL>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<args.n_tiles, T * S, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+#define ACVMB_CONFIGS(X) X(1, 128) X(2, 64) X(4, 32) X(8, 16) X(16, 8) X(32, 4) X(4, 16) X(8, 8) X(16, 16) X(8, 32) X(32, 8) X(32, 1) X(32, 2)
+
+bool vm_config_supported(int T, int S) {
+#define X(t, s) if (T == t && S == s) return true;
+    ACVMB_CONFIGS(X)
+#undef X
+    return false;
+}
+
+cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream) {
+#define X(t, s)                                                                        \
+    if (cfg.T == t && cfg.S == s) {                                                    \
+        return cfg.full ? launch_one<t, s, true>(args, stream) : launch_one<t, s, false>(args, stream); \
+    }
+    ACVMB_CONFIGS(X)
+#undef X
+    return cudaErrorInvalidConfiguration;
+}
+
+// ---------------------------------------------------------------------------------------------
+// input scatter: [inst][k][32 B big-endian]  ->  canonical LE limbs in column input_slots[k]
+// (FieldElement::from_be_bytes_reduce semantics, acir_field/src/generic_ark.rs:281-283)
+// ---------------------------------------------------------------------------------------------
+__global__ void scatter_inputs_kernel(const uint8_t* __restrict__ in_be, const uint32_t* __restrict__ input_slots,
+                                      uint32_t n_inputs, uint4* cols, uint32_t n_slots, int T, uint32_t n_inst) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)n_inst * n_inputs) return;
+    uint32_t inst = (uint32_t)(gid / n_inputs), k = (uint32_t)(gid % n_inputs);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in_be + gid * 32);
+    Fe v;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v.l[7 - m] = __byte_perm(src[m], 0, 0x0123);
+    fr::reduce_256(v);
+    uint32_t tile = inst / T, lane = inst % T;
+    uint4* p = cols + ((size_t)tile * n_slots + input_slots[k]) * (2 * T) + lane;
+    p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_slots, uint32_t n_inputs, uint4* cols,
+                                  uint32_t n_slots, int T, uint32_t n_inst, cudaStream_t stream) {
+    size_t n = (size_t)n_inst * n_inputs;
+    if (n == 0) return cudaSuccess;
+    scatter_inputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in_be, input_slots, n_inputs, cols, n_slots, T, n_inst);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// output gather: columns -> [inst][n_out][32 B big-endian]; a witness that the instance never
+// assigned (it failed earlier, or nothing assigns it) is written as zeros.
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_outputs_kernel(const uint4* __restrict__ cols, uint32_t n_slots, int T,
+                                      const uint32_t* __restrict__ witness_ids, uint32_t n_out, uint32_t first_inst,
+                                      uint32_t n_inst, const unsigned long long* __restrict__ fail,
+                                      const uint32_t* __restrict__ assign_opcode, uint32_t static_fail_opcode,
+                                      uint8_t* __restrict__ out_be) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)n_inst * n_out) return;
+    uint32_t li = (uint32_t)(gid / n_out), k = (uint32_t)(gid % n_out);
+    uint32_t inst = first_inst + li;
+    uint32_t w = witness_ids ? witness_ids[k] : k;
+    uint32_t fail_op = (uint32_t)(fail[inst] >> 32);
+    if (static_fail_opcode < fail_op) fail_op = static_fail_opcode;
+    uint32_t ao = assign_opcode[w];
+    bool present = (ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op);
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+    if (present) {
+        uint32_t tile = inst / T, lane = inst % T;
+        const uint4* p = cols + ((size_t)tile * n_slots + w) * (2 * T) + lane;
+        lo = p[0];
+        hi = p[T];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out_be + gid * 32);
+    dst[0] = make_uint4(__byte_perm(hi.w, 0, 0x0123), __byte_perm(hi.z, 0, 0x0123), __byte_perm(hi.y, 0, 0x0123), __byte_perm(hi.x, 0, 0x0123));
+    dst[1] = make_uint4(__byte_perm(lo.w, 0, 0x0123), __byte_perm(lo.z, 0, 0x0123), __byte_perm(lo.y, 0, 0x0123), __byte_perm(lo.x, 0, 0x0123));
+}
+
+cudaError_t launch_gather_outputs(const uint4* cols, uint32_t n_slots, int T, const uint32_t* witness_ids, uint32_t n_out,
+                                  uint32_t first_inst, uint32_t n_inst, const unsigned long long* fail,
+                                  const uint32_t* assign_opcode, uint32_t static_fail_opcode, uint8_t* out_be,
+                                  cudaStream_t stream) {
+    size_t n = (size_t)n_inst * n_out;
+    if (n == 0) return cudaSuccess;
+    gather_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cols, n_slots, T, witness_ids, n_out, first_inst, n_inst,
+                                                                          fail, assign_opcode, static_fail_opcode, out_be);
+    return cudaGetLastError();
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// IMAD roofline micro-benchmark ("IMAD_peak must be measured on the box").
+// Each thread runs 8 independent chains; variant 0: 32-bit IMAD, 1: IMAD.WIDE.U32 (64-bit
+// accumulate), 2: IMAD.WIDE.U32 with the carry-in/out pattern the Montgomery rows use.
+// ---------------------------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_bench_kernel(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    if (VARIANT == 0) {
+        uint32_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = a + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = acc[i] * a + b;
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= acc[i];
+        if (s == 0x12345678u) out[0] = s;
+    } else if (VARIANT == 1) {
+        unsigned long long acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = a + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(b));
+            }
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= acc[i];
+        if (s == 0x12345678ull) out[0] = (uint32_t)s;
+    } else {
+        uint32_t e[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = a + i; o[i] = b + i; }
+        uint32_t av[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = a * (i + 1);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                fr::cmad_n(o, av + 1 - 1, b + u);   // 4 wide IMADs in one carry chain
+                fr::cmad_n(e, av, a + u);           // 4 more in an independent chain
+                fr::cmad_n(o, av, a ^ u);
+                fr::cmad_n(e, av, b ^ u);
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= e[i] ^ o[i];
+        if (s == 0x12345678u) out[0] = s;
+    }
+}
+
+cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s, double* sm_clock_mhz) {
+    int dev = 0, sms = 0, khz = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    double res[3] = {0, 0, 0};
+    for (int v = 0; v < 3; ++v) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(t0);
+            if (v == 0) imad_bench_kernel<0><<<blocks, threads>>>(d, 17 + rep, iters);
+            if (v == 1) imad_bench_kernel<1><<<blocks, threads>>>(d, 17 + rep, iters);
+            if (v == 2) imad_bench_kernel<2><<<blocks, threads>>>(d, 17 + rep, iters);
+            cudaEventRecord(t1);
+            e = cudaEventSynchronize(t1);
+            if (e != cudaSuccess) return e;
+            float ms;
+            cudaEventElapsedTime(&ms, t0, t1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        double per_thread = (v == 2) ? (double)iters * 2 * 16 : (double)iters * 4 * 8;
+        res[v] = per_thread * blocks * threads / (best * 1e-3);
+    }
+    if (imad32_per_s) *imad32_per_s = res[0];
+    if (imad_wide_per_s) *imad_wide_per_s = res[1];
+    if (imad_wide_carry_per_s) *imad_wide_carry_per_s = res[2];
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
+}  // namespace acvmb

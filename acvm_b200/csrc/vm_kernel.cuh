@@ -1,0 +1,43 @@
+// Device-side interface between the host runtime (runtime.cu) and the step-VM kernels (vm_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acvmb {
+
+// Witness storage ("columns"), tile-major so one CTA streams one contiguous region:
+//   uint4 cols[tile][slot][plane(2)][T]      plane 0 = limbs 0..3, plane 1 = limbs 4..7 (canonical, LE)
+// A tile is T consecutive instances; every load/store of a witness by a tile is T*16 contiguous bytes
+// per plane (one 128 B line for T = 8).
+struct VmArgs {
+    const uint8_t* stream;        // OpRec[n_steps][S]
+    const uint32_t* payload;      // variable-length operand lists
+    uint4* cols;
+    unsigned long long* fail;     // per instance: min over failures of (opcode<<32 | kind<<28 | aux)
+    uint32_t n_steps;             // multiple of chunk_steps
+    uint32_t chunk_steps;
+    uint32_t n_slots;
+    uint32_t n_tiles;
+};
+
+struct KernelConfig {
+    int T, S;
+    bool full;
+};
+
+// returns cudaSuccess or the launch error; smem_bytes/regs reported for the run record
+cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream);
+bool vm_config_supported(int T, int S);
+
+cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_slots, uint32_t n_inputs, uint4* cols,
+                                  uint32_t n_slots, int T, uint32_t n_inst, cudaStream_t stream);
+cudaError_t launch_gather_outputs(const uint4* cols, uint32_t n_slots, int T, const uint32_t* witness_ids,
+                                  uint32_t n_out, uint32_t first_inst, uint32_t n_inst,
+                                  const unsigned long long* fail, const uint32_t* assign_opcode, uint32_t static_fail_opcode,
+                                  uint8_t* out_be, cudaStream_t stream);
+cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t stream);
+
+// IMAD roofline micro-benchmark: returns measured multiply-accumulates per second for each variant
+cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s, double* sm_clock_mhz);
+
+}  // namespace acvmb

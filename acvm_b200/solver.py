@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's solver surface, on top of the C ABI.
+
+Reference interface mirrored (acvm/src/pwg/mod.rs):
+  ACVM::new / solve / get_status / witness_map / instruction_pointer / finalize   :145-241
+  ACVMStatus / OpcodeResolutionError                                             :33-127
+plus the batch form this project exists for: the same circuit, many initial witnesses.
+Everything numerical happens in libacvm_b200.so on the GPU; this file only marshals buffers.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+from . import _lib
+
+STATUS_NAMES = {0: "Solved", 1: "InProgress", 2: "Failure", 3: "RequiresForeignCall"}
+ERR_NAMES = {0: None, 1: "OpcodeNotSolvable.MissingAssignment", 2: "OpcodeNotSolvable.ExpressionHasTooManyUnknowns",
+             3: "UnsupportedBlackBoxFunc", 4: "UnsatisfiedConstrain", 5: "IndexOutOfBounds", 6: "BlackBoxFunctionFailed",
+             7: "BrilligFunctionFailed", 8: "ReferencePanic"}
+
+
+class AcvmError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"acvm_b200 rc={rc}: {msg}")
+        self.rc = rc
+
+
+@dataclass
+class InstanceStatus:
+    status: str
+    error: Optional[str]
+    opcode_index: int
+    aux: int
+
+
+_lib_handle = None
+
+
+def lib():
+    global _lib_handle
+    if _lib_handle is None:
+        _lib_handle = _lib.load()
+    return _lib_handle
+
+
+def _check(rc):
+    if rc != 0:
+        raise AcvmError(rc, lib().acvmb_last_error().decode(errors="replace"))
+
+
+def _u32_array(xs):
+    return (C.c_uint32 * len(xs))(*xs) if len(xs) else None
+
+
+class Context:
+    """One CUDA device.  Fails loudly when there is no sm_100 GPU (no CPU fallback)."""
+
+    def __init__(self, device: int = 0, **options):
+        self._h = C.c_void_p()
+        _check(lib().acvmb_ctx_create(device, C.byref(self._h)))
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def set_option(self, key, value):
+        _check(lib().acvmb_ctx_set_option(self._h, key.encode(), int(value)))
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        _check(lib().acvmb_device_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    def imad_microbench(self):
+        v = [C.c_double() for _ in range(4)]
+        _check(lib().acvmb_imad_microbench(self._h, *[C.byref(x) for x in v]))
+        return dict(imad32_per_s=v[0].value, imad_wide_per_s=v[1].value, imad_wide_carry_per_s=v[2].value,
+                    sm_clock_mhz=v[3].value)
+
+    def close(self):
+        if self._h:
+            lib().acvmb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- BlackBoxFunctionSolver trait, batched (blackbox_solver/src/lib.rs:27-45) ----
+    def fixed_base_scalar_mul(self, lows: Sequence[int], highs: Sequence[int]):
+        n = len(lows)
+        lo = b"".join(int(v).to_bytes(32, "big") for v in lows)
+        hi = b"".join(int(v).to_bytes(32, "big") for v in highs)
+        out = C.create_string_buffer(n * 64)
+        st = (_lib.Status * n)()
+        _check(lib().acvmb_fixed_base_scalar_mul(self._h, lo, hi, n, out, st))
+        raw = out.raw
+        pts = [(int.from_bytes(raw[i * 64:i * 64 + 32], "big"), int.from_bytes(raw[i * 64 + 32:i * 64 + 64], "big")) for i in range(n)]
+        return pts, [_status(s) for s in st]
+
+    def pedersen(self, inputs: Sequence[Sequence[int]], domain_separator: int = 0):
+        n = len(inputs)
+        k = len(inputs[0]) if n else 0
+        buf = b"".join(int(v).to_bytes(32, "big") for row in inputs for v in row)
+        out = C.create_string_buffer(n * 64)
+        st = (_lib.Status * n)()
+        _check(lib().acvmb_pedersen(self._h, buf, k, n, domain_separator, out, st))
+        raw = out.raw
+        pts = [(int.from_bytes(raw[i * 64:i * 64 + 32], "big"), int.from_bytes(raw[i * 64 + 32:i * 64 + 64], "big")) for i in range(n)]
+        return pts, [_status(s) for s in st]
+
+    def sha256(self, msgs: Sequence[bytes]):
+        return self._hash("acvmb_sha256", msgs)
+
+    def keccak256(self, msgs: Sequence[bytes]):
+        return self._hash("acvmb_keccak256", msgs)
+
+    def _hash(self, fn, msgs):
+        n = len(msgs)
+        ln = len(msgs[0]) if n else 0
+        assert all(len(m) == ln for m in msgs), "one call hashes messages of one length"
+        out = C.create_string_buffer(n * 32)
+        _check(getattr(lib(), fn)(self._h, b"".join(msgs), ln, n, out))
+        return [out.raw[i * 32:(i + 1) * 32] for i in range(n)]
+
+
+def _status(s) -> InstanceStatus:
+    return InstanceStatus(STATUS_NAMES[s.code], ERR_NAMES.get(s.err_kind), int(s.opcode_index), int(s.aux))
+
+
+class CompiledCircuit:
+    """Circuit::read + plan compilation for a fixed set of initial-witness indices."""
+
+    def __init__(self, ctx: Context, acir_bytes: Optional[bytes], input_witnesses: Sequence[int] = (), _blob: Optional[bytes] = None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        self.input_witnesses = list(input_witnesses)
+        if _blob is not None:
+            buf = (C.c_uint8 * len(_blob)).from_buffer_copy(_blob)
+            _check(lib().acvmb_circuit_deserialize(ctx._h, buf, len(_blob), C.byref(self._h)))
+        else:
+            _check(lib().acvmb_circuit_from_acir(ctx._h, acir_bytes, len(acir_bytes), _u32_array(self.input_witnesses),
+                                                 len(self.input_witnesses), C.byref(self._h)))
+        info = _lib.PlanInfo()
+        _check(lib().acvmb_circuit_info(self._h, C.byref(info)))
+        self.info = info.as_dict()
+        self.num_witnesses = self.info["num_witnesses"]
+
+    @classmethod
+    def from_blob(cls, ctx, blob: bytes, input_witnesses: Sequence[int]):
+        return cls(ctx, None, input_witnesses, _blob=blob)
+
+    def serialize(self) -> bytes:
+        need = C.c_size_t()
+        _check(lib().acvmb_circuit_serialize(self._h, None, 0, C.byref(need)))
+        buf = (C.c_uint8 * need.value)()
+        _check(lib().acvmb_circuit_serialize(self._h, buf, need.value, C.byref(need)))
+        return bytes(buf)
+
+    def assign_opcodes(self) -> List[int]:
+        arr = (C.c_uint32 * self.num_witnesses)()
+        _check(lib().acvmb_circuit_assign_opcodes(self._h, arr, self.num_witnesses))
+        return list(arr)
+
+    def run_info(self):
+        ri = _lib.RunInfo()
+        _check(lib().acvmb_last_run_info(self._h, C.byref(ri)))
+        return {n: getattr(ri, n) for n, _ in ri._fields_}
+
+    def solve_batch(self, inputs_be32, batch: int, out_ids: Optional[Sequence[int]] = None, want_witness=True, out_buffer=None):
+        """inputs_be32: bytes-like [batch][n_inputs][32].  Returns (witness bytes or None, [InstanceStatus])."""
+        n_in = len(self.input_witnesses)
+        assert len(inputs_be32) == batch * n_in * 32, "inputs must be [batch][n_inputs][32]"
+        n_out = len(out_ids) if out_ids is not None else self.num_witnesses
+        out = None
+        outp = None
+        if want_witness:
+            if out_buffer is not None:
+                outp = out_buffer
+            else:
+                out = C.create_string_buffer(batch * n_out * 32)
+                outp = out
+        st = (_lib.Status * batch)()
+        inp = (C.c_uint8 * len(inputs_be32)).from_buffer_copy(inputs_be32) if not isinstance(inputs_be32, C.Array) else inputs_be32
+        ids = _u32_array(list(out_ids)) if out_ids is not None else None
+        _check(lib().acvmb_solve_batch(self._h, batch, inp, ids, len(out_ids) if out_ids is not None else 0, outp, st))
+        return (out.raw if out is not None else None), [_status(s) for s in st]
+
+    def close(self):
+        if self._h:
+            lib().acvmb_circuit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch:
+    """Witness columns of `n` instances resident in HBM (acvmb_batch_*)."""
+
+    def __init__(self, circuit: CompiledCircuit, n: int):
+        self.circuit = circuit
+        self.n = n
+        self._h = C.c_void_p()
+        _check(lib().acvmb_batch_create(circuit._h, n, C.byref(self._h)))
+
+    def upload(self, inputs_be32):
+        buf = (C.c_uint8 * len(inputs_be32)).from_buffer_copy(inputs_be32) if not isinstance(inputs_be32, (C.Array, int)) else inputs_be32
+        _check(lib().acvmb_batch_upload(self._h, buf))
+
+    def run(self) -> float:
+        ms = C.c_float()
+        _check(lib().acvmb_batch_run(self._h, C.byref(ms)))
+        return ms.value
+
+    def status(self):
+        st = (_lib.Status * self.n)()
+        _check(lib().acvmb_batch_status(self._h, st))
+        return [_status(s) for s in st]
+
+    def download(self, first=0, n=None, out_ids=None, out_buffer=None):
+        n = self.n - first if n is None else n
+        n_out = len(out_ids) if out_ids is not None else self.circuit.num_witnesses
+        out = out_buffer if out_buffer is not None else C.create_string_buffer(n * n_out * 32)
+        ids = _u32_array(list(out_ids)) if out_ids is not None else None
+        _check(lib().acvmb_batch_download(self._h, first, n, ids, len(out_ids) if out_ids is not None else 0, out))
+        return out.raw if out_buffer is None else out_buffer
+
+    def close(self):
+        if self._h:
+            lib().acvmb_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ACVM:
+    """Single-instance mirror of acvm::pwg::ACVM (acvm/src/pwg/mod.rs:129-304) -- a batch of one."""
+
+    def __init__(self, ctx: Context, acir_bytes: bytes, initial_witness: Dict[int, int]):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        keys = sorted(initial_witness)
+        vals = b"".join(int(initial_witness[k]).to_bytes(32, "big") for k in keys)
+        _check(lib().acvmb_vm_new(ctx._h, acir_bytes, len(acir_bytes), _u32_array(keys), vals, len(keys), C.byref(self._h)))
+
+    def solve(self) -> InstanceStatus:
+        st = _lib.Status()
+        _check(lib().acvmb_vm_solve(self._h, C.byref(st)))
+        return _status(st)
+
+    def get_status(self) -> InstanceStatus:
+        st = _lib.Status()
+        _check(lib().acvmb_vm_status(self._h, C.byref(st)))
+        return _status(st)
+
+    def instruction_pointer(self) -> int:
+        v = C.c_uint32()
+        _check(lib().acvmb_vm_instruction_pointer(self._h, C.byref(v)))
+        return v.value
+
+    def witness_map(self) -> Dict[int, int]:
+        n = C.c_uint32()
+        _check(lib().acvmb_vm_num_witnesses(self._h, C.byref(n)))
+        out = {}
+        buf = C.create_string_buffer(32)
+        present = C.c_int()
+        for w in range(n.value):
+            _check(lib().acvmb_vm_witness(self._h, w, buf, C.byref(present)))
+            if present.value:
+                out[w] = int.from_bytes(buf.raw, "big")
+        return out
+
+    def finalize(self) -> Dict[int, int]:
+        n = C.c_uint32()
+        _check(lib().acvmb_vm_num_witnesses(self._h, C.byref(n)))
+        vals = C.create_string_buffer(n.value * 32)
+        pres = C.create_string_buffer(n.value)
+        _check(lib().acvmb_vm_finalize(self._h, vals, pres, n.value))
+        return {w: int.from_bytes(vals.raw[w * 32:(w + 1) * 32], "big") for w in range(n.value) if pres.raw[w]}
+
+    def close(self):
+        if self._h:
+            lib().acvmb_vm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int = 16):
+    """Decode + compile on the host only (no device): returns (info dict, plan blob)."""
+    info = _lib.PlanInfo()
+    need = C.c_size_t()
+    ids = _u32_array(list(input_witnesses))
+    _check(lib().acvmb_plan_compile_host(acir_bytes, len(acir_bytes), ids, len(input_witnesses), S, C.byref(info), None, 0, C.byref(need)))
+    buf = (C.c_uint8 * need.value)()
+    _check(lib().acvmb_plan_compile_host(acir_bytes, len(acir_bytes), ids, len(input_witnesses), S, None, buf, need.value, C.byref(need)))
+    return info.as_dict(), bytes(buf)

@@ -1,0 +1,171 @@
+/* acvm_b200 -- C ABI of the B200-native batched ACIR witness solver.
+ *
+ * This is the drop-in boundary for ONE hot path of noir-lang/acvm 0.27.0: solving the same
+ * compiled Circuit for many independent initial witnesses.  Every entry point cites the reference
+ * interface it replaces (paths relative to the acvm repository root).  Plain pointers and sizes
+ * only; the caller owns every buffer; nothing unwinds across the boundary (all functions return
+ * 0 on success or a negative acvmb_rc, with a message available from acvmb_last_error()).
+ *
+ * A context is bound to one CUDA device and is single-threaded, like the reference's
+ * `Barretenberg` (RefCell<Store>, barretenberg_blackbox_solver/src/wasm/mod.rs:59-63).
+ * There is NO CPU fallback: creating a context without a usable sm_100 device fails.
+ *
+ * Byte conventions: a field element is 32 bytes big-endian, canonical value of BN254 Fr
+ * (FieldElement::to_be_bytes, acir_field/src/generic_ark.rs:269-277); inputs are reduced mod p
+ * like FieldElement::from_be_bytes_reduce (:281-283).
+ */
+#ifndef ACVM_B200_H
+#define ACVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct acvmb_ctx acvmb_ctx;
+typedef struct acvmb_circuit acvmb_circuit;
+typedef struct acvmb_batch acvmb_batch;
+typedef struct acvmb_vm acvmb_vm;
+
+typedef enum {
+    ACVMB_OK = 0,
+    ACVMB_ERR_INVALID_ARG = -1,
+    ACVMB_ERR_NO_DEVICE = -2,   /* no CUDA device / not sm_100: the product never falls back to the CPU */
+    ACVMB_ERR_CUDA = -3,
+    ACVMB_ERR_DECODE = -4,      /* bytes are not gzip(bincode(Circuit)) */
+    ACVMB_ERR_UNSUPPORTED = -5, /* opcode outside the device scope */
+    ACVMB_ERR_OOM = -6,
+    ACVMB_ERR_STATE = -7        /* API misuse where the reference would panic (e.g. finalize before Solved) */
+} acvmb_rc;
+
+/* ACVMStatus (acvm/src/pwg/mod.rs:33-51) */
+typedef enum { ACVMB_SOLVED = 0, ACVMB_IN_PROGRESS = 1, ACVMB_FAILURE = 2, ACVMB_REQUIRES_FOREIGN_CALL = 3 } acvmb_status_code;
+
+/* OpcodeResolutionError variants (acvm/src/pwg/mod.rs:100-114) + "the reference panics here" */
+typedef enum {
+    ACVMB_E_NONE = 0,
+    ACVMB_E_MISSING_ASSIGNMENT = 1,   /* OpcodeNotSolvable(MissingAssignment(aux)) */
+    ACVMB_E_TOO_MANY_UNKNOWNS = 2,    /* OpcodeNotSolvable(ExpressionHasTooManyUnknowns) */
+    ACVMB_E_UNSUPPORTED_BLACKBOX = 3, /* UnsupportedBlackBoxFunc(aux) */
+    ACVMB_E_UNSATISFIED_CONSTRAIN = 4,/* opcode_location = Resolved(Acir(opcode_index)) (mod.rs:286-296) */
+    ACVMB_E_INDEX_OUT_OF_BOUNDS = 5,
+    ACVMB_E_BLACKBOX_FAILED = 6,      /* BlackBoxFunctionFailed(aux = func, ...) */
+    ACVMB_E_BRILLIG_FAILED = 7,
+    ACVMB_E_REFERENCE_PANIC = 8
+} acvmb_err_kind;
+
+/* one per instance */
+typedef struct {
+    uint32_t code;          /* acvmb_status_code */
+    uint32_t err_kind;      /* acvmb_err_kind */
+    uint32_t opcode_index;  /* instruction pointer at failure (ACVM::instruction_pointer, mod.rs:171-173) */
+    uint32_t aux;           /* witness index / blackbox func, per err_kind */
+} acvmb_status;
+
+/* run record of the last device solve of a batch (for bench.py's roofline) */
+typedef struct {
+    double kernel_ms;            /* CUDA-event time of the step-VM kernel(s) on the library's stream */
+    double scatter_ms, gather_ms;/* input scatter / output gather kernels */
+    uint64_t kernel_launches;    /* number of OUR kernels launched */
+    uint32_t T, S;               /* tile width (instances per CTA), slots per step */
+    uint32_t n_tiles, threads_per_cta;
+    uint32_t resident_instances; /* instances per sub-batch */
+    uint32_t n_subbatches;
+} acvmb_run_info;
+
+typedef struct {
+    uint64_t n_opcodes, n_micro_ops, n_steps, n_slots_filled;
+    uint64_t n_gate_assign, n_gate_check, n_logic, n_range, n_hash, n_curve;
+    uint64_t ref_fr_mul;     /* Fr multiplications the reference performs per instance */
+    uint64_t ref_fr_inv;     /* field inversions the reference performs per instance */
+    uint64_t dev_imad;       /* 32x32 multiply-accumulates executed per instance on the device */
+    uint64_t alg_bytes;      /* algorithmic HBM bytes per instance */
+    uint64_t n_temps;
+    uint32_t num_witnesses, n_slots, S, needs_full_kernel;
+    uint32_t static_fail_present, static_fail_opcode, static_fail_kind, static_fail_aux;
+} acvmb_plan_info;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int acvmb_ctx_create(int device, acvmb_ctx** out);
+void acvmb_ctx_destroy(acvmb_ctx* ctx);
+const char* acvmb_last_error(void);           /* thread-local message of the last failing call */
+int acvmb_device_name(acvmb_ctx* ctx, char* buf, size_t len);
+/* pinned host memory for the I/O buffers of acvmb_solve_batch (pageable buffers work, slower) */
+void* acvmb_host_alloc(size_t bytes);
+void acvmb_host_free(void* p);
+
+/* ---- circuit: replaces Circuit::read (acir/src/circuit/mod.rs:155-161) + ACVM::new's opcode
+ * ownership (acvm/src/pwg/mod.rs:146-156).  `input_witnesses` are the keys of the initial
+ * WitnessMap -- identical for every instance of a batch.  The plan is compiled here, once. ---- */
+int acvmb_circuit_from_acir(acvmb_ctx* ctx, const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses,
+                            uint32_t n_inputs, acvmb_circuit** out);
+void acvmb_circuit_destroy(acvmb_circuit* c);
+int acvmb_circuit_info(const acvmb_circuit* c, acvmb_plan_info* out);
+/* per witness: opcode index that assigns it, 0xFFFFFFFE = initial witness, 0xFFFFFFFF = never */
+int acvmb_circuit_assign_opcodes(const acvmb_circuit* c, uint32_t* out, uint32_t n);
+/* one-time multi-GPU distribution: rank 0 serialises the compiled plan, every other rank loads it */
+int acvmb_circuit_serialize(const acvmb_circuit* c, uint8_t* buf, size_t cap, size_t* needed);
+int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, size_t len, acvmb_circuit** out);
+
+/* ---- batched ACVM::new + solve + finalize (acvm/src/pwg/mod.rs:146-156,236-241,176-181) ----
+ * inputs_be32  [batch][n_inputs][32]   initial witness values, order of `input_witnesses`
+ * out_witness  [batch][n_out][32]      solved witnesses; n_out = num_witnesses when out_ids == NULL
+ *                                      (dense WitnessMap, index 0..current_witness_index), else the
+ *                                      listed witness indices only.  Unassigned entries are zero.
+ *                                      May be NULL (statuses only).
+ * out_status   [batch] */
+int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                      uint32_t n_out_ids, uint8_t* out_witness_be32, acvmb_status* out_status);
+int acvmb_last_run_info(const acvmb_circuit* c, acvmb_run_info* out);
+
+/* ---- device-resident batch: the same solve split into its phases, so callers (and bench.py) can
+ * keep the witness columns in HBM, time the kernel alone, or overlap their own I/O. ---- */
+int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_batch** out);
+void acvmb_batch_destroy(acvmb_batch* b);
+int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32);         /* H2D + scatter */
+int acvmb_batch_run(acvmb_batch* b, float* kernel_ms);                      /* step-VM kernel(s), synchronous */
+int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status);           /* D2H of the fail words */
+int acvmb_batch_download(acvmb_batch* b, uint32_t first_instance, uint32_t n_instances, const uint32_t* out_ids,
+                         uint32_t n_out_ids, uint8_t* out_witness_be32);    /* gather + D2H */
+/* on-device checksum of all witness columns (xor-fold), for size-independent property tests */
+int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out);
+
+/* ---- single-instance mirror of the ACVM struct (acvm/src/pwg/mod.rs:129-304), batch of 1 ---- */
+int acvmb_vm_new(acvmb_ctx* ctx, const uint8_t* gz_bincode, size_t len, const uint32_t* witness_idx,
+                 const uint8_t* witness_be32, uint32_t n_initial, acvmb_vm** out);
+void acvmb_vm_destroy(acvmb_vm* vm);
+int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out);                         /* ACVM::solve */
+int acvmb_vm_status(const acvmb_vm* vm, acvmb_status* out);                  /* ACVM::get_status */
+int acvmb_vm_instruction_pointer(const acvmb_vm* vm, uint32_t* out);         /* ACVM::instruction_pointer */
+int acvmb_vm_num_witnesses(const acvmb_vm* vm, uint32_t* out);
+/* ACVM::witness_map: copies value of `witness`; *present = 0 when unassigned */
+int acvmb_vm_witness(const acvmb_vm* vm, uint32_t witness, uint8_t out_be32[32], int* present);
+/* ACVM::finalize: ACVMB_ERR_STATE unless Solved (the reference panics); dense map + presence flags */
+int acvmb_vm_finalize(acvmb_vm* vm, uint8_t* out_be32, uint8_t* present, uint32_t n);
+
+/* ---- BlackBoxFunctionSolver trait, batched (blackbox_solver/src/lib.rs:27-45) and the free hash
+ * functions (:47-60).  Thin wrappers: each builds a one-opcode circuit and runs the same kernels. ---- */
+int acvmb_fixed_base_scalar_mul(acvmb_ctx* ctx, const uint8_t* low_be32, const uint8_t* high_be32, uint32_t batch,
+                                uint8_t* out_xy_be32 /*[batch][2][32]*/, acvmb_status* out_status);
+int acvmb_pedersen(acvmb_ctx* ctx, const uint8_t* inputs_be32 /*[batch][n_inputs][32]*/, uint32_t n_inputs, uint32_t batch,
+                   uint32_t domain_separator, uint8_t* out_xy_be32, acvmb_status* out_status);
+int acvmb_sha256(acvmb_ctx* ctx, const uint8_t* msgs /*[batch][msg_len]*/, uint32_t msg_len, uint32_t batch,
+                 uint8_t* digests /*[batch][32]*/);
+int acvmb_keccak256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint32_t batch, uint8_t* digests);
+
+/* ---- host-only: decode + compile without a device (CPU tests of the decoder / plan compiler) ---- */
+int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
+                            acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
+
+/* ---- measurement helpers ---- */
+int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,
+                          double* sm_clock_mhz);
+/* tuning knobs: "T" (instances per CTA), "S" (slots per step; recompile plan), "max_resident_bytes" */
+int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACVM_B200_H */

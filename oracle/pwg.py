@@ -214,10 +214,8 @@ def _bb_inputs(bb):  # black_box_function_call.rs:205-292 get_inputs_vec
     if n in ("EcdsaSecp256k1", "EcdsaSecp256r1"):
         return list(bb["public_key_x"]) + list(bb["public_key_y"]) + list(bb["signature"]) + list(bb["hashed_message"])
     if n == "RecursiveAggregation":
-        v = list(bb["verification_key"]) + list(bb["proof"]) + list(bb["public_inputs"]) + [bb["key_hash"]]
-        if bb["input_aggregation_object"] is not None:
-            v += list(bb["input_aggregation_object"])
-        return v
+        # the input aggregation object is deliberately NOT an input (black_box_function_call.rs:276-279)
+        return list(bb["verification_key"]) + list(bb["proof"]) + list(bb["public_inputs"]) + [bb["key_hash"]]
     raise ValueError(n)
 
 

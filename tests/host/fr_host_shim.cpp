@@ -1,0 +1,25 @@
+// Host build of acvm_b200/csrc/fr.cuh (carry flag emulated) so the limb algorithms can be
+// checked against Python big ints on a CPU-only box.  Test shim only -- never shipped.
+#include "../../acvm_b200/csrc/fr.cuh"
+#include <cstring>
+using namespace fr;
+extern "C" {
+void t_mont_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); mont_mul(R, A, B); memcpy(r, R.l, 32);
+}
+void t_mont_dot(int k, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    Fe A[4], B[4], R;
+    for (int i = 0; i < k; ++i) { memcpy(A[i].l, a + 8 * i, 32); memcpy(B[i].l, b + 8 * i, 32); }
+    const Fe* pa[4] = {&A[0], &A[1], &A[2], &A[3]};
+    const Fe* pb[4] = {&B[0], &B[1], &B[2], &B[3]};
+    if (k == 1) mont_dot_raw<1>(R, pa, pb);
+    else if (k == 2) mont_dot_raw<2>(R, pa, pb);
+    else if (k == 3) mont_dot_raw<3>(R, pa, pb);
+    else mont_dot_raw<4>(R, pa, pb);
+    memcpy(r, R.l, 32);
+}
+void t_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); add_mod(R, A, B); memcpy(r, R.l, 32); }
+void t_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); sub_mod(R, A, B); memcpy(r, R.l, 32); }
+void t_reduce(uint32_t* a) { Fe A; memcpy(A.l, a, 32); reduce_256(A); memcpy(a, A.l, 32); }
+uint32_t t_num_bits(const uint32_t* a) { Fe A; memcpy(A.l, a, 32); return num_bits(A); }
+}

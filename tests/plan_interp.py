@@ -1,0 +1,138 @@
+"""Test-only Python interpreter of a compiled plan blob (acvmb_circuit_serialize / acvmb_plan_compile_host).
+
+It executes the device record stream step by step on Python ints with the SAME hazards the kernel
+has (all slots of a step read the state left by earlier steps), so the CPU suite can check the C++
+decoder + plan compiler + record semantics against the oracle without a GPU.  Never shipped.
+"""
+import struct
+
+P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+RINV = pow(1 << 256, -1, P)
+NONE = 0xFFFFFFFF
+
+MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
+          GATE_GENERAL=10, COPY_CHECK=11)
+GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
+EK_MISSING, EK_TOO_MANY, EK_UNSAT, EK_BB_FAILED = 1, 2, 4, 6
+
+
+class PlanBlob:
+    def __init__(self, blob: bytes):
+        o = 0
+        magic, = struct.unpack_from("<Q", blob, o)
+        o += 8
+        assert magic == 0x3130304E414C5042, "bad magic"
+        (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
+         self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, _) = struct.unpack_from("<12I", blob, o)
+        o += 48
+        self.stats = struct.unpack_from("<15Q", blob, o)
+        o += 120
+        o = (o + 15) // 16 * 16
+
+        def vec(fmt, size):
+            nonlocal o
+            n, = struct.unpack_from("<Q", blob, o)
+            o += 8
+            data = blob[o:o + n * size]
+            o += n * size
+            o = (o + 15) // 16 * 16
+            return n, data
+
+        n, d = vec("I", 4)
+        self.input_witnesses = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("I", 4)
+        self.assign_opcode = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("I", 4)
+        self.payload = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("rec", 192)
+        self.n_records = n
+        self.stream = d
+        assert n == self.n_steps * self.S
+
+    def record(self, i):
+        w = struct.unpack_from("<48I", self.stream, i * 192)
+        hdr = w[:8]
+        coefs = [sum(w[8 + 8 * k + j] << (32 * j) for j in range(8)) for k in range(5)]
+        return hdr, coefs
+
+
+def run_plan(plan: PlanBlob, inputs, hooks=None):
+    """inputs: dict witness->int.  Returns (status tuple, witness dict).
+
+    status = ("Solved",) or ("Failure", err_kind, opcode_index, aux).  `hooks` maps heavy micro-op
+    kinds to python callables (cols, hdr, payload) -> list of (slot, value) or raises."""
+    cols = {}
+    for w in plan.input_witnesses:
+        cols[w] = inputs[w] % P
+    fail = None  # (opcode, kind, aux)
+
+    def record_fail(opcode, kind, aux=0):
+        nonlocal fail
+        key = (opcode, kind, aux)
+        if fail is None or key < fail:
+            fail = key
+
+    for step in range(plan.n_steps):
+        writes = []
+        for s in range(plan.S):
+            hdr, c = plan.record(step * plan.S + s)
+            kind, flags = hdr[0] & 0xFF, hdr[0] >> 8
+            opcode, out, x, y, w1, w2, aux = hdr[1:8]
+            if kind == MK["NOP"]:
+                continue
+            if kind in (MK["GATE_ASSIGN"], MK["GATE_CHECK"]):
+                res = c[4]
+                if flags & GF_Y:
+                    if flags & GF_MUL:
+                        first = (c[0] * RINV * RINV * cols[x] + c[1] * RINV) % P
+                    else:
+                        first = c[1] * RINV % P
+                    res += first * cols[y]
+                    nlin = (flags >> GF_NLIN_SHIFT) & 3
+                    if nlin >= 1:
+                        if flags & GF_W1_IS_X:
+                            assert w1 == x
+                        res += c[2] * RINV * cols[w1]
+                    if nlin >= 2:
+                        res += c[3] * RINV * cols[w2]
+                res %= P
+                if kind == MK["GATE_ASSIGN"]:
+                    if flags & GF_OUT_CHECK:
+                        if cols[out] != res:
+                            record_fail(opcode, EK_UNSAT)
+                    else:
+                        writes.append((out, res))
+                elif res != 0:
+                    record_fail(opcode, EK_UNSAT)
+            elif kind in (MK["AND"], MK["XOR"]):
+                m = (1 << aux) - 1 if aux < 256 else (1 << 256) - 1
+                a, b = cols[x] & m, cols[y] & m
+                res = ((a & b) if kind == MK["AND"] else (a ^ b)) % P
+                if flags & GF_OUT_CHECK:
+                    if cols[out] != res:
+                        record_fail(opcode, EK_UNSAT)
+                else:
+                    writes.append((out, res))
+            elif kind == MK["RANGE"]:
+                if cols[x].bit_length() > aux:
+                    record_fail(opcode, EK_UNSAT)
+            elif hooks and kind in hooks:
+                writes.extend(hooks[kind](cols, hdr, plan.payload, record_fail))
+            else:
+                raise NotImplementedError(f"plan_interp: micro-op kind {kind}")
+        for (slot, v) in writes:
+            cols[slot] = v
+    fop = fail[0] if fail else 0xFFFFFFFF
+    if plan.sf_present and plan.sf_opcode <= fop:
+        status = ("Failure", plan.sf_kind, plan.sf_opcode, plan.sf_aux)
+        fop = plan.sf_opcode
+    elif fail:
+        status = ("Failure", fail[1], fail[0], fail[2])
+    else:
+        status = ("Solved",)
+    wm = {}
+    for w in range(plan.num_witnesses):
+        ao = plan.assign_opcode[w]
+        if ao == 0xFFFFFFFE or (ao != 0xFFFFFFFF and ao < fop):
+            wm[w] = cols[w]
+    return status, wm

@@ -1,0 +1,123 @@
+"""GPU parity: arithmetic-gate path through the C ABI vs the oracle (bit-exact canonical values)."""
+import pytest
+
+import acvm_b200
+from acvm_b200 import acir_builder as ab
+from conftest import inputs_to_dicts, witness_rows
+from oracle import acir, pwg
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, data, input_witnesses, batch, inp, expect_all_solved=True):
+    circ = acvm_b200.CompiledCircuit(ctx, data, input_witnesses)
+    out, st = circ.solve_batch(inp, batch)
+    rows = witness_rows(out, batch, circ.num_witnesses)
+    oc = acir.decode_circuit(data)
+    assign = circ.assign_opcodes()
+    for i, iw in enumerate(inputs_to_dicts(inp, batch, input_witnesses)):
+        ost, owm, oerr = pwg.solve_circuit(oc, iw)
+        assert st[i].status == ost, (i, st[i], oerr)
+        if ost == "Failure":
+            assert st[i].error == oerr.kind
+            if oerr.opcode_location is not None:
+                assert st[i].opcode_index == oerr.opcode_location
+        limit = 0xFFFFFFFF if ost == "Solved" else st[i].opcode_index
+        got = {w: rows[i][w] for w in range(circ.num_witnesses)
+               if assign[w] == 0xFFFFFFFE or (assign[w] != 0xFFFFFFFF and assign[w] < limit)}
+        assert got == owm, f"instance {i}: witness map differs"
+    circ.close()
+    return st
+
+
+@pytest.mark.parametrize("batch", [1, 33, 257])
+@pytest.mark.parametrize("mode,coeffs", [("local", "dense"), ("global", "noir-like")])
+def test_synthetic_1k(ctx, batch, mode, coeffs):
+    data, inputs, _ = ab.synthetic_arith_circuit(1024, mode=mode, coeffs=coeffs)
+    _check(ctx, data, inputs, batch, ab.synthetic_inputs(batch))
+
+
+def test_addition_golden(ctx, golden):
+    fx = golden["acvm_js_shared"]["addition"]
+    data = bytes(fx["bytecode"])
+    iw = {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()}
+    vm = acvm_b200.ACVM(ctx, data, iw)
+    st = vm.solve()
+    assert st.status == "Solved"
+    wm = vm.finalize()
+    assert wm[fx["resultWitness"]] == int(fx["expectedResult"], 16)
+    assert wm == {1: 1, 2: 2, 3: 3}
+
+
+def test_unsatisfied_constraint_location(ctx):
+    # acvm/tests/solver.rs:490-525 : a == b with a != b  -> UnsatisfiedConstrain at Acir(0)
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 1), (ab.P - 1, 2)], 0)
+    data = b.to_bytes()
+    inp = (5).to_bytes(32, "big") + (6).to_bytes(32, "big") + (7).to_bytes(32, "big") + (7).to_bytes(32, "big")
+    circ = acvm_b200.CompiledCircuit(ctx, data, [1, 2])
+    _, st = circ.solve_batch(inp, 2, want_witness=False)
+    assert (st[0].status, st[0].error, st[0].opcode_index) == ("Failure", "UnsatisfiedConstrain", 0)
+    assert st[1].status == "Solved"
+
+
+def test_mixed_failures_lowest_opcode_wins(ctx):
+    # instance-dependent failures at different opcodes; reordering by the scheduler must not change which one is reported
+    b = ab.CircuitBuilder()
+    b.arithmetic([(1, 1, 2)], [(ab.P - 1, 3)], 0)        # w3 = w1*w2
+    b.arithmetic([], [(1, 3), (ab.P - 1, 4)], 5)         # w4 = w3 + 5
+    b.arithmetic([], [(1, 1)], ab.P - 2)                 # check w1 == 2
+    b.arithmetic([(1, 4, 4)], [(ab.P - 1, 5)], 0)        # w5 = w4^2
+    b.arithmetic([], [(1, 2)], ab.P - 3)                 # check w2 == 3
+    data = b.to_bytes()
+    cases = [(2, 3), (9, 3), (2, 9), (9, 9)]
+    inp = b"".join(a.to_bytes(32, "big") + c.to_bytes(32, "big") for a, c in cases)
+    _check(ctx, data, [1, 2], len(cases), inp)
+
+
+def test_wide_expression_chain(ctx):
+    # pre-CSat style gate with many terms: exercises chained micro-gates through temporaries
+    rng = ab.SplitMix64(7)
+    b = ab.CircuitBuilder()
+    lin = [(rng.nonzero_field(), w) for w in range(1, 10)]
+    mul = [(rng.nonzero_field(), 1 + rng.below(9), 1 + rng.below(9)) for _ in range(3)]
+    b.arithmetic(mul[:1], lin + [(rng.nonzero_field(), 10)], rng.field())
+    b.arithmetic([], [(3, 10), (5, 11)], 1)
+    b.arithmetic(mul[1:2], [(1, 10), (1, 11), (1, 12)], 0)
+    data = b.to_bytes()
+    batch = 5
+    inp = ab.synthetic_inputs(batch, n_inputs=9, seed_id=3)
+    _check(ctx, data, list(range(1, 10)), batch, inp)
+
+
+def test_too_many_unknowns_static(ctx):
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 1), (1, 2), (1, 3)], 0)  # w2, w3 unknown
+    data = b.to_bytes()
+    circ = acvm_b200.CompiledCircuit(ctx, data, [1])
+    _, st = circ.solve_batch((4).to_bytes(32, "big"), 1, want_witness=False)
+    assert (st[0].status, st[0].error, st[0].opcode_index) == ("Failure", "OpcodeNotSolvable.ExpressionHasTooManyUnknowns", 0)
+
+
+def test_logic_and_range(ctx):
+    b = ab.CircuitBuilder()
+    b.logic("AND", (1, 32), (2, 32), 3)
+    b.logic("XOR", (1, 32), (2, 32), 4)
+    b.logic("XOR", (1, 254), (2, 254), 5)
+    b.logic("AND", (1, 13), (2, 13), 6)
+    b.range((3, 32))
+    b.range((1, 64))
+    data = b.to_bytes()
+    vals = [(0xDEADBEEF12345678, 0x0F0F0F0FF0F0F0F0), (ab.P - 1, ab.P - 2), (1 << 64, 3), (0, 0), ((1 << 64) - 1, 1 << 253)]
+    inp = b"".join(a.to_bytes(32, "big") + c.to_bytes(32, "big") for a, c in vals)
+    _check(ctx, data, [1, 2], len(vals), inp)
+
+
+def test_no_gpu_fallback_symbols():
+    # the library must be the thing that ran: a run record with kernel launches exists
+    c = acvm_b200.Context(0)
+    data, inputs, _ = ab.synthetic_arith_circuit(64)
+    circ = acvm_b200.CompiledCircuit(c, data, inputs)
+    circ.solve_batch(ab.synthetic_inputs(4), 4)
+    ri = circ.run_info()
+    assert ri["kernel_launches"] >= 3 and ri["kernel_ms"] > 0
