@@ -57,6 +57,8 @@ def load():
         "acvmb_batch_destroy": (None, [vp]),
         "acvmb_batch_upload": (C.c_int, [vp, vp]),
         "acvmb_batch_run": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "acvmb_batch_stage_inputs": (C.c_int, [vp, C.c_uint32, vp]),
+        "acvmb_batch_run_staged": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "acvmb_batch_status": (C.c_int, [vp, C.POINTER(Status)]),
         "acvmb_batch_download": (C.c_int, [vp, C.c_uint32, C.c_uint32, u32p, C.c_uint32, vp]),
         "acvmb_batch_checksum": (C.c_int, [vp, u64p]),
@@ -75,6 +77,7 @@ def load():
         "acvmb_plan_compile_host": (C.c_int, [C.c_char_p, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.POINTER(PlanInfo), vp,
                                               C.c_size_t, C.POINTER(C.c_size_t)]),
         "acvmb_imad_microbench": (C.c_int, [vp] + [C.POINTER(C.c_double)] * 4),
+        "acvmb_frmul_microbench": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "acvmb_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_uint64]),
     }
     for name, (res, args) in sig.items():

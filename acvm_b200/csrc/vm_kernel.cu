@@ -426,6 +426,51 @@ __global__ void __launch_bounds__(256) imad_bench_kernel(uint32_t* out, uint32_t
     }
 }
 
+// Fr-mul ceiling: register-resident Montgomery multiplications, two dependent chains per thread.
+__global__ void __launch_bounds__(256) frmul_bench_kernel(uint32_t* out, uint32_t seed, int iters) {
+    fr::Fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a.l[i] = seed * (i + 3) + threadIdx.x; b.l[i] = seed * (i + 7) + blockIdx.x; }
+    a.l[7] &= 0x0FFFFFFF; b.l[7] &= 0x0FFFFFFF;
+    for (int it = 0; it < iters; ++it) {
+        fr::mont_mul(a, a, b);
+        fr::mont_mul(b, b, a);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= a.l[i] ^ b.l[i];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+cudaError_t frmul_microbench(double* fr_mul_per_s) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int iters = 512, blocks = sms * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(t0);
+        frmul_bench_kernel<<<blocks, threads>>>(d, 17 + rep, iters);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) return e;
+        float ms;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (fr_mul_per_s) *fr_mul_per_s = 2.0 * iters * blocks * threads / (best * 1e-3);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
 cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s, double* sm_clock_mhz) {
     int dev = 0, sms = 0, khz = 0;
     cudaGetDevice(&dev);

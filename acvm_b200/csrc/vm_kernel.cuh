@@ -40,4 +40,7 @@ cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long 
 // IMAD roofline micro-benchmark: returns measured multiply-accumulates per second for each variant
 cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s, double* sm_clock_mhz);
 
+// register-resident Montgomery multiplications per second (practical Fr-mul ceiling of this field library)
+cudaError_t frmul_microbench(double* fr_mul_per_s);
+
 }  // namespace acvmb

@@ -71,8 +71,10 @@ class Context:
     def imad_microbench(self):
         v = [C.c_double() for _ in range(4)]
         _check(lib().acvmb_imad_microbench(self._h, *[C.byref(x) for x in v]))
+        f = C.c_double()
+        _check(lib().acvmb_frmul_microbench(self._h, C.byref(f)))
         return dict(imad32_per_s=v[0].value, imad_wide_per_s=v[1].value, imad_wide_carry_per_s=v[2].value,
-                    sm_clock_mhz=v[3].value)
+                    sm_clock_mhz=v[3].value, fr_mul_per_s=f.value)
 
     def close(self):
         if self._h:
@@ -214,6 +216,16 @@ class DeviceBatch:
         ms = C.c_float()
         _check(lib().acvmb_batch_run(self._h, C.byref(ms)))
         return ms.value
+
+    def stage_inputs(self, slot: int, inputs_be32):
+        buf = (C.c_uint8 * len(inputs_be32)).from_buffer_copy(inputs_be32) if not isinstance(inputs_be32, C.Array) else inputs_be32
+        _check(lib().acvmb_batch_stage_inputs(self._h, slot, buf))
+
+    def run_staged(self, slot: int):
+        """status reset + input scatter + step-VM kernel from resident inputs; returns (total_ms, vm_kernel_ms)."""
+        t, v = C.c_float(), C.c_float()
+        _check(lib().acvmb_batch_run_staged(self._h, slot, C.byref(t), C.byref(v)))
+        return t.value, v.value
 
     def status(self):
         st = (_lib.Status * self.n)()

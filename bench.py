@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""bench.py -- witnesses solved / second on the BASELINE.json headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gates G] [--batch B]
+
+Workload (config.workload): BASELINE.json configs[1] -- 2^20 arithmetic-only width-3 PLONK gates over
+BN254 Fr ("local" operands, "dense" coefficients, every 16th opcode an all-known check), batch 8192
+per GPU, synthetic splitmix64 inputs, serialised in the reference's own ACIR wire format.
+
+One "step" = one pass of the hot path over the whole batch (all sub-batches).
+  value : witnesses/s with the inputs resident in HBM; per step = status reset + input scatter +
+          step-VM kernel for every sub-batch; timed with CUDA events on the library's stream.
+  e2e   : the same metric through the C ABI with HOST buffers (acvmb_solve_batch): H2D of the
+          inputs, solve, gather + D2H of the FULL dense witness map of every instance (what
+          ACVM::finalize returns), wall-clock around the synchronous calls.
+N > 1 : one process per GPU (torchrun), plan compiled on rank 0 and broadcast once over NCCL, batch
+        sharded 8192 instances per GPU, no traffic during the solve ("scaling": "weak").
+--impl reference : the CPU reference-algorithm restatement (oracle/ref_solver.cpp; the Rust reference
+        cannot be built here) on all host cores, same circuit bytes, same JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "witnesses_per_s_2^20_gate_bn254_acir"
+UNIT = "witnesses/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cached_circuit(gates, mode, coeffs):
+    from acvm_b200 import acir_builder as ab
+    cache = os.path.join("/tmp", f"acvmb_circuit_{gates}_{mode}_{coeffs}.bin")
+    if os.path.exists(cache):
+        with open(cache, "rb") as f:
+            data = f.read()
+        return data, list(range(ab.N_INPUTS))
+    t = time.time()
+    data, inputs, _ = ab.synthetic_arith_circuit(gates, seed_id=1, mode=mode, coeffs=coeffs)
+    log(f"[bench] generated {gates}-gate circuit ({len(data) / 1e6:.1f} MB gz) in {time.time() - t:.1f}s")
+    try:
+        with open(cache, "wb") as f:
+            f.write(data)
+    except OSError:
+        pass
+    return data, inputs
+
+
+def cpu_reference_rate(data, inputs, gates, threads, n_inst=None, label="cpu_baseline"):
+    """Times the C++ reference-algorithm restatement: `n_inst` full solves spread over `threads` host threads."""
+    from acvm_b200 import acir_builder as ab
+    from oracle import acir as oacir, cref
+    cref.build()
+    t = time.time()
+    circ = oacir.decode_circuit(data)
+    packed = cref.pack_circuit(circ)
+    log(f"[{label}] oracle decode+pack {time.time() - t:.1f}s")
+    n_inst = n_inst or threads
+    inp = ab.synthetic_inputs(n_inst, seed_id=1)
+    nw = circ.current_witness_index + 1
+
+    def run():
+        t0 = time.perf_counter()
+        res, _, _ = cref.solve_batch(circ, inputs, inp, n_inst, nw, threads=threads, packed=packed)
+        dt = time.perf_counter() - t0
+        assert (res[:, 0] == 0).all(), "cpu reference failed to solve the synthetic circuit"
+        return dt
+
+    return run, n_inst
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    data, inputs = cached_circuit(args.gates, args.mode, args.coeffs)
+    run, n_inst = cpu_reference_rate(data, inputs, args.gates, threads, label="reference")
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    total = sum(times)
+    value = n_inst * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (4x64 Montgomery, BN254 Fr)", "data": "synthetic",
+        "config": workload_config(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_inst} full solves of the {args.gates}-gate circuit per step, one solver instance per thread "
+                                   "(oracle/ref_solver.cpp: std::map witness map, per-gate evaluate + inversion)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Rust acvm 0.27.0 cannot be built in this image (no cargo/rustc); this is the reference-algorithm restatement",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, extra):
+    cfg = {"workload": f"configs[1]: {args.gates} arithmetic-only width-3 PLONK gates (BN254 Fr), batch {args.batch} per GPU, "
+                       f"operands={args.mode}, coefficients={args.coeffs}, every 16th opcode an all-known check",
+           "gates": args.gates, "batch_per_gpu": args.batch, "operand_mode": args.mode, "coefficients": args.coeffs,
+           "l2_policy": "inputs larger than L2: witness columns of one sub-batch are >> 126 MB and are rewritten every step"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_ours(args):
+    import acvm_b200
+    from acvm_b200 import acir_builder as ab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = acvm_b200.Context(local_rank)
+    if args.S:
+        ctx.set_option("S", args.S)
+    if args.T:
+        ctx.set_option("T", args.T)
+
+    # ---- circuit: compiled on rank 0, broadcast once (the only collective on this path) ----
+    data, inputs = (None, list(range(ab.N_INPUTS)))
+    t0 = time.time()
+    if rank == 0:
+        data, inputs = cached_circuit(args.gates, args.mode, args.coeffs)
+        circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+        log(f"[bench] plan compiled in {time.time() - t0:.1f}s: {circ.info}")
+    if world > 1:
+        from acvm_b200.dist import broadcast_circuit
+        circ = broadcast_circuit(ctx, circ if rank == 0 else None, inputs, src=0)
+    info = circ.info
+    nw = circ.num_witnesses
+
+    # ---- sub-batching: witness columns of the whole batch do not fit in HBM ----
+    import torch
+    free_b, total_b = torch.cuda.mem_get_info(local_rank)
+    per_inst = info["n_slots"] * 32 + 8 + len(inputs) * 32
+    T = args.T or max(1, 128 // info["S"])
+    budget = int(free_b * 0.88)
+    fit = max(T, (budget // per_inst) // T * T)
+    n_sub = -(-args.batch // fit)
+    # equal sub-batches, multiple of T
+    sub = -(-args.batch // n_sub)
+    sub = -(-sub // T) * T
+    sizes = [min(sub, args.batch - i * sub) for i in range(n_sub) if args.batch - i * sub > 0]
+    log(f"[bench] rank {rank}: free {free_b / 2**30:.1f} GiB, {per_inst / 2**20:.1f} MiB/instance -> sub-batches {sizes}")
+    first_inst = rank * args.batch
+    batch_obj = acvm_b200.DeviceBatch(circ, sizes[0])
+    off = 0
+    for k, sz in enumerate(sizes):
+        inp = ab.synthetic_inputs(sz, seed_id=1, first_instance=first_inst + off)
+        if sz < sizes[0]:
+            inp = inp + bytes((sizes[0] - sz) * len(inputs) * 32)  # pad the last sub-batch (not counted)
+        batch_obj.stage_inputs(k, inp)
+        off += sz
+
+    def step():
+        tot = vm = 0.0
+        for k in range(len(sizes)):
+            t, v = batch_obj.run_staged(k)
+            tot += t
+            vm += v
+        return tot, vm
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # correctness gate on the last warm-up pass: every instance solved
+    st = batch_obj.status()
+    assert all(s.status == "Solved" for s in st[:sizes[-1]]), "synthetic circuit must solve for every instance"
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = vm_ms = 0.0
+    for _ in range(args.steps):
+        t, v = step()
+        dev_ms += t
+        vm_ms += v
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches_per_step = 3 * len(sizes)
+
+    # ---- end-to-end through acvmb_solve_batch with host buffers (full dense witness map back) ----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        avail = psutil.virtual_memory().available
+        e2e_chunk = int(min(args.batch, max(1, min(args.e2e_chunk_gib * 2**30, avail * 0.4) // (nw * 32))))
+        n_calls = -(-args.batch // e2e_chunk)
+        out_bytes = e2e_chunk * nw * 32
+        batch_obj.close()
+        lib = acvm_b200.lib()
+        t0 = time.time()
+        host_out = lib.acvmb_host_alloc(out_bytes)
+        if not host_out:
+            raise RuntimeError("pinned host allocation failed")
+        log(f"[bench] e2e: {n_calls} calls of {e2e_chunk} instances, pinned {out_bytes / 2**30:.1f} GiB in {time.time() - t0:.1f}s")
+        ins = []
+        o = 0
+        while o < args.batch:
+            c = min(e2e_chunk, args.batch - o)
+            ins.append((c, (C.c_uint8 * (c * len(inputs) * 32)).from_buffer_copy(ab.synthetic_inputs(c, 1, first_inst + o))))
+            o += c
+        st_arr = (acvm_b200._lib.Status * e2e_chunk)()
+
+        def e2e_step():
+            for c, buf in ins:
+                rc = lib.acvmb_solve_batch(circ._h, c, buf, None, 0, C.c_void_p(host_out), st_arr)
+                if rc:
+                    raise RuntimeError(lib.acvmb_last_error().decode())
+
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        e2e_step()  # warm-up (also faults in the pinned pages)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_wall = (time.perf_counter() - w0) / e2e_steps
+        # spot-check the last chunk against the kernel statuses
+        assert all(st_arr[i].code == 0 for i in range(ins[-1][0]))
+        lib.acvmb_host_free(C.c_void_p(host_out))
+        e2e = {"wall_s_per_step": e2e_wall, "h2d": args.batch * len(inputs) * 32, "d2h": args.batch * (nw * 32 + 16),
+               "calls_per_step": n_calls, "instances_per_call": e2e_chunk}
+
+    # ---- reduce over ranks (max time) ----
+    vals = [dev_ms, vm_ms, wall, e2e["wall_s_per_step"] if e2e else 0.0]
+    if dist is not None:
+        t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = t.tolist()
+    dev_ms, vm_ms, wall, e2e_wall = vals
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    total_inst = args.batch * world
+    ms_per_step = dev_ms / args.steps
+    value = total_inst / (ms_per_step * 1e-3)
+    hbm_peak, peak_src = measured_peaks()
+    vm_launch_ms = vm_ms / (args.steps * len(sizes))          # average step-VM kernel launch
+    inst_per_launch = args.batch / len(sizes)
+    alg_bytes_launch = info["alg_bytes"] * inst_per_launch
+    achieved_gbs = alg_bytes_launch / (vm_launch_ms * 1e-3) / 1e9
+    imad = ctx.imad_microbench()
+    imad_achieved = info["dev_imad"] * inst_per_launch / (vm_launch_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8x32-bit limbs, Montgomery, BN254 Fr)", "data": "synthetic",
+        "config": workload_config(args, {"sub_batches": sizes, "T": T, "S": info["S"], "n_steps": info["n_steps"],
+                                         "slot_fill": info["n_slots_filled"] / max(1, info["n_steps"] * info["S"])}),
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "kernel": "vm_kernel", "kernel_ms_per_launch": vm_launch_ms,
+            "algorithmic_bytes_per_launch": alg_bytes_launch,
+            "note": "dense-coefficient gates are integer-multiply bound, not HBM bound: see imad",
+            "imad": {"achieved_per_s": imad_achieved, "peak_per_s": imad["imad_wide_per_s"], "frac": imad_achieved / imad["imad_wide_per_s"],
+                     "peak_source": "measured in this run: independent mad.wide.u32 chains on all SMs",
+                     "peak_imad32_per_s": imad["imad32_per_s"], "peak_wide_carry_per_s": imad["imad_wide_carry_per_s"],
+                     "imad_per_instance": info["dev_imad"]},
+            "fr_mul": {"reference_fr_mul_per_instance": info["ref_fr_mul"], "reference_fr_inv_per_instance": info["ref_fr_inv"],
+                       "algorithmic_fr_mul_per_s": info["ref_fr_mul"] * inst_per_launch / (vm_launch_ms * 1e-3)},
+        },
+    }
+    if e2e:
+        line["e2e"] = {"value": total_inst / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "calls_per_step": e2e["calls_per_step"], "instances_per_call": e2e["instances_per_call"],
+                       "output": "full dense witness map of every instance (ACVM::finalize), pinned host buffer"}
+    # ---- cpu baseline beside it (rank 0, N=1 only) ----
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        run, n_inst = cpu_reference_rate(data, inputs, args.gates, threads)
+        dt = run()
+        line["cpu_baseline"] = {"value": n_inst / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_inst} full solves of the same {args.gates}-gate circuit, one per host thread "
+                                          f"({dt:.1f}s; oracle/ref_solver.cpp reference-algorithm restatement)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gates", type=int, default=1 << 20)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--mode", default="local", choices=["local", "global"])
+    ap.add_argument("--coeffs", default="dense", choices=["dense", "noir-like"])
+    ap.add_argument("--S", type=int, default=0)
+    ap.add_argument("--T", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-chunk-gib", type=float, default=16.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -126,6 +126,10 @@ int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_batch** out
 void acvmb_batch_destroy(acvmb_batch* b);
 int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32);         /* H2D + scatter */
 int acvmb_batch_run(acvmb_batch* b, float* kernel_ms);                      /* step-VM kernel(s), synchronous */
+/* resident inputs: copy input sets to HBM once, then re-run (status reset + scatter + kernel) from HBM;
+ * total_ms / vm_ms are CUDA-event times on the library's stream */
+int acvmb_batch_stage_inputs(acvmb_batch* b, uint32_t slot, const uint8_t* inputs_be32);
+int acvmb_batch_run_staged(acvmb_batch* b, uint32_t slot, float* total_ms, float* vm_ms);
 int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status);           /* D2H of the fail words */
 int acvmb_batch_download(acvmb_batch* b, uint32_t first_instance, uint32_t n_instances, const uint32_t* out_ids,
                          uint32_t n_out_ids, uint8_t* out_witness_be32);    /* gather + D2H */
@@ -162,6 +166,8 @@ int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_
 /* ---- measurement helpers ---- */
 int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,
                           double* sm_clock_mhz);
+/* register-resident Montgomery multiplications per second: the practical Fr-mul ceiling of the K0 field library */
+int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step; recompile plan), "max_resident_bytes" */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);
 

@@ -1,0 +1,140 @@
+"""CPU tests of the product's host side: library loads and exports the header's symbols, the C++ decoder
+and plan compiler agree with the oracle (through the test-only plan interpreter), field limb algorithms."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+
+import pytest
+
+import acvm_b200
+from acvm_b200 import acir_builder as ab
+from conftest import ROOT
+from oracle import acir, pwg
+import plan_interp
+
+
+def test_library_exports_every_declared_symbol():
+    lib = acvm_b200.lib()
+    hdr = open(os.path.join(ROOT, "include", "acvm_b200.h")).read()
+    declared = set(re.findall(r"\b(acvmb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/acvm_b200.h but not exported"
+    assert declared <= set(lib._acvmb_signatures) | {"acvmb_last_error"}
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(acvm_b200.AcvmError) as e:
+        acvm_b200.Context(0)
+    assert e.value.rc == -2 and "no CPU fallback" in str(e.value)
+
+
+def _interp_vs_oracle(data, inputs, inp, batch, S=16):
+    info, blob = acvm_b200.compile_plan_host(data, inputs, S)
+    plan = plan_interp.PlanBlob(blob)
+    oc = acir.decode_circuit(data)
+    n = len(inputs)
+    for i in range(batch):
+        iw = {w: int.from_bytes(inp[(i * n + k) * 32:(i * n + k + 1) * 32], "big") for k, w in enumerate(inputs)}
+        st, wm = plan_interp.run_plan(plan, iw)
+        ost, owm, oerr = pwg.solve_circuit(oc, iw)
+        assert st[0] == ost
+        if ost == "Failure":
+            assert acvm_b200.solver.ERR_NAMES[st[1]] == oerr.kind
+            if oerr.opcode_location is not None:
+                assert st[2] == oerr.opcode_location
+        assert wm == owm
+    return info
+
+
+@pytest.mark.parametrize("S", [1, 4, 16, 32])
+@pytest.mark.parametrize("mode,coeffs", [("local", "dense"), ("global", "noir-like")])
+def test_plan_matches_oracle_synthetic(S, mode, coeffs):
+    data, inputs, _ = ab.synthetic_arith_circuit(600, mode=mode, coeffs=coeffs)
+    info = _interp_vs_oracle(data, inputs, ab.synthetic_inputs(2), 2, S)
+    assert info["n_micro_ops"] == 600 and info["ref_fr_inv"] == 600 - 600 // 16
+
+
+def test_plan_failures_and_chains():
+    rng = ab.SplitMix64(11)
+    b = ab.CircuitBuilder()
+    lin = [(rng.nonzero_field(), w) for w in range(1, 10)]
+    b.arithmetic([(rng.nonzero_field(), 2, 3)], lin + [(rng.nonzero_field(), 10)], rng.field())
+    b.arithmetic([(rng.nonzero_field(), 10, 10), ], [(3, 10), (5, 11)], 1)
+    b.arithmetic([], [(1, 1)], ab.P - 2)  # check w1 == 2  (fails unless input is 2)
+    b.logic("XOR", (10, 64), (11, 64), 12)
+    b.range((12, 64))
+    b.range((11, 8))                      # almost surely fails
+    data = b.to_bytes()
+    inp = ab.synthetic_inputs(3, n_inputs=9, seed_id=5)
+    inp = (2).to_bytes(32, "big") + inp[32:]   # instance 0 passes the w1 == 2 check
+    info = _interp_vs_oracle(data, list(range(1, 10)), inp, 3)
+    assert info["n_temps"] > 0
+
+
+def test_static_failures():
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 1), (1, 2), (1, 3)], 0)
+    info, _ = acvm_b200.compile_plan_host(b.to_bytes(), [1], 16)
+    assert (info["static_fail_present"], info["static_fail_kind"], info["static_fail_opcode"]) == (1, 2, 0)
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 1), (ab.P - 1, 2)], 0)
+    b.logic("AND", (2, 8), (3, 8), 4)     # witness 3 never assigned -> MissingAssignment(3) at opcode 1
+    _interp_vs_oracle(b.to_bytes(), [1], (9).to_bytes(32, "big"), 1)
+    info, _ = acvm_b200.compile_plan_host(b.to_bytes(), [1], 16)
+    assert (info["static_fail_kind"], info["static_fail_opcode"], info["static_fail_aux"]) == (1, 1, 3)
+
+
+def test_decoder_rejects_garbage_and_accepts_golden(golden):
+    with pytest.raises(acvm_b200.AcvmError) as e:
+        acvm_b200.compile_plan_host(b"\x1f\x8b\x08\x00garbage", [], 16)
+    assert e.value.rc == -4
+    info, _ = acvm_b200.compile_plan_host(bytes(golden["rust_serialization"]["addition_circuit"]), [1, 2], 16)
+    assert info["n_opcodes"] == 1 and info["num_witnesses"] == 5 and info["n_gate_assign"] == 1
+    # circuits with opcodes outside the device scope decode fine and are refused loudly, never silently skipped
+    for name in ("simple_brillig_foreign_call", "memory_op_circuit"):
+        with pytest.raises(acvm_b200.AcvmError) as e:
+            acvm_b200.compile_plan_host(bytes(golden["rust_serialization"][name]), [1, 2, 3], 16)
+        assert e.value.rc == -5
+
+
+def test_fr_limb_algorithms_on_host(tmp_path):
+    so = tmp_path / "fr_host_shim.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "host", "fr_host_shim.cpp")], check=True)
+    L = ctypes.CDLL(str(so))
+    P = ab.P
+    Rinv = pow(1 << 256, -1, P)
+    rnd = random.Random(1)
+
+    def arr(vals):
+        return (ctypes.c_uint32 * (8 * len(vals)))(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vals for i in range(8)])
+
+    def val(a):
+        return sum(int(a[i]) << (32 * i) for i in range(8))
+
+    for it in range(3000):
+        k = rnd.choice([1, 2, 3, 4])
+        A = [rnd.choice([0, 1, P - 1, rnd.randrange(P)]) for _ in range(k)]
+        B = [rnd.choice([0, 1, P - 1, rnd.randrange(P)]) for _ in range(k)]
+        if k <= 3 and rnd.random() < 0.3:
+            A[0] += P // 6  # lazily reduced operand (< 1.19 p)
+        r = (ctypes.c_uint32 * 8)()
+        L.t_mont_dot(k, arr(A), arr(B), r)
+        got = val(r)
+        assert got < 2 * P and got % P == sum(x * y for x, y in zip(A, B)) * Rinv % P
+    for it in range(1000):
+        x, y, z = rnd.randrange(P), rnd.randrange(P), rnd.randrange(1 << 256)
+        r = (ctypes.c_uint32 * 8)()
+        L.t_add(arr([x]), arr([y]), r)
+        assert val(r) == (x + y) % P
+        L.t_sub(arr([x]), arr([y]), r)
+        assert val(r) == (x - y) % P
+        a = arr([z])
+        L.t_reduce(a)
+        assert val(a) == z % P
+        assert L.t_num_bits(arr([z])) == z.bit_length()
