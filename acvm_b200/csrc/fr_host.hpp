@@ -49,6 +49,11 @@ inline uint64_t sub_raw(U256& r, const U256& a, const U256& b) {
     }
     return (uint64_t)br;
 }
+inline U256 from_u64_(uint64_t v) {
+    U256 r;
+    r.l[0] = v;
+    return r;
+}
 inline U256 add(const U256& a, const U256& b) {
     U256 r;
     uint64_t c = add_raw(r, a, b);
@@ -126,13 +131,43 @@ inline U256 pow(const U256& a, const U256& e) {
     }
     return from_mont(acc);
 }
-inline U256 inverse(const U256& a) {  // 0 -> 0, like FieldElement::inverse
+inline void shr1(U256& a, uint64_t top) {
+    a.l[0] = (a.l[0] >> 1) | (a.l[1] << 63);
+    a.l[1] = (a.l[1] >> 1) | (a.l[2] << 63);
+    a.l[2] = (a.l[2] >> 1) | (a.l[3] << 63);
+    a.l[3] = (a.l[3] >> 1) | (top << 63);
+}
+inline bool is_one(const U256& a) { return a.l[0] == 1 && !(a.l[1] | a.l[2] | a.l[3]); }
+// binary extended Euclid on canonical values (plan time: one inversion per solving gate); 0 -> 0
+inline U256 inverse(const U256& a) {
     if (a.is_zero()) return a;
-    U256 e;
-    U256 two;
-    two.l[0] = 2;
-    sub_raw(e, P, two);
-    return pow(a, e);
+    U256 u = a, v = P, x1 = from_u64_(1), x2;
+    auto halve = [](U256& x) {
+        if (x.l[0] & 1) {
+            uint64_t c = add_raw(x, x, P);
+            shr1(x, c);
+        } else {
+            shr1(x, 0);
+        }
+    };
+    while (!is_one(u) && !is_one(v)) {
+        while (!(u.l[0] & 1)) {
+            shr1(u, 0);
+            halve(x1);
+        }
+        while (!(v.l[0] & 1)) {
+            shr1(v, 0);
+            halve(x2);
+        }
+        if (cmp(u, v) >= 0) {
+            sub_raw(u, u, v);
+            x1 = sub(x1, x2);
+        } else {
+            sub_raw(v, v, u);
+            x2 = sub(x2, x1);
+        }
+    }
+    return is_one(u) ? x1 : x2;
 }
 inline U256 reduce(U256 a) {  // arbitrary 256-bit -> mod p
     while (cmp(a, P) >= 0) sub_raw(a, a, P);

@@ -144,19 +144,36 @@ struct Compiler {
             uint32_t reads[4];
             size_t nr = 0;
             uint64_t imad = 0;
+            U256 alpha, beta, gamma_part;
             if (!prods.empty()) {
+                // cM*x*y + cX*x + cY*y  ==  cM*(x + cY/cM)*(y + cX/cM) - cX*cY/cM : two Montgomery products
+                // instead of three; the x/y linear terms ride along as plan-time constants.
                 Prod p = prods.back();
                 prods.pop_back();
                 flags |= GF_MUL | GF_Y;
                 x = p.a;
                 y = p.b;
                 cM = p.c;
+                U256 cX;
                 for (size_t i = 0; i < lins.size(); ++i)
                     if (lins[i].w == y) {
                         cY = lins[i].c;
                         lins.erase(lins.begin() + i);
                         break;
                     }
+                if (x != y)
+                    for (size_t i = 0; i < lins.size(); ++i)
+                        if (lins[i].w == x) {
+                            cX = lins[i].c;
+                            lins.erase(lins.begin() + i);
+                            break;
+                        }
+                if (!cX.is_zero() || !cY.is_zero()) {
+                    U256 invM = hf::inverse(cM);
+                    alpha = hf::mul(cY, invM);
+                    beta = hf::mul(cX, invM);
+                    gamma_part = hf::neg(hf::mul(hf::mul(cX, cY), invM));
+                }
                 imad += 136;
             } else if (acc != NONE) {
                 flags |= GF_Y;
@@ -169,6 +186,7 @@ struct Compiler {
                 cY = lins.back().c;
                 lins.pop_back();
             }
+            const uint32_t max_lin = (flags & GF_MUL) ? 1u : 2u;
             uint32_t nlin = 0;
             auto push_lin = [&](const U256& cc, uint32_t w) {
                 if (nlin == 0) {
@@ -180,21 +198,11 @@ struct Compiler {
                 }
                 ++nlin;
             };
-            if (flags & GF_MUL) {
-                // prefer the x-term in w1 so the kernel reuses the registers it already holds
-                for (size_t i = 0; i < lins.size(); ++i)
-                    if (lins[i].w == x) {
-                        push_lin(lins[i].c, x);
-                        flags |= GF_W1_IS_X;
-                        lins.erase(lins.begin() + i);
-                        break;
-                    }
-            }
-            if (acc != NONE && nlin < 2) {
+            if (acc != NONE && nlin < max_lin) {
                 push_lin(one, acc);
                 acc = NONE;
             }
-            while (nlin < 2 && !lins.empty() && acc == NONE) {
+            while (nlin < max_lin && !lins.empty() && acc == NONE) {
                 push_lin(lins.back().c, lins.back().w);
                 lins.pop_back();
             }
@@ -202,13 +210,14 @@ struct Compiler {
             flags |= nlin << GF_NLIN_SHIFT;
             uint32_t kind;
             uint32_t dst = NONE;
+            U256 c4 = gamma_part;
             if (final_gate) {
                 kind = assign ? MK_GATE_ASSIGN : MK_GATE_CHECK;
                 if (assign) {
                     dst = out;
                     if (out_check) flags |= GF_OUT_CHECK;
                 }
-                put(r.c[4], constant);
+                c4 = hf::add(c4, constant);
             } else {
                 kind = MK_GATE_ASSIGN;
                 dst = new_temp();
@@ -222,13 +231,20 @@ struct Compiler {
             r.w[5] = w1;
             r.w[6] = w2;
             r.w[7] = 0;
-            put(r.c[0], hf::to_mont2(cM));
-            put(r.c[1], hf::to_mont(cY));
-            put(r.c[2], hf::to_mont(c1));
-            put(r.c[3], hf::to_mont(c2));
+            if (flags & GF_MUL) {
+                put(r.c[0], hf::to_mont2(cM));
+                put(r.c[1], alpha);
+                put(r.c[2], beta);
+                put(r.c[3], hf::to_mont(c1));
+            } else {
+                put(r.c[1], hf::to_mont(cY));
+                put(r.c[2], hf::to_mont(c1));
+                put(r.c[3], hf::to_mont(c2));
+            }
+            put(r.c[4], c4);
             if (flags & GF_MUL) reads[nr++] = x;
             if (flags & GF_Y) reads[nr++] = y;
-            if (nlin >= 1 && !(flags & GF_W1_IS_X)) reads[nr++] = w1;
+            if (nlin >= 1) reads[nr++] = w1;
             if (nlin >= 2) reads[nr++] = w2;
             uint32_t K = ((flags & GF_Y) ? 1 : 0) + nlin;
             if (K) imad += 64 * K + 72;

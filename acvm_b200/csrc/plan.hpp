@@ -21,13 +21,16 @@ namespace acvmb {
 // ---- device record (192 B, 16 B aligned) ------------------------------------------------------
 struct OpRec {
     uint32_t w[8];      // [0]=kind|flags<<8  [1]=acir opcode index  [2]=out slot  [3]=x  [4]=y  [5]=w1  [6]=w2  [7]=aux
-    uint32_t c[5][8];   // gate: cM*R^2, cY*R, c1*R, c2*R, cC (canonical)   (8 x u32 little-endian limbs)
+    // gate constants (8 x u32 little-endian limbs each), layout by flag:
+    //   GF_MUL   : c0 = cM*R^2, c1 = alpha, c2 = beta, c3 = c1*R (w1), c4 = gamma     out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma
+    //   otherwise: c1 = cY*R (y), c2 = c1*R (w1), c3 = c2*R (w2), c4 = cC            out = cY*y + c1*w1 + c2*w2 + cC
+    uint32_t c[5][8];
 };
 static_assert(sizeof(OpRec) == 192, "OpRec layout");
 
 enum MicroKind : uint32_t {
     MK_NOP = 0,
-    MK_GATE_ASSIGN = 1,   // out := cM*x*y + cY*y + c1*w1 + c2*w2 + cC
+    MK_GATE_ASSIGN = 1,   // out := gate expression (see OpRec::c)
     MK_GATE_CHECK = 2,    // same expression must be 0 else UnsatisfiedConstrain@opcode
     MK_AND = 3,           // out := (x & y) masked to aux bits, mod p       (logic.rs:11-56)
     MK_XOR = 4,
@@ -45,7 +48,7 @@ enum : uint32_t {
     GF_MUL = 1u << 0,        // cM term present (x and y loaded)
     GF_Y = 1u << 1,          // y term present (always set when GF_MUL)
     GF_NLIN_SHIFT = 2,       // bits 2..3: number of extra linear terms (0..2) -> w1, w2
-    GF_W1_IS_X = 1u << 4,    // w1 is the same slot as x (saves a reload)
+    GF_W1_IS_X = 1u << 4,    // (unused since the x/y linear terms are folded into alpha/beta)
     GF_OUT_CHECK = 1u << 5,  // output slot already holds a value: compare instead of store (insert_value, mod.rs:338-357)
     GF_HEAVY = 1u << 6,      // needs the FULL kernel variant
 };

@@ -86,54 +86,63 @@ __device__ __forceinline__ void record_fail(unsigned long long* fail, uint32_t o
     atomicMin(fail, key);
 }
 
-// b-limb source for the gate dot product: term 0 lives in registers, terms 1,2 are plan constants in smem
-struct GateLimbs {
-    const Fe& first;
+// b-limb source for the gate dot products: plan constants, fetched limb by limb from shared memory
+struct SmemLimbs3 {
+    const uint32_t* c0;
     const uint32_t* c1;
     const uint32_t* c2;
-    __device__ __forceinline__ uint32_t operator()(int k, int i) const {
-        return k == 0 ? first.l[i] : (k == 1 ? c1[i] : c2[i]);
-    }
+    __device__ __forceinline__ uint32_t operator()(int k, int i) const { return k == 0 ? c0[i] : (k == 1 ? c1[i] : c2[i]); }
 };
-struct SmemLimbs {
-    const uint32_t* c;
-    __device__ __forceinline__ uint32_t operator()(int, int i) const { return c[i]; }
+struct RegLimbs {
+    const Fe& b;
+    __device__ __forceinline__ uint32_t operator()(int, int i) const { return b.l[i]; }
 };
 
-// out = cM*x*y + cY*y + c1*w1 + c2*w2 + cC  -- evaluated as ((cM*x + cY)*y + c1*w1 + c2*w2) + cC with
-// one Montgomery reduction for the bracket and one for cM*x (see fr.cuh / DESIGN.md for the bounds).
+// GF_MUL : out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma   -- two Montgomery reductions: u = (x+alpha)(y+beta)/R,
+//          then <u, w1> . <cM*R^2, c1*R> / R in ONE interleaved reduction (fr::mont_dot_fn).
+// linear : out = cY*y + c1*w1 + c2*w2 + cC               -- one reduction for up to three products.
 template <int T>
 __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
     Fe res;
     if (flags & GF_Y) {
-        Fe x, y, first;
-        load_w<T>(y, cb, r->w[4]);
-        if (flags & GF_MUL) {
-            load_w<T>(x, cb, r->w[3]);
-            const Fe* a1[1] = {&x};
-            fr::mont_dot_fn<1>(first, a1, SmemLimbs{r->c[0]});  // cM*R^2 * x / R = cM*x*R  (< 1.19p)
-            Fe cY;
-            lds_fe(cY, r->c[1]);
-            fr::add_raw(first, first, cY);
-            fr::cond_sub_p(first);                               // < 1.19p
-        } else {
-            lds_fe(first, r->c[1]);
-        }
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
-        if (nlin == 0) {
-            const Fe* a[1] = {&y};
-            fr::mont_dot_fn<1>(res, a, GateLimbs{first, nullptr, nullptr});
-        } else {
-            Fe w1;
-            if (flags & GF_W1_IS_X) w1 = x; else load_w<T>(w1, cb, r->w[5]);
-            if (nlin == 1) {
-                const Fe* a[2] = {&y, &w1};
-                fr::mont_dot_fn<2>(res, a, GateLimbs{first, r->c[2], nullptr});
+        if (flags & GF_MUL) {
+            Fe x, y, u, t;
+            load_w<T>(x, cb, r->w[3]);
+            load_w<T>(y, cb, r->w[4]);
+            lds_fe(t, r->c[1]);
+            fr::add_mod(x, x, t);
+            lds_fe(t, r->c[2]);
+            fr::add_mod(y, y, t);
+            const Fe* a1[1] = {&x};
+            fr::mont_dot_fn<1>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R, < 1.19p, used unreduced
+            if (nlin == 0) {
+                const Fe* a[1] = {&u};
+                fr::mont_dot_fn<1>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});
             } else {
-                Fe w2;
-                load_w<T>(w2, cb, r->w[6]);
-                const Fe* a[3] = {&y, &w1, &w2};
-                fr::mont_dot_fn<3>(res, a, GateLimbs{first, r->c[2], r->c[3]});
+                Fe w1;
+                load_w<T>(w1, cb, r->w[5]);
+                const Fe* a[2] = {&u, &w1};
+                fr::mont_dot_fn<2>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
+            }
+        } else {
+            Fe y;
+            load_w<T>(y, cb, r->w[4]);
+            if (nlin == 0) {
+                const Fe* a[1] = {&y};
+                fr::mont_dot_fn<1>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr});
+            } else {
+                Fe w1;
+                load_w<T>(w1, cb, r->w[5]);
+                if (nlin == 1) {
+                    const Fe* a[2] = {&y, &w1};
+                    fr::mont_dot_fn<2>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr});
+                } else {
+                    Fe w2;
+                    load_w<T>(w2, cb, r->w[6]);
+                    const Fe* a[3] = {&y, &w1, &w2};
+                    fr::mont_dot_fn<3>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]});
+                }
             }
         }
         fr::cond_sub_p(res);

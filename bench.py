@@ -282,7 +282,7 @@ def run_ours(args):
         o = 0
         while o < args.batch:
             c = min(e2e_chunk, args.batch - o)
-            ins.append((c, (C.c_uint8 * (c * len(inputs) * 32)).from_buffer_copy(ab.synthetic_inputs(c, 1, first_inst + o))))
+            ins.append((c, (C.c_uint8 * (c * len(inputs) * 32)).from_buffer_copy(ab.synthetic_inputs(c, seed_id=1, first_instance=first_inst + o))))
             o += c
         st_arr = (acvm_b200._lib.Status * e2e_chunk)()
 

@@ -83,18 +83,18 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
             if kind in (MK["GATE_ASSIGN"], MK["GATE_CHECK"]):
                 res = c[4]
                 if flags & GF_Y:
-                    if flags & GF_MUL:
-                        first = (c[0] * RINV * RINV * cols[x] + c[1] * RINV) % P
-                    else:
-                        first = c[1] * RINV % P
-                    res += first * cols[y]
                     nlin = (flags >> GF_NLIN_SHIFT) & 3
-                    if nlin >= 1:
-                        if flags & GF_W1_IS_X:
-                            assert w1 == x
-                        res += c[2] * RINV * cols[w1]
-                    if nlin >= 2:
-                        res += c[3] * RINV * cols[w2]
+                    if flags & GF_MUL:
+                        assert nlin <= 1
+                        res += c[0] * RINV * RINV * (cols[x] + c[1]) * (cols[y] + c[2])
+                        if nlin >= 1:
+                            res += c[3] * RINV * cols[w1]
+                    else:
+                        res += c[1] * RINV * cols[y]
+                        if nlin >= 1:
+                            res += c[2] * RINV * cols[w1]
+                        if nlin >= 2:
+                            res += c[3] * RINV * cols[w2]
                 res %= P
                 if kind == MK["GATE_ASSIGN"]:
                     if flags & GF_OUT_CHECK:
