@@ -1,11 +1,445 @@
-// Heavy blackbox micro-ops (SHA-256, Keccak-256, Grumpkin) -- FULL kernel variant only.
+// Heavy blackbox micro-ops for the FULL step-VM kernel variant: SHA-256, Keccak-256, Grumpkin
+// fixed-base scalar multiplication and Pedersen (plookup) hashing.
+//
+// Replaces (reference):
+//   hash glue     acvm/src/pwg/blackbox/hash.rs:28-103  (get_hash_input / write_digest_to_outputs)
+//   sha256        blackbox_solver/src/lib.rs:47-50   -> sha2 0.10.7   (FIPS 180-4)
+//   keccak256     blackbox_solver/src/lib.rs:57-60   -> sha3 0.10.8   (Keccak, pad 0x01..0x80, rate 136)
+//   fixed base    acvm/src/pwg/blackbox/fixed_base_scalar_mul.rs:11-27 -> barretenberg_blackbox_solver/src/wasm/scalar_mul.rs:17-65
+//   pedersen      acvm/src/pwg/blackbox/pedersen.rs:11-28 -> barretenberg_blackbox_solver/src/wasm/pedersen.rs:14-35
+//
+// One lane executes one call-instance.  Message bytes are gathered straight from the witness
+// columns (each message byte is its own 32-byte witness, hash.rs:51-66) and the 32 digest bytes
+// are scattered to 32 output columns.
 #pragma once
 #include "fr.cuh"
 #include "plan.hpp"
+
 namespace acvmb {
+
+using fr::Fe;
+
+// tables built on the host at context creation (runtime.cu) and shared by every launch
+struct CurveTables {
+    const uint32_t* fixed_base;   // [32 windows][255][16]  affine (x,y) of (d * 256^w) * G, Montgomery form
+    const uint32_t* pedersen;     // see pedersen section
+};
+__constant__ CurveTables g_curve_tables;
+
+template <int T>
+__device__ __forceinline__ void hv_load(Fe& v, const uint4* cb, uint32_t w) {
+    const uint4* p = cb + (size_t)w * (2 * T);
+    uint4 lo = p[0], hi = p[T];
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+}
+template <int T>
+__device__ __forceinline__ void hv_store(uint4* cb, uint32_t w, const Fe& v) {
+    uint4* p = cb + (size_t)w * (2 * T);
+    p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ void hv_fail(unsigned long long* fail, uint32_t opcode, uint32_t kind, uint32_t aux) {
+    unsigned long long key = ((unsigned long long)opcode << 32) | ((unsigned long long)(kind & 0xF) << 28) | (aux & 0x0FFFFFFFu);
+    atomicMin(fail, key);
+}
+
+// write digest byte i to output witness i (insert_value semantics when the output is pre-assigned)
+template <int T>
+__device__ __forceinline__ void write_digest(const uint8_t* digest, const uint32_t* outs, uint32_t check_mask, uint4* cb,
+                                             unsigned long long* fail, uint32_t opcode) {
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) {
+        Fe v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.l[k] = 0;
+        v.l[0] = digest[i];
+        if ((check_mask >> i) & 1) {
+            Fe old;
+            hv_load<T>(old, cb, outs[i]);
+            if (!fr::eq(old, v)) hv_fail(fail, opcode, EK_UNSATISFIED_CONSTRAIN, 0);
+        } else {
+            hv_store<T>(cb, outs[i], v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SHA-256
+// ---------------------------------------------------------------------------------------------
+__constant__ uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+__device__ __noinline__ void sha256_compress(uint32_t* h, const uint32_t* blk) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = blk[i];
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        uint32_t wi;
+        if (i < 16) {
+            wi = w[i];
+        } else {
+            uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            w[i & 15] = wi;
+        }
+        uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = hh + S1 + ch + SHA_K[i] + wi;
+        uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// payload: [n_in][check_mask][var_size witness | NONE][0][ (witness, num_bits) * n_in ][ 32 output witnesses ]
+template <int T>
+__device__ __noinline__ void exec_sha256(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_in = pl[0], check_mask = pl[1];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t blk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) blk[i] = 0;
+    uint32_t pos = 0;
+    unsigned long long total = 0;
+    auto push = [&](uint32_t byte) {
+        blk[pos >> 2] |= byte << (24 - 8 * (pos & 3));
+        if (++pos == 64) {
+            sha256_compress(h, blk);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) blk[i] = 0;
+            pos = 0;
+        }
+    };
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_in; ++k) {
+        Fe v;
+        hv_load<T>(v, cb, ins[2 * k]);
+        uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;   // fetch_nearest_bytes: low ceil(bits/8) bytes, little-endian
+        if (nbytes > 32) nbytes = 32;
+#pragma unroll 1
+        for (uint32_t j = 0; j < nbytes; ++j) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
+        total += nbytes;
+    }
+    push(0x80);
+    while (pos != 56) push(0);
+    unsigned long long bits = total * 8;
+    blk[14] = (uint32_t)(bits >> 32);
+    blk[15] = (uint32_t)bits;
+    sha256_compress(h, blk);
+    uint8_t digest[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) digest[i] = (uint8_t)(h[i >> 2] >> (24 - 8 * (i & 3)));
+    write_digest<T>(digest, outs, check_mask, cb, fail, r->w[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keccak-256 (original Keccak padding 0x01 .. 0x80, rate 136 bytes)
+// ---------------------------------------------------------------------------------------------
+__constant__ unsigned long long KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
+    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
+    0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
+    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+__device__ __forceinline__ unsigned long long rol64(unsigned long long x, int n) { return n ? ((x << n) | (x >> (64 - n))) : x; }
+
+// state index = x + 5*y
+__device__ __noinline__ void keccak_f1600(unsigned long long* st) {
+    unsigned long long a[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) a[i] = st[i];
+#pragma unroll 1
+    for (int rnd = 0; rnd < 24; ++rnd) {
+        unsigned long long c[5], d[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; ++i) a[i] ^= d[i % 5];
+        // rho + pi : B[y, 2x+3y] = rot(A[x,y], r[x,y])
+        constexpr int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+#pragma unroll
+        for (int y = 0; y < 5; ++y)
+#pragma unroll
+            for (int x = 0; x < 5; ++x) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(a[x + 5 * y], ROT[x + 5 * y]);
+#pragma unroll
+        for (int y = 0; y < 5; ++y)
+#pragma unroll
+            for (int x = 0; x < 5; ++x) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        a[0] ^= KECCAK_RC[rnd];
+    }
+#pragma unroll
+    for (int i = 0; i < 25; ++i) st[i] = a[i];
+}
+
+template <int T>
+__device__ __noinline__ void exec_keccak256(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_in = pl[0], check_mask = pl[1], var_w = pl[2];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    // Keccak256VariableLength: keep only the first to_u128(var_message_size) bytes (hash.rs:67-85)
+    unsigned long long take = ~0ULL;
+    if (var_w != 0xFFFFFFFFu) {
+        Fe sz;
+        hv_load<T>(sz, cb, var_w);
+        unsigned long long total = 0;
+        for (uint32_t k = 0; k < n_in; ++k) {
+            uint32_t nb = (ins[2 * k + 1] + 7) >> 3;
+            total += nb > 32 ? 32 : nb;
+        }
+        unsigned long long lo = ((unsigned long long)sz.l[1] << 32) | sz.l[0];
+        if ((sz.l[2] | sz.l[3]) || lo > total) {
+            hv_fail(fail, r->w[1], EK_BLACKBOX_FAILED, BB_Keccak256);
+            return;
+        }
+        take = lo;
+    }
+    unsigned long long st[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) st[i] = 0;
+    uint32_t pos = 0;
+    auto push = [&](uint32_t byte) {
+        st[pos >> 3] ^= (unsigned long long)byte << (8 * (pos & 7));
+        if (++pos == 136) {
+            keccak_f1600(st);
+            pos = 0;
+        }
+    };
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_in && take; ++k) {
+        Fe v;
+        hv_load<T>(v, cb, ins[2 * k]);
+        uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;
+        if (nbytes > 32) nbytes = 32;
+#pragma unroll 1
+        for (uint32_t j = 0; j < nbytes && take; ++j, --take) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
+    }
+    // pad10*1 with the Keccak domain byte 0x01: the two pad bits may share one byte (0x81)
+    st[pos >> 3] ^= 0x01ULL << (8 * (pos & 7));
+    st[16] ^= 0x8000000000000000ULL;   // byte 135
+    keccak_f1600(st);
+    uint8_t digest[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) digest[i] = (uint8_t)(st[i >> 3] >> (8 * (i & 7)));
+    write_digest<T>(digest, outs, check_mask, cb, fail, r->w[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grumpkin: y^2 = x^3 - 17 over BN254 Fr (the VM's own field).  Jacobian accumulator + affine table
+// points, all in Montgomery form.
+// ---------------------------------------------------------------------------------------------
+struct Jac {
+    Fe X, Y, Z;
+    bool inf;
+};
+
+__device__ __forceinline__ void fe_mul(Fe& r, const Fe& a, const Fe& b) { fr::mont_mul(r, a, b); }
+__device__ __forceinline__ void fe_sqr(Fe& r, const Fe& a) { fr::mont_mul(r, a, a); }
+__device__ __forceinline__ void fe_dbl(Fe& r, const Fe& a) { fr::add_mod(r, a, a); }
+
+// mixed addition acc += (px, py)  ("madd-2007-bl": 7M + 4S); the plan-level invariants of fixed-base /
+// Pedersen windows exclude acc == +-P except through the explicit checks below.
+__device__ __noinline__ void jac_madd(Jac& acc, const Fe& px, const Fe& py) {
+    if (acc.inf) {
+        acc.X = px;
+        acc.Y = py;
+        // Z = R mod p (Montgomery one)
+        acc.Z.l[0] = 0x4ffffffbu; acc.Z.l[1] = 0xac96341cu; acc.Z.l[2] = 0x9f60cd29u; acc.Z.l[3] = 0x36fc7695u;
+        acc.Z.l[4] = 0x7879462eu; acc.Z.l[5] = 0x666ea36fu; acc.Z.l[6] = 0x9a07df2fu; acc.Z.l[7] = 0x0e0a77c1u;
+        acc.inf = false;
+        return;
+    }
+    Fe z1z1, u2, s2, h, hh, i, j, rr, v, t;
+    fe_sqr(z1z1, acc.Z);
+    fe_mul(u2, px, z1z1);
+    fe_mul(s2, py, acc.Z);
+    fe_mul(s2, s2, z1z1);
+    fr::sub_mod(h, u2, acc.X);
+    fr::sub_mod(rr, s2, acc.Y);
+    if (fr::is_zero(h)) {
+        if (fr::is_zero(rr)) {
+            // doubling (a = 0): "dbl-2009-l"
+            Fe A, B, C, D, E, F;
+            fe_sqr(A, acc.X);
+            fe_sqr(B, acc.Y);
+            fe_sqr(C, B);
+            fr::add_mod(D, acc.X, B);
+            fe_sqr(D, D);
+            fr::sub_mod(D, D, A);
+            fr::sub_mod(D, D, C);
+            fe_dbl(D, D);
+            fe_dbl(E, A);
+            fr::add_mod(E, E, A);
+            fe_sqr(F, E);
+            Fe X3, Y3, Z3;
+            fe_dbl(t, D);
+            fr::sub_mod(X3, F, t);
+            fr::sub_mod(t, D, X3);
+            fe_mul(Y3, E, t);
+            fe_dbl(C, C); fe_dbl(C, C); fe_dbl(C, C);
+            fr::sub_mod(Y3, Y3, C);
+            fe_mul(Z3, acc.Y, acc.Z);
+            fe_dbl(Z3, Z3);
+            acc.X = X3; acc.Y = Y3; acc.Z = Z3;
+        } else {
+            acc.inf = true;
+        }
+        return;
+    }
+    fe_sqr(hh, h);
+    fe_dbl(i, hh);
+    fe_dbl(i, i);             // I = 4*HH
+    fe_mul(j, h, i);          // J = H*I
+    fe_dbl(rr, rr);           // r = 2*(S2-Y1)
+    fe_mul(v, acc.X, i);      // V = X1*I
+    Fe X3, Y3, Z3;
+    fe_sqr(X3, rr);
+    fr::sub_mod(X3, X3, j);
+    fe_dbl(t, v);
+    fr::sub_mod(X3, X3, t);   // X3 = r^2 - J - 2V
+    fr::sub_mod(t, v, X3);
+    fe_mul(Y3, rr, t);
+    fe_mul(t, acc.Y, j);
+    fe_dbl(t, t);
+    fr::sub_mod(Y3, Y3, t);   // Y3 = r*(V-X3) - 2*Y1*J
+    fr::add_mod(Z3, acc.Z, h);
+    fe_sqr(Z3, Z3);
+    fr::sub_mod(Z3, Z3, z1z1);
+    fr::sub_mod(Z3, Z3, hh);  // Z3 = (Z1+H)^2 - Z1Z1 - HH
+    acc.X = X3; acc.Y = Y3; acc.Z = Z3;
+}
+
+// a^(p-2) in Montgomery form (Fermat); a != 0
+__device__ __noinline__ void fe_inv(Fe& r, const Fe& a) {
+    // p - 2, little-endian limbs
+    const uint32_t e[8] = {FR_P0 - 2u, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    Fe acc = a;   // top bit of the exponent (bit 253) is set
+#pragma unroll 1
+    for (int bit = 252; bit >= 0; --bit) {
+        fe_sqr(acc, acc);
+        if ((e[bit >> 5] >> (bit & 31)) & 1) fe_mul(acc, acc, a);
+    }
+    r = acc;
+}
+
+// Jacobian (Montgomery) -> affine canonical
+__device__ __noinline__ void jac_to_affine_canonical(Fe& x, Fe& y, const Jac& p) {
+    if (p.inf) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x.l[k] = 0; y.l[k] = 0; }
+        return;
+    }
+    Fe zi, zi2, zi3, one;
+    fe_inv(zi, p.Z);
+    fe_sqr(zi2, zi);
+    fe_mul(zi3, zi2, zi);
+    fe_mul(x, p.X, zi2);
+    fe_mul(y, p.Y, zi3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) one.l[k] = 0;
+    one.l[0] = 1;
+    fe_mul(x, x, one);   // from Montgomery
+    fe_mul(y, y, one);
+}
+
+template <int T>
+__device__ __forceinline__ void write_point(const OpRec* r, uint32_t flags, const Fe& x, const Fe& y, uint32_t out_x, uint32_t out_y,
+                                            uint4* cb, unsigned long long* fail) {
+    // insert_value(outputs.0), insert_value(outputs.1)   (pwg/mod.rs:338-357)
+    if (flags & GF_OUT_CHECK) {
+        Fe old;
+        hv_load<T>(old, cb, out_x);
+        if (!fr::eq(old, x)) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+    } else {
+        hv_store<T>(cb, out_x, x);
+    }
+    if (flags & GF_OUT2_CHECK) {
+        Fe old;
+        hv_load<T>(old, cb, out_y);
+        if (!fr::eq(old, y)) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+    } else {
+        hv_store<T>(cb, out_y, y);
+    }
+}
+
+// FixedBaseScalarMul: x = low, y = high, out = w[2] (x coordinate), w[5] = y coordinate slot.
+// 8-bit fixed windows over the precomputed table: 32 mixed additions + one inversion.
+template <int T>
+__device__ __noinline__ void exec_fixed_base(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    Fe lo, hi;
+    hv_load<T>(lo, cb, r->w[3]);
+    hv_load<T>(hi, cb, r->w[4]);
+    // limbs must be < 2^128 (scalar_mul.rs:25-35)
+    if ((lo.l[4] | lo.l[5] | lo.l[6] | lo.l[7]) || (hi.l[4] | hi.l[5] | hi.l[6] | hi.l[7])) {
+        hv_fail(fail, r->w[1], EK_BLACKBOX_FAILED, BB_FixedBaseScalarMul);
+        return;
+    }
+    uint32_t s[8] = {lo.l[0], lo.l[1], lo.l[2], lo.l[3], hi.l[0], hi.l[1], hi.l[2], hi.l[3]};
+    // scalar < Grumpkin group order n (scalar_mul.rs:40-51)
+    const uint32_t n[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    bool lt = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (s[i] != n[i]) { lt = s[i] < n[i]; break; }
+    }
+    if (!lt) {
+        hv_fail(fail, r->w[1], EK_BLACKBOX_FAILED, BB_FixedBaseScalarMul);
+        return;
+    }
+    Jac acc;
+    acc.inf = true;
+#pragma unroll 1
+    for (int w = 0; w < 32; ++w) {
+        uint32_t d = (s[w >> 2] >> (8 * (w & 3))) & 0xFF;
+        if (d == 0) continue;
+        const uint4* tp = reinterpret_cast<const uint4*>(g_curve_tables.fixed_base + ((size_t)w * 255 + (d - 1)) * 16);
+        uint4 a = tp[0], b = tp[1], c = tp[2], e = tp[3];
+        Fe px, py;
+        px.l[0] = a.x; px.l[1] = a.y; px.l[2] = a.z; px.l[3] = a.w; px.l[4] = b.x; px.l[5] = b.y; px.l[6] = b.z; px.l[7] = b.w;
+        py.l[0] = c.x; py.l[1] = c.y; py.l[2] = c.z; py.l[3] = c.w; py.l[4] = e.x; py.l[5] = e.y; py.l[6] = e.z; py.l[7] = e.w;
+        jac_madd(acc, px, py);
+    }
+    Fe x, y;
+    jac_to_affine_canonical(x, y, acc);   // scalar 0 -> (0, 0): encoding of infinity is unpinned in the reference
+    write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
+}
+
 template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
                                            const uint32_t* payload) {
-    (void)r; (void)kind; (void)flags; (void)cb; (void)fail; (void)payload;
+    switch (kind) {
+        case MK_SHA256:
+            exec_sha256<T>(r, cb, fail, payload);
+            break;
+        case MK_KECCAK256:
+            exec_keccak256<T>(r, cb, fail, payload);
+            break;
+        case MK_FIXED_BASE:
+            exec_fixed_base<T>(r, flags, cb, fail);
+            break;
+        default:
+            break;
+    }
 }
+
 }  // namespace acvmb

@@ -391,6 +391,74 @@ struct Compiler {
                 plan.stats.alg_bytes += 32;
                 return true;
             }
+            case BB_SHA256:
+            case BB_Keccak256:
+            case BB_Keccak256VariableLength: {
+                if (b.outputs.size() != 32) {  // hash.rs:39-44
+                    fail_static(idx, EK_BLACKBOX_FAILED, b.func, "Expected 32 outputs but encountered " + std::to_string(b.outputs.size()));
+                    return false;
+                }
+                for (uint32_t k = 0; k < b.n_message_inputs; ++k)
+                    if (b.inputs[k].num_bits > 256) {  // fetch_nearest_bytes slices past 32 bytes: the reference panics
+                        fail_static(idx, EK_REFERENCE_PANIC, 0, "hash input wider than 256 bits");
+                        return false;
+                    }
+                std::vector<uint32_t> rd, wr;
+                uint32_t off = (uint32_t)plan.payload.size();
+                uint32_t mask = 0;
+                for (uint32_t i = 0; i < 32; ++i)
+                    if (known[b.outputs[i]]) mask |= 1u << i;
+                plan.payload.push_back(b.n_message_inputs);
+                plan.payload.push_back(mask);
+                plan.payload.push_back(b.func == BB_Keccak256VariableLength ? b.inputs.back().witness : NONE);
+                plan.payload.push_back(0);
+                for (uint32_t k = 0; k < b.n_message_inputs; ++k) {
+                    plan.payload.push_back(b.inputs[k].witness);
+                    plan.payload.push_back(b.inputs[k].num_bits);
+                    rd.push_back(b.inputs[k].witness);
+                    plan.stats.alg_bytes += 32;
+                }
+                if (b.func == BB_Keccak256VariableLength) rd.push_back(b.inputs.back().witness);
+                for (uint32_t i = 0; i < 32; ++i) {
+                    plan.payload.push_back(b.outputs[i]);
+                    if (mask & (1u << i)) rd.push_back(b.outputs[i]); else wr.push_back(b.outputs[i]);
+                    plan.stats.alg_bytes += 32;
+                }
+                r.w[0] = (b.func == BB_SHA256 ? MK_SHA256 : MK_KECCAK256) | (GF_HEAVY << 8);
+                r.w[1] = idx;
+                r.w[2] = r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+                r.w[7] = off;
+                sched.place(r, rd.data(), rd.size(), wr.data(), wr.size());
+                for (uint32_t i = 0; i < 32; ++i)
+                    if (!known[b.outputs[i]]) mark_assigned(b.outputs[i], idx);
+                plan.needs_full_kernel = true;
+                ++plan.stats.n_micro;
+                ++plan.stats.n_hash;
+                return true;
+            }
+            case BB_FixedBaseScalarMul: {
+                uint32_t ox = b.outputs[0], oy = b.outputs[1];
+                uint32_t flags = GF_HEAVY;
+                std::vector<uint32_t> rd = {b.inputs[0].witness, b.inputs[1].witness}, wr;
+                if (known[ox]) { flags |= GF_OUT_CHECK; rd.push_back(ox); } else wr.push_back(ox);
+                if (known[oy] || oy == ox) { flags |= GF_OUT2_CHECK; rd.push_back(oy); } else wr.push_back(oy);
+                r.w[0] = MK_FIXED_BASE | (flags << 8);
+                r.w[1] = idx;
+                r.w[2] = ox;
+                r.w[3] = b.inputs[0].witness;
+                r.w[4] = b.inputs[1].witness;
+                r.w[5] = oy;
+                r.w[6] = NONE;
+                r.w[7] = 0;
+                sched.place(r, rd.data(), rd.size(), wr.data(), wr.size());
+                if (!known[ox]) mark_assigned(ox, idx);
+                if (!known[oy]) mark_assigned(oy, idx);
+                plan.needs_full_kernel = true;
+                ++plan.stats.n_micro;
+                ++plan.stats.n_curve;
+                plan.stats.alg_bytes += 128;
+                return true;
+            }
             default:
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": blackbox function " + blackbox_name(b.func) +
                                          " is not supported by the device plan yet");

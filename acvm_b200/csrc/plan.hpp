@@ -35,7 +35,7 @@ enum MicroKind : uint32_t {
     MK_AND = 3,           // out := (x & y) masked to aux bits, mod p       (logic.rs:11-56)
     MK_XOR = 4,
     MK_RANGE = 5,         // num_bits(x) > aux  => UnsatisfiedConstrain     (range.rs:7-18)
-    MK_SHA256 = 6,        // payload[aux..]: n_in, (witness,num_bits)*, 32 outputs
+    MK_SHA256 = 6,        // payload[aux..]: n_in, out_check_mask, var_size_witness|NONE, 0, (witness,num_bits)*n_in, 32 outputs
     MK_KECCAK256 = 7,
     MK_FIXED_BASE = 8,    // x=low y=high out=x-coord w1=y-coord slot
     MK_PEDERSEN = 9,      // payload[aux..]: n_in, domain_separator, witness*, out_x, out_y
@@ -51,6 +51,7 @@ enum : uint32_t {
     GF_W1_IS_X = 1u << 4,    // (unused since the x/y linear terms are folded into alpha/beta)
     GF_OUT_CHECK = 1u << 5,  // output slot already holds a value: compare instead of store (insert_value, mod.rs:338-357)
     GF_HEAVY = 1u << 6,      // needs the FULL kernel variant
+    GF_OUT2_CHECK = 1u << 7, // second output (point y coordinate) already holds a value
 };
 
 // error kinds mirrored from OpcodeResolutionError (acvm/src/pwg/mod.rs:100-114) + reference panics

@@ -12,6 +12,7 @@
 
 #include "../../include/acvm_b200.h"
 #include "acir.hpp"
+#include "curve_host.hpp"
 #include "plan.hpp"
 #include "vm_kernel.cuh"
 
@@ -39,6 +40,9 @@ struct acvmb_ctx {
     uint32_t opt_chunk_steps = 2;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
     uint64_t staging_bytes = 512ull << 20;
+    uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
+    uint32_t* d_pedersen = nullptr;
+    bool tables_ready = false;
 };
 
 struct acvmb_circuit {
@@ -123,6 +127,8 @@ extern "C" int acvmb_ctx_create(int device, acvmb_ctx** out) {
 extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->d_fixed_base) cudaFree(ctx->d_fixed_base);
+    if (ctx->d_pedersen) cudaFree(ctx->d_pedersen);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -159,9 +165,23 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
 }
 
 // ---------------------------------------------------------------------------------------------
+static int ensure_curve_tables(acvmb_ctx* ctx) {
+    if (ctx->tables_ready) return ACVMB_OK;
+    std::vector<uint32_t> fb = gk::build_fixed_base_table();
+    CUDA_TRY(cudaMalloc(&ctx->d_fixed_base, fb.size() * 4));
+    CUDA_TRY(cudaMemcpy(ctx->d_fixed_base, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(set_curve_tables(ctx->d_fixed_base, ctx->d_pedersen));
+    ctx->tables_ready = true;
+    return ACVMB_OK;
+}
+
 static int upload_plan(acvmb_circuit* c) {
     const Plan& p = c->plan;
     CUDA_TRY(cudaSetDevice(c->ctx->device));
+    if (p.stats.n_curve) {
+        int rc = ensure_curve_tables(c->ctx);
+        if (rc) return rc;
+    }
     size_t sb = p.stream.size() * sizeof(OpRec);
     CUDA_TRY(cudaMalloc(&c->d_stream, std::max<size_t>(sb, 16)));
     CUDA_TRY(cudaMemcpy(c->d_stream, p.stream.data(), sb, cudaMemcpyHostToDevice));

@@ -277,6 +277,16 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
 
 #define ACVMB_CONFIGS(X) X(1, 128) X(2, 64) X(4, 32) X(8, 16) X(16, 8) X(32, 4) X(4, 16) X(8, 8) X(16, 16) X(8, 32) X(32, 8) X(32, 1) X(32, 2)
 
+cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pedersen) {
+#ifdef ACVMB_HEAVY_OPS
+    CurveTables t{fixed_base, pedersen};
+    return cudaMemcpyToSymbol(g_curve_tables, &t, sizeof(t));
+#else
+    (void)fixed_base; (void)pedersen;
+    return cudaSuccess;
+#endif
+}
+
 bool vm_config_supported(int T, int S) {
 #define X(t, s) if (T == t && S == s) return true;
     ACVMB_CONFIGS(X)

@@ -28,6 +28,8 @@ struct KernelConfig {
 // returns cudaSuccess or the launch error; smem_bytes/regs reported for the run record
 cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream);
 bool vm_config_supported(int T, int S);
+// device pointers of the Grumpkin lookup tables (built by the host once per context)
+cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pedersen);
 
 cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_slots, uint32_t n_inputs, uint4* cols,
                                   uint32_t n_slots, int T, uint32_t n_inst, cudaStream_t stream);

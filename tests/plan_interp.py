@@ -56,11 +56,65 @@ class PlanBlob:
         return hdr, coefs
 
 
+def default_hooks():
+    """Heavy micro-ops evaluated with the oracle's primitives (test code may use the oracle)."""
+    from oracle import grumpkin, hashes
+    GF_OUT_CHECK_, GF_OUT2_CHECK_ = 32, 128
+
+    def hash_hook(fn):
+        def run(cols, hdr, payload, record_fail):
+            opcode, off = hdr[1], hdr[7]
+            n_in, mask, var_w = payload[off], payload[off + 1], payload[off + 2]
+            ins = payload[off + 4: off + 4 + 2 * n_in]
+            outs = payload[off + 4 + 2 * n_in: off + 4 + 2 * n_in + 32]
+            msg = bytearray()
+            for k in range(n_in):
+                nbytes = min(32, (ins[2 * k + 1] + 7) // 8)
+                msg += cols[ins[2 * k]].to_bytes(32, "little")[:nbytes]
+            if var_w != NONE:
+                take = cols[var_w] & ((1 << 128) - 1)
+                if take > len(msg):
+                    record_fail(opcode, EK_BB_FAILED, 11)
+                    return []
+                msg = msg[:take]
+            d = fn(bytes(msg))
+            w = []
+            for i in range(32):
+                if (mask >> i) & 1:
+                    if cols[outs[i]] != d[i]:
+                        record_fail(opcode, EK_UNSAT)
+                else:
+                    w.append((outs[i], d[i]))
+            return w
+        return run
+
+    def fixed_base(cols, hdr, payload, record_fail):
+        flags = hdr[0] >> 8
+        opcode, ox, lo_w, hi_w, oy = hdr[1], hdr[2], hdr[3], hdr[4], hdr[5]
+        try:
+            x, y = grumpkin.fixed_base_scalar_mul(cols[lo_w], cols[hi_w])
+        except grumpkin.BlackBoxFailed:
+            record_fail(opcode, EK_BB_FAILED, 10)
+            return []
+        w = []
+        for (slot, v, chk) in ((ox, x, flags & GF_OUT_CHECK_), (oy, y, flags & GF_OUT2_CHECK_)):
+            if chk:
+                if cols[slot] != v:
+                    record_fail(opcode, EK_UNSAT)
+            else:
+                w.append((slot, v))
+        return w
+
+    return {MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
+
+
 def run_plan(plan: PlanBlob, inputs, hooks=None):
     """inputs: dict witness->int.  Returns (status tuple, witness dict).
 
     status = ("Solved",) or ("Failure", err_kind, opcode_index, aux).  `hooks` maps heavy micro-op
     kinds to python callables (cols, hdr, payload) -> list of (slot, value) or raises."""
+    if hooks is None:
+        hooks = default_hooks()
     cols = {}
     for w in plan.input_witnesses:
         cols[w] = inputs[w] % P

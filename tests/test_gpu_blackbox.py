@@ -1,0 +1,152 @@
+"""GPU parity for the blackbox kernels (SHA-256, Keccak-256, fixed-base scalar mul) through the C ABI."""
+import hashlib
+import random
+
+import pytest
+
+import acvm_b200
+from acvm_b200 import acir_builder as ab
+from conftest import inputs_to_dicts, witness_rows
+from oracle import acir, field as F, grumpkin, hashes, pwg
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_circuit(ctx, data, input_witnesses, batch, inp):
+    circ = acvm_b200.CompiledCircuit(ctx, data, input_witnesses)
+    out, st = circ.solve_batch(inp, batch)
+    rows = witness_rows(out, batch, circ.num_witnesses)
+    oc = acir.decode_circuit(data)
+    assign = circ.assign_opcodes()
+    for i, iw in enumerate(inputs_to_dicts(inp, batch, input_witnesses)):
+        ost, owm, oerr = pwg.solve_circuit(oc, iw)
+        assert st[i].status == ost, (i, st[i], oerr)
+        if ost == "Failure":
+            assert st[i].error == oerr.kind, (i, st[i], oerr)
+            assert st[i].opcode_index == (oerr.opcode_location if oerr.opcode_location is not None else st[i].opcode_index)
+        limit = 0xFFFFFFFF if ost == "Solved" else st[i].opcode_index
+        got = {w: rows[i][w] for w in range(circ.num_witnesses)
+               if assign[w] == 0xFFFFFFFE or (assign[w] != 0xFFFFFFFF and assign[w] < limit)}
+        assert got == owm, f"instance {i}"
+    circ.close()
+    return st
+
+
+def test_sha256_kat(ctx, golden):  # brillig_vm/src/black_box.rs:203-209
+    d = ctx.sha256([b"hello world"])
+    assert d[0].hex() == golden["kats"]["sha256_hello_world"]
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 55, 56, 63, 64, 65, 119, 120, 136, 200])
+def test_hash_bytes_vs_hashlib_and_oracle(ctx, n):
+    rnd = random.Random(n)
+    msgs = [bytes(rnd.randrange(256) for _ in range(n)) for _ in range(5)]
+    assert ctx.sha256(msgs) == [hashlib.sha256(m).digest() for m in msgs]
+    assert ctx.keccak256(msgs) == [hashes.keccak256(m) for m in msgs]
+
+
+def test_keccak_empty(ctx):
+    assert ctx.keccak256([b""])[0].hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+def test_hash_circuit_mixed_widths_and_chaining(ctx):
+    # inputs with different num_bits (fetch_nearest_bytes, generic_ark.rs:305-317), a digest fed into the next hash,
+    # and arithmetic on digest bytes
+    b = ab.CircuitBuilder()
+    ins = [(1, 8), (2, 16), (3, 254), (4, 1), (5, 64)]
+    b.hash256("SHA256", ins, list(range(10, 42)))
+    b.hash256("Keccak256", [(w, 8) for w in range(10, 42)] + [(2, 13)], list(range(50, 82)))
+    b.arithmetic([(1, 50, 51)], [(1, 10), (ab.P - 1, 90)], 7)       # w90 = w50*w51 + w10 + 7
+    b.hash256("SHA256", [(90, 254)] + [(w, 8) for w in range(50, 82)], list(range(100, 132)))
+    data = b.to_bytes()
+    batch = 9
+    inp = ab.synthetic_inputs(batch, n_inputs=5, seed_id=21)
+    _check_circuit(ctx, data, [1, 2, 3, 4, 5], batch, inp)
+
+
+def test_keccak_variable_length(ctx):
+    b = ab.CircuitBuilder()
+    b.keccak_var([(w, 8) for w in range(1, 11)], (11, 32), list(range(20, 52)))
+    data = b.to_bytes()
+    rows = []
+    for take in (0, 1, 5, 10, 11, 1 << 40):   # the last two exceed the message: BlackBoxFunctionFailed
+        rows.append([(7 * i + take) % 256 for i in range(10)] + [take])
+    inp = b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+    st = _check_circuit(ctx, data, list(range(1, 12)), len(rows), inp)
+    assert [s.status for s in st] == ["Solved"] * 4 + ["Failure"] * 2
+    assert st[4].error == "BlackBoxFunctionFailed"
+
+
+def test_hash_output_preassigned_is_checked(ctx):
+    # insert_value on an already-assigned witness compares (pwg/mod.rs:338-357)
+    b = ab.CircuitBuilder()
+    b.hash256("SHA256", [(1, 8)], list(range(2, 34)))
+    data = b.to_bytes()
+    good = hashlib.sha256(b"\x05").digest()
+    inp = (5).to_bytes(32, "big") + good[0].to_bytes(32, "big") + (5).to_bytes(32, "big") + ((good[0] + 1) % 256).to_bytes(32, "big")
+    st = _check_circuit(ctx, data, [1, 2], 2, inp)
+    assert st[0].status == "Solved" and (st[1].status, st[1].error) == ("Failure", "UnsatisfiedConstrain")
+
+
+def test_fixed_base_kats(ctx, golden):  # barretenberg_blackbox_solver/src/wasm/scalar_mul.rs:72-97
+    ks = golden["kats"]["fixed_base"]
+    pts, st = ctx.fixed_base_scalar_mul([k["low"] for k in ks], [k["high"] for k in ks])
+    for (x, y), k, s in zip(pts, ks, st):
+        assert s.status == "Solved"
+        assert (F.to_hex(x), F.to_hex(y)) == (k["x"], k["y"])
+
+
+def test_fixed_base_random_and_failures(ctx):
+    rnd = random.Random(5)
+    n = grumpkin.ORDER
+    scalars = [0, 1, 2, 255, 256, n - 1, (1 << 128) - 1, 1 << 128, (1 << 253) + 12345] + [rnd.randrange(n) for _ in range(24)]
+    lows = [s & ((1 << 128) - 1) for s in scalars]
+    highs = [s >> 128 for s in scalars]
+    # failure rows: limb >= 2^128, scalar >= group order
+    lows += [1 << 128, 5, n & ((1 << 128) - 1)]
+    highs += [0, 1 << 128, n >> 128]
+    pts, st = ctx.fixed_base_scalar_mul(lows, highs)
+    for i, s in enumerate(scalars):
+        assert st[i].status == "Solved", (i, st[i])
+        assert pts[i] == grumpkin.fixed_base_scalar_mul(lows[i], highs[i]), hex(s)
+    for i in range(len(scalars), len(lows)):
+        assert (st[i].status, st[i].error, st[i].aux) == ("Failure", "BlackBoxFunctionFailed", 10)
+
+
+def test_fixed_base_golden_circuit(ctx, golden):  # acvm_js/test/shared/fixed_base_scalar_mul.ts
+    fx = golden["acvm_js_shared"]["fixed_base_scalar_mul"]
+    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
+    assert vm.solve().status == "Solved"
+    assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}
+
+
+def test_mixed_circuit_config4_style(ctx):
+    # arithmetic + RANGE/AND/XOR + hashes + fixed base in one plan (BASELINE config 4 shape, tiny)
+    rng = ab.SplitMix64(99)
+    b = ab.CircuitBuilder()
+    nxt = 9
+    for i in range(60):
+        k = rng.below(20)
+        if k < 14:
+            a, c = 1 + rng.below(nxt - 1), 1 + rng.below(nxt - 1)
+            b.arithmetic([(rng.nonzero_field(), a, c)], [(rng.nonzero_field(), a), (rng.nonzero_field(), c), (rng.nonzero_field(), nxt)], rng.field())
+            nxt += 1
+        elif k < 16:
+            a, c = 1 + rng.below(nxt - 1), 1 + rng.below(nxt - 1)
+            b.logic("XOR" if k == 14 else "AND", (a, 32), (c, 32), nxt)
+            b.range((nxt, 32))
+            nxt += 1
+        elif k < 18:
+            ins = [(1 + rng.below(nxt - 1), 8) for _ in range(8)]
+            b.hash256("SHA256" if k == 16 else "Keccak256", ins, list(range(nxt, nxt + 32)))
+            nxt += 32
+        else:
+            a, c = 1 + rng.below(nxt - 1), 1 + rng.below(nxt - 1)
+            b.logic("AND", (a, 100), (c, 100), nxt)          # < 2^128 limbs
+            b.logic("AND", (a, 120), (c, 120), nxt + 1)
+            b.fixed_base_scalar_mul((nxt, 128), (nxt + 1, 128), (nxt + 2, nxt + 3))
+            nxt += 4
+    data = b.to_bytes()
+    batch = 7
+    inp = ab.synthetic_inputs(batch, n_inputs=8, seed_id=33)
+    _check_circuit(ctx, data, list(range(1, 9)), batch, inp)

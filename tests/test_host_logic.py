@@ -138,3 +138,18 @@ def test_fr_limb_algorithms_on_host(tmp_path):
         L.t_reduce(a)
         assert val(a) == z % P
         assert L.t_num_bits(arr([z])) == z.bit_length()
+
+
+def test_plan_heavy_ops_match_oracle():
+    b = ab.CircuitBuilder()
+    b.hash256("SHA256", [(1, 8), (2, 16), (3, 254)], list(range(10, 42)))
+    b.hash256("Keccak256", [(w, 8) for w in range(10, 42)], list(range(50, 82)))
+    b.logic("AND", (1, 100), (2, 100), 90)
+    b.logic("AND", (3, 120), (2, 120), 91)
+    b.fixed_base_scalar_mul((90, 128), (91, 128), (92, 93))
+    b.keccak_var([(w, 8) for w in range(50, 60)], (94, 32), list(range(100, 132)))
+    data = b.to_bytes()
+    inp = ab.synthetic_inputs(2, n_inputs=3, seed_id=4)
+    rows = [inp[i * 96:(i + 1) * 96] + v.to_bytes(32, "big") for i, v in enumerate((4, 11))]
+    info = _interp_vs_oracle(data, [1, 2, 3, 94], b"".join(rows), 2)
+    assert info["needs_full_kernel"] == 1 and info["n_hash"] == 3 and info["n_curve"] == 1
