@@ -57,7 +57,10 @@ __device__ __forceinline__ void write_digest(const uint8_t* digest, const uint32
         if ((check_mask >> i) & 1) {
             Fe old;
             hv_load<T>(old, cb, outs[i]);
-            if (!fr::eq(old, v)) hv_fail(fail, opcode, EK_UNSATISFIED_CONSTRAIN, 0);
+            if (!fr::eq(old, v)) {  // insert_value replaces the old value before it reports the mismatch
+                hv_fail(fail, opcode, EK_UNSATISFIED_CONSTRAIN, 0);
+                hv_store<T>(cb, outs[i], v);
+            }
         } else {
             hv_store<T>(cb, outs[i], v);
         }
@@ -369,14 +372,20 @@ __device__ __forceinline__ void write_point(const OpRec* r, uint32_t flags, cons
     if (flags & GF_OUT_CHECK) {
         Fe old;
         hv_load<T>(old, cb, out_x);
-        if (!fr::eq(old, x)) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        if (!fr::eq(old, x)) {
+            hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+            hv_store<T>(cb, out_x, x);
+        }
     } else {
         hv_store<T>(cb, out_x, x);
     }
     if (flags & GF_OUT2_CHECK) {
         Fe old;
         hv_load<T>(old, cb, out_y);
-        if (!fr::eq(old, y)) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        if (!fr::eq(old, y)) {
+            hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+            hv_store<T>(cb, out_y, y);
+        }
     } else {
         hv_store<T>(cb, out_y, y);
     }
@@ -424,6 +433,69 @@ __device__ __noinline__ void exec_fixed_base(const OpRec* r, uint32_t flags, uin
     write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pedersen (plookup-structured): see oracle/pedersen.py for the exact function and DESIGN.md for the
+// parity status.  payload: [n_in][domain_separator][witness * n_in]; out = w[2] (x), w[5] (y).
+// ---------------------------------------------------------------------------------------------
+constexpr int PED_WINDOWS = 29, PED_TABLE_SIZE = 512, PED_IV_SIZE = 1024;
+
+__device__ __noinline__ void ped_hash_single(Jac& acc, const Fe& v, int parity) {
+    uint32_t l[9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = v.l[i];
+    l[8] = 0;
+#pragma unroll 1
+    for (int i = 0; i < PED_WINDOWS; ++i) {
+        const int o = 9 * i, limb = o >> 5, sh = o & 31;
+        uint32_t s = __funnelshift_r(l[limb], l[limb + 1], sh) & 0x1FF;
+        const uint4* tp = reinterpret_cast<const uint4*>(g_curve_tables.pedersen +
+                                                         (((size_t)(parity * PED_WINDOWS + i)) * PED_TABLE_SIZE + s) * 16);
+        uint4 a = tp[0], b = tp[1], c = tp[2], e = tp[3];
+        Fe px, py;
+        px.l[0] = a.x; px.l[1] = a.y; px.l[2] = a.z; px.l[3] = a.w; px.l[4] = b.x; px.l[5] = b.y; px.l[6] = b.z; px.l[7] = b.w;
+        py.l[0] = c.x; py.l[1] = c.y; py.l[2] = c.z; py.l[3] = c.w; py.l[4] = e.x; py.l[5] = e.y; py.l[6] = e.z; py.l[7] = e.w;
+        jac_madd(acc, px, py);
+    }
+}
+
+template <int T>
+__device__ __noinline__ void exec_pedersen(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_in = pl[0], iv = pl[1];
+    Fe x, y;
+    if (n_in == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x.l[k] = 0; y.l[k] = 0; }
+        write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
+        return;
+    }
+    Fe rr;
+    {
+        const uint32_t* ivp = g_curve_tables.pedersen + (size_t)2 * PED_WINDOWS * PED_TABLE_SIZE * 16 + (size_t)(iv % PED_IV_SIZE) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rr.l[k] = ivp[k];
+    }
+    Jac acc;
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_in; ++k) {
+        Fe v;
+        hv_load<T>(v, cb, pl[2 + k]);
+        acc.inf = true;
+        ped_hash_single(acc, rr, 0);
+        ped_hash_single(acc, v, 1);
+        jac_to_affine_canonical(rr, y, acc);     // chaining value = x coordinate (0 at infinity)
+    }
+    acc.inf = true;
+    ped_hash_single(acc, rr, 0);
+    Fe cnt;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cnt.l[k] = 0;
+    cnt.l[0] = n_in;
+    ped_hash_single(acc, cnt, 1);
+    jac_to_affine_canonical(x, y, acc);
+    write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
+}
+
 template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
                                            const uint32_t* payload) {
@@ -436,6 +508,9 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_FIXED_BASE:
             exec_fixed_base<T>(r, flags, cb, fail);
+            break;
+        case MK_PEDERSEN:
+            exec_pedersen<T>(r, flags, cb, fail, payload);
             break;
         default:
             break;

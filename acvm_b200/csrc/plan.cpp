@@ -264,7 +264,9 @@ struct Compiler {
             size_t nw = 0;
             if (dst != NONE) {
                 if (flags & GF_OUT_CHECK) {
+                    // compared, and REPLACED on mismatch (insert_value): order it like a write
                     reads[nr++] = dst;
+                    writes[nw++] = dst;
                     plan.stats.alg_bytes += 32;
                 } else {
                     writes[nw++] = dst;
@@ -360,9 +362,8 @@ struct Compiler {
                 if (known[out]) {
                     flags |= GF_OUT_CHECK;
                     reads[nr++] = out;
-                } else {
-                    writes[nw++] = out;
                 }
+                writes[nw++] = out;
                 r.w[0] = (b.func == BB_AND ? MK_AND : MK_XOR) | (flags << 8);
                 r.w[1] = idx;
                 r.w[2] = out;
@@ -421,7 +422,8 @@ struct Compiler {
                 if (b.func == BB_Keccak256VariableLength) rd.push_back(b.inputs.back().witness);
                 for (uint32_t i = 0; i < 32; ++i) {
                     plan.payload.push_back(b.outputs[i]);
-                    if (mask & (1u << i)) rd.push_back(b.outputs[i]); else wr.push_back(b.outputs[i]);
+                    if (mask & (1u << i)) rd.push_back(b.outputs[i]);
+                    wr.push_back(b.outputs[i]);
                     plan.stats.alg_bytes += 32;
                 }
                 r.w[0] = (b.func == BB_SHA256 ? MK_SHA256 : MK_KECCAK256) | (GF_HEAVY << 8);
@@ -440,8 +442,10 @@ struct Compiler {
                 uint32_t ox = b.outputs[0], oy = b.outputs[1];
                 uint32_t flags = GF_HEAVY;
                 std::vector<uint32_t> rd = {b.inputs[0].witness, b.inputs[1].witness}, wr;
-                if (known[ox]) { flags |= GF_OUT_CHECK; rd.push_back(ox); } else wr.push_back(ox);
-                if (known[oy] || oy == ox) { flags |= GF_OUT2_CHECK; rd.push_back(oy); } else wr.push_back(oy);
+                if (known[ox]) { flags |= GF_OUT_CHECK; rd.push_back(ox); }
+                wr.push_back(ox);
+                if (known[oy] || oy == ox) { flags |= GF_OUT2_CHECK; rd.push_back(oy); }
+                if (oy != ox) wr.push_back(oy);
                 r.w[0] = MK_FIXED_BASE | (flags << 8);
                 r.w[1] = idx;
                 r.w[2] = ox;
@@ -457,6 +461,36 @@ struct Compiler {
                 ++plan.stats.n_micro;
                 ++plan.stats.n_curve;
                 plan.stats.alg_bytes += 128;
+                return true;
+            }
+            case BB_Pedersen: {
+                uint32_t ox = b.outputs[0], oy = b.outputs[1];
+                uint32_t flags = GF_HEAVY;
+                std::vector<uint32_t> rd, wr;
+                uint32_t off = (uint32_t)plan.payload.size();
+                plan.payload.push_back((uint32_t)b.inputs.size());
+                plan.payload.push_back(b.domain_separator);
+                for (auto& in : b.inputs) {   // num_bits is ignored: the full field value is hashed (pedersen.rs:18-20)
+                    plan.payload.push_back(in.witness);
+                    rd.push_back(in.witness);
+                }
+                if (known[ox]) { flags |= GF_OUT_CHECK; rd.push_back(ox); }
+                wr.push_back(ox);
+                if (known[oy] || oy == ox) { flags |= GF_OUT2_CHECK; rd.push_back(oy); }
+                if (oy != ox) wr.push_back(oy);
+                r.w[0] = MK_PEDERSEN | (flags << 8);
+                r.w[1] = idx;
+                r.w[2] = ox;
+                r.w[3] = r.w[4] = r.w[6] = NONE;
+                r.w[5] = oy;
+                r.w[7] = off;
+                sched.place(r, rd.data(), rd.size(), wr.data(), wr.size());
+                if (!known[ox]) mark_assigned(ox, idx);
+                if (!known[oy]) mark_assigned(oy, idx);
+                plan.needs_full_kernel = true;
+                ++plan.stats.n_micro;
+                ++plan.stats.n_curve;
+                plan.stats.alg_bytes += 32 * b.inputs.size() + 64;
                 return true;
             }
             default:

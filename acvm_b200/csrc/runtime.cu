@@ -170,6 +170,9 @@ static int ensure_curve_tables(acvmb_ctx* ctx) {
     std::vector<uint32_t> fb = gk::build_fixed_base_table();
     CUDA_TRY(cudaMalloc(&ctx->d_fixed_base, fb.size() * 4));
     CUDA_TRY(cudaMemcpy(ctx->d_fixed_base, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> pt = gk::build_pedersen_tables();
+    CUDA_TRY(cudaMalloc(&ctx->d_pedersen, pt.size() * 4));
+    CUDA_TRY(cudaMemcpy(ctx->d_pedersen, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(set_curve_tables(ctx->d_fixed_base, ctx->d_pedersen));
     ctx->tables_ready = true;
     return ACVMB_OK;
@@ -798,5 +801,15 @@ extern "C" int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s) {
     if (!ctx) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(frmul_microbench(fr_mul_per_s));
+    return ACVMB_OK;
+}
+
+// host-only test hook: generator `index` of the Pedersen tables (canonical x, y big-endian) -- lets the CPU
+// suite check the C++ derivation against the oracle's without a device
+extern "C" int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]) {
+    if (!out_xy_be32) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    gk::Pt p = gk::derive_pedersen_generator(index);
+    hf::to_be_bytes(p.x, out_xy_be32);
+    hf::to_be_bytes(p.y, out_xy_be32 + 32);
     return ACVMB_OK;
 }

@@ -157,7 +157,10 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
         if (flags & GF_OUT_CHECK) {
             Fe old;
             load_w<T>(old, cb, r->w[2]);
-            if (!fr::eq(old, res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+            if (!fr::eq(old, res)) {  // insert_value replaces the old value before it reports the mismatch (mod.rs:343-354)
+                record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+                store_w<T>(cb, r->w[2], res);
+            }
         } else {
             store_w<T>(cb, r->w[2], res);
         }
@@ -186,7 +189,10 @@ __device__ __forceinline__ void exec_logic(const OpRec* r, uint32_t kind, uint32
     if (flags & GF_OUT_CHECK) {
         Fe old;
         load_w<T>(old, cb, r->w[2]);
-        if (!fr::eq(old, res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        if (!fr::eq(old, res)) {  // insert_value replaces the old value before it reports the mismatch (mod.rs:343-354)
+                record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+                store_w<T>(cb, r->w[2], res);
+            }
     } else {
         store_w<T>(cb, r->w[2], res);
     }

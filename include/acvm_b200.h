@@ -163,6 +163,8 @@ int acvmb_keccak256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint3
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
+int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]);
+
 /* ---- measurement helpers ---- */
 int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,
                           double* sm_clock_mhz);

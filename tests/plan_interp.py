@@ -83,6 +83,7 @@ def default_hooks():
                 if (mask >> i) & 1:
                     if cols[outs[i]] != d[i]:
                         record_fail(opcode, EK_UNSAT)
+                        w.append((outs[i], d[i]))
                 else:
                     w.append((outs[i], d[i]))
             return w
@@ -101,11 +102,28 @@ def default_hooks():
             if chk:
                 if cols[slot] != v:
                     record_fail(opcode, EK_UNSAT)
+                    w.append((slot, v))
             else:
                 w.append((slot, v))
         return w
 
-    return {MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
+    def pedersen_hook(cols, hdr, payload, record_fail):
+        from oracle import pedersen
+        flags = hdr[0] >> 8
+        opcode, ox, oy, off = hdr[1], hdr[2], hdr[5], hdr[7]
+        n_in, iv = payload[off], payload[off + 1]
+        x, y = pedersen.commit_native([cols[w] for w in payload[off + 2: off + 2 + n_in]], iv)
+        w = []
+        for (slot, v, chk) in ((ox, x, flags & GF_OUT_CHECK_), (oy, y, flags & GF_OUT2_CHECK_)):
+            if chk:
+                if cols[slot] != v:
+                    record_fail(opcode, EK_UNSAT)
+                    w.append((slot, v))
+            else:
+                w.append((slot, v))
+        return w
+
+    return {MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
 
 
 def run_plan(plan: PlanBlob, inputs, hooks=None):
@@ -154,6 +172,7 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
                     if flags & GF_OUT_CHECK:
                         if cols[out] != res:
                             record_fail(opcode, EK_UNSAT)
+                            writes.append((out, res))
                     else:
                         writes.append((out, res))
                 elif res != 0:
@@ -165,6 +184,7 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
                 if flags & GF_OUT_CHECK:
                     if cols[out] != res:
                         record_fail(opcode, EK_UNSAT)
+                        writes.append((out, res))
                 else:
                     writes.append((out, res))
             elif kind == MK["RANGE"]:
