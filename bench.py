@@ -268,7 +268,7 @@ def run_ours(args):
     if not args.no_e2e:
         import psutil
         avail = psutil.virtual_memory().available
-        e2e_chunk = int(min(args.batch, max(1, min(args.e2e_chunk_gib * 2**30, avail * 0.4) // (nw * 32))))
+        e2e_chunk = int(min(args.batch, max(1, min(args.e2e_chunk_gib * 2**30, avail * 0.4 / world) // (nw * 32))))
         n_calls = -(-args.batch // e2e_chunk)
         out_bytes = e2e_chunk * nw * 32
         batch_obj.close()
