@@ -54,6 +54,7 @@ def load():
         "acvmb_solve_batch": (C.c_int, [vp, C.c_uint32, vp, u32p, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_last_run_info": (C.c_int, [vp, C.POINTER(RunInfo)]),
         "acvmb_batch_create": (C.c_int, [vp, C.c_uint32, C.POINTER(vp)]),
+        "acvmb_batch_resize": (C.c_int, [vp, C.c_uint32]),
         "acvmb_batch_destroy": (None, [vp]),
         "acvmb_batch_upload": (C.c_int, [vp, vp]),
         "acvmb_batch_run": (C.c_int, [vp, C.POINTER(C.c_float)]),

@@ -38,6 +38,7 @@ struct acvmb_ctx {
     uint32_t opt_T = 0;   // 0 = auto
     uint32_t opt_S = 16;
     uint32_t opt_chunk_steps = 2;
+    int opt_split = -1;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
     uint64_t staging_bytes = 512ull << 20;
     uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
@@ -64,6 +65,7 @@ struct acvmb_circuit {
 struct acvmb_batch {
     acvmb_circuit* c = nullptr;
     uint32_t n_inst = 0, T = 0, n_tiles = 0;
+    uint32_t capacity = 0;               // instances the buffers were sized for (n_inst <= capacity)
     uint4* d_cols = nullptr;
     unsigned long long* d_fail = nullptr;
     uint8_t* d_in = nullptr;
@@ -158,6 +160,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     if (k == "T") ctx->opt_T = (uint32_t)value;
     else if (k == "S") ctx->opt_S = (uint32_t)value;
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
+    else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
     else if (k == "staging_bytes") ctx->staging_bytes = value;
     else return set_err(ACVMB_ERR_INVALID_ARG, "unknown option " + k);
@@ -314,6 +317,7 @@ extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_
     b->T = pick_T(c->ctx, c->plan);
     if (!vm_config_supported((int)b->T, (int)c->plan.S))
         return set_err(ACVMB_ERR_INVALID_ARG, "no kernel instantiation for T=" + std::to_string(b->T) + " S=" + std::to_string(c->plan.S));
+    b->capacity = n_instances;
     b->n_tiles = (n_instances + b->T - 1) / b->T;
     size_t col_bytes = (size_t)b->n_tiles * b->T * c->plan.n_slots * 32;
     CUDA_TRY(cudaMalloc(&b->d_cols, col_bytes));
@@ -327,6 +331,14 @@ extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_
         CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming));
     }
     *out = b.release();
+    return ACVMB_OK;
+}
+
+// run fewer instances than the buffers were sized for (sub-batches of unequal size share one buffer)
+extern "C" int acvmb_batch_resize(acvmb_batch* b, uint32_t n_instances) {
+    if (!b || n_instances == 0 || n_instances > b->capacity) return set_err(ACVMB_ERR_INVALID_ARG, "resize beyond capacity");
+    b->n_inst = n_instances;
+    b->n_tiles = (n_instances + b->T - 1) / b->T;
     return ACVMB_OK;
 }
 
@@ -371,7 +383,7 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     a.chunk_steps = c->plan.chunk_steps;
     a.n_slots = c->plan.n_slots;
     a.n_tiles = b->n_tiles;
-    KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel};
+    KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel, c->ctx->opt_split};
     CUDA_TRY(cudaEventRecord(b->ev0, s));
     CUDA_TRY(launch_vm(cfg, a, s));
     CUDA_TRY(cudaEventRecord(b->ev1, s));
@@ -395,8 +407,9 @@ extern "C" int acvmb_batch_stage_inputs(acvmb_batch* b, uint32_t slot, const uin
     if (!b || !inputs_be32 || slot > 4096) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(b->c->ctx->device));
     size_t in_bytes = (size_t)b->n_inst * b->c->plan.input_witnesses.size() * 32;
+    size_t cap_bytes = (size_t)b->capacity * b->c->plan.input_witnesses.size() * 32;
     if (b->d_staged_in.size() <= slot) b->d_staged_in.resize(slot + 1, nullptr);
-    if (!b->d_staged_in[slot]) CUDA_TRY(cudaMalloc(&b->d_staged_in[slot], std::max<size_t>(in_bytes, 16)));
+    if (!b->d_staged_in[slot]) CUDA_TRY(cudaMalloc(&b->d_staged_in[slot], std::max<size_t>(cap_bytes, 16)));
     CUDA_TRY(cudaMemcpy(b->d_staged_in[slot], inputs_be32, in_bytes, cudaMemcpyHostToDevice));
     return ACVMB_OK;
 }
@@ -797,7 +810,7 @@ extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint
     return ACVMB_OK;
 }
 
-extern "C" int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s) {
+extern "C" int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s /*[5]*/) {
     if (!ctx) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(frmul_microbench(fr_mul_per_s));

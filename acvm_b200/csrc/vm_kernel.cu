@@ -101,7 +101,7 @@ struct RegLimbs {
 // GF_MUL : out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma   -- two Montgomery reductions: u = (x+alpha)(y+beta)/R,
 //          then <u, w1> . <cM*R^2, c1*R> / R in ONE interleaved reduction (fr::mont_dot_fn).
 // linear : out = cY*y + c1*w1 + c2*w2 + cC               -- one reduction for up to three products.
-template <int T>
+template <int T, int SPLIT>
 __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
     Fe res;
     if (flags & GF_Y) {
@@ -115,33 +115,33 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
             lds_fe(t, r->c[2]);
             fr::add_mod(y, y, t);
             const Fe* a1[1] = {&x};
-            fr::mont_dot_fn<1>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R, < 1.19p, used unreduced
+            fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R, < 1.19p, used unreduced
             if (nlin == 0) {
                 const Fe* a[1] = {&u};
-                fr::mont_dot_fn<1>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 const Fe* a[2] = {&u, &w1};
-                fr::mont_dot_fn<2>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
+                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
             }
         } else {
             Fe y;
             load_w<T>(y, cb, r->w[4]);
             if (nlin == 0) {
                 const Fe* a[1] = {&y};
-                fr::mont_dot_fn<1>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr});
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 if (nlin == 1) {
                     const Fe* a[2] = {&y, &w1};
-                    fr::mont_dot_fn<2>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr});
+                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr});
                 } else {
                     Fe w2;
                     load_w<T>(w2, cb, r->w[6]);
                     const Fe* a[3] = {&y, &w1, &w2};
-                    fr::mont_dot_fn<3>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]});
+                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]});
                 }
             }
         }
@@ -205,7 +205,7 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
     if (fr::num_bits(x) > r->w[7]) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
 }
 
-template <int T, int S, bool FULL>
+template <int T, int S, bool FULL, int SPLIT>
 __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
                     break;
                 case MK_GATE_ASSIGN:
                 case MK_GATE_CHECK:
-                    exec_gate<T>(r, kind, flags, cb, fail);
+                    exec_gate<T, SPLIT>(r, kind, flags, cb, fail);
                     break;
                 case MK_AND:
                 case MK_XOR:
@@ -271,10 +271,10 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     }
 }
 
-template <int T, int S, bool FULL>
+template <int T, int S, bool FULL, int SPLIT = FR_ALU_SPLIT>
 static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     size_t smem = (size_t)NSTAGE * args.chunk_steps * S * sizeof(OpRec) + NSTAGE * sizeof(uint64_t);
-    auto k = vm_kernel<T, S, FULL>;
+    auto k = vm_kernel<T, S, FULL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<args.n_tiles, T * S, smem, stream>>>(args);
@@ -301,6 +301,12 @@ bool vm_config_supported(int T, int S) {
 }
 
 cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream) {
+    // tuning hook: explicit FMA/ALU pipe-split level for the two production tile shapes of the arithmetic kernel
+    if (cfg.split >= 0 && !cfg.full && cfg.S == 16 && (cfg.T == 8 || cfg.T == 4)) {
+#define Y(t, sp) if (cfg.T == t && cfg.split == sp) return launch_one<t, 16, false, sp>(args, stream);
+        Y(8, 0) Y(8, 1) Y(8, 2) Y(8, 3) Y(8, 4) Y(4, 0) Y(4, 2) Y(4, 4)
+#undef Y
+    }
 #define X(t, s)                                                                        \
     if (cfg.T == t && cfg.S == s) {                                                    \
         return cfg.full ? launch_one<t, s, true>(args, stream) : launch_one<t, s, false>(args, stream); \
@@ -452,14 +458,15 @@ __global__ void __launch_bounds__(256) imad_bench_kernel(uint32_t* out, uint32_t
 }
 
 // Fr-mul ceiling: register-resident Montgomery multiplications, two dependent chains per thread.
+template <int SPLIT>
 __global__ void __launch_bounds__(256) frmul_bench_kernel(uint32_t* out, uint32_t seed, int iters) {
     fr::Fe a, b;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a.l[i] = seed * (i + 3) + threadIdx.x; b.l[i] = seed * (i + 7) + blockIdx.x; }
     a.l[7] &= 0x0FFFFFFF; b.l[7] &= 0x0FFFFFFF;
     for (int it = 0; it < iters; ++it) {
-        fr::mont_mul(a, a, b);
-        fr::mont_mul(b, b, a);
+        fr::mont_mul_s<SPLIT>(a, a, b);
+        fr::mont_mul_s<SPLIT>(b, b, a);
     }
     uint32_t s = 0;
 #pragma unroll
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(256) frmul_bench_kernel(uint32_t* out, uint32_
     if (s == 0x12345678u) out[0] = s;
 }
 
-cudaError_t frmul_microbench(double* fr_mul_per_s) {
+cudaError_t frmul_microbench(double* fr_mul_per_s /*[5]: pipe-split level 0..4*/) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -478,18 +485,26 @@ cudaError_t frmul_microbench(double* fr_mul_per_s) {
     cudaEventCreate(&t0);
     cudaEventCreate(&t1);
     const int iters = 512, blocks = sms * 8, threads = 256;
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
-        cudaEventRecord(t0);
-        frmul_bench_kernel<<<blocks, threads>>>(d, 17 + rep, iters);
-        cudaEventRecord(t1);
-        e = cudaEventSynchronize(t1);
-        if (e != cudaSuccess) return e;
-        float ms;
-        cudaEventElapsedTime(&ms, t0, t1);
-        if (rep > 0 && ms < best) best = ms;
+    for (int sp = 0; sp < 5; ++sp) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(t0);
+            switch (sp) {
+                case 0: frmul_bench_kernel<0><<<blocks, threads>>>(d, 17 + rep, iters); break;
+                case 1: frmul_bench_kernel<1><<<blocks, threads>>>(d, 17 + rep, iters); break;
+                case 2: frmul_bench_kernel<2><<<blocks, threads>>>(d, 17 + rep, iters); break;
+                case 3: frmul_bench_kernel<3><<<blocks, threads>>>(d, 17 + rep, iters); break;
+                default: frmul_bench_kernel<4><<<blocks, threads>>>(d, 17 + rep, iters); break;
+            }
+            cudaEventRecord(t1);
+            e = cudaEventSynchronize(t1);
+            if (e != cudaSuccess) return e;
+            float ms;
+            cudaEventElapsedTime(&ms, t0, t1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        if (fr_mul_per_s) fr_mul_per_s[sp] = 2.0 * iters * blocks * threads / (best * 1e-3);
     }
-    if (fr_mul_per_s) *fr_mul_per_s = 2.0 * iters * blocks * threads / (best * 1e-3);
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     cudaFree(d);

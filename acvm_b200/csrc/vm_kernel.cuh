@@ -23,6 +23,7 @@ struct VmArgs {
 struct KernelConfig {
     int T, S;
     bool full;
+    int split = -1;   // FMA/ALU pipe-split level of the field multiplier (-1 = build default), see fr.cuh
 };
 
 // returns cudaSuccess or the launch error; smem_bytes/regs reported for the run record
@@ -43,6 +44,6 @@ cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long 
 cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s, double* sm_clock_mhz);
 
 // register-resident Montgomery multiplications per second (practical Fr-mul ceiling of this field library)
-cudaError_t frmul_microbench(double* fr_mul_per_s);
+cudaError_t frmul_microbench(double* fr_mul_per_s /*[5]*/);
 
 }  // namespace acvmb

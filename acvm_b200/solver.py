@@ -71,10 +71,10 @@ class Context:
     def imad_microbench(self):
         v = [C.c_double() for _ in range(4)]
         _check(lib().acvmb_imad_microbench(self._h, *[C.byref(x) for x in v]))
-        f = C.c_double()
-        _check(lib().acvmb_frmul_microbench(self._h, C.byref(f)))
+        f = (C.c_double * 5)()
+        _check(lib().acvmb_frmul_microbench(self._h, f))
         return dict(imad32_per_s=v[0].value, imad_wide_per_s=v[1].value, imad_wide_carry_per_s=v[2].value,
-                    sm_clock_mhz=v[3].value, fr_mul_per_s=f.value)
+                    sm_clock_mhz=v[3].value, fr_mul_per_s_by_split=list(f), fr_mul_per_s=max(f))
 
     def close(self):
         if self._h:
@@ -207,6 +207,10 @@ class DeviceBatch:
         self.n = n
         self._h = C.c_void_p()
         _check(lib().acvmb_batch_create(circuit._h, n, C.byref(self._h)))
+
+    def resize(self, n: int):
+        _check(lib().acvmb_batch_resize(self._h, n))
+        self.n = n
 
     def upload(self, inputs_be32):
         buf = (C.c_uint8 * len(inputs_be32)).from_buffer_copy(inputs_be32) if not isinstance(inputs_be32, (C.Array, int)) else inputs_be32

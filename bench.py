@@ -214,25 +214,30 @@ def run_ours(args):
     T = args.T or max(1, 128 // info["S"])
     budget = int(free_b * 0.88)
     fit = max(T, (budget // per_inst) // T * T)
-    n_sub = -(-args.batch // fit)
-    # equal sub-batches, multiple of T
-    sub = -(-args.batch // n_sub)
-    sub = -(-sub // T) * T
-    sizes = [min(sub, args.batch - i * sub) for i in range(n_sub) if args.batch - i * sub > 0]
+    # sub-batch sizes: whole waves of CTAs (148 SMs x k CTAs x T instances) so no SM idles while another holds an
+    # extra CTA; the remainder goes last
+    wave = 148 * T
+    sizes, left = [], args.batch
+    while left > 0:
+        take = min(left, fit)
+        if take >= wave and left > take:
+            take = take // wave * wave
+        sizes.append(take)
+        left -= take
     log(f"[bench] rank {rank}: free {free_b / 2**30:.1f} GiB, {per_inst / 2**20:.1f} MiB/instance -> sub-batches {sizes}")
     first_inst = rank * args.batch
-    batch_obj = acvm_b200.DeviceBatch(circ, sizes[0])
+    # the sub-batches share ONE column buffer in time (capacity = the largest); resize() selects the active count
+    batch_obj = acvm_b200.DeviceBatch(circ, max(sizes))
     off = 0
     for k, sz in enumerate(sizes):
-        inp = ab.synthetic_inputs(sz, seed_id=1, first_instance=first_inst + off)
-        if sz < sizes[0]:
-            inp = inp + bytes((sizes[0] - sz) * len(inputs) * 32)  # pad the last sub-batch (not counted)
-        batch_obj.stage_inputs(k, inp)
+        batch_obj.resize(sz)
+        batch_obj.stage_inputs(k, ab.synthetic_inputs(sz, seed_id=1, first_instance=first_inst + off))
         off += sz
 
     def step():
         tot = vm = 0.0
         for k in range(len(sizes)):
+            batch_obj.resize(sizes[k])
             t, v = batch_obj.run_staged(k)
             tot += t
             vm += v
@@ -247,7 +252,7 @@ def run_ours(args):
         step()
     # correctness gate on the last warm-up pass: every instance solved
     st = batch_obj.status()
-    assert all(s.status == "Solved" for s in st[:sizes[-1]]), "synthetic circuit must solve for every instance"
+    assert len(st) == sizes[-1] and all(s.status == "Solved" for s in st), "synthetic circuit must solve for every instance"
 
     sampler = ClockSampler(local_rank)
     barrier()
@@ -323,7 +328,7 @@ def run_ours(args):
     value = total_inst / (ms_per_step * 1e-3)
     hbm_peak, peak_src = measured_peaks()
     vm_launch_ms = vm_ms / (args.steps * len(sizes))          # average step-VM kernel launch
-    inst_per_launch = args.batch / len(sizes)
+    inst_per_launch = sum(sizes) / len(sizes)
     alg_bytes_launch = info["alg_bytes"] * inst_per_launch
     achieved_gbs = alg_bytes_launch / (vm_launch_ms * 1e-3) / 1e9
     imad = ctx.imad_microbench()
@@ -383,7 +388,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-chunk-gib", type=float, default=16.0)
+    ap.add_argument("--e2e-chunk-gib", type=float, default=64.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")

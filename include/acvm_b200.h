@@ -123,6 +123,7 @@ int acvmb_last_run_info(const acvmb_circuit* c, acvmb_run_info* out);
 /* ---- device-resident batch: the same solve split into its phases, so callers (and bench.py) can
  * keep the witness columns in HBM, time the kernel alone, or overlap their own I/O. ---- */
 int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_batch** out);
+int acvmb_batch_resize(acvmb_batch* b, uint32_t n_instances);              /* active instances <= created capacity */
 void acvmb_batch_destroy(acvmb_batch* b);
 int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32);         /* H2D + scatter */
 int acvmb_batch_run(acvmb_batch* b, float* kernel_ms);                      /* step-VM kernel(s), synchronous */
@@ -168,7 +169,8 @@ int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]);
 /* ---- measurement helpers ---- */
 int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,
                           double* sm_clock_mhz);
-/* register-resident Montgomery multiplications per second: the practical Fr-mul ceiling of the K0 field library */
+/* register-resident Montgomery multiplications per second for the 5 FMA/ALU pipe-split levels of the K0 field
+ * library (fr_mul_per_s[0..4]): the practical Fr-mul ceiling */
 int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step; recompile plan), "max_resident_bytes" */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);

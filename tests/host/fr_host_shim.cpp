@@ -18,6 +18,12 @@ void t_mont_dot(int k, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     else mont_dot_raw<4>(R, pa, pb);
     memcpy(r, R.l, 32);
 }
+void t_mont_mul_split(int split, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32);
+    switch (split) { case 0: mont_mul_s<0>(R, A, B); break; case 1: mont_mul_s<1>(R, A, B); break; case 2: mont_mul_s<2>(R, A, B); break;
+                     case 3: mont_mul_s<3>(R, A, B); break; default: mont_mul_s<4>(R, A, B); break; }
+    memcpy(r, R.l, 32);
+}
 void t_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); add_mod(R, A, B); memcpy(r, R.l, 32); }
 void t_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); sub_mod(R, A, B); memcpy(r, R.l, 32); }
 void t_reduce(uint32_t* a) { Fe A; memcpy(A.l, a, 32); reduce_256(A); memcpy(a, A.l, 32); }

@@ -127,6 +127,12 @@ def test_fr_limb_algorithms_on_host(tmp_path):
         L.t_mont_dot(k, arr(A), arr(B), r)
         got = val(r)
         assert got < 2 * P and got % P == sum(x * y for x, y in zip(A, B)) * Rinv % P
+    for it in range(1500):  # every FMA/ALU pipe split level of the row helpers computes the same product
+        x, y = rnd.choice([0, 1, P - 1, rnd.randrange(P)]), rnd.choice([0, 1, P - 1, rnd.randrange(P)])
+        for split in range(5):
+            r = (ctypes.c_uint32 * 8)()
+            L.t_mont_mul_split(split, arr([x]), arr([y]), r)
+            assert val(r) == x * y * Rinv % P, (split, hex(x), hex(y))
     for it in range(1000):
         x, y, z = rnd.randrange(P), rnd.randrange(P), rnd.randrange(1 << 256)
         r = (ctypes.c_uint32 * 8)()
