@@ -126,12 +126,15 @@ FR_PRIM void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
 
 // Same chain, split across the two integer pipes: the four wide products are carry-free IMAD.WIDE.U32
 // (full rate on the FMA-heavy pipe) and the eight limb additions run as an IADD3/IADD3.X chain on the ALU
-// pipe.  Measured on B200: IMAD.WIDE.U32.X (carry in/out) issues at HALF the rate of the carry-free form, so
-// moving half of the chains here shortens the FMA-pipe critical path by 25 %.
+// pipe.  Measured on B200: IMAD.WIDE.U32.X (carry in/out) issues at HALF the rate of the carry-free form; the
+// hypothesis that moving chains to the ALU pipe would help was tested and REJECTED (see FR_ALU_SPLIT below).
 // SPLIT level (template parameter of dot_row / mont_dot_fn): 0 = every chain on the FMA pipe, 1 = even
 // a-chains on the ALU pipe, 2 = + even modulus chains, 3 = + odd modulus chains, 4 = + odd a-chains.
+// MEASURED (B200, profiles/r1_pipe_split_sweep.txt): every level > 0 is SLOWER (67.6 -> 46.8 G Fr-mul/s from level
+// 0 to 4): carry-consuming IADD3.X chains are no cheaper than IMAD.WIDE.U32.X, so the default stays 0 and the
+// levels remain only as a tuning/measurement hook.
 #ifndef FR_ALU_SPLIT
-#define FR_ALU_SPLIT 2
+#define FR_ALU_SPLIT 0
 #endif
 FR_PRIM void cmad_n_alu(uint32_t* acc, const uint32_t* a, uint32_t bi) {
     uint32_t lo[N / 2], hi[N / 2];
