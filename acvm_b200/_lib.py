@@ -52,6 +52,8 @@ def load():
         "acvmb_circuit_serialize": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "acvmb_circuit_deserialize": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(vp)]),
         "acvmb_solve_batch": (C.c_int, [vp, C.c_uint32, vp, u32p, C.c_uint32, vp, C.POINTER(Status)]),
+        "acvmb_solve_batch_ex": (C.c_int, [vp, C.c_uint32, vp, u32p, C.c_uint32, vp, vp, C.POINTER(Status)]),
+        "acvmb_batch_download_ex": (C.c_int, [vp, C.c_uint32, C.c_uint32, u32p, C.c_uint32, vp, vp]),
         "acvmb_last_run_info": (C.c_int, [vp, C.POINTER(RunInfo)]),
         "acvmb_batch_create": (C.c_int, [vp, C.c_uint32, C.POINTER(vp)]),
         "acvmb_batch_resize": (C.c_int, [vp, C.c_uint32]),

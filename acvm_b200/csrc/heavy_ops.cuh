@@ -496,9 +496,123 @@ __device__ __noinline__ void exec_pedersen(const OpRec* r, uint32_t flags, uint4
     write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Value-dependent arithmetic gate: the reference's evaluate() + solve() run per lane
+// (acvm/src/pwg/arithmetic.rs:27-127,212-239).  `mu` is this lane's "assigned by opcode" table for the witnesses
+// whose assignment depends on instance values (entry = opcode index that assigned it, NONE = unassigned).
+// payload layout: see plan.cpp general_gate().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pl_fe(Fe& v, const uint32_t* p) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.l[k] = p[k];
+}
+
+template <int T>
+__device__ __noinline__ void exec_general(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload, uint32_t* mu) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_mul = pl[0], n_lin = pl[1];
+    Fe q;
+    pl_fe(q, pl + 2);
+    const uint32_t* p = pl + 10;
+    uint32_t n_entries = 0, n_mulrem = 0, ew = 0xFFFFFFFFu, emu = 0xFFFFFFFFu;
+    Fe ecoef;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ecoef.l[k] = 0;
+    auto is_known = [&](uint32_t m) { return m == 0xFFFFFFFFu || mu[(size_t)m * T] != 0xFFFFFFFFu; };
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_mul; ++i, p += 20) {
+        Fe cR, cR2;
+        pl_fe(cR, p);
+        pl_fe(cR2, p + 8);
+        const uint32_t w1 = p[16], m1 = p[17], w2 = p[18], m2 = p[19];
+        const bool k1 = is_known(m1), k2 = is_known(m2);
+        if (k1 && k2) {          // MulTerm::Solved: q_c += c * w1 * w2
+            Fe a, b, t;
+            hv_load<T>(a, cb, w1);
+            hv_load<T>(b, cb, w2);
+            fr::mont_mul(t, cR2, a);
+            fr::mont_mul(t, t, b);
+            fr::add_mod(q, q, t);
+        } else if (!k1 && !k2) { // both unknown: kept as a mul term unless c == 0
+            if (!fr::is_zero(cR)) ++n_mulrem;
+        } else {                 // one unknown: (c * w_known, w_unknown) unless the product is zero
+            Fe a, v;
+            hv_load<T>(a, cb, k1 ? w1 : w2);
+            fr::mont_mul(v, cR, a);
+            if (!fr::is_zero(v)) {
+                ++n_entries;
+                ecoef = v;
+                ew = k1 ? w2 : w1;
+                emu = k1 ? m2 : m1;
+            }
+        }
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_lin; ++i, p += 18) {
+        Fe cR;
+        pl_fe(cR, p);
+        const uint32_t w = p[16], m = p[17];
+        if (is_known(m)) {
+            Fe a, t;
+            hv_load<T>(a, cb, w);
+            fr::mont_mul(t, cR, a);
+            fr::add_mod(q, q, t);
+        } else {
+            Fe c;
+            pl_fe(c, p + 8);
+            if (!fr::is_zero(c)) {
+                ++n_entries;
+                ecoef = c;
+                ew = w;
+                emu = m;
+            }
+        }
+    }
+    if (n_mulrem > 1) {          // arithmetic.rs:142 panics
+        hv_fail(fail, r->w[1], EK_REFERENCE_PANIC, 0);
+    } else if (n_mulrem == 1 || n_entries > 1) {
+        hv_fail(fail, r->w[1], EK_TOO_MANY_UNKNOWNS, 0);
+    } else if (n_entries == 0) {
+        if (!fr::is_zero(q)) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+    } else {
+        // w := -(q / coeff)     (arithmetic.rs:103-125; Div = multiply by the inverse, generic_ark.rs:375-380)
+        Fe R2, one, cm, inv, qm, val;
+        R2.l[0] = 0xae216da7u; R2.l[1] = 0x1bb8e645u; R2.l[2] = 0xe35c59e3u; R2.l[3] = 0x53fe3ab1u;
+        R2.l[4] = 0x53bb8085u; R2.l[5] = 0x8c49833du; R2.l[6] = 0x7f4e44a5u; R2.l[7] = 0x0216d0b1u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) one.l[k] = 0;
+        one.l[0] = 1;
+        fr::mont_mul(cm, ecoef, R2);     // coeff * R
+        fe_inv(inv, cm);                 // coeff^-1 * R
+        fr::mont_mul(qm, q, R2);         // q * R
+        fr::mont_mul(val, qm, inv);      // q/coeff * R
+        fr::mont_mul(val, val, one);     // q/coeff
+        if (!fr::is_zero(val)) {
+            Fe zero;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) zero.l[k] = 0;
+            fr::sub_mod(val, zero, val);
+        }
+        hv_store<T>(cb, ew, val);
+        mu[(size_t)emu * T] = r->w[1];
+    }
+}
+
+template <int T>
+__device__ __noinline__ void exec_require(const OpRec* r, unsigned long long* fail, const uint32_t* payload, const uint32_t* mu) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n = pl[0];
+    for (uint32_t i = 0; i < n; ++i) {
+        if (mu[(size_t)pl[2 + 2 * i] * T] == 0xFFFFFFFFu) {   // blackbox/mod.rs:55-62: first missing input
+            hv_fail(fail, r->w[1], EK_MISSING_ASSIGNMENT, pl[1 + 2 * i]);
+            return;
+        }
+    }
+}
+
 template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
-                                           const uint32_t* payload) {
+                                           const uint32_t* payload, uint32_t* mu) {
     switch (kind) {
         case MK_SHA256:
             exec_sha256<T>(r, cb, fail, payload);
@@ -511,6 +625,12 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_PEDERSEN:
             exec_pedersen<T>(r, flags, cb, fail, payload);
+            break;
+        case MK_GATE_GENERAL:
+            exec_general<T>(r, cb, fail, payload, mu);
+            break;
+        case MK_REQUIRE:
+            exec_require<T>(r, fail, payload, mu);
             break;
         default:
             break;

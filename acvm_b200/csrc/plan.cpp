@@ -15,6 +15,9 @@ namespace {
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t ASSIGN_NEVER = 0xFFFFFFFFu;
 constexpr uint32_t ASSIGN_INPUT = 0xFFFFFFFEu;
+constexpr uint32_t ASSIGN_DYNAMIC = 0xFFFFFFFDu;
+// static knowledge about a witness when an opcode is reached
+enum : uint8_t { W_UNKNOWN = 0, W_KNOWN = 1, W_MAYBE = 2 };
 
 struct Prod {
     U256 c;
@@ -281,7 +284,117 @@ struct Compiler {
     }
 
     // returns false when compilation must stop (static failure)
+    uint32_t mu_index(uint32_t w) {
+        if (plan.mu_index_of[w] == NONE) plan.mu_index_of[w] = plan.n_mu++;
+        return plan.mu_index_of[w];
+    }
+
+    void make_maybe(uint32_t w) {
+        mu_index(w);
+        known[w] = W_MAYBE;
+        plan.assign_opcode[w] = ASSIGN_DYNAMIC;
+    }
+
+    // Value-dependent arithmetic opcode: which terms survive evaluate() (arithmetic.rs:212-239) depends on
+    // per-instance VALUES (q_M * w_known == 0 drops the term) or on witnesses that only some instances have
+    // assigned.  The whole reference decision procedure then runs per lane (exec_general, heavy_ops.cuh).
+    // payload: n_mul, n_lin, qc[8], then per mul term {cR[8], cR2[8], w1, mu1, w2, mu2}, per lin term {cR[8], c[8], w, mu}
+    // (mu = NONE for a statically known witness).
+    void general_gate(uint32_t idx, const Expression& e) {
+        OpRec r{};
+        std::vector<uint32_t> rd, wr;
+        uint32_t off = (uint32_t)plan.payload.size();
+        auto put_fe = [&](const U256& v) {
+            uint32_t l[8];
+            hf::to_limbs32(v, l);
+            plan.payload.insert(plan.payload.end(), l, l + 8);
+        };
+        auto wref = [&](uint32_t w) {
+            plan.payload.push_back(w);
+            if (known[w] == W_KNOWN) {
+                plan.payload.push_back(NONE);
+                rd.push_back(w);
+            } else {
+                plan.payload.push_back(mu_index(w));
+                rd.push_back(w);
+                wr.push_back(w);
+            }
+        };
+        plan.payload.push_back((uint32_t)e.mul_terms.size());
+        plan.payload.push_back((uint32_t)e.linear_combinations.size());
+        put_fe(e.q_c);
+        for (auto& t : e.mul_terms) {
+            put_fe(hf::to_mont(t.c));
+            put_fe(hf::to_mont2(t.c));
+            wref(t.a);
+            wref(t.b);
+            plan.stats.ref_fr_mul += 2;
+        }
+        for (auto& t : e.linear_combinations) {
+            put_fe(hf::to_mont(t.c));
+            put_fe(t.c);
+            wref(t.w);
+            plan.stats.ref_fr_mul += 1;
+        }
+        plan.stats.ref_fr_inv += 1;
+        r.w[0] = MK_GATE_GENERAL | (GF_HEAVY << 8);
+        r.w[1] = idx;
+        r.w[2] = r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+        r.w[7] = off;
+        std::sort(rd.begin(), rd.end());
+        rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+        std::sort(wr.begin(), wr.end());
+        wr.erase(std::unique(wr.begin(), wr.end()), wr.end());
+        sched.place(r, rd.data(), rd.size(), wr.data(), wr.size());
+        for (uint32_t w : wr) make_maybe(w);
+        plan.needs_full_kernel = true;
+        ++plan.stats.n_micro;
+        ++plan.stats.n_gate_general;
+        plan.stats.alg_bytes += 32 * (rd.size() + 1);
+    }
+
+    // every input of a blackbox call must be assigned (blackbox/mod.rs:55-62); for value-dependent witnesses that is a
+    // per-lane test, reported as MissingAssignment(first missing).  Survivors have them: they become statically known.
+    void require_assigned(uint32_t idx, const std::vector<FunctionInput>& inputs) {
+        std::vector<uint32_t> ws;
+        for (auto& in : inputs)
+            if (known[in.witness] == W_MAYBE) ws.push_back(in.witness);
+        if (ws.empty()) return;
+        OpRec r{};
+        uint32_t off = (uint32_t)plan.payload.size();
+        plan.payload.push_back((uint32_t)ws.size());
+        for (uint32_t w : ws) {
+            plan.payload.push_back(w);
+            plan.payload.push_back(mu_index(w));
+        }
+        r.w[0] = MK_REQUIRE | (GF_HEAVY << 8);
+        r.w[1] = idx;
+        r.w[2] = r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+        r.w[7] = off;
+        std::vector<uint32_t> rd(ws);
+        std::sort(rd.begin(), rd.end());
+        rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+        sched.place(r, rd.data(), rd.size(), rd.data(), rd.size());   // ordered like a write: later readers wait for it
+        for (uint32_t w : rd) known[w] = W_KNOWN;                     // presence in the output stays per-lane (ASSIGN_DYNAMIC)
+        plan.needs_full_kernel = true;
+        ++plan.stats.n_micro;
+    }
+
     bool arithmetic(uint32_t idx, const Expression& e) {
+        {
+            bool general = false;
+            for (auto& t : e.mul_terms) {
+                uint8_t ka = known[t.a], kb = known[t.b];
+                if (ka == W_MAYBE || kb == W_MAYBE) general = true;
+                if (!t.c.is_zero() && ((ka == W_KNOWN) != (kb == W_KNOWN))) general = true;
+            }
+            for (auto& t : e.linear_combinations)
+                if (known[t.w] == W_MAYBE) general = true;
+            if (general) {
+                general_gate(idx, e);
+                return true;
+            }
+        }
         std::vector<Prod> prods;
         std::vector<Lin> lins;
         // unknown linear entries after the reference's evaluate()
@@ -308,10 +421,7 @@ struct Compiler {
                 unknown.push_back({t.c, t.w});
             }
         }
-        if (value_dependent)
-            throw std::runtime_error("opcode " + std::to_string(idx) +
-                                     ": arithmetic gate whose unknown is a multiplication operand (value-dependent "
-                                     "coefficient) is not supported by the device plan yet");
+        (void)value_dependent;  // handled by general_gate() above
         if (n_both_unknown > 1) {
             fail_static(idx, EK_REFERENCE_PANIC, 0, "Mul term in the arithmetic opcode must contain either zero or one term");
             return false;
@@ -338,11 +448,16 @@ struct Compiler {
     }
 
     bool blackbox(uint32_t idx, const BlackBoxCall& b) {
+        for (uint32_t w : b.outputs)
+            if (known[w] == W_MAYBE)
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": blackbox output witness " + std::to_string(w) +
+                                         " is only conditionally assigned by an earlier value-dependent gate; not supported yet");
         for (auto& in : b.inputs)
             if (!known[in.witness]) {  // blackbox/mod.rs:55-62
                 fail_static(idx, EK_MISSING_ASSIGNMENT, in.witness, "missing assignment for witness index " + std::to_string(in.witness));
                 return false;
             }
+        require_assigned(idx, b.inputs);
         OpRec r{};
         uint32_t reads[3];
         size_t nr = 0;
@@ -506,6 +621,7 @@ struct Compiler {
         plan.n_opcodes = (uint32_t)c.opcodes.size();
         plan.input_witnesses = inputs;
         plan.assign_opcode.assign(known.size(), ASSIGN_NEVER);
+        plan.mu_index_of.assign(known.size(), NONE);
         for (uint32_t w : inputs) {
             known[w] = 1;
             plan.assign_opcode[w] = ASSIGN_INPUT;
@@ -624,11 +740,12 @@ std::vector<uint8_t> serialize_plan(const Plan& p) {
     put_pod<uint32_t>(b, p.static_fail.opcode);
     put_pod<uint32_t>(b, p.static_fail.kind);
     put_pod<uint32_t>(b, p.static_fail.aux);
-    put_pod<uint32_t>(b, 0u);
+    put_pod<uint32_t>(b, p.n_mu);
     put_pod<PlanStats>(b, p.stats);
     while (b.size() % 16) b.push_back(0);
     put_vec(b, p.input_witnesses);
     put_vec(b, p.assign_opcode);
+    put_vec(b, p.mu_index_of);
     put_vec(b, p.payload);
     put_vec(b, p.stream);
     return b;
@@ -649,11 +766,12 @@ Plan deserialize_plan(const uint8_t* data, size_t len) {
     p.static_fail.opcode = c.pod<uint32_t>();
     p.static_fail.kind = c.pod<uint32_t>();
     p.static_fail.aux = c.pod<uint32_t>();
-    c.pod<uint32_t>();
+    p.n_mu = c.pod<uint32_t>();
     p.stats = c.pod<PlanStats>();
     while (c.o % 16) ++c.o;
     p.input_witnesses = c.vec<uint32_t>();
     p.assign_opcode = c.vec<uint32_t>();
+    p.mu_index_of = c.vec<uint32_t>();
     p.payload = c.vec<uint32_t>();
     p.stream = c.vec<OpRec>();
     if (p.stream.size() != (size_t)p.n_steps * p.S) throw std::runtime_error("plan blob: stream size mismatch");

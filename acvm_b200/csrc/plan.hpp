@@ -40,7 +40,8 @@ enum MicroKind : uint32_t {
     MK_FIXED_BASE = 8,    // x=low y=high out=x-coord w1=y-coord slot
     MK_PEDERSEN = 9,      // payload[aux..]: n_in, domain_separator, witness*, out_x, out_y
     MK_GATE_GENERAL = 10, // value-dependent arithmetic gate (unknown is a mul operand)
-    MK_COPY_CHECK = 11,   // insert_value on an already assigned witness: x must equal y
+    MK_COPY_CHECK = 11,   // (reserved)
+    MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
 };
 
 // flags (w[0] >> 8)
@@ -83,6 +84,7 @@ struct PlanStats {
     uint64_t dev_imad = 0;         // 32x32 multiply-accumulates the device executes per instance (gate ops)
     uint64_t alg_bytes = 0;        // algorithmic HBM bytes per instance: 32 B per operand read + 32 B per witness written
     uint64_t n_temps = 0;
+    uint64_t n_gate_general = 0;   // value-dependent gates resolved per lane
 };
 
 struct Plan {
@@ -96,7 +98,10 @@ struct Plan {
     std::vector<OpRec> stream;         // n_steps_padded * S records
     uint32_t n_steps = 0;              // padded to a multiple of chunk_steps
     std::vector<uint32_t> payload;     // variable-length operand lists (hash inputs ...)
-    std::vector<uint32_t> assign_opcode;  // per witness: opcode index that assigns it, 0xFFFFFFFF = never, 0xFFFFFFFE = input
+    std::vector<uint32_t> assign_opcode;  // per witness: opcode index that assigns it, 0xFFFFFFFF = never, 0xFFFFFFFE = input,
+                                          // 0xFFFFFFFD = value-dependent: the per-lane table mu_assign[mu_index_of[w]] decides
+    std::vector<uint32_t> mu_index_of;    // per witness: index into the per-lane "maybe assigned" table, or 0xFFFFFFFF
+    uint32_t n_mu = 0;
     StaticFail static_fail;            // the whole batch fails here (unless an instance failed earlier)
     PlanStats stats;
 };

@@ -53,12 +53,14 @@ struct acvmb_circuit {
     uint32_t* d_payload = nullptr;
     uint32_t* d_assign = nullptr;
     uint32_t* d_input_slots = nullptr;
+    uint32_t* d_mu_index_of = nullptr;
     acvmb_run_info run{};
     ~acvmb_circuit() {
         if (d_stream) cudaFree(d_stream);
         if (d_payload) cudaFree(d_payload);
         if (d_assign) cudaFree(d_assign);
         if (d_input_slots) cudaFree(d_input_slots);
+        if (d_mu_index_of) cudaFree(d_mu_index_of);
     }
 };
 
@@ -71,6 +73,9 @@ struct acvmb_batch {
     uint8_t* d_in = nullptr;
     std::vector<uint8_t*> d_staged_in;   // resident input sets (acvmb_batch_stage_inputs)
     uint8_t* d_stage[2] = {nullptr, nullptr};
+    uint8_t* d_stage_present[2] = {nullptr, nullptr};
+    size_t stage_present_bytes = 0;
+    uint32_t* d_mu = nullptr;            // per-lane assignment table of value-dependent witnesses
     uint32_t* d_out_ids = nullptr;
     size_t out_ids_cap = 0;
     size_t stage_bytes = 0;
@@ -82,6 +87,9 @@ struct acvmb_batch {
         for (uint8_t* p : d_staged_in) if (p) cudaFree(p);
         if (d_stage[0]) cudaFree(d_stage[0]);
         if (d_stage[1]) cudaFree(d_stage[1]);
+        if (d_stage_present[0]) cudaFree(d_stage_present[0]);
+        if (d_stage_present[1]) cudaFree(d_stage_present[1]);
+        if (d_mu) cudaFree(d_mu);
         if (d_out_ids) cudaFree(d_out_ids);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -98,6 +106,7 @@ struct acvmb_vm {
     std::vector<uint8_t> inputs;      // [n_initial][32]
     acvmb_status status{ACVMB_IN_PROGRESS, 0, 0, 0};
     std::vector<uint8_t> witness;     // dense [num_witnesses][32] after solve
+    std::vector<uint8_t> present;     // dense [num_witnesses] after solve
     std::vector<uint32_t> assign;
     bool solved_once = false;
 };
@@ -184,7 +193,7 @@ static int ensure_curve_tables(acvmb_ctx* ctx) {
 static int upload_plan(acvmb_circuit* c) {
     const Plan& p = c->plan;
     CUDA_TRY(cudaSetDevice(c->ctx->device));
-    if (p.stats.n_curve) {
+    if (p.needs_full_kernel) {
         int rc = ensure_curve_tables(c->ctx);
         if (rc) return rc;
     }
@@ -198,6 +207,9 @@ static int upload_plan(acvmb_circuit* c) {
     CUDA_TRY(cudaMalloc(&c->d_input_slots, std::max<size_t>(p.input_witnesses.size() * 4, 16)));
     if (!p.input_witnesses.empty())
         CUDA_TRY(cudaMemcpy(c->d_input_slots, p.input_witnesses.data(), p.input_witnesses.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_mu_index_of, std::max<size_t>(p.mu_index_of.size() * 4, 16)));
+    if (!p.mu_index_of.empty())
+        CUDA_TRY(cudaMemcpy(c->d_mu_index_of, p.mu_index_of.data(), p.mu_index_of.size() * 4, cudaMemcpyHostToDevice));
     return ACVMB_OK;
 }
 
@@ -322,6 +334,7 @@ extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_
     size_t col_bytes = (size_t)b->n_tiles * b->T * c->plan.n_slots * 32;
     CUDA_TRY(cudaMalloc(&b->d_cols, col_bytes));
     CUDA_TRY(cudaMalloc(&b->d_fail, (size_t)b->n_tiles * b->T * 8));
+    if (c->plan.n_mu) CUDA_TRY(cudaMalloc(&b->d_mu, (size_t)b->n_tiles * b->T * c->plan.n_mu * 4));
     size_t in_bytes = (size_t)n_instances * c->plan.input_witnesses.size() * 32;
     CUDA_TRY(cudaMalloc(&b->d_in, std::max<size_t>(in_bytes, 16)));
     CUDA_TRY(cudaEventCreate(&b->ev0));
@@ -359,6 +372,7 @@ extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
     CUDA_TRY(cudaEventRecord(b->ev0, s));
     if (in_bytes) CUDA_TRY(cudaMemcpyAsync(b->d_in, inputs_be32, in_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(launch_fill_u64(b->d_fail, (size_t)b->n_tiles * b->T, ~0ull, s));
+    if (b->d_mu) CUDA_TRY(cudaMemsetAsync(b->d_mu, 0xFF, (size_t)b->n_tiles * b->T * c->plan.n_mu * 4, s));
     CUDA_TRY(launch_scatter_inputs(b->d_in, c->d_input_slots, n_in, b->d_cols, c->plan.n_slots, (int)b->T, b->n_inst, s));
     CUDA_TRY(cudaEventRecord(b->ev1, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -383,6 +397,8 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     a.chunk_steps = c->plan.chunk_steps;
     a.n_slots = c->plan.n_slots;
     a.n_tiles = b->n_tiles;
+    a.mu_assign = b->d_mu;
+    a.n_mu = c->plan.n_mu;
     KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel, c->ctx->opt_split};
     CUDA_TRY(cudaEventRecord(b->ev0, s));
     CUDA_TRY(launch_vm(cfg, a, s));
@@ -424,6 +440,7 @@ extern "C" int acvmb_batch_run_staged(acvmb_batch* b, uint32_t slot, float* tota
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, s));
     CUDA_TRY(launch_fill_u64(b->d_fail, (size_t)b->n_tiles * b->T, ~0ull, s));
+    if (b->d_mu) CUDA_TRY(cudaMemsetAsync(b->d_mu, 0xFF, (size_t)b->n_tiles * b->T * c->plan.n_mu * 4, s));
     CUDA_TRY(launch_scatter_inputs(b->d_staged_in[slot], c->d_input_slots, (uint32_t)c->plan.input_witnesses.size(), b->d_cols,
                                    c->plan.n_slots, (int)b->T, b->n_inst, s));
     c->run.kernel_launches += 2;
@@ -471,9 +488,9 @@ extern "C" int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status) {
     return ACVMB_OK;
 }
 
-extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids,
-                                    uint8_t* out) {
-    if (!b || !out || first + n > b->n_inst) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+extern "C" int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids,
+                                       uint8_t* out, uint8_t* out_present) {
+    if (!b || (!out && !out_present) || first + n > b->n_inst) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     acvmb_circuit* c = b->c;
     acvmb_ctx* ctx = c->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -493,7 +510,7 @@ extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, 
     size_t row = (size_t)n_out * 32;
     uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n, ctx->staging_bytes / row));
     size_t need = (size_t)chunk * row;
-    if (b->stage_bytes < need) {
+    if (out && b->stage_bytes < need) {
         for (int i = 0; i < 2; ++i) {
             cudaFree(b->d_stage[i]);
             b->d_stage[i] = nullptr;
@@ -503,18 +520,47 @@ extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, 
         CUDA_TRY(cudaMalloc(&b->d_stage[1], need));
         b->stage_bytes = need;
     }
-    uint32_t sf = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
+    size_t need_p = (size_t)chunk * n_out;
+    if (out_present && b->stage_present_bytes < need_p) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(b->d_stage_present[i]);
+            b->d_stage_present[i] = nullptr;
+        }
+        b->stage_present_bytes = 0;
+        CUDA_TRY(cudaMalloc(&b->d_stage_present[0], need_p));
+        CUDA_TRY(cudaMalloc(&b->d_stage_present[1], need_p));
+        b->stage_present_bytes = need_p;
+    }
+    GatherArgs g{};
+    g.cols = b->d_cols;
+    g.n_slots = c->plan.n_slots;
+    g.T = (int)b->T;
+    g.witness_ids = out_ids ? b->d_out_ids : nullptr;
+    g.n_out = n_out;
+    g.fail = b->d_fail;
+    g.assign_opcode = c->d_assign;
+    g.mu_index_of = c->d_mu_index_of;
+    g.mu_assign = b->d_mu;
+    g.n_mu = c->plan.n_mu;
+    g.static_fail_opcode = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
     CUDA_TRY(cudaEventRecord(b->ev0, ctx->stream));
     uint32_t k = 0;
     for (uint32_t off = 0; off < n; off += chunk, ++k) {
         uint32_t cnt = std::min(chunk, n - off);
         int buf = k & 1;
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, b->ev_copy[buf], 0));  // staging buffer is free again
-        CUDA_TRY(launch_gather_outputs(b->d_cols, c->plan.n_slots, (int)b->T, out_ids ? b->d_out_ids : nullptr, n_out, first + off,
-                                       cnt, b->d_fail, c->d_assign, sf, b->d_stage[buf], ctx->stream));
+        g.first_inst = first + off;
+        g.n_inst = cnt;
+        g.out_be = out ? b->d_stage[buf] : nullptr;
+        g.out_present = out_present ? b->d_stage_present[buf] : nullptr;
+        CUDA_TRY(launch_gather_outputs(g, ctx->stream));
         CUDA_TRY(cudaEventRecord(b->ev_gather[buf], ctx->stream));
         CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev_gather[buf], 0));
-        CUDA_TRY(cudaMemcpyAsync(out + (size_t)off * row, b->d_stage[buf], (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out)
+            CUDA_TRY(cudaMemcpyAsync(out + (size_t)off * row, b->d_stage[buf], (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_present)
+            CUDA_TRY(cudaMemcpyAsync(out_present + (size_t)off * n_out, b->d_stage_present[buf], (size_t)cnt * n_out,
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
         CUDA_TRY(cudaEventRecord(b->ev_copy[buf], ctx->copy_stream));
         c->run.kernel_launches += 1;
     }
@@ -525,6 +571,12 @@ extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, 
     cudaEventElapsedTime(&ms, b->ev0, b->ev1);
     c->run.gather_ms += ms;
     return ACVMB_OK;
+}
+
+extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids,
+                                    uint8_t* out) {
+    if (!out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    return acvmb_batch_download_ex(b, first, n, out_ids, n_out_ids, out, nullptr);
 }
 
 extern "C" int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out) {
@@ -546,15 +598,23 @@ static uint32_t resident_instances(acvmb_circuit* c, uint32_t batch, uint32_t T,
     return (uint32_t)std::min<uint64_t>(fit, batch);
 }
 
+extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                                    uint32_t n_out_ids, uint8_t* out_witness, uint8_t* out_present, acvmb_status* out_status);
+
 extern "C" int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
                                  uint32_t n_out_ids, uint8_t* out_witness, acvmb_status* out_status) {
+    return acvmb_solve_batch_ex(c, batch, inputs_be32, out_ids, n_out_ids, out_witness, nullptr, out_status);
+}
+
+extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                                    uint32_t n_out_ids, uint8_t* out_witness, uint8_t* out_present, acvmb_status* out_status) {
     if (!c) return set_err(ACVMB_ERR_INVALID_ARG, "circuit is NULL");
     if (batch == 0) return ACVMB_OK;
     CUDA_TRY(cudaSetDevice(c->ctx->device));
     memset(&c->run, 0, sizeof(c->run));
     uint32_t T = pick_T(c->ctx, c->plan);
     uint32_t n_out = out_ids ? n_out_ids : c->plan.num_witnesses;
-    uint32_t resident = resident_instances(c, batch, T, out_witness ? n_out : 0);
+    uint32_t resident = resident_instances(c, batch, T, (out_witness || out_present) ? n_out : 0);
     size_t n_in = c->plan.input_witnesses.size();
     acvmb_batch* b = nullptr;
     uint32_t cap = 0;
@@ -577,7 +637,9 @@ extern "C" int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t
             rc = acvmb_batch_status(b, out_status + off);
             if (rc) break;
         }
-        if (out_witness) rc = acvmb_batch_download(b, 0, cnt, out_ids, n_out_ids, out_witness + (size_t)off * n_out * 32);
+        if (out_witness || out_present)
+            rc = acvmb_batch_download_ex(b, 0, cnt, out_ids, n_out_ids, out_witness ? out_witness + (size_t)off * n_out * 32 : nullptr,
+                                         out_present ? out_present + (size_t)off * n_out : nullptr);
     }
     if (b) acvmb_batch_destroy(b);
     c->run.resident_instances = resident;
@@ -619,7 +681,8 @@ extern "C" int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out) {
     if (!vm) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     if (!vm->solved_once) {
         vm->witness.assign((size_t)vm->c->plan.num_witnesses * 32, 0);
-        int rc = acvmb_solve_batch(vm->c, 1, vm->inputs.data(), nullptr, 0, vm->witness.data(), &vm->status);
+        vm->present.assign((size_t)vm->c->plan.num_witnesses, 0);
+        int rc = acvmb_solve_batch_ex(vm->c, 1, vm->inputs.data(), nullptr, 0, vm->witness.data(), vm->present.data(), &vm->status);
         if (rc) return rc;
         vm->solved_once = true;
     }
@@ -646,6 +709,7 @@ extern "C" int acvmb_vm_num_witnesses(const acvmb_vm* vm, uint32_t* out) {
 }
 
 static bool vm_present(const acvmb_vm* vm, uint32_t w) {
+    if (vm->solved_once && !vm->present.empty()) return vm->present[w] != 0;
     uint32_t ao = vm->assign[w];
     if (ao == 0xFFFFFFFEu) return true;
     if (!vm->solved_once || ao == 0xFFFFFFFFu) return false;
@@ -678,8 +742,12 @@ extern "C" int acvmb_vm_finalize(acvmb_vm* vm, uint8_t* out, uint8_t* present, u
     if (n != vm->c->plan.num_witnesses) return set_err(ACVMB_ERR_INVALID_ARG, "n must equal num_witnesses");
     if (!vm->solved_once) {  // no opcodes: the map is the initial witness
         vm->witness.assign((size_t)n * 32, 0);
+        vm->present.assign((size_t)n, 0);
         const auto& in = vm->c->plan.input_witnesses;
-        for (size_t i = 0; i < in.size(); ++i) memcpy(vm->witness.data() + (size_t)in[i] * 32, vm->inputs.data() + i * 32, 32);
+        for (size_t i = 0; i < in.size(); ++i) {
+            memcpy(vm->witness.data() + (size_t)in[i] * 32, vm->inputs.data() + i * 32, 32);
+            vm->present[in[i]] = 1;
+        }
         vm->solved_once = true;
     }
     memcpy(out, vm->witness.data(), (size_t)n * 32);

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     const uint32_t tile = blockIdx.x;
     uint4* cb = a.cols + (size_t)tile * a.n_slots * (2 * T) + lane;
     unsigned long long* fail = a.fail + (size_t)tile * T + lane;
+    uint32_t* mu = a.mu_assign + (size_t)tile * a.n_mu * T + lane;
 
     const uint32_t n_chunks = a.n_steps / a.chunk_steps;
     if (tid == 0) {
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
                     break;
                 default:
 #ifdef ACVMB_HEAVY_OPS
-                    if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload);
+                    if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload, mu);
 #endif
                     break;
             }
@@ -348,40 +349,36 @@ cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_sl
 // output gather: columns -> [inst][n_out][32 B big-endian]; a witness that the instance never
 // assigned (it failed earlier, or nothing assigns it) is written as zeros.
 // ---------------------------------------------------------------------------------------------
-__global__ void gather_outputs_kernel(const uint4* __restrict__ cols, uint32_t n_slots, int T,
-                                      const uint32_t* __restrict__ witness_ids, uint32_t n_out, uint32_t first_inst,
-                                      uint32_t n_inst, const unsigned long long* __restrict__ fail,
-                                      const uint32_t* __restrict__ assign_opcode, uint32_t static_fail_opcode,
-                                      uint8_t* __restrict__ out_be) {
+__global__ void gather_outputs_kernel(const GatherArgs g) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)n_inst * n_out) return;
-    uint32_t li = (uint32_t)(gid / n_out), k = (uint32_t)(gid % n_out);
-    uint32_t inst = first_inst + li;
-    uint32_t w = witness_ids ? witness_ids[k] : k;
-    uint32_t fail_op = (uint32_t)(fail[inst] >> 32);
-    if (static_fail_opcode < fail_op) fail_op = static_fail_opcode;
-    uint32_t ao = assign_opcode[w];
+    if (gid >= (size_t)g.n_inst * g.n_out) return;
+    uint32_t li = (uint32_t)(gid / g.n_out), k = (uint32_t)(gid % g.n_out);
+    uint32_t inst = g.first_inst + li;
+    uint32_t w = g.witness_ids ? g.witness_ids[k] : k;
+    uint32_t fail_op = (uint32_t)(g.fail[inst] >> 32);
+    if (g.static_fail_opcode < fail_op) fail_op = g.static_fail_opcode;
+    uint32_t tile = inst / g.T, lane = inst % g.T;
+    uint32_t ao = g.assign_opcode[w];
+    if (ao == 0xFFFFFFFDu)   // value-dependent: this lane's own record of which opcode assigned it
+        ao = g.mu_assign[((size_t)tile * g.n_mu + g.mu_index_of[w]) * g.T + lane];
     bool present = (ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op);
+    if (g.out_present) g.out_present[gid] = present ? 1 : 0;
+    if (!g.out_be) return;
     uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
     if (present) {
-        uint32_t tile = inst / T, lane = inst % T;
-        const uint4* p = cols + ((size_t)tile * n_slots + w) * (2 * T) + lane;
+        const uint4* p = g.cols + ((size_t)tile * g.n_slots + w) * (2 * g.T) + lane;
         lo = p[0];
-        hi = p[T];
+        hi = p[g.T];
     }
-    uint4* dst = reinterpret_cast<uint4*>(out_be + gid * 32);
+    uint4* dst = reinterpret_cast<uint4*>(g.out_be + gid * 32);
     dst[0] = make_uint4(__byte_perm(hi.w, 0, 0x0123), __byte_perm(hi.z, 0, 0x0123), __byte_perm(hi.y, 0, 0x0123), __byte_perm(hi.x, 0, 0x0123));
     dst[1] = make_uint4(__byte_perm(lo.w, 0, 0x0123), __byte_perm(lo.z, 0, 0x0123), __byte_perm(lo.y, 0, 0x0123), __byte_perm(lo.x, 0, 0x0123));
 }
 
-cudaError_t launch_gather_outputs(const uint4* cols, uint32_t n_slots, int T, const uint32_t* witness_ids, uint32_t n_out,
-                                  uint32_t first_inst, uint32_t n_inst, const unsigned long long* fail,
-                                  const uint32_t* assign_opcode, uint32_t static_fail_opcode, uint8_t* out_be,
-                                  cudaStream_t stream) {
-    size_t n = (size_t)n_inst * n_out;
+cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream) {
+    size_t n = (size_t)g.n_inst * g.n_out;
     if (n == 0) return cudaSuccess;
-    gather_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cols, n_slots, T, witness_ids, n_out, first_inst, n_inst,
-                                                                          fail, assign_opcode, static_fail_opcode, out_be);
+    gather_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(g);
     return cudaGetLastError();
 }
 

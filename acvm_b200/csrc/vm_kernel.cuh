@@ -18,6 +18,8 @@ struct VmArgs {
     uint32_t chunk_steps;
     uint32_t n_slots;
     uint32_t n_tiles;
+    uint32_t* mu_assign;          // [tile][n_mu][T]: opcode index that assigned a value-dependent witness, ~0 = unassigned
+    uint32_t n_mu;
 };
 
 struct KernelConfig {
@@ -34,10 +36,22 @@ cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pederse
 
 cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_slots, uint32_t n_inputs, uint4* cols,
                                   uint32_t n_slots, int T, uint32_t n_inst, cudaStream_t stream);
-cudaError_t launch_gather_outputs(const uint4* cols, uint32_t n_slots, int T, const uint32_t* witness_ids,
-                                  uint32_t n_out, uint32_t first_inst, uint32_t n_inst,
-                                  const unsigned long long* fail, const uint32_t* assign_opcode, uint32_t static_fail_opcode,
-                                  uint8_t* out_be, cudaStream_t stream);
+struct GatherArgs {
+    const uint4* cols;
+    uint32_t n_slots;
+    int T;
+    const uint32_t* witness_ids;   // NULL = dense 0..n_out-1
+    uint32_t n_out, first_inst, n_inst;
+    const unsigned long long* fail;
+    const uint32_t* assign_opcode;
+    const uint32_t* mu_index_of;   // per witness, for value-dependent presence
+    const uint32_t* mu_assign;
+    uint32_t n_mu;
+    uint32_t static_fail_opcode;
+    uint8_t* out_be;               // [n_inst][n_out][32] or NULL
+    uint8_t* out_present;          // [n_inst][n_out] or NULL
+};
+cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream);
 cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t stream);
 
 // IMAD roofline micro-benchmark: returns measured multiply-accumulates per second for each variant

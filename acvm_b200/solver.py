@@ -168,8 +168,10 @@ class CompiledCircuit:
         _check(lib().acvmb_last_run_info(self._h, C.byref(ri)))
         return {n: getattr(ri, n) for n, _ in ri._fields_}
 
-    def solve_batch(self, inputs_be32, batch: int, out_ids: Optional[Sequence[int]] = None, want_witness=True, out_buffer=None):
-        """inputs_be32: bytes-like [batch][n_inputs][32].  Returns (witness bytes or None, [InstanceStatus])."""
+    def solve_batch(self, inputs_be32, batch: int, out_ids: Optional[Sequence[int]] = None, want_witness=True, out_buffer=None,
+                    want_present=False):
+        """inputs_be32: bytes-like [batch][n_inputs][32].  Returns (witness bytes or None, [InstanceStatus]) and, with
+        want_present, a third value: bytes [batch][n_out] (1 = the instance's witness map holds that witness)."""
         n_in = len(self.input_witnesses)
         assert len(inputs_be32) == batch * n_in * 32, "inputs must be [batch][n_inputs][32]"
         n_out = len(out_ids) if out_ids is not None else self.num_witnesses
@@ -184,7 +186,10 @@ class CompiledCircuit:
         st = (_lib.Status * batch)()
         inp = (C.c_uint8 * len(inputs_be32)).from_buffer_copy(inputs_be32) if not isinstance(inputs_be32, C.Array) else inputs_be32
         ids = _u32_array(list(out_ids)) if out_ids is not None else None
-        _check(lib().acvmb_solve_batch(self._h, batch, inp, ids, len(out_ids) if out_ids is not None else 0, outp, st))
+        pres = C.create_string_buffer(batch * n_out) if want_present else None
+        _check(lib().acvmb_solve_batch_ex(self._h, batch, inp, ids, len(out_ids) if out_ids is not None else 0, outp, pres, st))
+        if want_present:
+            return (out.raw if out is not None else None), [_status(s) for s in st], pres.raw
         return (out.raw if out is not None else None), [_status(s) for s in st]
 
     def close(self):

@@ -118,6 +118,10 @@ int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, size_t len, a
  * out_status   [batch] */
 int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
                       uint32_t n_out_ids, uint8_t* out_witness_be32, acvmb_status* out_status);
+/* same, plus out_present [batch][n_out]: 1 where the instance's WitnessMap holds the witness (needed when a circuit
+ * has value-dependent gates, arithmetic.rs:217-221: which witnesses get assigned then differs per instance) */
+int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                         uint32_t n_out_ids, uint8_t* out_witness_be32, uint8_t* out_present, acvmb_status* out_status);
 int acvmb_last_run_info(const acvmb_circuit* c, acvmb_run_info* out);
 
 /* ---- device-resident batch: the same solve split into its phases, so callers (and bench.py) can
@@ -134,6 +138,8 @@ int acvmb_batch_run_staged(acvmb_batch* b, uint32_t slot, float* total_ms, float
 int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status);           /* D2H of the fail words */
 int acvmb_batch_download(acvmb_batch* b, uint32_t first_instance, uint32_t n_instances, const uint32_t* out_ids,
                          uint32_t n_out_ids, uint8_t* out_witness_be32);    /* gather + D2H */
+int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first_instance, uint32_t n_instances, const uint32_t* out_ids,
+                            uint32_t n_out_ids, uint8_t* out_witness_be32, uint8_t* out_present);
 /* on-device checksum of all witness columns (xor-fold), for size-independent property tests */
 int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out);
 

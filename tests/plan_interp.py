@@ -11,7 +11,8 @@ RINV = pow(1 << 256, -1, P)
 NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
-          GATE_GENERAL=10, COPY_CHECK=11)
+          GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12)
+EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
 EK_MISSING, EK_TOO_MANY, EK_UNSAT, EK_BB_FAILED = 1, 2, 4, 6
 
@@ -23,10 +24,10 @@ class PlanBlob:
         o += 8
         assert magic == 0x3130304E414C5042, "bad magic"
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
-         self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, _) = struct.unpack_from("<12I", blob, o)
+         self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
         o += 48
-        self.stats = struct.unpack_from("<15Q", blob, o)
-        o += 120
+        self.stats = struct.unpack_from("<16Q", blob, o)
+        o += 128
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):
@@ -42,6 +43,8 @@ class PlanBlob:
         self.input_witnesses = list(struct.unpack(f"<{n}I", d))
         n, d = vec("I", 4)
         self.assign_opcode = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("I", 4)
+        self.mu_index_of = list(struct.unpack(f"<{n}I", d))
         n, d = vec("I", 4)
         self.payload = list(struct.unpack(f"<{n}I", d))
         n, d = vec("rec", 192)
@@ -133,9 +136,15 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
     kinds to python callables (cols, hdr, payload) -> list of (slot, value) or raises."""
     if hooks is None:
         hooks = default_hooks()
-    cols = {}
+
+    class Cols(dict):
+        """a lane that already failed keeps executing on the device and reads garbage: model that as 0"""
+        def __missing__(self, k):
+            return 0
+    cols = Cols()
     for w in plan.input_witnesses:
         cols[w] = inputs[w] % P
+    mu = {}      # mu index -> opcode that assigned it (this lane)
     fail = None  # (opcode, kind, aux)
 
     def record_fail(opcode, kind, aux=0):
@@ -190,6 +199,53 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
             elif kind == MK["RANGE"]:
                 if cols[x].bit_length() > aux:
                     record_fail(opcode, EK_UNSAT)
+            elif kind == MK["GATE_GENERAL"]:
+                pl = plan.payload
+                off = aux
+                n_mul, n_lin = pl[off], pl[off + 1]
+                fe = lambda o_: sum(pl[o_ + j] << (32 * j) for j in range(8))
+                q = fe(off + 2)
+                p_ = off + 10
+                known = lambda m: m == NONE or m in mu
+                entries, mulrem = [], 0
+                for _ in range(n_mul):
+                    c = fe(p_) * RINV % P
+                    w1_, m1, w2_, m2 = pl[p_ + 16:p_ + 20]
+                    p_ += 20
+                    k1, k2 = known(m1), known(m2)
+                    if k1 and k2:
+                        q = (q + c * cols[w1_] * cols[w2_]) % P
+                    elif not k1 and not k2:
+                        mulrem += c != 0
+                    else:
+                        v = c * cols[w1_ if k1 else w2_] % P
+                        if v:
+                            entries.append((v, w2_ if k1 else w1_, m2 if k1 else m1))
+                for _ in range(n_lin):
+                    c = fe(p_ + 8)
+                    w_, m_ = pl[p_ + 16], pl[p_ + 17]
+                    p_ += 18
+                    if known(m_):
+                        q = (q + c * cols[w_]) % P
+                    elif c:
+                        entries.append((c, w_, m_))
+                if mulrem > 1:
+                    record_fail(opcode, EK_PANIC)
+                elif mulrem == 1 or len(entries) > 1:
+                    record_fail(opcode, EK_TOO_MANY)
+                elif not entries:
+                    if q:
+                        record_fail(opcode, EK_UNSAT)
+                else:
+                    coef, w_, m_ = entries[0]
+                    writes.append((w_, (-q * pow(coef, P - 2, P)) % P))
+                    mu[m_] = opcode
+            elif kind == MK["REQUIRE"]:
+                pl = plan.payload
+                for i in range(pl[aux]):
+                    if pl[aux + 2 + 2 * i] not in mu:
+                        record_fail(opcode, EK_MISSING, pl[aux + 1 + 2 * i])
+                        break
             elif hooks and kind in hooks:
                 writes.extend(hooks[kind](cols, hdr, plan.payload, record_fail))
             else:
@@ -207,6 +263,8 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
     wm = {}
     for w in range(plan.num_witnesses):
         ao = plan.assign_opcode[w]
+        if ao == 0xFFFFFFFD:
+            ao = mu.get(plan.mu_index_of[w], 0xFFFFFFFF)
         if ao == 0xFFFFFFFE or (ao != 0xFFFFFFFF and ao < fop):
             wm[w] = cols[w]
     return status, wm

@@ -11,10 +11,11 @@ pytestmark = pytest.mark.gpu
 
 def _check(ctx, data, input_witnesses, batch, inp, expect_all_solved=True):
     circ = acvm_b200.CompiledCircuit(ctx, data, input_witnesses)
-    out, st = circ.solve_batch(inp, batch)
+    out, st, pres = circ.solve_batch(inp, batch, want_present=True)
     rows = witness_rows(out, batch, circ.num_witnesses)
     oc = acir.decode_circuit(data)
     assign = circ.assign_opcodes()
+    nw = circ.num_witnesses
     for i, iw in enumerate(inputs_to_dicts(inp, batch, input_witnesses)):
         ost, owm, oerr = pwg.solve_circuit(oc, iw)
         assert st[i].status == ost, (i, st[i], oerr)
@@ -23,9 +24,10 @@ def _check(ctx, data, input_witnesses, batch, inp, expect_all_solved=True):
             if oerr.opcode_location is not None:
                 assert st[i].opcode_index == oerr.opcode_location
         limit = 0xFFFFFFFF if ost == "Solved" else st[i].opcode_index
-        got = {w: rows[i][w] for w in range(circ.num_witnesses)
-               if assign[w] == 0xFFFFFFFE or (assign[w] != 0xFFFFFFFF and assign[w] < limit)}
+        got = {w: rows[i][w] for w in range(nw) if pres[i * nw + w]}
         assert got == owm, f"instance {i}: witness map differs"
+        if 0xFFFFFFFD not in assign:  # static plans: presence is derivable from the plan alone
+            assert got.keys() == {w for w in range(nw) if assign[w] == 0xFFFFFFFE or (assign[w] != 0xFFFFFFFF and assign[w] < limit)}
     circ.close()
     return st
 
@@ -121,3 +123,26 @@ def test_no_gpu_fallback_symbols():
     circ.solve_batch(ab.synthetic_inputs(4), 4)
     ri = circ.run_info()
     assert ri["kernel_launches"] >= 3 and ri["kernel_ms"] > 0
+
+
+def test_value_dependent_gates(ctx):
+    # the unknown is a multiplication operand: per-instance known-set divergence (SURVEY 8a quirks 2+3)
+    from test_host_logic import _vd_circuit, _vd_inputs
+    rows, inp = _vd_inputs()
+    st = _check(ctx, _vd_circuit(), [1, 2, 3, 4], len(rows), inp)
+    assert {s.status for s in st} == {"Solved", "Failure"}
+
+
+def test_inverse_gate_pattern(ctx):
+    # x * x_inv - 1 = 0 solved for x_inv (per-lane field inversion), then used downstream
+    b = ab.CircuitBuilder()
+    b.arithmetic([(1, 1, 2)], [], ab.P - 1)
+    b.arithmetic([(1, 2, 2)], [(ab.P - 1, 3)], 0)
+    data = b.to_bytes()
+    vals = [5, 1, ab.P - 1, 123456789, 0]
+    inp = b"".join(v.to_bytes(32, "big") for v in vals)
+    st = _check(ctx, data, [1], len(vals), inp)
+    assert [s.status for s in st] == ["Solved"] * 4 + ["Failure"]
+    vm = acvm_b200.ACVM(ctx, data, {1: 5})
+    assert vm.solve().status == "Solved"
+    assert vm.finalize()[2] == int("135b52945a13d9aa49b9b57c33cd568ba9ae5ce9ca4a2d06e7f3fbd4c6666667", 16)  # 1/5, foreign_call.ts:20-27

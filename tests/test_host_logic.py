@@ -159,3 +159,26 @@ def test_plan_heavy_ops_match_oracle():
     rows = [inp[i * 96:(i + 1) * 96] + v.to_bytes(32, "big") for i, v in enumerate((4, 11))]
     info = _interp_vs_oracle(data, [1, 2, 3, 94], b"".join(rows), 2)
     assert info["needs_full_kernel"] == 1 and info["n_hash"] == 3 and info["n_curve"] == 1
+
+
+def _vd_circuit():
+    """Value-dependent gates: the unknown is a multiplication operand (arithmetic.rs:217-221 quirks)."""
+    b = ab.CircuitBuilder()
+    b.arithmetic([(1, 1, 5)], [], ab.P - 7)                    # w1*w5 = 7        : w5 = 7/w1, or (w1==0) unsat
+    b.arithmetic([(3, 2, 6)], [(1, 3)], 0)                     # 3*w2*w6 + w3 = 0 : w6 assigned unless w2 == 0 (then needs w3 == 0)
+    b.arithmetic([(1, 2, 7)], [(5, 7), (1, 4)], 0)             # w2*w7 + 5*w7 + w4: two entries for w7 unless w2 == 0
+    b.arithmetic([], [(1, 6), (ab.P - 1, 8)], 0)               # w8 = w6           : fails where w6 never got assigned
+    b.logic("XOR", (5, 254), (1, 254), 9)                      # blackbox over a conditionally assigned input
+    b.arithmetic([(1, 9, 9)], [(ab.P - 1, 10)], 0)             # w10 = w9^2
+    return b.to_bytes()
+
+
+def _vd_inputs():
+    rows = [(3, 4, 5, 6), (0, 4, 5, 6), (3, 0, 0, 6), (3, 0, 5, 6), (3, 4, 5, 0), (1, ab.P - 5, 2, 9), (2, 0, 0, 0)]
+    return rows, b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+
+
+def test_value_dependent_gates_plan_vs_oracle():
+    rows, inp = _vd_inputs()
+    info = _interp_vs_oracle(_vd_circuit(), [1, 2, 3, 4], inp, len(rows))
+    assert info["needs_full_kernel"] == 1
