@@ -180,6 +180,57 @@ class CircuitBuilder:
         self._see(*outputs)
         self.n_opcodes += 1
 
+    def _expr(self, e):
+        """e = (mul_terms, lin, q_c)"""
+        w_expression(self.w, e[0], e[1], e[2])
+        for (_, a, b) in e[0]:
+            self._see(a, b)
+        for (_, x) in e[1]:
+            self._see(x)
+
+    def _opt_expr(self, e):
+        if e is None:
+            self.w.u8(0)
+        else:
+            self.w.u8(1)
+            self._expr(e)
+
+    def directive_quotient(self, a, b, q, r, predicate=None):
+        """Directive::Quotient (acir/src/circuit/directives.rs:5-11); a, b, predicate are (mul, lin, q_c) expressions."""
+        self.w.u32(2)
+        self.w.u32(0)
+        self._expr(a)
+        self._expr(b)
+        self.w.u32(q)
+        self.w.u32(r)
+        self._see(q, r)
+        self._opt_expr(predicate)
+        self.n_opcodes += 1
+
+    def directive_to_le_radix(self, a, b, radix):
+        self.w.u32(2)
+        self.w.u32(1)
+        self._expr(a)
+        self._vw(b)
+        self.w.u32(radix)
+        self.n_opcodes += 1
+
+    def memory_init(self, block_id, init):
+        self.w.u32(5)
+        self.w.u32(block_id)
+        self._vw(init)
+        self.n_opcodes += 1
+
+    def memory_op(self, block_id, operation, index, value, predicate=None):
+        """Opcode::MemoryOp (acir/src/circuit/opcodes.rs:24-31); operation/index/value/predicate are expressions."""
+        self.w.u32(4)
+        self.w.u32(block_id)
+        self._expr(operation)
+        self._expr(index)
+        self._expr(value)
+        self._opt_expr(predicate)
+        self.n_opcodes += 1
+
     def to_raw(self, current_witness_index=None):
         head = Writer()
         head.u32(self.max_witness + 1 if current_witness_index is None else current_witness_index)
@@ -194,6 +245,16 @@ class CircuitBuilder:
 
     def to_bytes(self, current_witness_index=None, level=1):
         return gzip.compress(self.to_raw(current_witness_index), compresslevel=level, mtime=0)
+
+
+def wexpr(w):
+    """the expression `1*w`"""
+    return ([], [(1, w)], 0)
+
+
+def cexpr(c):
+    """a constant expression"""
+    return ([], [], c % P)
 
 
 SEED_BASE = 0xAC1DB20000000000

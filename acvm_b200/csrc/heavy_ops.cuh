@@ -610,6 +610,162 @@ __device__ __noinline__ void exec_require(const OpRec* r, unsigned long long* fa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Directives and memory blocks
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void insert_value_dev(const OpRec* r, bool check, uint32_t slot, const Fe& v, uint4* cb, unsigned long long* fail) {
+    if (check) {   // insert_value on an assigned witness: replace, then report a mismatch (pwg/mod.rs:338-357)
+        Fe old;
+        hv_load<T>(old, cb, slot);
+        if (!fr::eq(old, v)) {
+            hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+            hv_store<T>(cb, slot, v);
+        }
+    } else {
+        hv_store<T>(cb, slot, v);
+    }
+}
+
+// Directive::ToLeRadix (directives/mod.rs:60-87): little-endian base-`radix` digits of the canonical value; missing high
+// digits are 0; more digits than output witnesses => UnsatisfiedConstrain; zero decomposes to the single digit [0].
+template <int T>
+__device__ __noinline__ void exec_to_le_radix(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_b = pl[0], radix = pl[1];
+    const uint32_t* mask = pl + 2;
+    const uint32_t* outs = mask + (n_b + 31) / 32;
+    Fe v;
+    hv_load<T>(v, cb, r->w[3]);
+    uint32_t l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = v.l[k];
+    if (n_b == 0) {   // [0] has length 1 > 0, and any non-zero value has >= 1 digit
+        hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        return;
+    }
+    const bool pow2 = (radix & (radix - 1)) == 0;
+    const int sh = 31 - __clz(radix);
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_b; ++i) {
+        uint32_t digit;
+        if (pow2) {
+            digit = l[0] & (radix - 1);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) l[k] = __funnelshift_r(l[k], l[k + 1], sh);
+            l[7] >>= sh;
+        } else {
+            unsigned long long rem = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                unsigned long long cur = (rem << 32) | l[k];
+                l[k] = (uint32_t)(cur / radix);
+                rem = cur % radix;
+            }
+            digit = (uint32_t)rem;
+        }
+        Fe d;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d.l[k] = 0;
+        d.l[0] = digit & 0xFF;
+        insert_value_dev<T>(r, (mask[i >> 5] >> (i & 31)) & 1, outs[i], d, cb, fail);
+    }
+    if (l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7]) hv_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+}
+
+// Directive::Quotient (directives/mod.rs:28-59): euclidean division of the canonical 256-bit integers; predicate == 0 or
+// b == 0 gives q = r = 0.
+template <int T>
+__device__ __noinline__ void exec_quotient(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    Fe a, b, q, rem;
+    hv_load<T>(a, cb, r->w[3]);
+    hv_load<T>(b, cb, r->w[4]);
+    bool pred = true;
+    if (r->w[5] != 0xFFFFFFFFu) {
+        Fe p;
+        hv_load<T>(p, cb, r->w[5]);
+        pred = !fr::is_zero(p);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { q.l[k] = 0; rem.l[k] = 0; }
+    if (pred && !fr::is_zero(b)) {
+        uint32_t al[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) al[k] = a.l[k];
+        const int top = (int)fr::num_bits(a) - 1;
+#pragma unroll 1
+        for (int i = top; i >= 0; --i) {
+            // rem = (rem << 1) | bit_i(a)
+#pragma unroll
+            for (int k = 7; k > 0; --k) rem.l[k] = __funnelshift_l(rem.l[k - 1], rem.l[k], 1);
+            rem.l[0] = (rem.l[0] << 1) | ((al[i >> 5] >> (i & 31)) & 1);
+            // if rem >= b: rem -= b, set quotient bit
+            uint32_t t[8], borrow;
+            fr::sub_cc(t[0], rem.l[0], b.l[0]);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) fr::subc_cc(t[k], rem.l[k], b.l[k]);
+            fr::subc(borrow, 0, 0);
+            if (borrow == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rem.l[k] = t[k];
+                uint32_t ql[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ql[k] = q.l[k];
+                ql[i >> 5] |= 1u << (i & 31);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q.l[k] = ql[k];
+            }
+        }
+    }
+    insert_value_dev<T>(r, flags & GF_OUT_CHECK, r->w[2], q, cb, fail);
+    insert_value_dev<T>(r, flags & GF_OUT2_CHECK, r->w[6], rem, cb, fail);
+}
+
+// index.try_to_u64().unwrap() as u32  (memory_op.rs:70-72): > 64 bits panics in the reference
+__device__ __forceinline__ bool mem_index(const Fe& idx, uint32_t& out) {
+    out = idx.l[0];
+    return (idx.l[2] | idx.l[3] | idx.l[4] | idx.l[5] | idx.l[6] | idx.l[7]) == 0;
+}
+
+template <int T>
+__device__ __noinline__ void exec_mem(const OpRec* r, uint32_t kind, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t base = payload[r->w[7]], len = payload[r->w[7] + 1];
+    Fe idx;
+    hv_load<T>(idx, cb, r->w[3]);
+    uint32_t mi;
+    if (!mem_index(idx, mi)) {
+        hv_fail(fail, r->w[1], EK_REFERENCE_PANIC, 0);
+        return;
+    }
+    bool pred = true;
+    if (r->w[5] != 0xFFFFFFFFu) {
+        Fe p;
+        hv_load<T>(p, cb, r->w[5]);
+        pred = !fr::is_zero(p);
+    }
+    if (kind == MK_MEM_READ) {
+        Fe v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.l[k] = 0;
+        if (pred) {   // a zero predicate skips the read and zeroes the output (memory_op.rs:98-104)
+            if (mi >= len) {
+                hv_fail(fail, r->w[1], EK_INDEX_OUT_OF_BOUNDS, mi);
+                return;
+            }
+            hv_load<T>(v, cb, base + mi);
+        }
+        hv_store<T>(cb, r->w[2], v);
+    } else if (pred) {
+        if (mi >= len) {
+            hv_fail(fail, r->w[1], EK_INDEX_OUT_OF_BOUNDS, mi);
+            return;
+        }
+        Fe v;
+        hv_load<T>(v, cb, r->w[4]);
+        hv_store<T>(cb, base + mi, v);
+    }
+}
+
 template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
                                            const uint32_t* payload, uint32_t* mu) {
@@ -631,6 +787,22 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_REQUIRE:
             exec_require<T>(r, fail, payload, mu);
+            break;
+        case MK_COPY: {
+            Fe v;
+            hv_load<T>(v, cb, r->w[3]);
+            hv_store<T>(cb, r->w[2], v);
+            break;
+        }
+        case MK_TO_LE_RADIX:
+            exec_to_le_radix<T>(r, cb, fail, payload);
+            break;
+        case MK_QUOTIENT:
+            exec_quotient<T>(r, flags, cb, fail);
+            break;
+        case MK_MEM_READ:
+        case MK_MEM_WRITE:
+            exec_mem<T>(r, kind, cb, fail, payload);
             break;
         default:
             break;

@@ -105,9 +105,10 @@ struct Compiler {
     std::vector<uint8_t> known;
     Scheduler sched;
     uint32_t temp_base, temp_next = 0;
+    uint32_t extra_slots_base = 0, extra_slots = 0;   // memory-block columns live after the temporaries
 
     Compiler(const Circuit& circ, const PlanOptions& o, uint32_t nw)
-        : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw) {}
+        : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw), extra_slots_base(nw + o.temp_pool) {}
 
     uint32_t new_temp() {
         uint32_t t = temp_base + (temp_next % opt.temp_pool);
@@ -380,6 +381,244 @@ struct Compiler {
         ++plan.stats.n_micro;
     }
 
+    // get_value(expr) (pwg/mod.rs:321-332) for an expression whose witnesses are all statically known: returns the slot
+    // that holds the value (the witness itself for `1*w`, else a temporary).  false => static MissingAssignment recorded.
+    bool expr_to_slot(uint32_t idx, const Expression& e, uint32_t& slot) {
+        std::vector<Prod> prods;
+        std::vector<Lin> lins;
+        uint32_t missing = NONE;
+        for (auto& t : e.mul_terms) {
+            if (known[t.a] == W_MAYBE || known[t.b] == W_MAYBE)
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": expression over a conditionally assigned witness is not supported here yet");
+            if (known[t.a] && known[t.b]) {
+                if (!t.c.is_zero()) prods.push_back({t.c, t.a, t.b});
+            } else if (!t.c.is_zero() && missing == NONE) {
+                missing = known[t.a] ? t.b : t.a;
+            }
+        }
+        for (auto& t : e.linear_combinations) {
+            if (known[t.w] == W_MAYBE)
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": expression over a conditionally assigned witness is not supported here yet");
+            if (known[t.w]) {
+                if (!t.c.is_zero()) lins.push_back({t.c, t.w});
+            } else if (!t.c.is_zero() && missing == NONE) {
+                missing = t.w;
+            }
+        }
+        if (missing != NONE) {
+            fail_static(idx, EK_MISSING_ASSIGNMENT, missing, "missing assignment for witness index " + std::to_string(missing));
+            return false;
+        }
+        if (prods.empty() && lins.size() == 1 && e.q_c.is_zero() && lins[0].c == hf::from_u64(1)) {
+            slot = lins[0].w;
+            return true;
+        }
+        slot = new_temp();
+        ++plan.stats.n_temps;
+        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, slot, idx, false);
+        return true;
+    }
+
+    static bool expr_is_const(const Expression& e, U256& v) {
+        for (auto& t : e.mul_terms)
+            if (!t.c.is_zero()) return false;
+        for (auto& t : e.linear_combinations)
+            if (!t.c.is_zero()) return false;
+        v = e.q_c;
+        return true;
+    }
+
+    void place_heavy(OpRec& r, std::vector<uint32_t>& rd, std::vector<uint32_t>& wr) {
+        r.w[0] |= GF_HEAVY << 8;
+        std::sort(rd.begin(), rd.end());
+        rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+        std::sort(wr.begin(), wr.end());
+        wr.erase(std::unique(wr.begin(), wr.end()), wr.end());
+        sched.place(r, rd.data(), rd.size(), wr.data(), wr.size());
+        plan.needs_full_kernel = true;
+        ++plan.stats.n_micro;
+    }
+
+    // Directive::Quotient / ToLeRadix (acvm/src/pwg/directives/mod.rs:28-87)
+    bool directive(uint32_t idx, const Directive& d) {
+        if (d.kind == DIR_Quotient) {
+            uint32_t sa, sb, sp = NONE;
+            if (!expr_to_slot(idx, d.a, sa)) return false;
+            if (!expr_to_slot(idx, d.b, sb)) return false;
+            if (d.predicate.present && !expr_to_slot(idx, d.predicate, sp)) return false;
+            for (uint32_t w : {d.q, d.r})
+                if (known[w] == W_MAYBE) throw std::runtime_error("opcode " + std::to_string(idx) + ": directive output is conditionally assigned; not supported yet");
+            OpRec r{};
+            uint32_t flags = 0;
+            std::vector<uint32_t> rd = {sa, sb}, wr = {d.q, d.r};
+            if (sp != NONE) rd.push_back(sp);
+            if (known[d.q]) { flags |= GF_OUT_CHECK; rd.push_back(d.q); }
+            if (known[d.r] || d.r == d.q) { flags |= GF_OUT2_CHECK; rd.push_back(d.r); }
+            r.w[0] = MK_QUOTIENT | (flags << 8);
+            r.w[1] = idx;
+            r.w[2] = d.q;
+            r.w[3] = sa;
+            r.w[4] = sb;
+            r.w[5] = sp;
+            r.w[6] = d.r;
+            r.w[7] = 0;
+            place_heavy(r, rd, wr);
+            if (!known[d.q]) mark_assigned(d.q, idx);
+            if (!known[d.r]) mark_assigned(d.r, idx);
+            ++plan.stats.n_directive;
+            plan.stats.alg_bytes += 128;
+            return true;
+        }
+        if (d.kind == DIR_ToLeRadix) {
+            if (d.radix < 2 || d.radix > 256) {  // num-bigint to_radix_le asserts 2 <= radix <= 256
+                fail_static(idx, EK_REFERENCE_PANIC, 0, "The radix must be within 2...256");
+                return false;
+            }
+            uint32_t sa;
+            if (!expr_to_slot(idx, d.a, sa)) return false;
+            OpRec r{};
+            std::vector<uint32_t> rd = {sa}, wr;
+            uint32_t off = (uint32_t)plan.payload.size();
+            uint32_t n_b = (uint32_t)d.out.size();
+            plan.payload.push_back(n_b);
+            plan.payload.push_back(d.radix);
+            size_t mask_at = plan.payload.size();
+            for (uint32_t i = 0; i < (n_b + 31) / 32; ++i) plan.payload.push_back(0);
+            for (uint32_t i = 0; i < n_b; ++i) {
+                uint32_t w = d.out[i];
+                if (known[w] == W_MAYBE) throw std::runtime_error("opcode " + std::to_string(idx) + ": directive output is conditionally assigned; not supported yet");
+                bool dup = false;   // the same witness listed twice: the second insert_value compares
+                for (uint32_t j = 0; j < i; ++j) dup |= d.out[j] == w;
+                if (known[w] || dup) {
+                    plan.payload[mask_at + i / 32] |= 1u << (i % 32);
+                    rd.push_back(w);
+                }
+                wr.push_back(w);
+                plan.payload.push_back(w);
+            }
+            r.w[0] = MK_TO_LE_RADIX;
+            r.w[1] = idx;
+            r.w[2] = r.w[4] = r.w[5] = r.w[6] = NONE;
+            r.w[3] = sa;
+            r.w[7] = off;
+            place_heavy(r, rd, wr);
+            for (uint32_t w : d.out)
+                if (!known[w]) mark_assigned(w, idx);
+            ++plan.stats.n_directive;
+            plan.stats.alg_bytes += 32 * (1 + n_b);
+            return true;
+        }
+        throw std::runtime_error("opcode " + std::to_string(idx) + ": Directive::PermutationSort is out of scope (SURVEY 2)");
+    }
+
+    // MemoryInit / MemoryOp (acvm/src/pwg/memory_op.rs:16-123).  A block is a run of extra columns; the dynamic index of
+    // a MemoryOp is a per-lane column offset.
+    struct Block {
+        uint32_t base = 0, len = 0;
+        bool inited = false;
+    };
+    std::vector<std::pair<uint32_t, Block>> blocks;
+    std::vector<uint32_t> block_slots_scratch;
+
+    Block& block_of(uint32_t id) {
+        for (auto& b : blocks)
+            if (b.first == id) return b.second;
+        blocks.push_back({id, Block{}});
+        return blocks.back().second;
+    }
+
+    bool memory_init(uint32_t idx, uint32_t block_id, const std::vector<uint32_t>& init) {
+        for (uint32_t w : init) {
+            if (!known[w]) {
+                fail_static(idx, EK_MISSING_ASSIGNMENT, w, "missing assignment for witness index " + std::to_string(w));
+                return false;
+            }
+            if (known[w] == W_MAYBE) throw std::runtime_error("opcode " + std::to_string(idx) + ": MemoryInit over a conditionally assigned witness; not supported yet");
+        }
+        Block& b = block_of(block_id);
+        b.base = extra_slots_base + extra_slots;      // a re-init gets fresh columns
+        b.len = (uint32_t)init.size();
+        b.inited = true;
+        extra_slots += b.len;
+        sched.grow_slots(b.base + b.len);
+        for (uint32_t i = 0; i < b.len; ++i) {
+            OpRec r{};
+            r.w[0] = MK_COPY;
+            r.w[1] = idx;
+            r.w[2] = b.base + i;
+            r.w[3] = init[i];
+            r.w[4] = r.w[5] = r.w[6] = NONE;
+            std::vector<uint32_t> rd = {init[i]}, wr = {b.base + i};
+            place_heavy(r, rd, wr);
+        }
+        ++plan.stats.n_memory;
+        plan.stats.alg_bytes += 64ull * b.len;
+        return true;
+    }
+
+    bool memory_op(uint32_t idx, const MemOp& m) {
+        Block& b = block_of(m.block_id);
+        U256 opv;
+        if (!expr_is_const(m.operation, opv))
+            throw std::runtime_error("opcode " + std::to_string(idx) + ": MemoryOp whose read/write selector is not a constant is not supported yet");
+        uint32_t si, sp = NONE;
+        if (!expr_to_slot(idx, m.index, si)) return false;
+        bool is_read = opv.is_zero();
+        // `value` is evaluated (not required) before the predicate (memory_op.rs:75-87)
+        uint32_t sv = NONE, out_w = NONE;
+        if (is_read) {
+            // to_witness(): exactly 1*w + 0 over a witness (after evaluate); anything else panics in the reference
+            std::vector<LinTerm> lin;
+            bool has_mul = false;
+            for (auto& t : m.value.mul_terms) has_mul |= !t.c.is_zero();
+            for (auto& t : m.value.linear_combinations)
+                if (!t.c.is_zero()) lin.push_back(t);
+            // (an already-known witness is folded into the constant by evaluate(), so to_witness() is None there too)
+            if (has_mul || lin.size() != 1 || !(lin[0].c == hf::from_u64(1)) || !m.value.q_c.is_zero() || known[lin[0].w]) {
+                if (m.predicate.present && !expr_to_slot(idx, m.predicate, sp)) return false;
+                fail_static(idx, EK_REFERENCE_PANIC, 0, "Memory must be read into a specified witness index, encountered an Expression");
+                return false;
+            }
+            out_w = lin[0].w;
+        }
+        if (m.predicate.present && !expr_to_slot(idx, m.predicate, sp)) return false;
+        if (!is_read) {
+            // get_value(value) only happens when the predicate is non-zero; statically unknown witnesses there would be a
+            // value-dependent MissingAssignment -- require them known at plan time
+            if (!expr_to_slot(idx, m.value, sv)) return false;
+        }
+        OpRec r{};
+        uint32_t off = (uint32_t)plan.payload.size();
+        plan.payload.push_back(b.base);
+        plan.payload.push_back(b.len);
+        std::vector<uint32_t> rd = {si}, wr;
+        if (sp != NONE) rd.push_back(sp);
+        for (uint32_t i = 0; i < b.len; ++i) rd.push_back(b.base + i);
+        r.w[1] = idx;
+        r.w[3] = si;
+        r.w[5] = sp;
+        r.w[6] = NONE;
+        r.w[7] = off;
+        if (is_read) {
+            r.w[0] = MK_MEM_READ;
+            r.w[2] = out_w;
+            r.w[4] = NONE;
+            wr.push_back(out_w);
+            place_heavy(r, rd, wr);
+            mark_assigned(out_w, idx);
+        } else {
+            r.w[0] = MK_MEM_WRITE;
+            r.w[2] = NONE;
+            r.w[4] = sv;
+            rd.push_back(sv);
+            for (uint32_t i = 0; i < b.len; ++i) wr.push_back(b.base + i);
+            place_heavy(r, rd, wr);
+        }
+        ++plan.stats.n_memory;
+        plan.stats.alg_bytes += 96;
+        return true;
+    }
+
     bool arithmetic(uint32_t idx, const Expression& e) {
         {
             bool general = false;
@@ -636,14 +875,23 @@ struct Compiler {
                 case OP_BlackBox:
                     ok = blackbox(i, op.bb);
                     break;
+                case OP_Directive:
+                    ok = directive(i, op.dir);
+                    break;
+                case OP_MemoryInit:
+                    ok = memory_init(i, op.block_id, op.init);
+                    break;
+                case OP_MemoryOp:
+                    ok = memory_op(i, op.mem);
+                    break;
                 default:
                     throw std::runtime_error("opcode " + std::to_string(i) + ": opcode kind " + std::to_string(op.kind) +
-                                             " (Directive/Brillig/Memory) is not supported by the device plan yet");
+                                             " (Brillig) is not supported by the device plan yet");
             }
             if (!ok) break;
         }
         sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
-        plan.n_slots = temp_base + opt.temp_pool;
+        plan.n_slots = temp_base + opt.temp_pool + extra_slots;
         plan.stats.n_opcodes = c.opcodes.size();
         plan.stats.n_steps = sched.n_steps();
         plan.stats.n_slots_filled = sched.n_ops();
@@ -669,6 +917,23 @@ uint32_t witness_span(const Circuit& c, const std::vector<uint32_t>& inputs) {
             case OP_BlackBox:
                 for (auto& in : op.bb.inputs) upd(in.witness);
                 for (uint32_t w : op.bb.outputs) upd(w);
+                break;
+            case OP_Directive:
+                expr(op.dir.a);
+                expr(op.dir.b);
+                if (op.dir.predicate.present) expr(op.dir.predicate);
+                upd(op.dir.q);
+                upd(op.dir.r);
+                for (uint32_t w : op.dir.out) upd(w);
+                break;
+            case OP_MemoryInit:
+                for (uint32_t w : op.init) upd(w);
+                break;
+            case OP_MemoryOp:
+                expr(op.mem.operation);
+                expr(op.mem.index);
+                expr(op.mem.value);
+                if (op.mem.predicate.present) expr(op.mem.predicate);
                 break;
             default:
                 break;

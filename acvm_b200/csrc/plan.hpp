@@ -41,6 +41,11 @@ enum MicroKind : uint32_t {
     MK_PEDERSEN = 9,      // payload[aux..]: n_in, domain_separator, witness*, out_x, out_y
     MK_GATE_GENERAL = 10, // value-dependent arithmetic gate (unknown is a mul operand)
     MK_COPY_CHECK = 11,   // (reserved)
+    MK_COPY = 13,         // out := x                                   (MemoryInit, memory_op.rs:47-60)
+    MK_TO_LE_RADIX = 14,  // x = value; payload[aux..]: n_b, radix, check-mask words, b witnesses   (directives/mod.rs:60-87)
+    MK_QUOTIENT = 15,     // x = a, y = b, w1 = predicate|NONE, out = q, w2 = r                     (directives/mod.rs:28-59)
+    MK_MEM_READ = 16,     // x = index, w1 = predicate|NONE, out = witness; payload[aux..]: base, len  (memory_op.rs:62-110)
+    MK_MEM_WRITE = 17,    // x = index, y = value, w1 = predicate|NONE;     payload[aux..]: base, len  (memory_op.rs:111-123)
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
 };
 
@@ -85,6 +90,7 @@ struct PlanStats {
     uint64_t alg_bytes = 0;        // algorithmic HBM bytes per instance: 32 B per operand read + 32 B per witness written
     uint64_t n_temps = 0;
     uint64_t n_gate_general = 0;   // value-dependent gates resolved per lane
+    uint64_t n_directive = 0, n_memory = 0;
 };
 
 struct Plan {

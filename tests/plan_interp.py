@@ -11,7 +11,8 @@ RINV = pow(1 << 256, -1, P)
 NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
-          GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12)
+          GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17)
+EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
 EK_MISSING, EK_TOO_MANY, EK_UNSAT, EK_BB_FAILED = 1, 2, 4, 6
@@ -26,8 +27,8 @@ class PlanBlob:
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
          self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
         o += 48
-        self.stats = struct.unpack_from("<16Q", blob, o)
-        o += 128
+        self.stats = struct.unpack_from("<18Q", blob, o)
+        o += 144
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):
@@ -240,6 +241,59 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
                     coef, w_, m_ = entries[0]
                     writes.append((w_, (-q * pow(coef, P - 2, P)) % P))
                     mu[m_] = opcode
+            elif kind == MK["COPY"]:
+                writes.append((out, cols[x]))
+            elif kind == MK["TO_LE_RADIX"]:
+                pl = plan.payload
+                n_b, radix = pl[aux], pl[aux + 1]
+                nm = (n_b + 31) // 32
+                mask = pl[aux + 2: aux + 2 + nm]
+                outs = pl[aux + 2 + nm: aux + 2 + nm + n_b]
+                v = cols[x]
+                if n_b == 0:
+                    record_fail(opcode, EK_UNSAT)
+                else:
+                    local = {}
+                    for i in range(n_b):
+                        d, v = (v % radix) & 0xFF, v // radix
+                        if (mask[i // 32] >> (i % 32)) & 1:
+                            old = local.get(outs[i], cols[outs[i]])
+                            if old != d:
+                                record_fail(opcode, EK_UNSAT)
+                        local[outs[i]] = d
+                    writes.extend(local.items())
+                    if v:
+                        record_fail(opcode, EK_UNSAT)
+            elif kind == MK["QUOTIENT"]:
+                a_, b_ = cols[x], cols[y]
+                pred = cols[w1] != 0 if w1 != NONE else True
+                qv, rv = (a_ // b_, a_ % b_) if (pred and b_) else (0, 0)
+                local = {}
+                for (slot, val, chk) in ((out, qv, flags & GF_OUT_CHECK), (w2, rv, flags & 128)):
+                    if chk and local.get(slot, cols[slot]) != val:
+                        record_fail(opcode, EK_UNSAT)
+                    local[slot] = val
+                writes.extend(local.items())
+            elif kind in (MK["MEM_READ"], MK["MEM_WRITE"]):
+                base, ln = plan.payload[aux], plan.payload[aux + 1]
+                idx_v = cols[x]
+                if idx_v.bit_length() > 64:
+                    record_fail(opcode, EK_PANIC)
+                else:
+                    mi = idx_v & 0xFFFFFFFF
+                    pred = cols[w1] != 0 if w1 != NONE else True
+                    if kind == MK["MEM_READ"]:
+                        if not pred:
+                            writes.append((out, 0))
+                        elif mi >= ln:
+                            record_fail(opcode, EK_OOB, mi)
+                        else:
+                            writes.append((out, cols[base + mi]))
+                    elif pred:
+                        if mi >= ln:
+                            record_fail(opcode, EK_OOB, mi)
+                        else:
+                            writes.append((base + mi, cols[y]))
             elif kind == MK["REQUIRE"]:
                 pl = plan.payload
                 for i in range(pl[aux]):

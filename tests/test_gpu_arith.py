@@ -146,3 +146,14 @@ def test_inverse_gate_pattern(ctx):
     vm = acvm_b200.ACVM(ctx, data, {1: 5})
     assert vm.solve().status == "Solved"
     assert vm.finalize()[2] == int("135b52945a13d9aa49b9b57c33cd568ba9ae5ce9ca4a2d06e7f3fbd4c6666667", 16)  # 1/5, foreign_call.ts:20-27
+
+
+def test_directives_and_memory(ctx, golden):
+    from test_host_logic import _dir_mem_circuit, _dir_mem_inputs
+    rows, inp = _dir_mem_inputs()
+    st = _check(ctx, _dir_mem_circuit(), [1, 2, 3], len(rows), inp)
+    assert "Solved" in {s.status for s in st}
+    fx = golden["acvm_js_shared"]["memory_op"]   # acvm_js/test/shared/memory_op.ts
+    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
+    assert vm.solve().status == "Solved"
+    assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}

@@ -97,7 +97,7 @@ def test_decoder_rejects_garbage_and_accepts_golden(golden):
     info, _ = acvm_b200.compile_plan_host(bytes(golden["rust_serialization"]["addition_circuit"]), [1, 2], 16)
     assert info["n_opcodes"] == 1 and info["num_witnesses"] == 5 and info["n_gate_assign"] == 1
     # circuits with opcodes outside the device scope decode fine and are refused loudly, never silently skipped
-    for name in ("simple_brillig_foreign_call", "memory_op_circuit"):
+    for name in ("simple_brillig_foreign_call", "complex_brillig_foreign_call"):
         with pytest.raises(acvm_b200.AcvmError) as e:
             acvm_b200.compile_plan_host(bytes(golden["rust_serialization"][name]), [1, 2, 3], 16)
         assert e.value.rc == -5
@@ -166,7 +166,7 @@ def _vd_circuit():
     b = ab.CircuitBuilder()
     b.arithmetic([(1, 1, 5)], [], ab.P - 7)                    # w1*w5 = 7        : w5 = 7/w1, or (w1==0) unsat
     b.arithmetic([(3, 2, 6)], [(1, 3)], 0)                     # 3*w2*w6 + w3 = 0 : w6 assigned unless w2 == 0 (then needs w3 == 0)
-    b.arithmetic([(1, 2, 7)], [(5, 7), (1, 4)], 0)             # w2*w7 + 5*w7 + w4: two entries for w7 unless w2 == 0
+    b.arithmetic([(1, 3, 7)], [(5, 7), (1, 4)], 0)             # w3*w7 + 5*w7 + w4: two entries for w7 unless w3 == 0
     b.arithmetic([], [(1, 6), (ab.P - 1, 8)], 0)               # w8 = w6           : fails where w6 never got assigned
     b.logic("XOR", (5, 254), (1, 254), 9)                      # blackbox over a conditionally assigned input
     b.arithmetic([(1, 9, 9)], [(ab.P - 1, 10)], 0)             # w10 = w9^2
@@ -174,7 +174,7 @@ def _vd_circuit():
 
 
 def _vd_inputs():
-    rows = [(3, 4, 5, 6), (0, 4, 5, 6), (3, 0, 0, 6), (3, 0, 5, 6), (3, 4, 5, 0), (1, ab.P - 5, 2, 9), (2, 0, 0, 0)]
+    rows = [(3, 4, 0, 6), (3, 4, 5, 6), (0, 4, 0, 6), (3, 0, 0, 6), (3, 0, 5, 6), (1, ab.P - 5, 0, 9), (2, 0, 0, 0), (7, 9, 0, 0)]
     return rows, b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
 
 
@@ -182,3 +182,43 @@ def test_value_dependent_gates_plan_vs_oracle():
     rows, inp = _vd_inputs()
     info = _interp_vs_oracle(_vd_circuit(), [1, 2, 3, 4], inp, len(rows))
     assert info["needs_full_kernel"] == 1
+
+
+def _dir_mem_circuit():
+    """Directives + memory blocks: bit/byte decomposition, euclidean division, dynamic array access."""
+    b = ab.CircuitBuilder()
+    b.logic("AND", (1, 40), (1, 40), 10)                                            # w10 = low 40 bits of w1
+    b.directive_to_le_radix(ab.wexpr(10), list(range(20, 60)), 2)                   # 40 bits
+    b.directive_to_le_radix(([], [(1, 10)], 3), list(range(60, 66)), 256)           # bytes of w10 + 3
+    b.directive_to_le_radix(ab.wexpr(10), list(range(66, 80)), 10)                  # decimal digits (general radix)
+    b.directive_quotient(ab.wexpr(1), ab.wexpr(2), 80, 81)                          # w1 / w2
+    b.directive_quotient(ab.wexpr(1), ([], [(1, 10)], 1), 82, 83, predicate=ab.wexpr(3))
+    b.arithmetic([(1, 80, 2)], [(1, 81), (ab.P - 1, 1)], 0)                         # check q*b + r == a
+    b.memory_init(0, [20, 21, 22, 23, 60, 61, 62, 63])
+    b.logic("AND", (10, 3), (10, 3), 84)                                            # index in 0..7
+    b.memory_op(0, ab.cexpr(0), ab.wexpr(84), ab.wexpr(85))                         # w85 = mem[w84]
+    b.memory_op(0, ab.cexpr(1), ab.wexpr(84), ([], [(5, 85)], 1))                   # mem[w84] = 5*w85 + 1
+    b.memory_op(0, ab.cexpr(0), ab.wexpr(84), ab.wexpr(86))                         # w86 = mem[w84]
+    b.memory_op(0, ab.cexpr(0), ab.cexpr(3), ab.wexpr(87), predicate=ab.wexpr(3))   # predicated read at a constant index
+    b.memory_op(0, ab.cexpr(1), ([], [(1, 84)], 4), ab.wexpr(86), predicate=ab.wexpr(3))  # may go out of bounds (index+4)
+    b.memory_op(0, ab.cexpr(0), ab.cexpr(7), ab.wexpr(88))
+    return b.to_bytes()
+
+
+def _dir_mem_inputs():
+    rows = [(0x1234567890ABCDEF, 77, 1), (0xFFFFFFFFFF, 1, 0), (5, 0, 1), (ab.P - 1, 3, 7), (0, 9, 0), ((1 << 200) + 12345, (1 << 100) + 7, 1)]
+    return rows, b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+
+
+def test_directives_and_memory_plan_vs_oracle(golden):
+    rows, inp = _dir_mem_inputs()
+    _interp_vs_oracle(_dir_mem_circuit(), [1, 2, 3], inp, len(rows))
+    # the reference's own memory_op fixture (acvm_js/test/shared/memory_op.ts)
+    fx = golden["acvm_js_shared"]["memory_op"]
+    iw = {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()}
+    keys = sorted(iw)
+    _interp_vs_oracle(bytes(fx["bytecode"]), keys, b"".join(iw[k].to_bytes(32, "big") for k in keys), 1)
+    # too few output witnesses for the value -> UnsatisfiedConstrain (directives/mod.rs:67-71)
+    b = ab.CircuitBuilder()
+    b.directive_to_le_radix(ab.wexpr(1), [2, 3, 4], 2)
+    _interp_vs_oracle(b.to_bytes(), [1], (7).to_bytes(32, "big") + (8).to_bytes(32, "big") + (0).to_bytes(32, "big"), 3)
