@@ -231,6 +231,101 @@ class CircuitBuilder:
         self._opt_expr(predicate)
         self.n_opcodes += 1
 
+    # ---- Brillig (acir/src/circuit/brillig.rs:9-33, brillig/src/opcodes.rs:60-134) ----
+    _BRILLIG_TAGS = {"BinaryFieldOp": 0, "BinaryIntOp": 1, "JumpIfNot": 2, "JumpIf": 3, "Jump": 4, "Call": 5, "Const": 6, "Return": 7,
+                     "ForeignCall": 8, "Mov": 9, "Load": 10, "Store": 11, "BlackBox": 12, "Trap": 13, "Stop": 14}
+    _BRILLIG_BB_TAGS = {"Sha256": 0, "Blake2s": 1, "Keccak256": 2, "HashToField128Security": 3, "EcdsaSecp256k1": 4,
+                        "EcdsaSecp256r1": 5, "SchnorrVerify": 6, "Pedersen": 7, "FixedBaseScalarMul": 8}
+
+    def _reg_or_mem(self, d):
+        kind = {"Register": 0, "HeapArray": 1, "HeapVector": 2}[d[0]]
+        self.w.u32(kind)
+        self.w.u64(d[1])
+        if kind:
+            self.w.u64(d[2])
+
+    def _brillig_op(self, o):
+        w = self.w
+        op = o["op"]
+        w.u32(self._BRILLIG_TAGS[op])
+        if op == "BinaryFieldOp":
+            w.u64(o["destination"]); w.u32(o["bop"]); w.u64(o["lhs"]); w.u64(o["rhs"])
+        elif op == "BinaryIntOp":
+            w.u64(o["destination"]); w.u32(o["bop"]); w.u32(o["bit_size"]); w.u64(o["lhs"]); w.u64(o["rhs"])
+        elif op in ("JumpIfNot", "JumpIf"):
+            w.u64(o["condition"]); w.u64(o["location"])
+        elif op in ("Jump", "Call"):
+            w.u64(o["location"])
+        elif op == "Const":
+            w.u64(o["destination"]); w.fe(o["value"])
+        elif op == "ForeignCall":
+            w.string(o["function"])
+            w.u64(len(o["destinations"]))
+            for d in o["destinations"]:
+                self._reg_or_mem(d)
+            w.u64(len(o["inputs"]))
+            for d in o["inputs"]:
+                self._reg_or_mem(d)
+        elif op == "Mov":
+            w.u64(o["destination"]); w.u64(o["source"])
+        elif op == "Load":
+            w.u64(o["destination"]); w.u64(o["source_pointer"])
+        elif op == "Store":
+            w.u64(o["destination_pointer"]); w.u64(o["source"])
+        elif op == "BlackBox":
+            bb = o["bb"]
+            w.u32(self._BRILLIG_BB_TAGS[bb["name"]])
+            if bb["name"] in ("Sha256", "Blake2s", "Keccak256"):
+                for v in (*bb["message"], *bb["output"]):
+                    w.u64(v)
+            elif bb["name"] == "FixedBaseScalarMul":
+                for v in (bb["low"], bb["high"], *bb["result"]):
+                    w.u64(v)
+            else:
+                raise NotImplementedError(bb["name"])
+
+    def brillig(self, inputs, outputs, bytecode, foreign_call_results=(), predicate=None):
+        """inputs: [("Single", expr) | ("Array", [expr..])], outputs: [("Simple", w) | ("Array", [w..])],
+        bytecode: list of dicts shaped like oracle/acir.py decodes them, foreign_call_results: [[("Single", v)|("Array",[v..])..]..]"""
+        w = self.w
+        w.u32(3)
+        w.u64(len(inputs))
+        for kind, e in inputs:
+            if kind == "Single":
+                w.u32(0)
+                self._expr(e)
+            else:
+                w.u32(1)
+                w.u64(len(e))
+                for x in e:
+                    self._expr(x)
+        w.u64(len(outputs))
+        for kind, o in outputs:
+            if kind == "Simple":
+                w.u32(0)
+                w.u32(o)
+                self._see(o)
+            else:
+                w.u32(1)
+                self._vw(o)
+        w.u64(len(foreign_call_results))
+        for res in foreign_call_results:
+            w.u64(len(res))
+            for kind, v in res:
+                if kind == "Single":
+                    w.u32(0)
+                    w.fe(v)
+                else:
+                    w.u32(1)
+                    w.u64(len(v))
+                    for x in v:
+                        w.fe(x)
+        w.u64(len(bytecode))
+        for o in bytecode:
+            self._brillig_op(o)
+        self._opt_expr(predicate)
+        self.n_opcodes += 1
+
     def to_raw(self, current_witness_index=None):
         head = Writer()
         head.u32(self.max_witness + 1 if current_witness_index is None else current_witness_index)

@@ -39,8 +39,15 @@ class Scheduler {
         }
     }
 
+    // everything placed so far completes before anything placed later starts (segment boundary)
+    uint32_t barrier(uint32_t chunk_steps) {
+        floor_ = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
+        n_steps_ = floor_;
+        return floor_;
+    }
+
     void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
-        uint32_t e = 0;
+        uint32_t e = floor_;
         for (size_t i = 0; i < nr; ++i) e = std::max(e, ready_[reads[i]]);
         for (size_t i = 0; i < nw; ++i) e = std::max(e, std::max(ready_[writes[i]], war_[writes[i]]));
         uint32_t s = find(e);
@@ -96,6 +103,7 @@ class Scheduler {
     std::vector<uint32_t> steps_;
     std::vector<OpRec> ops_;
     uint32_t n_steps_ = 0;
+    uint32_t floor_ = 0;
 };
 
 struct Compiler {
@@ -619,6 +627,63 @@ struct Compiler {
         return true;
     }
 
+    uint32_t seg_start = 0;
+    void close_device_segment() {
+        uint32_t end = sched.barrier(opt.chunk_steps);
+        if (end > seg_start) plan.segments.push_back(Segment{0, seg_start, end - seg_start, 0});
+        seg_start = end;
+    }
+
+    // Opcode::Brillig (acvm/src/pwg/brillig.rs:20-131): predicate and input expressions are evaluated on the device into
+    // slots; the VM itself runs on the host between two device segments.
+    bool brillig(uint32_t idx, const Brillig& br) {
+        for (auto& o : br.bytecode)
+            if (o.tag == 12 && !(o.bb_tag == 0 || o.bb_tag == 2 || o.bb_tag == 8))
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": Brillig BlackBox op " + std::to_string(o.bb_tag) +
+                                         " is not supported by the host VM yet");
+        uint32_t sp = NONE;
+        if (br.predicate.present && !expr_to_slot(idx, br.predicate, sp)) return false;
+        std::vector<uint32_t> desc;
+        desc.push_back(sp);
+        desc.push_back((uint32_t)br.inputs.size());
+        for (auto& in : br.inputs) {
+            desc.push_back(in.is_array ? 1u : 0u);
+            desc.push_back((uint32_t)in.exprs.size());
+            for (auto& e : in.exprs) {
+                uint32_t s;
+                if (!expr_to_slot(idx, e, s)) {
+                    // get_value() failure on an input is reported as ExpressionHasTooManyUnknowns (brillig.rs:49-55)
+                    plan.static_fail.kind = EK_TOO_MANY_UNKNOWNS;
+                    plan.static_fail.aux = 0;
+                    return false;
+                }
+                desc.push_back(s);
+            }
+        }
+        desc.push_back((uint32_t)br.outputs.size());
+        std::vector<uint32_t> outs;
+        for (auto& out : br.outputs) {
+            desc.push_back(out.is_array ? 1u : 0u);
+            desc.push_back((uint32_t)out.witnesses.size());
+            for (uint32_t w : out.witnesses) {
+                if (known[w] == W_MAYBE)
+                    throw std::runtime_error("opcode " + std::to_string(idx) + ": Brillig output is conditionally assigned; not supported yet");
+                bool dup = std::find(outs.begin(), outs.end(), w) != outs.end();
+                desc.push_back(w);
+                desc.push_back((known[w] || dup) ? 1u : 0u);
+                outs.push_back(w);
+            }
+        }
+        close_device_segment();
+        uint32_t off = (uint32_t)plan.host_desc.size();
+        plan.host_desc.insert(plan.host_desc.end(), desc.begin(), desc.end());
+        plan.segments.push_back(Segment{1, idx, off, 0});
+        for (uint32_t w : outs)
+            if (!known[w]) mark_assigned(w, idx);
+        ++plan.stats.n_brillig;
+        return true;
+    }
+
     bool arithmetic(uint32_t idx, const Expression& e) {
         {
             bool general = false;
@@ -878,6 +943,9 @@ struct Compiler {
                 case OP_Directive:
                     ok = directive(i, op.dir);
                     break;
+                case OP_Brillig:
+                    ok = brillig(i, op.brillig);
+                    break;
                 case OP_MemoryInit:
                     ok = memory_init(i, op.block_id, op.init);
                     break;
@@ -890,6 +958,7 @@ struct Compiler {
             }
             if (!ok) break;
         }
+        close_device_segment();
         sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
         plan.n_slots = temp_base + opt.temp_pool + extra_slots;
         plan.stats.n_opcodes = c.opcodes.size();
@@ -928,6 +997,13 @@ uint32_t witness_span(const Circuit& c, const std::vector<uint32_t>& inputs) {
                 break;
             case OP_MemoryInit:
                 for (uint32_t w : op.init) upd(w);
+                break;
+            case OP_Brillig:
+                for (auto& in : op.brillig.inputs)
+                    for (auto& e : in.exprs) expr(e);
+                for (auto& out : op.brillig.outputs)
+                    for (uint32_t w : out.witnesses) upd(w);
+                if (op.brillig.predicate.present) expr(op.brillig.predicate);
                 break;
             case OP_MemoryOp:
                 expr(op.mem.operation);
@@ -1012,6 +1088,9 @@ std::vector<uint8_t> serialize_plan(const Plan& p) {
     put_vec(b, p.assign_opcode);
     put_vec(b, p.mu_index_of);
     put_vec(b, p.payload);
+    put_vec(b, p.segments);
+    put_vec(b, p.host_desc);
+    put_vec(b, p.acir_gz);
     put_vec(b, p.stream);
     return b;
 }
@@ -1038,6 +1117,9 @@ Plan deserialize_plan(const uint8_t* data, size_t len) {
     p.assign_opcode = c.vec<uint32_t>();
     p.mu_index_of = c.vec<uint32_t>();
     p.payload = c.vec<uint32_t>();
+    p.segments = c.vec<Segment>();
+    p.host_desc = c.vec<uint32_t>();
+    p.acir_gz = c.vec<uint8_t>();
     p.stream = c.vec<OpRec>();
     if (p.stream.size() != (size_t)p.n_steps * p.S) throw std::runtime_error("plan blob: stream size mismatch");
     return p;

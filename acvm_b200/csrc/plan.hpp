@@ -90,7 +90,17 @@ struct PlanStats {
     uint64_t alg_bytes = 0;        // algorithmic HBM bytes per instance: 32 B per operand read + 32 B per witness written
     uint64_t n_temps = 0;
     uint64_t n_gate_general = 0;   // value-dependent gates resolved per lane
-    uint64_t n_directive = 0, n_memory = 0;
+    uint64_t n_directive = 0, n_memory = 0, n_brillig = 0;
+};
+
+// The opcode list is cut into segments: device segments are step ranges of the record stream; a host segment is one
+// Brillig opcode executed by the host VM on columns copied out of / back into HBM (north star: "Brillig opcodes
+// execute on the host brillig_vm with results DMA'd back into the device WitnessMap").
+struct Segment {
+    uint32_t kind;   // 0 = device, 1 = host Brillig
+    uint32_t a;      // device: first step        host: ACIR opcode index
+    uint32_t b;      // device: number of steps   host: offset into Plan::host_desc
+    uint32_t c;
 };
 
 struct Plan {
@@ -108,6 +118,10 @@ struct Plan {
                                           // 0xFFFFFFFD = value-dependent: the per-lane table mu_assign[mu_index_of[w]] decides
     std::vector<uint32_t> mu_index_of;    // per witness: index into the per-lane "maybe assigned" table, or 0xFFFFFFFF
     uint32_t n_mu = 0;
+    std::vector<Segment> segments;
+    // host segment descriptors: pred_slot, n_inputs, {is_array, count, slots...}*, n_outputs, {is_array, count, {witness, known}...}*
+    std::vector<uint32_t> host_desc;
+    std::vector<uint8_t> acir_gz;      // original circuit bytes, kept only when host segments need the Brillig bytecode
     StaticFail static_fail;            // the whole batch fails here (unless an instance failed earlier)
     PlanStats stats;
 };

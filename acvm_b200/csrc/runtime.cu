@@ -8,10 +8,12 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/acvm_b200.h"
 #include "acir.hpp"
+#include "brillig_host.hpp"
 #include "curve_host.hpp"
 #include "plan.hpp"
 #include "vm_kernel.cuh"
@@ -49,6 +51,8 @@ struct acvmb_ctx {
 struct acvmb_circuit {
     acvmb_ctx* ctx = nullptr;
     Plan plan;
+    Circuit circuit;            // kept only for plans with host (Brillig) segments
+    bool has_circuit = false;
     uint8_t* d_stream = nullptr;
     uint32_t* d_payload = nullptr;
     uint32_t* d_assign = nullptr;
@@ -241,7 +245,16 @@ extern "C" int acvmb_circuit_from_acir(acvmb_ctx* ctx, const uint8_t* gz, size_t
     } catch (const std::exception& e) {
         return set_err(ACVMB_ERR_DECODE, e.what());
     }
-    return circuit_from_struct(ctx, circ, input_witnesses, n_inputs, out);
+    int rc = circuit_from_struct(ctx, circ, input_witnesses, n_inputs, out);
+    if (rc) return rc;
+    bool host = false;
+    for (auto& sg : (*out)->plan.segments) host |= sg.kind == 1;
+    if (host) {
+        (*out)->plan.acir_gz.assign(gz, gz + len);
+        (*out)->circuit = std::move(circ);
+        (*out)->has_circuit = true;
+    }
+    return ACVMB_OK;
 }
 
 extern "C" void acvmb_circuit_destroy(acvmb_circuit* c) {
@@ -303,6 +316,10 @@ extern "C" int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, si
     c->ctx = ctx;
     try {
         c->plan = deserialize_plan(blob, len);
+        if (!c->plan.acir_gz.empty()) {
+            c->circuit = decode_circuit(c->plan.acir_gz.data(), c->plan.acir_gz.size());
+            c->has_circuit = true;
+        }
     } catch (const std::exception& e) {
         return set_err(ACVMB_ERR_DECODE, e.what());
     }
@@ -383,6 +400,8 @@ extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
     return ACVMB_OK;
 }
 
+static int run_host_brillig(acvmb_batch* b, const Segment& sg);
+
 extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     acvmb_circuit* c = b->c;
@@ -393,22 +412,32 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     a.payload = c->d_payload;
     a.cols = b->d_cols;
     a.fail = b->d_fail;
-    a.n_steps = c->plan.n_steps;
     a.chunk_steps = c->plan.chunk_steps;
     a.n_slots = c->plan.n_slots;
     a.n_tiles = b->n_tiles;
     a.mu_assign = b->d_mu;
     a.n_mu = c->plan.n_mu;
     KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel, c->ctx->opt_split};
-    CUDA_TRY(cudaEventRecord(b->ev0, s));
-    CUDA_TRY(launch_vm(cfg, a, s));
-    CUDA_TRY(cudaEventRecord(b->ev1, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
-    if (kernel_ms) *kernel_ms = ms;
-    c->run.kernel_ms += ms;
-    c->run.kernel_launches += 1;
+    float total = 0;
+    for (const Segment& sg : c->plan.segments) {
+        if (sg.kind == 0) {
+            a.first_step = sg.a;
+            a.n_steps = sg.b;
+            CUDA_TRY(cudaEventRecord(b->ev0, s));
+            CUDA_TRY(launch_vm(cfg, a, s));
+            CUDA_TRY(cudaEventRecord(b->ev1, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+            total += ms;
+            c->run.kernel_launches += 1;
+        } else {
+            int rc = run_host_brillig(b, sg);
+            if (rc) return rc;
+        }
+    }
+    if (kernel_ms) *kernel_ms = total;
+    c->run.kernel_ms += total;
     c->run.T = b->T;
     c->run.S = c->plan.S;
     c->run.n_tiles = b->n_tiles;
@@ -458,6 +487,174 @@ extern "C" int acvmb_batch_run_staged(acvmb_batch* b, uint32_t slot, float* tota
     return ACVMB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Host segment: one Brillig opcode for every live instance of the batch (acvm/src/pwg/brillig.rs:20-131).
+// D2H of exactly the columns the opcode reads, VM runs on all host threads, H2D + scatter of the outputs, failures
+// merged into the device status words.
+// ---------------------------------------------------------------------------------------------
+static inline unsigned long long fail_key(uint32_t opcode, uint32_t kind, uint32_t aux) {
+    return ((unsigned long long)opcode << 32) | ((unsigned long long)(kind & 0xF) << 28) | (aux & 0x0FFFFFFFu);
+}
+
+static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
+    acvmb_circuit* c = b->c;
+    acvmb_ctx* ctx = c->ctx;
+    if (!c->has_circuit) return set_err(ACVMB_ERR_STATE, "plan has a host segment but the circuit bytes are not attached");
+    const Brillig& br = c->circuit.opcodes[sg.a].brillig;
+    const uint32_t* d = c->plan.host_desc.data() + sg.b;
+    const uint32_t opcode = sg.a;
+    // ---- unpack the descriptor ----
+    std::vector<uint32_t> in_slots;          // gathered columns, in order
+    uint32_t pred_slot = *d++;
+    if (pred_slot != 0xFFFFFFFFu) in_slots.push_back(pred_slot);
+    struct In { bool arr; uint32_t first, count; };
+    std::vector<In> ins;
+    uint32_t n_in = *d++;
+    for (uint32_t i = 0; i < n_in; ++i) {
+        bool arr = *d++ != 0;
+        uint32_t cnt = *d++;
+        ins.push_back({arr, (uint32_t)in_slots.size(), cnt});
+        for (uint32_t k = 0; k < cnt; ++k) in_slots.push_back(*d++);
+    }
+    struct Out { bool arr; uint32_t first, count; };
+    std::vector<Out> outs;
+    std::vector<uint32_t> out_w, out_known;
+    uint32_t n_out = *d++;
+    for (uint32_t i = 0; i < n_out; ++i) {
+        bool arr = *d++ != 0;
+        uint32_t cnt = *d++;
+        outs.push_back({arr, (uint32_t)out_w.size(), cnt});
+        for (uint32_t k = 0; k < cnt; ++k) {
+            out_w.push_back(*d++);
+            out_known.push_back(*d++);
+        }
+    }
+    const uint32_t known_first = (uint32_t)in_slots.size();   // already-assigned outputs are read too (insert_value compares)
+    std::vector<int> known_pos(out_w.size(), -1);
+    for (size_t k = 0; k < out_w.size(); ++k)
+        if (out_known[k]) {
+            known_pos[k] = (int)in_slots.size();
+            in_slots.push_back(out_w[k]);
+        }
+    (void)known_first;
+    const uint32_t n = b->n_inst, n_g = (uint32_t)in_slots.size(), n_o = (uint32_t)out_w.size();
+    cudaStream_t s = ctx->stream;
+    // ---- D2H: status words + the input columns ----
+    std::vector<unsigned long long> fail(n);
+    CUDA_TRY(cudaMemcpyAsync(fail.data(), b->d_fail, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    std::vector<uint8_t> in_be((size_t)n * n_g * 32);
+    uint8_t* d_io = nullptr;
+    uint32_t* d_ids = nullptr;
+    size_t io_bytes = std::max<size_t>((size_t)n * std::max(n_g, n_o) * 32, 16);
+    CUDA_TRY(cudaMalloc(&d_io, io_bytes));
+    CUDA_TRY(cudaMalloc(&d_ids, std::max<size_t>((size_t)std::max(n_g, n_o) * 4, 16)));
+    if (n_g) {
+        CUDA_TRY(cudaMemcpyAsync(d_ids, in_slots.data(), (size_t)n_g * 4, cudaMemcpyHostToDevice, s));
+        GatherArgs g{};
+        g.cols = b->d_cols;
+        g.n_slots = c->plan.n_slots;
+        g.T = (int)b->T;
+        g.witness_ids = d_ids;
+        g.n_out = n_g;
+        g.first_inst = 0;
+        g.n_inst = n;
+        g.fail = b->d_fail;
+        g.out_be = d_io;
+        g.raw = 1;
+        CUDA_TRY(launch_gather_outputs(g, s));
+        CUDA_TRY(cudaMemcpyAsync(in_be.data(), d_io, (size_t)n * n_g * 32, cudaMemcpyDeviceToHost, s));
+        c->run.kernel_launches += 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    // ---- run the VM per instance on all host threads ----
+    std::vector<uint8_t> out_be((size_t)n * n_o * 32, 0);
+    unsigned n_thr = std::max(1u, std::thread::hardware_concurrency());
+    n_thr = std::min<unsigned>(n_thr, n);
+    auto work = [&](unsigned t) {
+        for (uint32_t i = t; i < n; i += n_thr) {
+            if ((uint32_t)(fail[i] >> 32) < opcode) continue;   // this instance stopped at an earlier opcode
+            auto val = [&](uint32_t pos) { return hf::from_be_bytes_reduce(&in_be[((size_t)i * n_g + pos) * 32], 32); };
+            std::vector<U256> result(n_o);
+            bool ran = true;
+            if (pred_slot != 0xFFFFFFFFu && val(0).is_zero()) {
+                ran = false;   // zero predicate: outputs are zeroed (brillig.rs:34-37,133-150)
+            } else {
+                bvm::VM vm;
+                for (auto& in : ins) {
+                    if (!in.arr) {
+                        vm.regs.push_back(val(in.first));
+                    } else {
+                        vm.regs.push_back(hf::from_u64(vm.mem.size()));
+                        for (uint32_t k = 0; k < in.count; ++k) vm.mem.push_back(val(in.first + k));
+                    }
+                }
+                bvm::Result r = vm.run(br);
+                if (r.status == bvm::Status::Failure) {
+                    fail[i] = std::min(fail[i], fail_key(opcode, EK_BRILLIG_FAILED, r.call_stack.empty() ? 0 : (uint32_t)r.call_stack.back()));
+                    continue;
+                }
+                if (r.status == bvm::Status::Panic) {
+                    fail[i] = std::min(fail[i], fail_key(opcode, EK_REFERENCE_PANIC, 0));
+                    continue;
+                }
+                if (r.status == bvm::Status::ForeignCallWait) {
+                    fail[i] = std::min(fail[i], fail_key(opcode, 0xF, 0));   // decoded as ACVMB_REQUIRES_FOREIGN_CALL
+                    continue;
+                }
+                bool bad = false;
+                for (size_t oi = 0; oi < outs.size() && !bad; ++oi) {
+                    U256 reg = oi < vm.regs.size() ? vm.regs[oi] : U256{};
+                    if (!outs[oi].arr) {
+                        result[outs[oi].first] = reg;
+                    } else {
+                        if (reg.l[1] | reg.l[2] | reg.l[3]) { bad = true; break; }
+                        for (uint32_t k = 0; k < outs[oi].count; ++k) {
+                            size_t p = (size_t)reg.l[0] + k;
+                            if (p >= vm.mem.size()) { bad = true; break; }   // Vec index out of bounds panics
+                            result[outs[oi].first + k] = vm.mem[p];
+                        }
+                    }
+                }
+                if (bad) {
+                    fail[i] = std::min(fail[i], fail_key(opcode, EK_REFERENCE_PANIC, 0));
+                    continue;
+                }
+            }
+            (void)ran;
+            // insert_value in output order: an already-assigned witness is replaced, a mismatch is UnsatisfiedConstrain
+            std::vector<std::pair<uint32_t, U256>> seen;
+            for (uint32_t k = 0; k < n_o; ++k) {
+                if (out_known[k]) {
+                    U256 old;
+                    bool found = false;
+                    for (auto& kv : seen)
+                        if (kv.first == out_w[k]) { old = kv.second; found = true; }
+                    if (!found) old = val((uint32_t)known_pos[k]);
+                    if (old != result[k]) fail[i] = std::min(fail[i], fail_key(opcode, EK_UNSATISFIED_CONSTRAIN, 0));
+                }
+                seen.emplace_back(out_w[k], result[k]);
+                hf::to_be_bytes(result[k], &out_be[((size_t)i * n_o + k) * 32]);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n_thr; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    // ---- H2D: outputs scattered into their columns, merged status words ----
+    if (n_o) {
+        CUDA_TRY(cudaMemcpyAsync(d_ids, out_w.data(), (size_t)n_o * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_io, out_be.data(), (size_t)n * n_o * 32, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_scatter_inputs(d_io, d_ids, n_o, b->d_cols, c->plan.n_slots, (int)b->T, n, s));
+        c->run.kernel_launches += 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_fail, fail.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(d_io);
+    cudaFree(d_ids);
+    return ACVMB_OK;
+}
+
 static void decode_status(const Plan& p, unsigned long long word, acvmb_status* st) {
     uint32_t fop = (uint32_t)(word >> 32);
     if (p.static_fail.present && p.static_fail.opcode <= fop) {
@@ -470,6 +667,12 @@ static void decode_status(const Plan& p, unsigned long long word, acvmb_status* 
         st->code = ACVMB_SOLVED;
         st->err_kind = ACVMB_E_NONE;
         st->opcode_index = p.n_opcodes;
+        st->aux = 0;
+    } else if (((word >> 28) & 0xF) == 0xF) {
+        // a Brillig foreign call has no recorded result: ACVMStatus::RequiresForeignCall, ip NOT advanced (mod.rs:267)
+        st->code = ACVMB_REQUIRES_FOREIGN_CALL;
+        st->err_kind = ACVMB_E_NONE;
+        st->opcode_index = fop;
         st->aux = 0;
     } else {
         st->code = ACVMB_FAILURE;
@@ -892,5 +1095,56 @@ extern "C" int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32
     gk::Pt p = gk::derive_pedersen_generator(index);
     hf::to_be_bytes(p.x, out_xy_be32);
     hf::to_be_bytes(p.y, out_xy_be32 + 32);
+    return ACVMB_OK;
+}
+
+// host-only test hook: run Brillig opcode `opcode_index` of a circuit on the C++ host VM with explicit input values
+// (flattened in input order) and return the flattened outputs -- lets the CPU suite compare the VM with the oracle's.
+extern "C" int acvmb_brillig_run_host(const uint8_t* gz, size_t len, uint32_t opcode_index, const uint8_t* in_values_be32,
+                                      uint32_t n_in_values, uint8_t* out_values_be32, uint32_t n_out_values, uint32_t* status,
+                                      uint32_t* fail_pc) {
+    if (!gz || !status) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Circuit circ;
+    try {
+        circ = decode_circuit(gz, len);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    if (opcode_index >= circ.opcodes.size() || circ.opcodes[opcode_index].kind != OP_Brillig)
+        return set_err(ACVMB_ERR_INVALID_ARG, "not a Brillig opcode");
+    const Brillig& br = circ.opcodes[opcode_index].brillig;
+    bvm::VM vm;
+    uint32_t pos = 0;
+    for (auto& in : br.inputs) {
+        if (pos + in.exprs.size() > n_in_values) return set_err(ACVMB_ERR_INVALID_ARG, "too few input values");
+        if (!in.is_array) {
+            vm.regs.push_back(hf::from_be_bytes_reduce(in_values_be32 + (size_t)pos * 32, 32));
+            ++pos;
+        } else {
+            vm.regs.push_back(hf::from_u64(vm.mem.size()));
+            for (size_t k = 0; k < in.exprs.size(); ++k, ++pos) vm.mem.push_back(hf::from_be_bytes_reduce(in_values_be32 + (size_t)pos * 32, 32));
+        }
+    }
+    bvm::Result r = vm.run(br);
+    *status = (uint32_t)r.status;
+    if (fail_pc) *fail_pc = r.call_stack.empty() ? 0 : (uint32_t)r.call_stack.back();
+    if (r.status != bvm::Status::Finished) return ACVMB_OK;
+    uint32_t k = 0;
+    for (size_t oi = 0; oi < br.outputs.size(); ++oi) {
+        U256 reg = oi < vm.regs.size() ? vm.regs[oi] : U256{};
+        if (!br.outputs[oi].is_array) {
+            if (k < n_out_values) hf::to_be_bytes(reg, out_values_be32 + (size_t)k * 32);
+            ++k;
+        } else {
+            for (size_t j = 0; j < br.outputs[oi].witnesses.size(); ++j, ++k) {
+                size_t p = (size_t)reg.l[0] + j;
+                if ((reg.l[1] | reg.l[2] | reg.l[3]) || p >= vm.mem.size()) {
+                    *status = (uint32_t)bvm::Status::Panic;
+                    return ACVMB_OK;
+                }
+                if (k < n_out_values) hf::to_be_bytes(vm.mem[p], out_values_be32 + (size_t)k * 32);
+            }
+        }
+    }
     return ACVMB_OK;
 }

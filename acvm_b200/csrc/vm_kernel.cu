@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     uint32_t* mu = a.mu_assign + (size_t)tile * a.n_mu * T + lane;
 
     const uint32_t n_chunks = a.n_steps / a.chunk_steps;
+    const uint8_t* stream = a.stream + (size_t)a.first_step * S * sizeof(OpRec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
         fence_barrier_init();
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
         const uint32_t pre = n_chunks < (uint32_t)NSTAGE ? n_chunks : (uint32_t)NSTAGE;
         for (uint32_t c = 0; c < pre; ++c) {
             mbar_expect_tx(&bars[c], chunk_bytes);
-            tma_bulk_g2s(smem + (size_t)c * chunk_bytes, a.stream + (size_t)c * chunk_bytes, chunk_bytes, &bars[c]);
+            tma_bulk_g2s(smem + (size_t)c * chunk_bytes, stream + (size_t)c * chunk_bytes, chunk_bytes, &bars[c]);
         }
     }
 
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
         // every thread is past the last read of this stage: refill it
         if (tid == 0 && c + NSTAGE < n_chunks) {
             mbar_expect_tx(&bars[st], chunk_bytes);
-            tma_bulk_g2s(smem + (size_t)st * chunk_bytes, a.stream + (size_t)(c + NSTAGE) * chunk_bytes, chunk_bytes, &bars[st]);
+            tma_bulk_g2s(smem + (size_t)st * chunk_bytes, stream + (size_t)(c + NSTAGE) * chunk_bytes, chunk_bytes, &bars[st]);
         }
     }
 }
@@ -358,10 +359,13 @@ __global__ void gather_outputs_kernel(const GatherArgs g) {
     uint32_t fail_op = (uint32_t)(g.fail[inst] >> 32);
     if (g.static_fail_opcode < fail_op) fail_op = g.static_fail_opcode;
     uint32_t tile = inst / g.T, lane = inst % g.T;
-    uint32_t ao = g.assign_opcode[w];
-    if (ao == 0xFFFFFFFDu)   // value-dependent: this lane's own record of which opcode assigned it
-        ao = g.mu_assign[((size_t)tile * g.n_mu + g.mu_index_of[w]) * g.T + lane];
-    bool present = (ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op);
+    bool present = true;
+    if (!g.raw) {
+        uint32_t ao = g.assign_opcode[w];
+        if (ao == 0xFFFFFFFDu)   // value-dependent: this lane's own record of which opcode assigned it
+            ao = g.mu_assign[((size_t)tile * g.n_mu + g.mu_index_of[w]) * g.T + lane];
+        present = (ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op);
+    }
     if (g.out_present) g.out_present[gid] = present ? 1 : 0;
     if (!g.out_be) return;
     uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;

@@ -14,6 +14,7 @@ struct VmArgs {
     const uint32_t* payload;      // variable-length operand lists
     uint4* cols;
     unsigned long long* fail;     // per instance: min over failures of (opcode<<32 | kind<<28 | aux)
+    uint32_t first_step;          // this launch covers steps [first_step, first_step + n_steps)
     uint32_t n_steps;             // multiple of chunk_steps
     uint32_t chunk_steps;
     uint32_t n_slots;
@@ -50,6 +51,7 @@ struct GatherArgs {
     uint32_t static_fail_opcode;
     uint8_t* out_be;               // [n_inst][n_out][32] or NULL
     uint8_t* out_present;          // [n_inst][n_out] or NULL
+    int raw;                       // 1 = witness_ids are raw column slots (temporaries allowed), no presence logic
 };
 cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream);
 cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t stream);

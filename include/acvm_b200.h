@@ -171,6 +171,10 @@ int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
 int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]);
+/* run one Brillig opcode of a circuit on the host VM (status: 0 finished, 1 failure, 2 foreign-call wait, 3 reference panic) */
+int acvmb_brillig_run_host(const uint8_t* gz_bincode, size_t len, uint32_t opcode_index, const uint8_t* in_values_be32,
+                           uint32_t n_in_values, uint8_t* out_values_be32, uint32_t n_out_values, uint32_t* status,
+                           uint32_t* fail_pc);
 
 /* ---- measurement helpers ---- */
 int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,

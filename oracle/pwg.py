@@ -397,6 +397,12 @@ class ACVM:
                     return self.status
             else:
                 raise ValueError(op.kind)
+        except ReferencePanic as e:
+            # the reference process would abort here; the oracle reports it as a distinguished failure so that
+            # batch tests can compare it with the device's ACVMB_E_REFERENCE_PANIC status
+            self.error = ResolutionError("ReferencePanic", message=str(e))
+            self.status = FAILURE
+            return self.status
         except ResolutionError as e:
             if e.kind in ("UnsatisfiedConstrain", "IndexOutOfBounds"):  # mod.rs:286-296
                 e.opcode_location = self.instruction_pointer
@@ -406,6 +412,12 @@ class ACVM:
         self.instruction_pointer += 1
         self.status = SOLVED if self.instruction_pointer == len(self.opcodes) else IN_PROGRESS
         return self.status
+
+    def resolve_pending_foreign_call(self, result):  # mod.rs:206-228; result = [("Single", v) | ("Array", [v..]), ...]
+        if self.status != REQUIRES_FOREIGN_CALL:
+            raise ReferencePanic("ACVM is not expecting a foreign call response as no call was made")
+        self.opcodes[self.instruction_pointer].body["foreign_call_results"].append(list(result))
+        self.status = IN_PROGRESS
 
     def finalize(self):  # mod.rs:176-181
         if self.status != SOLVED:

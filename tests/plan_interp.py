@@ -27,8 +27,8 @@ class PlanBlob:
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
          self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
         o += 48
-        self.stats = struct.unpack_from("<18Q", blob, o)
-        o += 144
+        self.stats = struct.unpack_from("<19Q", blob, o)
+        o += 152
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):
@@ -48,6 +48,12 @@ class PlanBlob:
         self.mu_index_of = list(struct.unpack(f"<{n}I", d))
         n, d = vec("I", 4)
         self.payload = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("seg", 16)
+        self.segments = [struct.unpack_from("<4I", d, 16 * i) for i in range(n)]
+        n, d = vec("I", 4)
+        self.host_desc = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("B", 1)
+        self.acir_gz = bytes(d)
         n, d = vec("rec", 192)
         self.n_records = n
         self.stream = d
@@ -130,7 +136,7 @@ def default_hooks():
     return {MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
 
 
-def run_plan(plan: PlanBlob, inputs, hooks=None):
+def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
     """inputs: dict witness->int.  Returns (status tuple, witness dict).
 
     status = ("Solved",) or ("Failure", err_kind, opcode_index, aux).  `hooks` maps heavy micro-op
@@ -154,7 +160,75 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
         if fail is None or key < fail:
             fail = key
 
-    for step in range(plan.n_steps):
+    def host_segment(opcode, off):
+        """Brillig on the 'host' of the interpreter: the oracle's VM (test code) on the gathered slots."""
+        from oracle import brillig_vm as obv, pwg as opwg
+        nonlocal fail
+        if fail is not None and fail[0] < opcode:
+            return
+        br = circuit.opcodes[opcode].body
+        d = plan.host_desc
+        p_ = off
+        pred_slot = d[p_]; p_ += 1
+        n_in = d[p_]; p_ += 1
+        regs, mem = [], []
+        for _ in range(n_in):
+            arr, cnt = d[p_], d[p_ + 1]; p_ += 2
+            vals = [cols[s_] for s_ in d[p_:p_ + cnt]]; p_ += cnt
+            if arr:
+                regs.append(len(mem)); mem += vals
+            else:
+                regs.append(vals[0])
+        n_out = d[p_]; p_ += 1
+        outs = []
+        for _ in range(n_out):
+            arr, cnt = d[p_], d[p_ + 1]; p_ += 2
+            outs.append((arr, [(d[p_ + 2 * k], d[p_ + 2 * k + 1]) for k in range(cnt)])); p_ += 2 * cnt
+        flat = [wk for _, ws in outs for wk in ws]
+        if pred_slot != NONE and cols[pred_slot] == 0:
+            result = [0] * len(flat)
+        else:
+            vm = obv.VM(regs, mem, br["bytecode"], br["foreign_call_results"], opwg.OracleBackend())
+            try:
+                st_ = vm.process_opcodes()
+            except opwg.ReferencePanic:
+                record_fail(opcode, EK_PANIC)
+                return
+            if st_[0] == "Failure":
+                record_fail(opcode, 7, st_[2][-1])
+                return
+            if st_[0] == "ForeignCallWait":
+                record_fail(opcode, 0xF)
+                return
+            result = []
+            for i, (arr, ws) in enumerate(outs):
+                reg = vm.get(i)
+                if not arr:
+                    result.append(reg)
+                else:
+                    if reg.bit_length() > 64 or reg + len(ws) > len(vm.memory):
+                        record_fail(opcode, EK_PANIC)
+                        return
+                    result += vm.memory[reg:reg + len(ws)]
+        for (w_, known_), v in zip(flat, result):
+            if known_ and cols[w_] != v:
+                record_fail(opcode, EK_UNSAT)
+            cols[w_] = v
+
+    step_plan = []
+    if plan.segments:
+        for (kind_, a_, b_, _c) in plan.segments:
+            if kind_ == 0:
+                step_plan += [("step", s_) for s_ in range(a_, a_ + b_)]
+            else:
+                step_plan.append(("host", a_, b_))
+    else:
+        step_plan = [("step", s_) for s_ in range(plan.n_steps)]
+    for item in step_plan:
+        if item[0] == "host":
+            host_segment(item[1], item[2])
+            continue
+        step = item[1]
         writes = []
         for s in range(plan.S):
             hdr, c = plan.record(step * plan.S + s)
@@ -310,6 +384,8 @@ def run_plan(plan: PlanBlob, inputs, hooks=None):
     if plan.sf_present and plan.sf_opcode <= fop:
         status = ("Failure", plan.sf_kind, plan.sf_opcode, plan.sf_aux)
         fop = plan.sf_opcode
+    elif fail and fail[1] == 0xF:
+        status = ("RequiresForeignCall", 0, fail[0], 0)
     elif fail:
         status = ("Failure", fail[1], fail[0], fail[2])
     else:

@@ -20,7 +20,7 @@ def _check(ctx, data, input_witnesses, batch, inp, expect_all_solved=True):
         ost, owm, oerr = pwg.solve_circuit(oc, iw)
         assert st[i].status == ost, (i, st[i], oerr)
         if ost == "Failure":
-            assert st[i].error == oerr.kind
+            assert st[i].error == oerr.kind, (i, st[i], oerr)
             if oerr.opcode_location is not None:
                 assert st[i].opcode_index == oerr.opcode_location
         limit = 0xFFFFFFFF if ost == "Solved" else st[i].opcode_index
@@ -157,3 +157,20 @@ def test_directives_and_memory(ctx, golden):
     vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
     assert vm.solve().status == "Solved"
     assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}
+
+
+def test_brillig_on_host_between_device_segments(ctx, golden):
+    # north star: "Brillig opcodes execute on the host brillig_vm with results DMA'd back into the device WitnessMap"
+    from test_host_logic import _brillig_circuit, _brillig_inputs
+    rows, inp = _brillig_inputs()
+    st = _check(ctx, _brillig_circuit(), [1, 2, 3], len(rows), inp)
+    assert {"Solved", "Failure"} <= {s.status for s in st}
+    # a larger batch through the same plan (threads on the host side, tiles on the device side)
+    big = inp * 40
+    _check(ctx, _brillig_circuit(), [1, 2, 3], len(rows) * 40, big)
+    # the reference's foreign-call fixtures stop at RequiresForeignCall with ip on the Brillig opcode (mod.rs:267)
+    fx = golden["acvm_js_shared"]["foreign_call"]
+    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {1: 5})
+    s = vm.solve()
+    assert (s.status, s.opcode_index) == ("RequiresForeignCall", 0)
+    assert vm.witness_map() == {1: 5}
