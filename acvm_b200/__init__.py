@@ -4,6 +4,7 @@ The product is libacvm_b200.so (hand-written sm_100a CUDA + C++ host, C ABI in i
 this package is the thin Python mirror of that ABI.  Importing the solver without the built
 library raises ImportError -- there is no CPU implementation behind it.
 """
-from .solver import ACVM, AcvmError, CompiledCircuit, Context, DeviceBatch, InstanceStatus, compile_plan_host, lib  # noqa: F401
+from .solver import (ACVM, AcvmError, CompiledCircuit, Context, DeviceBatch, InstanceStatus, compile_plan_host,  # noqa: F401
+                     compress_witness_map, decompress_witness_map, lib)
 
 __all__ = ["ACVM", "AcvmError", "CompiledCircuit", "Context", "DeviceBatch", "InstanceStatus", "compile_plan_host", "lib"]

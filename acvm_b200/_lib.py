@@ -73,6 +73,10 @@ def load():
         "acvmb_vm_num_witnesses": (C.c_int, [vp, u32p]),
         "acvmb_vm_witness": (C.c_int, [vp, C.c_uint32, C.c_char_p, C.POINTER(C.c_int)]),
         "acvmb_vm_finalize": (C.c_int, [vp, vp, vp, C.c_uint32]),
+        "acvmb_vm_pending_foreign_call": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p, u32p, C.c_uint32, vp, C.c_uint32, u32p]),
+        "acvmb_vm_resolve_foreign_call": (C.c_int, [vp, C.c_uint32, u32p, C.c_char_p]),
+        "acvmb_witness_map_compress": (C.c_int, [u32p, C.c_char_p, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "acvmb_witness_map_decompress": (C.c_int, [C.c_char_p, C.c_size_t, u32p, vp, C.c_uint32, u32p]),
         "acvmb_fixed_base_scalar_mul": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_pedersen": (C.c_int, [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_sha256": (C.c_int, [vp, C.c_char_p, C.c_uint32, C.c_uint32, vp]),

@@ -152,6 +152,14 @@ class CircuitBuilder:
         self._vw(outputs)
         self.n_opcodes += 1
 
+    def hash_to_field(self, inputs, output):
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["HashToField128Security"])
+        self._vfi(inputs)
+        self.w.u32(output)
+        self._see(output)
+        self.n_opcodes += 1
+
     def keccak_var(self, inputs, var_message_size, outputs):
         self.w.u32(1)
         self.w.u32(BLACKBOX_TAGS["Keccak256VariableLength"])
@@ -406,3 +414,90 @@ def synthetic_inputs(batch, n_inputs=N_INPUTS, seed_id=1, first_instance=0):
         for k in range(n_inputs):
             out[(i * n_inputs + k) * 32:(i * n_inputs + k + 1) * 32] = rng.field().to_bytes(32, "big")
     return bytes(out)
+
+
+# ---- BASELINE.json configs 2-4 as concrete synthetic circuits ------------------------------------
+def pedersen_chain_circuit(n_calls, n_fresh=64):
+    """Config 2: `n_calls` chained Pedersen{[prev.x, fresh_i], domain_separator 0}; fresh_i cycles over `n_fresh` inputs."""
+    b = CircuitBuilder()
+    inputs = list(range(1, n_fresh + 2))        # w1 = chain seed, w2.. = fresh values
+    prev, nxt = 1, n_fresh + 2
+    for i in range(n_calls):
+        b.pedersen([(prev, 254), (2 + (i % n_fresh), 254)], 0, (nxt, nxt + 1))
+        prev, nxt = nxt, nxt + 2
+    b.private_parameters = inputs
+    return b.to_bytes(), inputs, nxt
+
+
+def hash_chain_circuit(n_calls, n_fresh=32):
+    """Config 3: `n_calls` hash calls alternating SHA256 / Keccak256 over 64 byte-witnesses = previous 32-byte digest ||
+    32 fresh bytes (the fresh bytes cycle over `n_fresh` byte-valued inputs instead of 32 new inputs per call)."""
+    b = CircuitBuilder()
+    inputs = list(range(1, 32 + n_fresh + 1))   # w1..w32 = initial "digest", then the fresh byte pool
+    prev = list(range(1, 33))
+    pool = list(range(33, 33 + n_fresh))
+    nxt = 33 + n_fresh
+    for i in range(n_calls):
+        fresh = [pool[(i * 7 + k) % n_fresh] for k in range(32)]
+        outs = list(range(nxt, nxt + 32))
+        b.hash256("SHA256" if i % 2 == 0 else "Keccak256", [(w, 8) for w in prev + fresh], outs)
+        prev, nxt = outs, nxt + 32
+    b.private_parameters = inputs
+    return b.to_bytes(), inputs, nxt
+
+
+def mixed_circuit(n_ops, seed_id=4, window=64):
+    """Config 4: 93% dense arithmetic gates, 4% RANGE/AND/XOR (32-bit), 2% SHA256/Keccak256 over 64 byte-witnesses,
+    1% Pedersen(2)/FixedBaseScalarMul.  Returns (bytes, inputs, n_witnesses, counts)."""
+    rng = SplitMix64(SEED_BASE + seed_id)
+    b = CircuitBuilder()
+    n_in = N_INPUTS
+    fields = list(range(n_in))          # witnesses holding arbitrary field values (most recent last)
+    words = []                          # witnesses known to be < 2^32
+    counts = dict(arith=0, logic=0, range=0, hash=0, pedersen=0, fixed_base=0)
+    nxt = n_in
+
+    def pick(pool):
+        lo = max(0, len(pool) - window)
+        return pool[lo + rng.below(len(pool) - lo)]
+
+    for _ in range(n_ops):
+        k = rng.below(100)
+        if k < 93 or (k < 97 and len(fields) < 2):
+            a, c = pick(fields), pick(fields)
+            qm, ql, qr, qo, qc = (rng.nonzero_field() for _ in range(5))
+            b.arithmetic([(qm, a, c)], [(ql, a), (qr, c), (qo, nxt)], qc)
+            fields.append(nxt)
+            nxt += 1
+            counts["arith"] += 1
+        elif k < 97:
+            a, c = pick(fields), pick(fields)
+            sel = rng.below(3)
+            if sel == 2 and words:
+                b.range((pick(words), 32))
+                counts["range"] += 1
+            else:
+                b.logic("AND" if sel == 0 else "XOR", (a, 32), (c, 32), nxt)
+                words.append(nxt)
+                fields.append(nxt)
+                nxt += 1
+                counts["logic"] += 1
+        elif k < 99:
+            ins = [(pick(fields), 8) for _ in range(64)]
+            outs = list(range(nxt, nxt + 32))
+            b.hash256("SHA256" if rng.below(2) else "Keccak256", ins, outs)
+            words += outs
+            fields += outs
+            nxt += 32
+            counts["hash"] += 1
+        else:
+            if rng.below(2) or len(words) < 2:
+                b.pedersen([(pick(fields), 254), (pick(fields), 254)], 0, (nxt, nxt + 1))
+                counts["pedersen"] += 1
+            else:
+                b.fixed_base_scalar_mul((pick(words), 128), (pick(words), 128), (nxt, nxt + 1))
+                counts["fixed_base"] += 1
+            fields += [nxt, nxt + 1]
+            nxt += 2
+    b.private_parameters = list(range(n_in))
+    return b.to_bytes(), list(range(n_in)), nxt, counts

@@ -25,6 +25,7 @@ struct Result {
     Status status = Status::Finished;
     std::string message;
     std::vector<uint64_t> call_stack;   // Failure: call stack + failing pc (lib.rs:125-132)
+    std::vector<std::vector<U256>> fc_inputs;   // ForeignCallWait: resolved inputs (lib.rs:198-202)
 };
 
 constexpr size_t MAX_REGISTERS = 1u << 16;
@@ -310,6 +311,18 @@ struct VM {
                             Result r;
                             r.status = Status::ForeignCallWait;
                             r.message = o.function;
+                            for (const RegOrMem& in : o.inputs) {   // get_register_value_or_memory_values (lib.rs:334-354)
+                                std::vector<U256> vals;
+                                if (in.kind == 0) {
+                                    vals.push_back(get(in.a));
+                                } else {
+                                    size_t p = to_usize(get(in.a));
+                                    size_t n = in.kind == 1 ? (size_t)in.b : to_usize(get(in.b));
+                                    if (p + n > mem.size()) throw PanicEx{"memory read out of bounds"};
+                                    vals.assign(mem.begin() + p, mem.begin() + p + n);
+                                }
+                                r.fc_inputs.push_back(std::move(vals));
+                            }
                             return r;
                         }
                         const auto& values = b.foreign_call_results[fc_counter];

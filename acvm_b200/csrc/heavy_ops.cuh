@@ -44,6 +44,9 @@ __device__ __forceinline__ void hv_fail(unsigned long long* fail, uint32_t opcod
     atomicMin(fail, key);
 }
 
+template <int T>
+__device__ __forceinline__ void insert_value_dev(const OpRec* r, bool check, uint32_t slot, const Fe& v, uint4* cb, unsigned long long* fail);
+
 // write digest byte i to output witness i (insert_value semantics when the output is pre-assigned)
 template <int T>
 __device__ __forceinline__ void write_digest(const uint8_t* digest, const uint32_t* outs, uint32_t check_mask, uint4* cb,
@@ -150,6 +153,93 @@ __device__ __noinline__ void exec_sha256(const OpRec* r, uint4* cb, unsigned lon
 #pragma unroll
     for (int i = 0; i < 32; ++i) digest[i] = (uint8_t)(h[i >> 2] >> (24 - 8 * (i & 3)));
     write_digest<T>(digest, outs, check_mask, cb, fail, r->w[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BLAKE2s-256, unkeyed (RFC 7693) -- Blake2s opcode and HashToField128Security (blackbox_solver/src/lib.rs:52-55,62-65)
+// ---------------------------------------------------------------------------------------------
+__constant__ uint8_t BLAKE2S_SIGMA[10][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+
+__device__ __noinline__ void blake2s_compress(uint32_t* h, const uint32_t* m, unsigned long long t, bool last) {
+    const uint32_t IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = h[i]; v[i + 8] = IV[i]; }
+    v[12] ^= (uint32_t)t;
+    v[13] ^= (uint32_t)(t >> 32);
+    if (last) v[14] = ~v[14];
+#define B2S_G(a, b, c, d, x, y)                                       \
+    v[a] = v[a] + v[b] + (x); v[d] = rotr32(v[d] ^ v[a], 16);          \
+    v[c] = v[c] + v[d];       v[b] = rotr32(v[b] ^ v[c], 12);          \
+    v[a] = v[a] + v[b] + (y); v[d] = rotr32(v[d] ^ v[a], 8);           \
+    v[c] = v[c] + v[d];       v[b] = rotr32(v[b] ^ v[c], 7);
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        const uint8_t* s = BLAKE2S_SIGMA[r];
+        B2S_G(0, 4, 8, 12, m[s[0]], m[s[1]])
+        B2S_G(1, 5, 9, 13, m[s[2]], m[s[3]])
+        B2S_G(2, 6, 10, 14, m[s[4]], m[s[5]])
+        B2S_G(3, 7, 11, 15, m[s[6]], m[s[7]])
+        B2S_G(0, 5, 10, 15, m[s[8]], m[s[9]])
+        B2S_G(1, 6, 11, 12, m[s[10]], m[s[11]])
+        B2S_G(2, 7, 8, 13, m[s[12]], m[s[13]])
+        B2S_G(3, 4, 9, 14, m[s[14]], m[s[15]])
+    }
+#undef B2S_G
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[i + 8];
+}
+
+// to_field: one output = digest reduced mod p (HashToField128Security); else 32 byte outputs (Blake2s)
+template <int T>
+__device__ __noinline__ void exec_blake2s(const OpRec* r, bool to_field, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n_in = pl[0], check_mask = pl[1];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    uint32_t h[8] = {0x6A09E667u ^ 0x01010020u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    uint32_t blk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) blk[i] = 0;
+    uint32_t pos = 0;
+    unsigned long long total = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_in; ++k) {
+        Fe v;
+        hv_load<T>(v, cb, ins[2 * k]);
+        uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;
+        if (nbytes > 32) nbytes = 32;
+#pragma unroll 1
+        for (uint32_t j = 0; j < nbytes; ++j) {
+            if (pos == 64) {   // a full block is only compressed once more input follows (the last block carries the final flag)
+                blake2s_compress(h, blk, total, false);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) blk[i] = 0;
+                pos = 0;
+            }
+            blk[pos >> 2] |= ((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF) << (8 * (pos & 3));
+            ++pos;
+            ++total;
+        }
+    }
+    blake2s_compress(h, blk, total, true);
+    if (to_field) {
+        Fe f;   // from_be_bytes_reduce(digest): digest byte 0 is the most significant
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f.l[7 - k] = __byte_perm(h[k], 0, 0x0123);
+        fr::reduce_256(f);
+        insert_value_dev<T>(r, check_mask & 1, outs[0], f, cb, fail);
+    } else {
+        uint8_t digest[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) digest[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+        write_digest<T>(digest, outs, check_mask, cb, fail, r->w[1]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -775,6 +865,12 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_KECCAK256:
             exec_keccak256<T>(r, cb, fail, payload);
+            break;
+        case MK_BLAKE2S:
+            exec_blake2s<T>(r, false, cb, fail, payload);
+            break;
+        case MK_HASH_TO_FIELD:
+            exec_blake2s<T>(r, true, cb, fail, payload);
             break;
         case MK_FIXED_BASE:
             exec_fixed_base<T>(r, flags, cb, fail);

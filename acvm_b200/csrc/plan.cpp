@@ -811,7 +811,40 @@ struct Compiler {
                 plan.stats.alg_bytes += 32;
                 return true;
             }
+            case BB_HashToField128Security: {
+                for (uint32_t k = 0; k < b.n_message_inputs; ++k)
+                    if (b.inputs[k].num_bits > 256) {
+                        fail_static(idx, EK_REFERENCE_PANIC, 0, "hash input wider than 256 bits");
+                        return false;
+                    }
+                std::vector<uint32_t> rd, wr;
+                uint32_t off = (uint32_t)plan.payload.size();
+                uint32_t out = b.outputs[0];
+                plan.payload.push_back(b.n_message_inputs);
+                plan.payload.push_back(known[out] ? 1u : 0u);
+                plan.payload.push_back(NONE);
+                plan.payload.push_back(0);
+                for (uint32_t k = 0; k < b.n_message_inputs; ++k) {
+                    plan.payload.push_back(b.inputs[k].witness);
+                    plan.payload.push_back(b.inputs[k].num_bits);
+                    rd.push_back(b.inputs[k].witness);
+                    plan.stats.alg_bytes += 32;
+                }
+                plan.payload.push_back(out);
+                if (known[out]) rd.push_back(out);
+                wr.push_back(out);
+                r.w[0] = MK_HASH_TO_FIELD;
+                r.w[1] = idx;
+                r.w[2] = r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+                r.w[7] = off;
+                place_heavy(r, rd, wr);
+                if (!known[out]) mark_assigned(out, idx);
+                ++plan.stats.n_hash;
+                plan.stats.alg_bytes += 32;
+                return true;
+            }
             case BB_SHA256:
+            case BB_Blake2s:
             case BB_Keccak256:
             case BB_Keccak256VariableLength: {
                 if (b.outputs.size() != 32) {  // hash.rs:39-44
@@ -845,7 +878,7 @@ struct Compiler {
                     wr.push_back(b.outputs[i]);
                     plan.stats.alg_bytes += 32;
                 }
-                r.w[0] = (b.func == BB_SHA256 ? MK_SHA256 : MK_KECCAK256) | (GF_HEAVY << 8);
+                r.w[0] = (b.func == BB_SHA256 ? MK_SHA256 : b.func == BB_Blake2s ? MK_BLAKE2S : MK_KECCAK256) | (GF_HEAVY << 8);
                 r.w[1] = idx;
                 r.w[2] = r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
                 r.w[7] = off;

@@ -46,6 +46,8 @@ enum MicroKind : uint32_t {
     MK_QUOTIENT = 15,     // x = a, y = b, w1 = predicate|NONE, out = q, w2 = r                     (directives/mod.rs:28-59)
     MK_MEM_READ = 16,     // x = index, w1 = predicate|NONE, out = witness; payload[aux..]: base, len  (memory_op.rs:62-110)
     MK_MEM_WRITE = 17,    // x = index, y = value, w1 = predicate|NONE;     payload[aux..]: base, len  (memory_op.rs:111-123)
+    MK_BLAKE2S = 18,      // same payload as MK_SHA256                                  (hash.rs:28-48 -> blake2 0.10.6)
+    MK_HASH_TO_FIELD = 19,// payload: n_in, check, NONE, 0, (witness,num_bits)*, 1 output: blake2s digest reduced mod p (hash.rs:13-24)
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
 };
 

@@ -80,6 +80,10 @@ struct acvmb_batch {
     uint8_t* d_stage_present[2] = {nullptr, nullptr};
     size_t stage_present_bytes = 0;
     uint32_t* d_mu = nullptr;            // per-lane assignment table of value-dependent witnesses
+    // pending Brillig foreign call of instance 0 (kept for the single-instance ACVM mirror)
+    bool fc_pending = false;
+    std::string fc_function;
+    std::vector<std::vector<U256>> fc_inputs;
     uint32_t* d_out_ids = nullptr;
     size_t out_ids_cap = 0;
     size_t stage_bytes = 0;
@@ -107,6 +111,9 @@ struct acvmb_batch {
 struct acvmb_vm {
     acvmb_circuit* c = nullptr;
     acvmb_batch* b = nullptr;
+    bool fc_pending = false;
+    std::string fc_function;
+    std::vector<std::vector<U256>> fc_inputs;
     std::vector<uint8_t> inputs;      // [n_initial][32]
     acvmb_status status{ACVMB_IN_PROGRESS, 0, 0, 0};
     std::vector<uint8_t> witness;     // dense [num_witnesses][32] after solve
@@ -599,6 +606,11 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
                 }
                 if (r.status == bvm::Status::ForeignCallWait) {
                     fail[i] = std::min(fail[i], fail_key(opcode, 0xF, 0));   // decoded as ACVMB_REQUIRES_FOREIGN_CALL
+                    if (i == 0) {
+                        b->fc_pending = true;
+                        b->fc_function = r.message;
+                        b->fc_inputs = std::move(r.fc_inputs);
+                    }
                     continue;
                 }
                 bool bad = false;
@@ -885,7 +897,17 @@ extern "C" int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out) {
     if (!vm->solved_once) {
         vm->witness.assign((size_t)vm->c->plan.num_witnesses * 32, 0);
         vm->present.assign((size_t)vm->c->plan.num_witnesses, 0);
-        int rc = acvmb_solve_batch_ex(vm->c, 1, vm->inputs.data(), nullptr, 0, vm->witness.data(), vm->present.data(), &vm->status);
+        acvmb_batch* b = nullptr;
+        int rc = acvmb_batch_create(vm->c, 1, &b);
+        if (rc) return rc;
+        rc = acvmb_batch_upload(b, vm->inputs.data());
+        if (!rc) rc = acvmb_batch_run(b, nullptr);
+        if (!rc) rc = acvmb_batch_status(b, &vm->status);
+        if (!rc) rc = acvmb_batch_download_ex(b, 0, 1, nullptr, 0, vm->witness.data(), vm->present.data());
+        vm->fc_pending = b->fc_pending && vm->status.code == ACVMB_REQUIRES_FOREIGN_CALL;
+        vm->fc_function = b->fc_function;
+        vm->fc_inputs = b->fc_inputs;
+        acvmb_batch_destroy(b);
         if (rc) return rc;
         vm->solved_once = true;
     }
@@ -1145,6 +1167,91 @@ extern "C" int acvmb_brillig_run_host(const uint8_t* gz, size_t len, uint32_t op
                 if (k < n_out_values) hf::to_be_bytes(vm.mem[p], out_values_be32 + (size_t)k * 32);
             }
         }
+    }
+    return ACVMB_OK;
+}
+
+// ACVM::get_pending_foreign_call (acvm/src/pwg/mod.rs:197-203): name + resolved inputs of the call the VM is waiting on.
+// input_lens[i] = number of values of input i; values are flattened in order.
+extern "C" int acvmb_vm_pending_foreign_call(const acvmb_vm* vm, char* function, size_t function_cap, uint32_t* n_inputs,
+                                             uint32_t* input_lens, uint32_t max_inputs, uint8_t* values_be32, uint32_t max_values,
+                                             uint32_t* n_values) {
+    if (!vm || !n_inputs || !n_values) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (!vm->fc_pending) return set_err(ACVMB_ERR_STATE, "no pending foreign call");
+    if (function && function_cap) snprintf(function, function_cap, "%s", vm->fc_function.c_str());
+    *n_inputs = (uint32_t)vm->fc_inputs.size();
+    uint32_t k = 0;
+    for (size_t i = 0; i < vm->fc_inputs.size(); ++i) {
+        if (input_lens && i < max_inputs) input_lens[i] = (uint32_t)vm->fc_inputs[i].size();
+        for (const U256& v : vm->fc_inputs[i]) {
+            if (values_be32 && k < max_values) hf::to_be_bytes(v, values_be32 + (size_t)k * 32);
+            ++k;
+        }
+    }
+    *n_values = k;
+    return ACVMB_OK;
+}
+
+// ACVM::resolve_pending_foreign_call (acvm/src/pwg/mod.rs:206-228): the result is appended to the Brillig opcode that made
+// the call and execution resumes (the reference re-runs that opcode's VM from pc 0 and replays recorded results, :214-228;
+// this mirror re-solves the whole instance, which is observationally the same).  out_lens[i] == 0xFFFFFFFF marks a
+// ForeignCallOutput::Single, any other value an Array of that many values.
+extern "C" int acvmb_vm_resolve_foreign_call(acvmb_vm* vm, uint32_t n_outputs, const uint32_t* out_lens, const uint8_t* values_be32) {
+    if (!vm || (n_outputs && (!out_lens || !values_be32))) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (!vm->fc_pending || vm->status.code != ACVMB_REQUIRES_FOREIGN_CALL || !vm->c->has_circuit)
+        return set_err(ACVMB_ERR_STATE, "ACVM is not expecting a foreign call response as no call was made");   // mod.rs:207-209 panics
+    Opcode& op = vm->c->circuit.opcodes[vm->status.opcode_index];
+    std::vector<ForeignCallOutput> res;
+    size_t k = 0;
+    for (uint32_t i = 0; i < n_outputs; ++i) {
+        ForeignCallOutput o;
+        o.is_array = out_lens[i] != 0xFFFFFFFFu;
+        uint32_t cnt = o.is_array ? out_lens[i] : 1;
+        for (uint32_t j = 0; j < cnt; ++j, ++k) o.values.push_back(hf::from_be_bytes_reduce(values_be32 + k * 32, 32));
+        res.push_back(std::move(o));
+    }
+    op.brillig.foreign_call_results.push_back(std::move(res));
+    vm->fc_pending = false;
+    vm->solved_once = false;
+    vm->status = acvmb_status{ACVMB_IN_PROGRESS, 0, vm->status.opcode_index, 0};
+    return ACVMB_OK;
+}
+
+// WitnessMap (de)compression: gzip(bincode(BTreeMap<Witness, FieldElement>)) (acir/src/native_types/witness_map.rs:108-146)
+extern "C" int acvmb_witness_map_compress(const uint32_t* witness_idx, const uint8_t* values_be32, uint32_t n, uint8_t* out, size_t cap,
+                                          size_t* needed) {
+    if ((n && (!witness_idx || !values_be32)) || !needed) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    std::vector<std::pair<uint32_t, U256>> wm;
+    for (uint32_t i = 0; i < n; ++i) wm.emplace_back(witness_idx[i], hf::from_be_bytes_reduce(values_be32 + (size_t)i * 32, 32));
+    std::sort(wm.begin(), wm.end(), [](const auto& a, const auto& b) { return a.first < b.first; });   // BTreeMap order
+    std::vector<uint8_t> gz;
+    try {
+        gz = encode_witness_map(wm);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    *needed = gz.size();
+    if (!out) return ACVMB_OK;
+    if (cap < gz.size()) return set_err(ACVMB_ERR_INVALID_ARG, "buffer too small");
+    memcpy(out, gz.data(), gz.size());
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_witness_map_decompress(const uint8_t* gz, size_t len, uint32_t* witness_idx, uint8_t* values_be32, uint32_t cap,
+                                            uint32_t* n) {
+    if (!gz || !n) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    std::vector<std::pair<uint32_t, U256>> wm;
+    try {
+        wm = decode_witness_map(gz, len);
+    } catch (const std::exception& e) {
+        return set_err(ACVMB_ERR_DECODE, e.what());
+    }
+    *n = (uint32_t)wm.size();
+    if (!witness_idx || !values_be32) return ACVMB_OK;
+    if (cap < wm.size()) return set_err(ACVMB_ERR_INVALID_ARG, "buffer too small");
+    for (size_t i = 0; i < wm.size(); ++i) {
+        witness_idx[i] = wm[i].first;
+        hf::to_be_bytes(wm[i].second, values_be32 + i * 32);
     }
     return ACVMB_OK;
 }

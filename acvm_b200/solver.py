@@ -298,6 +298,34 @@ class ACVM:
                 out[w] = int.from_bytes(buf.raw, "big")
         return out
 
+    def get_pending_foreign_call(self):
+        """ACVM::get_pending_foreign_call: (function, [[values of input 0], ...]) or None."""
+        if self.get_status().status != "RequiresForeignCall":
+            return None
+        name = C.create_string_buffer(256)
+        n_in, n_val = C.c_uint32(), C.c_uint32()
+        lens = (C.c_uint32 * 64)()
+        vals = C.create_string_buffer(4096 * 32)
+        _check(lib().acvmb_vm_pending_foreign_call(self._h, name, 256, C.byref(n_in), lens, 64, vals, 4096, C.byref(n_val)))
+        out, k = [], 0
+        for i in range(n_in.value):
+            out.append([int.from_bytes(vals.raw[(k + j) * 32:(k + j + 1) * 32], "big") for j in range(lens[i])])
+            k += lens[i]
+        return name.value.decode(), out
+
+    def resolve_pending_foreign_call(self, outputs):
+        """outputs: list of int (ForeignCallOutput::Single) or list of ints (ForeignCallOutput::Array)."""
+        lens, flat = [], []
+        for o in outputs:
+            if isinstance(o, int):
+                lens.append(0xFFFFFFFF)
+                flat.append(o)
+            else:
+                lens.append(len(o))
+                flat += list(o)
+        buf = b"".join(int(v).to_bytes(32, "big") for v in flat)
+        _check(lib().acvmb_vm_resolve_foreign_call(self._h, len(lens), _u32_array(lens), buf))
+
     def finalize(self) -> Dict[int, int]:
         n = C.c_uint32()
         _check(lib().acvmb_vm_num_witnesses(self._h, C.byref(n)))
@@ -316,6 +344,26 @@ class ACVM:
             self.close()
         except Exception:
             pass
+
+
+def compress_witness_map(wm: Dict[int, int]) -> bytes:
+    """WitnessMap -> gzip(bincode) bytes the reference's `WitnessMap::try_from(&[u8])` accepts (witness_map.rs:108-146)."""
+    keys = sorted(wm)
+    vals = b"".join(int(wm[k]).to_bytes(32, "big") for k in keys)
+    need = C.c_size_t()
+    _check(lib().acvmb_witness_map_compress(_u32_array(keys), vals, len(keys), None, 0, C.byref(need)))
+    buf = (C.c_uint8 * need.value)()
+    _check(lib().acvmb_witness_map_compress(_u32_array(keys), vals, len(keys), buf, need.value, C.byref(need)))
+    return bytes(buf[:need.value])
+
+
+def decompress_witness_map(data: bytes) -> Dict[int, int]:
+    n = C.c_uint32()
+    _check(lib().acvmb_witness_map_decompress(data, len(data), None, None, 0, C.byref(n)))
+    idx = (C.c_uint32 * max(1, n.value))()
+    vals = C.create_string_buffer(max(1, n.value) * 32)
+    _check(lib().acvmb_witness_map_decompress(data, len(data), idx, vals, n.value, C.byref(n)))
+    return {idx[i]: int.from_bytes(vals.raw[i * 32:(i + 1) * 32], "big") for i in range(n.value)}
 
 
 def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int = 16):

@@ -156,6 +156,19 @@ int acvmb_vm_witness(const acvmb_vm* vm, uint32_t witness, uint8_t out_be32[32],
 /* ACVM::finalize: ACVMB_ERR_STATE unless Solved (the reference panics); dense map + presence flags */
 int acvmb_vm_finalize(acvmb_vm* vm, uint8_t* out_be32, uint8_t* present, uint32_t n);
 
+/* ACVM::get_pending_foreign_call / resolve_pending_foreign_call (acvm/src/pwg/mod.rs:197-228).  out_lens[i] == 0xFFFFFFFF
+ * marks a ForeignCallOutput::Single, any other value an Array of that many values; values are flattened in order. */
+int acvmb_vm_pending_foreign_call(const acvmb_vm* vm, char* function, size_t function_cap, uint32_t* n_inputs,
+                                  uint32_t* input_lens, uint32_t max_inputs, uint8_t* values_be32, uint32_t max_values,
+                                  uint32_t* n_values);
+int acvmb_vm_resolve_foreign_call(acvmb_vm* vm, uint32_t n_outputs, const uint32_t* out_lens, const uint8_t* values_be32);
+
+/* WitnessMap on disk: gzip(bincode(BTreeMap<Witness, FieldElement>)) (acir/src/native_types/witness_map.rs:108-146) */
+int acvmb_witness_map_compress(const uint32_t* witness_idx, const uint8_t* values_be32, uint32_t n, uint8_t* out, size_t cap,
+                               size_t* needed);
+int acvmb_witness_map_decompress(const uint8_t* gz, size_t len, uint32_t* witness_idx, uint8_t* values_be32, uint32_t cap,
+                                 uint32_t* n);
+
 /* ---- BlackBoxFunctionSolver trait, batched (blackbox_solver/src/lib.rs:27-45) and the free hash
  * functions (:47-60).  Thin wrappers: each builds a one-opcode circuit and runs the same kernels. ---- */
 int acvmb_fixed_base_scalar_mul(acvmb_ctx* ctx, const uint8_t* low_be32, const uint8_t* high_be32, uint32_t batch,

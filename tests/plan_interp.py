@@ -11,7 +11,8 @@ RINV = pow(1 << 256, -1, P)
 NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
-          GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17)
+          GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17,
+          BLAKE2S=18, HASH_TO_FIELD=19)
 EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
@@ -99,6 +100,19 @@ def default_hooks():
             return w
         return run
 
+    def hash_to_field(cols, hdr, payload, record_fail):
+        opcode, off = hdr[1], hdr[7]
+        n_in, mask = payload[off], payload[off + 1]
+        ins = payload[off + 4: off + 4 + 2 * n_in]
+        out = payload[off + 4 + 2 * n_in]
+        msg = bytearray()
+        for k in range(n_in):
+            msg += cols[ins[2 * k]].to_bytes(32, "little")[:min(32, (ins[2 * k + 1] + 7) // 8)]
+        v = int.from_bytes(hashes.blake2s(bytes(msg)), "big") % P
+        if (mask & 1) and cols[out] != v:
+            record_fail(opcode, EK_UNSAT)
+        return [(out, v)]
+
     def fixed_base(cols, hdr, payload, record_fail):
         flags = hdr[0] >> 8
         opcode, ox, lo_w, hi_w, oy = hdr[1], hdr[2], hdr[3], hdr[4], hdr[5]
@@ -133,7 +147,7 @@ def default_hooks():
                 w.append((slot, v))
         return w
 
-    return {MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
+    return {MK["BLAKE2S"]: hash_hook(hashes.blake2s), MK["HASH_TO_FIELD"]: hash_to_field, MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
 
 
 def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):

@@ -174,3 +174,22 @@ def test_brillig_on_host_between_device_segments(ctx, golden):
     s = vm.solve()
     assert (s.status, s.opcode_index) == ("RequiresForeignCall", 0)
     assert vm.witness_map() == {1: 5}
+
+
+def test_foreign_call_resolution_golden(ctx, golden):
+    # acvm_js/test/shared/{foreign_call,complex_foreign_call}.ts: stall, hand back inputs, resolve, finish
+    sh = golden["acvm_js_shared"]
+    fx = sh["foreign_call"]
+    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {1: 5})
+    assert vm.solve().status == "RequiresForeignCall" and vm.instruction_pointer() == 0
+    assert vm.get_pending_foreign_call() == ("invert", [[5]])
+    vm.resolve_pending_foreign_call([int(golden["kats"]["inv5"], 16)])
+    assert vm.solve().status == "Solved"
+    assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}
+    fx = sh["complex_foreign_call"]
+    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {1: 1, 2: 2, 3: 3})
+    assert vm.solve().status == "RequiresForeignCall"
+    assert vm.get_pending_foreign_call() == ("complex", [[1, 2, 3], [6]])
+    vm.resolve_pending_foreign_call([[2, 6, 12], 6, 12])
+    assert vm.solve().status == "Solved"
+    assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}

@@ -192,3 +192,17 @@ def test_pedersen_chain_circuit(ctx):
     batch = 5
     inp = ab.synthetic_inputs(batch, n_inputs=5, seed_id=44)
     _check_circuit(ctx, data, [1, 2, 3, 4, 5], batch, inp)
+
+
+def test_blake2s_and_hash_to_field(ctx):
+    # Blake2s opcode + HashToField128Security (hash.rs:13-48; blackbox_solver/src/lib.rs:52-65)
+    b = ab.CircuitBuilder()
+    ins = [(1, 8), (2, 16), (3, 254), (4, 1), (5, 64)]
+    b.hash256("Blake2s", ins, list(range(10, 42)))
+    b.hash256("Blake2s", [(w, 8) for w in range(10, 42)] * 2 + [(1, 8)], list(range(50, 82)))   # 65 bytes: two blocks
+    b.hash256("Blake2s", [(w, 8) for w in range(10, 42)] * 2, list(range(90, 122)))             # exactly one full block
+    b.hash_to_field([(w, 8) for w in range(50, 82)], 130)
+    b.hash_to_field([], 131)
+    data = b.to_bytes()
+    batch = 6
+    _check_circuit(ctx, data, [1, 2, 3, 4, 5], batch, ab.synthetic_inputs(batch, n_inputs=5, seed_id=77))

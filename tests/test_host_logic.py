@@ -153,11 +153,14 @@ def test_plan_heavy_ops_match_oracle():
     b.logic("AND", (3, 120), (2, 120), 91)
     b.fixed_base_scalar_mul((90, 128), (91, 128), (92, 93))
     b.keccak_var([(w, 8) for w in range(50, 60)], (94, 32), list(range(100, 132)))
+    b.hash256("Blake2s", [(w, 8) for w in range(100, 132)] + [(1, 254), (2, 254), (3, 70)], list(range(140, 172)))
+    b.hash_to_field([(w, 8) for w in range(140, 172)], 180)
+    b.hash_to_field([], 181)
     data = b.to_bytes()
     inp = ab.synthetic_inputs(2, n_inputs=3, seed_id=4)
     rows = [inp[i * 96:(i + 1) * 96] + v.to_bytes(32, "big") for i, v in enumerate((4, 11))]
     info = _interp_vs_oracle(data, [1, 2, 3, 94], b"".join(rows), 2)
-    assert info["needs_full_kernel"] == 1 and info["n_hash"] == 3 and info["n_curve"] == 1
+    assert info["needs_full_kernel"] == 1 and info["n_hash"] == 6 and info["n_curve"] == 1
 
 
 def _vd_circuit():
@@ -393,3 +396,12 @@ def test_cpp_brillig_vm_matches_oracle_vm():
             assert (sc, pcc if sc == 1 else 0) == (so, pco if so == 1 else 0), (idx, ins)
             if so == 0:
                 assert oc_ == oo, (idx, ins)
+
+
+def test_witness_map_compression_golden(golden):  # acvm_js/test/shared/witness_compression.ts
+    fx = golden["acvm_js_shared"]["witness_compression"]
+    expected = {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}
+    assert acvm_b200.decompress_witness_map(bytes(fx["expectedCompressedWitnessMap"])) == expected
+    ours = acvm_b200.compress_witness_map(expected)
+    assert acvm_b200.decompress_witness_map(ours) == expected
+    assert acir.decode_witness_map(ours) == expected        # the oracle's independent decoder accepts our bytes
