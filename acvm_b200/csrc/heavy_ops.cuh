@@ -70,6 +70,39 @@ __device__ __forceinline__ void write_digest(const uint8_t* digest, const uint32
     }
 }
 
+// Message gathering shared by the hash kernels (get_hash_input, hash.rs:51-66): input k contributes its low
+// ceil(num_bits/8) bytes, little-endian.  Each input is a separate witness column, i.e. a separate dependent global
+// load; they are issued in groups of 8 before any byte is consumed so the L2 latencies overlap instead of adding up.
+// `take` bounds the number of bytes pushed (Keccak256VariableLength).
+template <int T, typename Push>
+__device__ __forceinline__ void gather_message(const uint4* cb, const uint32_t* ins, uint32_t n_in, unsigned long long take, Push push) {
+#pragma unroll 1
+    for (uint32_t k0 = 0; k0 < n_in; k0 += 8) {
+        uint32_t w[8], nb[8], low[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t k = k0 + g < n_in ? k0 + g : n_in - 1;
+            w[g] = ins[2 * k];
+            uint32_t b = (ins[2 * k + 1] + 7) >> 3;
+            nb[g] = b > 32 ? 32 : b;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) low[g] = reinterpret_cast<const uint32_t*>(cb + (size_t)w[g] * (2 * T))[0];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (k0 + g >= n_in) break;
+            if (nb[g] <= 4) {
+                for (uint32_t j = 0; j < nb[g] && take; ++j, --take) push((low[g] >> (8 * j)) & 0xFF);
+            } else {
+                Fe v;
+                hv_load<T>(v, cb, w[g]);
+#pragma unroll 1
+                for (uint32_t j = 0; j < nb[g] && take; ++j, --take) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SHA-256
 // ---------------------------------------------------------------------------------------------
@@ -133,16 +166,11 @@ __device__ __noinline__ void exec_sha256(const OpRec* r, uint4* cb, unsigned lon
             pos = 0;
         }
     };
-#pragma unroll 1
     for (uint32_t k = 0; k < n_in; ++k) {
-        Fe v;
-        hv_load<T>(v, cb, ins[2 * k]);
         uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;   // fetch_nearest_bytes: low ceil(bits/8) bytes, little-endian
-        if (nbytes > 32) nbytes = 32;
-#pragma unroll 1
-        for (uint32_t j = 0; j < nbytes; ++j) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
-        total += nbytes;
+        total += nbytes > 32 ? 32 : nbytes;
     }
+    if (n_in) gather_message<T>(cb, ins, n_in, ~0ULL, push);
     push(0x80);
     while (pos != 56) push(0);
     unsigned long long bits = total * 8;
@@ -208,25 +236,18 @@ __device__ __noinline__ void exec_blake2s(const OpRec* r, bool to_field, uint4* 
     for (int i = 0; i < 16; ++i) blk[i] = 0;
     uint32_t pos = 0;
     unsigned long long total = 0;
-#pragma unroll 1
-    for (uint32_t k = 0; k < n_in; ++k) {
-        Fe v;
-        hv_load<T>(v, cb, ins[2 * k]);
-        uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;
-        if (nbytes > 32) nbytes = 32;
-#pragma unroll 1
-        for (uint32_t j = 0; j < nbytes; ++j) {
-            if (pos == 64) {   // a full block is only compressed once more input follows (the last block carries the final flag)
-                blake2s_compress(h, blk, total, false);
+    auto push = [&](uint32_t byte) {
+        if (pos == 64) {   // a full block is only compressed once more input follows (the last block carries the final flag)
+            blake2s_compress(h, blk, total, false);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) blk[i] = 0;
-                pos = 0;
-            }
-            blk[pos >> 2] |= ((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF) << (8 * (pos & 3));
-            ++pos;
-            ++total;
+            for (int i = 0; i < 16; ++i) blk[i] = 0;
+            pos = 0;
         }
-    }
+        blk[pos >> 2] |= byte << (8 * (pos & 3));
+        ++pos;
+        ++total;
+    };
+    if (n_in) gather_message<T>(cb, ins, n_in, ~0ULL, push);
     blake2s_compress(h, blk, total, true);
     if (to_field) {
         Fe f;   // from_be_bytes_reduce(digest): digest byte 0 is the most significant
@@ -318,15 +339,7 @@ __device__ __noinline__ void exec_keccak256(const OpRec* r, uint4* cb, unsigned 
             pos = 0;
         }
     };
-#pragma unroll 1
-    for (uint32_t k = 0; k < n_in && take; ++k) {
-        Fe v;
-        hv_load<T>(v, cb, ins[2 * k]);
-        uint32_t nbytes = (ins[2 * k + 1] + 7) >> 3;
-        if (nbytes > 32) nbytes = 32;
-#pragma unroll 1
-        for (uint32_t j = 0; j < nbytes && take; ++j, --take) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
-    }
+    if (n_in) gather_message<T>(cb, ins, n_in, take, push);
     // pad10*1 with the Keccak domain byte 0x01: the two pad bits may share one byte (0x81)
     st[pos >> 3] ^= 0x01ULL << (8 * (pos & 7));
     st[16] ^= 0x8000000000000000ULL;   // byte 135

@@ -72,6 +72,12 @@ class Scheduler {
             uint32_t s = steps_[i];
             stream[(size_t)s * S_ + cursor[s]++] = ops_[i];
         }
+        // slots of one step are independent: order them by (kind, flags) so that the slots sharing a warp run the same
+        // code path (a warp covers 32/T consecutive slots); NOPs (kind 0) go last
+        for (uint32_t s = 0; s < n_steps_padded; ++s) {
+            OpRec* first = &stream[(size_t)s * S_];
+            std::stable_sort(first, first + cursor[s], [](const OpRec& x, const OpRec& y) { return x.w[0] < y.w[0]; });
+        }
     }
 
    private:
@@ -243,6 +249,19 @@ struct Compiler {
             r.w[5] = w1;
             r.w[6] = w2;
             r.w[7] = 0;
+            if (!(flags & GF_MUL) && (flags & GF_Y)) {
+                // all coefficients +-1 (the common case in compiled Noir): additions only
+                const U256 pm1 = hf::neg(one);
+                auto pm = [&](const U256& v) { return v == one || v == pm1; };
+                if (pm(cY) && (nlin < 1 || pm(c1)) && (nlin < 2 || pm(c2))) {
+                    flags |= GF_ADDSUB;
+                    if (cY == pm1) flags |= GF_NEG_Y;
+                    if (nlin >= 1 && c1 == pm1) flags |= GF_NEG_W1;
+                    if (nlin >= 2 && c2 == pm1) flags |= GF_NEG_W2;
+                    imad = 0;
+                    r.w[0] = kind | (flags << 8);
+                }
+            }
             if (flags & GF_MUL) {
                 put(r.c[0], hf::to_mont2(cM));
                 put(r.c[1], alpha);
@@ -259,7 +278,7 @@ struct Compiler {
             if (nlin >= 1) reads[nr++] = w1;
             if (nlin >= 2) reads[nr++] = w2;
             uint32_t K = ((flags & GF_Y) ? 1 : 0) + nlin;
-            if (K) imad += 64 * K + 72;
+            if (K && !(flags & GF_ADDSUB)) imad += 64 * K + 72;
             plan.stats.dev_imad += imad;
             // distinct operand reads
             {

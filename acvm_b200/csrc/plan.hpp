@@ -60,6 +60,8 @@ enum : uint32_t {
     GF_OUT_CHECK = 1u << 5,  // output slot already holds a value: compare instead of store (insert_value, mod.rs:338-357)
     GF_HEAVY = 1u << 6,      // needs the FULL kernel variant
     GF_OUT2_CHECK = 1u << 7, // second output (point y coordinate) already holds a value
+    GF_ADDSUB = 1u << 8,     // linear gate whose coefficients are all +-1: out = +-y +-w1 +-w2 + cC, no multiplication
+    GF_NEG_Y = 1u << 9, GF_NEG_W1 = 1u << 10, GF_NEG_W2 = 1u << 11,
 };
 
 // error kinds mirrored from OpcodeResolutionError (acvm/src/pwg/mod.rs:100-114) + reference panics

@@ -125,6 +125,20 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
                 const Fe* a[2] = {&u, &w1};
                 fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
             }
+        } else if (flags & GF_ADDSUB) {
+            // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
+            Fe y, t;
+            load_w<T>(y, cb, r->w[4]);
+            lds_fe(res, r->c[4]);
+            if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
+            if (nlin >= 1) {
+                load_w<T>(t, cb, r->w[5]);
+                if (flags & GF_NEG_W1) fr::sub_mod(res, res, t); else fr::add_mod(res, res, t);
+            }
+            if (nlin >= 2) {
+                load_w<T>(t, cb, r->w[6]);
+                if (flags & GF_NEG_W2) fr::sub_mod(res, res, t); else fr::add_mod(res, res, t);
+            }
         } else {
             Fe y;
             load_w<T>(y, cb, r->w[4]);
@@ -145,11 +159,13 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
                 }
             }
         }
-        fr::cond_sub_p(res);
-        Fe cC;
-        lds_fe(cC, r->c[4]);
-        fr::add_raw(res, res, cC);
-        fr::cond_sub_p(res);
+        if (!(flags & GF_ADDSUB)) {
+            fr::cond_sub_p(res);
+            Fe cC;
+            lds_fe(cC, r->c[4]);
+            fr::add_raw(res, res, cC);
+            fr::cond_sub_p(res);
+        }
     } else {
         lds_fe(res, r->c[4]);
     }

@@ -259,6 +259,12 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                         res += c[0] * RINV * RINV * (cols[x] + c[1]) * (cols[y] + c[2])
                         if nlin >= 1:
                             res += c[3] * RINV * cols[w1]
+                    elif flags & 256:   # GF_ADDSUB: coefficients +-1, signs in flag bits 9..11
+                        res += -cols[y] if flags & 512 else cols[y]
+                        if nlin >= 1:
+                            res += -cols[w1] if flags & 1024 else cols[w1]
+                        if nlin >= 2:
+                            res += -cols[w2] if flags & 2048 else cols[w2]
                     else:
                         res += c[1] * RINV * cols[y]
                         if nlin >= 1:
