@@ -29,3 +29,28 @@ void t_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memc
 void t_reduce(uint32_t* a) { Fe A; memcpy(A.l, a, 32); reduce_256(A); memcpy(a, A.l, 32); }
 uint32_t t_num_bits(const uint32_t* a) { Fe A; memcpy(A.l, a, 32); return num_bits(A); }
 }
+
+// ---- 9 x 29-bit carry-free representation (fr29.cuh) ----
+#include "../../acvm_b200/csrc/fr29.cuh"
+extern "C" {
+void t_dot9(int k, const uint32_t* a8, const uint32_t* b8, uint32_t* r8) {
+    fr::Fe A[4], B[4];
+    fr29::Fe9 A9[4], B9[4];
+    for (int i = 0; i < k; ++i) {
+        memcpy(A[i].l, a8 + 8 * i, 32); memcpy(B[i].l, b8 + 8 * i, 32);
+        fr29::to9(A9[i], A[i]); fr29::to9(B9[i], B[i]);
+    }
+    const fr29::Fe9* pa[4] = {&A9[0], &A9[1], &A9[2], &A9[3]};
+    const fr29::Fe9* pb[4] = {&B9[0], &B9[1], &B9[2], &B9[3]};
+    uint32_t out[9];
+    if (k == 1) fr29::mont_dot9<1>(out, pa, fr29::PtrLimbs9{pb});
+    else if (k == 2) fr29::mont_dot9<2>(out, pa, fr29::PtrLimbs9{pb});
+    else if (k == 3) fr29::mont_dot9<3>(out, pa, fr29::PtrLimbs9{pb});
+    else fr29::mont_dot9<4>(out, pa, fr29::PtrLimbs9{pb});
+    fr::Fe R; fr29::from9(R, out); memcpy(r8, R.l, 32);
+}
+void t_roundtrip9(const uint32_t* a8, uint32_t* r8) {
+    fr::Fe A, R; memcpy(A.l, a8, 32);
+    fr29::Fe9 x; fr29::to9(x, A); fr29::from9(R, x.l); memcpy(r8, R.l, 32);
+}
+}
