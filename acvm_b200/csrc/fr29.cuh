@@ -8,6 +8,12 @@
 // and once at the end.  R = 2^261 >> p also makes every lazy bound trivial: inputs up to 2^257 still give results
 // below 1.1 p.
 //
+// STATUS: measured and NOT used by the gate kernel (profiles/r1_multiplier_experiments.txt).  Although every multiply
+// is the full-rate instruction (162 IMAD.WIDE.U32 + 11 IMAD per product in SASS), the representation needs ~180 extra
+// ALU instructions per product (64-bit column shifts/adds, limb conversions), and the kernel is bound by per-warp
+// dependent-issue latency at the occupancy HBM capacity allows (4 CTAs/SM), not by the FMA pipe: the gate kernel got
+// 1.5x SLOWER (21.4 vs 14.1 ms).  Kept as a tested building block and as the record of the experiment.
+//
 // Replaces the same reference arithmetic as fr.cuh (acir_field/src/generic_ark.rs:360-406 over ark-ff Fp256).
 // fr.cuh (8 x 32, R = 2^256) remains the representation of the curve / general-gate code and of the tables.
 // The header is plain C++ (no inline asm) and compiles for the host, where tests/test_host_logic.py checks it

@@ -132,6 +132,19 @@ def test_fr_limb_algorithms_on_host(tmp_path):
             r = (ctypes.c_uint32 * 8)()
             L.t_mont_mul_split(split, arr([x]), arr([y]), r)
             assert val(r) == x * y * Rinv % P, (split, hex(x), hex(y))
+    # carry-free 9 x 29-bit representation (fr29.cuh): conversions round-trip and the K-term dot product is exact
+    Rinv261 = pow(1 << 261, -1, P)
+    for it in range(3000):
+        z = rnd.randrange(1 << 256)
+        r = (ctypes.c_uint32 * 8)()
+        L.t_roundtrip9(arr([z]), r)
+        assert val(r) == z
+        k = rnd.choice([1, 2, 3, 4])
+        A = [rnd.choice([0, 1, P - 1, 2 * P - 1, (1 << 256) - 1, rnd.randrange(P)]) for _ in range(k)]
+        B = [rnd.choice([0, 1, P - 1, 2 * P - 1, (1 << 256) - 1, rnd.randrange(P)]) for _ in range(k)]
+        L.t_dot9(k, arr(A), arr(B), r)
+        ssum = sum(x * y for x, y in zip(A, B))
+        assert val(r) % P == ssum * Rinv261 % P and val(r) < P + ssum // (1 << 261) + 1
     for it in range(1000):
         x, y, z = rnd.randrange(P), rnd.randrange(P), rnd.randrange(1 << 256)
         r = (ctypes.c_uint32 * 8)()
