@@ -119,17 +119,6 @@ inline const Consts& consts() {
     static Consts c;
     return c;
 }
-// R' = 2^261 for the 9 x 29-bit device representation: a*2^261 = (a*32)*2^256 ; a*2^522 = (a*1024)*2^512
-inline U256 to_mont261(const U256& a) { return mont_mul(mont_mul(a, consts().R2), mont_mul(from_u64_(32), consts().R2)); }
-inline U256 to_mont261_2(const U256& a) { return mont_mul(mont_mul(a, consts().R3), mont_mul(from_u64_(1024), consts().R2)); }
-inline void to_limbs29(const U256& a, uint32_t out[9]) {
-    for (int i = 0; i < 9; ++i) {
-        int bit = 29 * i, w = bit / 64, s = bit % 64;
-        uint64_t v = a.l[w] >> s;
-        if (s > 35 && w + 1 < 4) v |= a.l[w + 1] << (64 - s);
-        out[i] = (uint32_t)(v & ((1u << 29) - 1));
-    }
-}
 inline U256 to_mont(const U256& a) { return mont_mul(a, consts().R2); }      // a*R
 inline U256 to_mont2(const U256& a) { return mont_mul(a, consts().R3); }     // a*R^2
 inline U256 from_mont(const U256& a) { return mont_mul(a, consts().one); }   // a/R

@@ -262,25 +262,17 @@ struct Compiler {
                     r.w[0] = kind | (flags << 8);
                 }
             }
-            if (opt.arith29 && (flags & GF_Y) && !(flags & GF_ADDSUB)) {
-                flags |= GF_L9;
-                r.w[0] = kind | (flags << 8);
-            }
-            auto put_m = [&](uint32_t* dst, const U256& c, bool squared) {
-                if (flags & GF_L9) hf::to_limbs29(squared ? hf::to_mont261_2(c) : hf::to_mont261(c), dst);
-                else hf::to_limbs32(squared ? hf::to_mont2(c) : hf::to_mont(c), dst);
-            };
             if (flags & GF_MUL) {
-                put_m(r.m[0], cM, true);
-                put_m(r.m[1], c1, false);
-                put(r.q[0], alpha);
-                put(r.q[1], beta);
+                put(r.c[0], hf::to_mont2(cM));
+                put(r.c[1], alpha);
+                put(r.c[2], beta);
+                put(r.c[3], hf::to_mont(c1));
             } else {
-                put_m(r.m[0], cY, false);
-                put_m(r.m[1], c1, false);
-                put_m(r.m[2], c2, false);
+                put(r.c[1], hf::to_mont(cY));
+                put(r.c[2], hf::to_mont(c1));
+                put(r.c[3], hf::to_mont(c2));
             }
-            put(r.q[2], c4);
+            put(r.c[4], c4);
             if (flags & GF_MUL) reads[nr++] = x;
             if (flags & GF_Y) reads[nr++] = y;
             if (nlin >= 1) reads[nr++] = w1;

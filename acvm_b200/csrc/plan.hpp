@@ -18,18 +18,15 @@
 
 namespace acvmb {
 
-// ---- device record (240 B, 16 B aligned) ------------------------------------------------------
+// ---- device record (192 B, 16 B aligned) ------------------------------------------------------
 struct OpRec {
     uint32_t w[8];      // [0]=kind|flags<<8  [1]=acir opcode index  [2]=out slot  [3]=x  [4]=y  [5]=w1  [6]=w2  [7]=aux
-    // gate constants.  q = canonical values (8 x u32 LE), m = Montgomery-scaled multipliers, stored either as
-    // 8 x 32-bit limbs with R = 2^256 (fr.cuh path) or, with GF_L9, as 9 x 29-bit limbs with R = 2^261 (fr29.cuh path):
-    //   GF_MUL   : q0 = alpha, q1 = beta, q2 = gamma, m0 = cM*R^2, m1 = c1*R      out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma
-    //   otherwise: q2 = cC,                m0 = cY*R, m1 = c1*R, m2 = c2*R        out = cY*y + c1*w1 + c2*w2 + cC
-    uint32_t q[3][8];
-    uint32_t m[3][9];
-    uint32_t pad;
+    // gate constants (8 x u32 little-endian limbs each), layout by flag:
+    //   GF_MUL   : c0 = cM*R^2, c1 = alpha, c2 = beta, c3 = c1*R (w1), c4 = gamma     out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma
+    //   otherwise: c1 = cY*R (y), c2 = c1*R (w1), c3 = c2*R (w2), c4 = cC            out = cY*y + c1*w1 + c2*w2 + cC
+    uint32_t c[5][8];
 };
-static_assert(sizeof(OpRec) == 240, "OpRec layout");
+static_assert(sizeof(OpRec) == 192, "OpRec layout");
 
 enum MicroKind : uint32_t {
     MK_NOP = 0,
@@ -65,7 +62,6 @@ enum : uint32_t {
     GF_OUT2_CHECK = 1u << 7, // second output (point y coordinate) already holds a value
     GF_ADDSUB = 1u << 8,     // linear gate whose coefficients are all +-1: out = +-y +-w1 +-w2 + cC, no multiplication
     GF_NEG_Y = 1u << 9, GF_NEG_W1 = 1u << 10, GF_NEG_W2 = 1u << 11,
-    GF_L9 = 1u << 12,        // multipliers are 9 x 29-bit limbs, R = 2^261 (carry-free multiplier, fr29.cuh)
 };
 
 // error kinds mirrored from OpcodeResolutionError (acvm/src/pwg/mod.rs:100-114) + reference panics
@@ -135,7 +131,6 @@ struct Plan {
 };
 
 struct PlanOptions {
-    bool arith29 = true;     // gate multipliers in the carry-free 9 x 29-bit representation
     uint32_t S = 16;
     uint32_t chunk_steps = 2;
     uint32_t temp_pool = 2048;

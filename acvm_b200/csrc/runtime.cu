@@ -41,7 +41,6 @@ struct acvmb_ctx {
     uint32_t opt_S = 16;
     uint32_t opt_chunk_steps = 2;
     int opt_split = -1;
-    bool opt_arith29 = true;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
     uint64_t staging_bytes = 512ull << 20;
     uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
@@ -182,7 +181,6 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "S") ctx->opt_S = (uint32_t)value;
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
-    else if (k == "arith29") ctx->opt_arith29 = value != 0;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
     else if (k == "staging_bytes") ctx->staging_bytes = value;
     else return set_err(ACVMB_ERR_INVALID_ARG, "unknown option " + k);
@@ -233,7 +231,6 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     PlanOptions opt;
     opt.S = ctx->opt_S;
     opt.chunk_steps = ctx->opt_chunk_steps;
-    opt.arith29 = ctx->opt_arith29;
     std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
     try {
         c->plan = compile_plan(circ, inputs, opt);

@@ -14,7 +14,6 @@
 #include <stdint.h>
 
 #include "fr.cuh"
-#include "fr29.cuh"
 #include "plan.hpp"
 #include "vm_kernel.cuh"
 #ifdef ACVMB_HEAVY_OPS
@@ -107,85 +106,30 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
     Fe res;
     if (flags & GF_Y) {
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
-        if (flags & GF_L9) {
-            // carry-free path (fr29.cuh): every wide multiply is the full-rate IMAD.WIDE.U32
-            uint32_t out9[fr29::L];
-            if (flags & GF_MUL) {
-                Fe x, y, t;
-                fr29::Fe9 x9, y9, u9;
-                load_w<T>(x, cb, r->w[3]);
-                load_w<T>(y, cb, r->w[4]);
-                lds_fe(t, r->q[0]);
-                fr::add_raw(x, x, t);          // x + alpha < 2p: the 2^261 radix leaves room, no reduction
-                lds_fe(t, r->q[1]);
-                fr::add_raw(y, y, t);
-                fr29::to9(x9, x);
-                fr29::to9(y9, y);
-                const fr29::Fe9* a1[1] = {&x9};
-                const fr29::Fe9* b1[1] = {&y9};
-                fr29::mont_dot9<1>(u9.l, a1, fr29::PtrLimbs9{b1});      // (x+alpha)(y+beta) / R
-                if (nlin == 0) {
-                    const fr29::Fe9* a[1] = {&u9};
-                    fr29::mont_dot9<1>(out9, a, SmemLimbs3{r->m[0], nullptr, nullptr});
-                } else {
-                    Fe w1;
-                    fr29::Fe9 w9;
-                    load_w<T>(w1, cb, r->w[5]);
-                    fr29::to9(w9, w1);
-                    const fr29::Fe9* a[2] = {&u9, &w9};
-                    fr29::mont_dot9<2>(out9, a, SmemLimbs3{r->m[0], r->m[1], nullptr});
-                }
-            } else {
-                Fe y;
-                fr29::Fe9 y9;
-                load_w<T>(y, cb, r->w[4]);
-                fr29::to9(y9, y);
-                if (nlin == 0) {
-                    const fr29::Fe9* a[1] = {&y9};
-                    fr29::mont_dot9<1>(out9, a, SmemLimbs3{r->m[0], nullptr, nullptr});
-                } else {
-                    Fe w1;
-                    fr29::Fe9 w19;
-                    load_w<T>(w1, cb, r->w[5]);
-                    fr29::to9(w19, w1);
-                    if (nlin == 1) {
-                        const fr29::Fe9* a[2] = {&y9, &w19};
-                        fr29::mont_dot9<2>(out9, a, SmemLimbs3{r->m[0], r->m[1], nullptr});
-                    } else {
-                        Fe w2;
-                        fr29::Fe9 w29;
-                        load_w<T>(w2, cb, r->w[6]);
-                        fr29::to9(w29, w2);
-                        const fr29::Fe9* a[3] = {&y9, &w19, &w29};
-                        fr29::mont_dot9<3>(out9, a, SmemLimbs3{r->m[0], r->m[1], r->m[2]});
-                    }
-                }
-            }
-            fr29::from9(res, out9);            // < 1.1 p
-        } else if (flags & GF_MUL) {
+        if (flags & GF_MUL) {
             Fe x, y, u, t;
             load_w<T>(x, cb, r->w[3]);
             load_w<T>(y, cb, r->w[4]);
-            lds_fe(t, r->q[0]);
+            lds_fe(t, r->c[1]);
             fr::add_mod(x, x, t);
-            lds_fe(t, r->q[1]);
+            lds_fe(t, r->c[2]);
             fr::add_mod(y, y, t);
             const Fe* a1[1] = {&x};
             fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R, < 1.19p, used unreduced
             if (nlin == 0) {
                 const Fe* a[1] = {&u};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->m[0], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 const Fe* a[2] = {&u, &w1};
-                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->m[0], r->m[1], nullptr});
+                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
             }
         } else if (flags & GF_ADDSUB) {
             // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
             Fe y, t;
             load_w<T>(y, cb, r->w[4]);
-            lds_fe(res, r->q[2]);
+            lds_fe(res, r->c[4]);
             if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
             if (nlin >= 1) {
                 load_w<T>(t, cb, r->w[5]);
@@ -200,30 +144,30 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
             load_w<T>(y, cb, r->w[4]);
             if (nlin == 0) {
                 const Fe* a[1] = {&y};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->m[0], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr});
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 if (nlin == 1) {
                     const Fe* a[2] = {&y, &w1};
-                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->m[0], r->m[1], nullptr});
+                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr});
                 } else {
                     Fe w2;
                     load_w<T>(w2, cb, r->w[6]);
                     const Fe* a[3] = {&y, &w1, &w2};
-                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->m[0], r->m[1], r->m[2]});
+                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]});
                 }
             }
         }
         if (!(flags & GF_ADDSUB)) {
             fr::cond_sub_p(res);
             Fe cC;
-            lds_fe(cC, r->q[2]);
+            lds_fe(cC, r->c[4]);
             fr::add_raw(res, res, cC);
             fr::cond_sub_p(res);
         }
     } else {
-        lds_fe(res, r->q[2]);
+        lds_fe(res, r->c[4]);
     }
     if (kind == MK_GATE_ASSIGN) {
         if (flags & GF_OUT_CHECK) {

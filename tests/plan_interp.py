@@ -8,7 +8,6 @@ import struct
 
 P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 RINV = pow(1 << 256, -1, P)
-RINV261 = pow(1 << 261, -1, P)
 NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
@@ -56,21 +55,16 @@ class PlanBlob:
         self.host_desc = list(struct.unpack(f"<{n}I", d))
         n, d = vec("B", 1)
         self.acir_gz = bytes(d)
-        n, d = vec("rec", 240)
+        n, d = vec("rec", 192)
         self.n_records = n
         self.stream = d
         assert n == self.n_steps * self.S
 
     def record(self, i):
-        """returns (header, q[3] canonical constants, m[3] Montgomery multipliers already divided by their R)"""
-        w = struct.unpack_from("<60I", self.stream, i * 240)
+        w = struct.unpack_from("<48I", self.stream, i * 192)
         hdr = w[:8]
-        q = [sum(w[8 + 8 * k + j] << (32 * j) for j in range(8)) for k in range(3)]
-        if (hdr[0] >> 8) & 4096:   # GF_L9: 9 x 29-bit limbs, R = 2^261
-            m = [sum(w[32 + 9 * k + j] << (29 * j) for j in range(9)) * RINV261 % P for k in range(3)]
-        else:
-            m = [sum(w[32 + 9 * k + j] << (32 * j) for j in range(8)) * RINV % P for k in range(3)]
-        return hdr, (q, m)
+        coefs = [sum(w[8 + 8 * k + j] << (32 * j) for j in range(8)) for k in range(5)]
+        return hdr, coefs
 
 
 def default_hooks():
@@ -257,17 +251,14 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
             if kind == MK["NOP"]:
                 continue
             if kind in (MK["GATE_ASSIGN"], MK["GATE_CHECK"]):
-                q, m = c
-                res = q[2]
+                res = c[4]
                 if flags & GF_Y:
                     nlin = (flags >> GF_NLIN_SHIFT) & 3
                     if flags & GF_MUL:
                         assert nlin <= 1
-                        # m0 = cM*R^2 / R  -> one more division by R
-                        rinv = RINV261 if flags & 4096 else RINV
-                        res += m[0] * rinv * (cols[x] + q[0]) * (cols[y] + q[1])
+                        res += c[0] * RINV * RINV * (cols[x] + c[1]) * (cols[y] + c[2])
                         if nlin >= 1:
-                            res += m[1] * cols[w1]
+                            res += c[3] * RINV * cols[w1]
                     elif flags & 256:   # GF_ADDSUB: coefficients +-1, signs in flag bits 9..11
                         res += -cols[y] if flags & 512 else cols[y]
                         if nlin >= 1:
@@ -275,11 +266,11 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                         if nlin >= 2:
                             res += -cols[w2] if flags & 2048 else cols[w2]
                     else:
-                        res += m[0] * cols[y]
+                        res += c[1] * RINV * cols[y]
                         if nlin >= 1:
-                            res += m[1] * cols[w1]
+                            res += c[2] * RINV * cols[w1]
                         if nlin >= 2:
-                            res += m[2] * cols[w2]
+                            res += c[3] * RINV * cols[w2]
                 res %= P
                 if kind == MK["GATE_ASSIGN"]:
                     if flags & GF_OUT_CHECK:
