@@ -138,36 +138,80 @@ inline void shr1(U256& a, uint64_t top) {
     a.l[3] = (a.l[3] >> 1) | (top << 63);
 }
 inline bool is_one(const U256& a) { return a.l[0] == 1 && !(a.l[1] | a.l[2] | a.l[3]); }
-// binary extended Euclid on canonical values (plan time: one inversion per solving gate); 0 -> 0
+// binary extended Euclid on canonical values (plan time: one inversion per solving gate); 0 -> 0.
+// Tight form: u, v shrink by whole runs of trailing zeros at a time (ctz), x1, x2 are halved modulo p with a
+// branch-free add of (x & 1) * p.
 inline U256 inverse(const U256& a) {
     if (a.is_zero()) return a;
-    U256 u = a, v = P, x1 = from_u64_(1), x2;
-    auto halve = [](U256& x) {
-        if (x.l[0] & 1) {
-            uint64_t c = add_raw(x, x, P);
-            shr1(x, c);
-        } else {
-            shr1(x, 0);
+    uint64_t u[4] = {a.l[0], a.l[1], a.l[2], a.l[3]}, v[4] = {P.l[0], P.l[1], P.l[2], P.l[3]};
+    uint64_t x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+    auto halve_mod = [](uint64_t* x) {   // x = x/2 mod p  (x < p)
+        uint64_t mask = 0 - (x[0] & 1);
+        unsigned __int128 c = 0;
+        uint64_t t[4];
+        for (int i = 0; i < 4; ++i) {
+            c += (unsigned __int128)x[i] + (P.l[i] & mask);
+            t[i] = (uint64_t)c;
+            c >>= 64;
+        }
+        x[0] = (t[0] >> 1) | (t[1] << 63);
+        x[1] = (t[1] >> 1) | (t[2] << 63);
+        x[2] = (t[2] >> 1) | (t[3] << 63);
+        x[3] = (t[3] >> 1) | ((uint64_t)c << 63);
+    };
+    auto shr1n = [](uint64_t* x) {
+        x[0] = (x[0] >> 1) | (x[1] << 63);
+        x[1] = (x[1] >> 1) | (x[2] << 63);
+        x[2] = (x[2] >> 1) | (x[3] << 63);
+        x[3] >>= 1;
+    };
+    auto geq = [](const uint64_t* x, const uint64_t* y) {
+        for (int i = 3; i >= 0; --i) {
+            if (x[i] != y[i]) return x[i] > y[i];
+        }
+        return true;
+    };
+    auto sub_n = [](uint64_t* x, const uint64_t* y) {   // x -= y, returns borrow
+        unsigned __int128 br = 0;
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 t = (unsigned __int128)x[i] - y[i] - br;
+            x[i] = (uint64_t)t;
+            br = (t >> 64) & 1;
+        }
+        return (uint64_t)br;
+    };
+    auto sub_mod = [&](uint64_t* x, const uint64_t* y) {   // x = x - y mod p
+        if (sub_n(x, y)) {
+            unsigned __int128 c = 0;
+            for (int i = 0; i < 4; ++i) {
+                c += (unsigned __int128)x[i] + P.l[i];
+                x[i] = (uint64_t)c;
+                c >>= 64;
+            }
         }
     };
-    while (!is_one(u) && !is_one(v)) {
-        while (!(u.l[0] & 1)) {
-            shr1(u, 0);
-            halve(x1);
+    auto is1 = [](const uint64_t* x) { return x[0] == 1 && !(x[1] | x[2] | x[3]); };
+    while (!is1(u) && !is1(v)) {
+        while (!(u[0] & 1)) {
+            shr1n(u);
+            halve_mod(x1);
         }
-        while (!(v.l[0] & 1)) {
-            shr1(v, 0);
-            halve(x2);
+        while (!(v[0] & 1)) {
+            shr1n(v);
+            halve_mod(x2);
         }
-        if (cmp(u, v) >= 0) {
-            sub_raw(u, u, v);
-            x1 = sub(x1, x2);
+        if (geq(u, v)) {
+            sub_n(u, v);
+            sub_mod(x1, x2);
         } else {
-            sub_raw(v, v, u);
-            x2 = sub(x2, x1);
+            sub_n(v, u);
+            sub_mod(x2, x1);
         }
     }
-    return is_one(u) ? x1 : x2;
+    const uint64_t* r = is1(u) ? x1 : x2;
+    U256 out;
+    for (int i = 0; i < 4; ++i) out.l[i] = r[i];
+    return out;
 }
 inline U256 reduce(U256 a) {  // arbitrary 256-bit -> mod p
     while (cmp(a, P) >= 0) sub_raw(a, a, P);

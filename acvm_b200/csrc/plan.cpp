@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace acvmb {
 
@@ -124,6 +125,21 @@ struct Compiler {
     Compiler(const Circuit& circ, const PlanOptions& o, uint32_t nw)
         : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw), extra_slots_base(nw + o.temp_pool) {}
 
+    // Field inversions are the dominant plan-time cost (one or two per solving gate).  The compiler therefore runs twice:
+    // a RECORD pass that only collects the values to invert (and gets a non-zero dummy back -- control flow never depends
+    // on an inverse's value), one batched Montgomery-trick inversion of the whole list, and the real REPLAY pass.
+    std::vector<U256>* inv_record = nullptr;
+    const std::vector<U256>* inv_replay = nullptr;
+    size_t inv_pos = 0;
+    U256 inv(const U256& v) {
+        if (inv_record) {
+            inv_record->push_back(v);
+            return hf::from_u64(1);
+        }
+        if (inv_replay) return (*inv_replay)[inv_pos++];
+        return hf::inverse(v);
+    }
+
     uint32_t new_temp() {
         uint32_t t = temp_base + (temp_next % opt.temp_pool);
         ++temp_next;
@@ -187,7 +203,7 @@ struct Compiler {
                             break;
                         }
                 if (!cX.is_zero() || !cY.is_zero()) {
-                    U256 invM = hf::inverse(cM);
+                    U256 invM = inv(cM);
                     alpha = hf::mul(cY, invM);
                     beta = hf::mul(cX, invM);
                     gamma_part = hf::neg(hf::mul(hf::mul(cX, cY), invM));
@@ -758,7 +774,7 @@ struct Compiler {
             return true;
         }
         // exactly one unknown (coeff != 0): w := -(sum)/coeff ; fold k = -1/coeff into every term
-        U256 k = hf::neg(hf::inverse(unknown[0].c));
+        U256 k = hf::neg(inv(unknown[0].c));
         plan.stats.ref_fr_mul += 1;
         plan.stats.ref_fr_inv += 1;
         for (auto& p : prods) p.c = hf::mul(p.c, k);
@@ -1072,11 +1088,53 @@ uint32_t witness_span(const Circuit& c, const std::vector<uint32_t>& inputs) {
 
 }  // namespace
 
+// all-at-once inversion (Montgomery's trick): 3 multiplications per element + one real inversion per chunk, chunks in parallel
+static std::vector<U256> batch_inverse(const std::vector<U256>& v) {
+    std::vector<U256> out(v.size());
+    const size_t n = v.size();
+    unsigned n_thr = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)(n / 4096 + 1)));
+    auto work = [&](size_t lo, size_t hi) {
+        if (lo >= hi) return;
+        std::vector<U256> prefix(hi - lo);
+        U256 acc = hf::consts().R;   // Montgomery one
+        for (size_t i = lo; i < hi; ++i) {   // zero stays zero (inverse(0) = 0) and is skipped in the running product
+            prefix[i - lo] = acc;
+            if (!v[i].is_zero()) acc = hf::mont_mul(acc, hf::to_mont(v[i]));
+        }
+        U256 inv_acc = hf::to_mont(hf::inverse(hf::from_mont(acc)));
+        for (size_t i = hi; i-- > lo;) {
+            if (v[i].is_zero()) continue;
+            out[i] = hf::from_mont(hf::mont_mul(inv_acc, prefix[i - lo]));
+            inv_acc = hf::mont_mul(inv_acc, hf::to_mont(v[i]));
+        }
+    };
+    std::vector<std::thread> th;
+    size_t per = (n + n_thr - 1) / n_thr;
+    for (unsigned t = 1; t < n_thr; ++t) th.emplace_back(work, t * per, std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto& x : th) x.join();
+    return out;
+}
+
 Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt) {
     if (opt.S == 0 || opt.S > 64) throw std::runtime_error("plan: S must be in 1..64");
     uint32_t nw = witness_span(c, input_witnesses);
+    if (c.opcodes.size() < 2048) {   // small circuits: direct inversions
+        Compiler comp(c, opt, nw);
+        comp.run(input_witnesses);
+        return std::move(comp.plan);
+    }
+    std::vector<U256> requests;
+    {
+        Compiler dry(c, opt, nw);
+        dry.inv_record = &requests;
+        dry.run(input_witnesses);
+    }
+    std::vector<U256> inverses = batch_inverse(requests);
     Compiler comp(c, opt, nw);
+    comp.inv_replay = &inverses;
     comp.run(input_witnesses);
+    if (comp.inv_pos != inverses.size()) throw std::runtime_error("plan: inversion replay out of sync");
     return std::move(comp.plan);
 }
 

@@ -60,6 +60,13 @@ def test_plan_matches_oracle_synthetic(S, mode, coeffs):
     assert info["n_micro_ops"] == 600 and info["ref_fr_inv"] == 600 - 600 // 16
 
 
+def test_plan_batched_inversion_path():
+    # circuits above 2048 opcodes compile in two passes with one batched (Montgomery-trick) inversion in between
+    data, inputs, _ = ab.synthetic_arith_circuit(3000, mode="local", coeffs="dense")
+    info = _interp_vs_oracle(data, inputs, ab.synthetic_inputs(1), 1, 16)
+    assert info["n_opcodes"] == 3000
+
+
 def test_plan_failures_and_chains():
     rng = ab.SplitMix64(11)
     b = ab.CircuitBuilder()
