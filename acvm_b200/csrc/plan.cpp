@@ -164,10 +164,13 @@ struct Compiler {
     // Lower  sum(products) + sum(linears) + constant  into chained micro-gates.
     // assign: write the value to `out`; otherwise CHECK it is zero.
     // out_check: `out` is already assigned -> compare instead of store (insert_value semantics).
+    // `k` scales the whole sum (k = -1/coeff of the unknown for ASSIGN gates).  Terms arrive UNSCALED so that the values
+    // handed to inv() never depend on another inverse (required by the record/replay batching of inversions).
     void lower_sum(std::vector<Prod> prods, std::vector<Lin> lins, const U256& constant, bool assign, uint32_t out,
-                   uint32_t opcode, bool out_check) {
+                   uint32_t opcode, bool out_check, const U256* k = nullptr) {
         uint32_t acc = NONE;
         const U256 one = hf::from_u64(1);
+        auto sc = [&](const U256& v) { return k ? hf::mul(v, *k) : v; };
         bool first_gate = true;
         while (first_gate || !prods.empty() || !lins.empty()) {
             first_gate = false;
@@ -179,6 +182,7 @@ struct Compiler {
             size_t nr = 0;
             uint64_t imad = 0;
             U256 alpha, beta, gamma_part;
+            bool y_is_acc = false, w1_is_acc = false, w2_is_acc = false;
             if (!prods.empty()) {
                 // cM*x*y + cX*x + cY*y  ==  cM*(x + cY/cM)*(y + cX/cM) - cX*cY/cM : two Montgomery products
                 // instead of three; the x/y linear terms ride along as plan-time constants.
@@ -213,6 +217,7 @@ struct Compiler {
                 flags |= GF_Y;
                 y = acc;
                 cY = one;
+                y_is_acc = true;
                 acc = NONE;
             } else if (!lins.empty()) {
                 flags |= GF_Y;
@@ -233,6 +238,7 @@ struct Compiler {
                 ++nlin;
             };
             if (acc != NONE && nlin < max_lin) {
+                (nlin == 0 ? w1_is_acc : w2_is_acc) = true;
                 push_lin(one, acc);
                 acc = NONE;
             }
@@ -244,14 +250,19 @@ struct Compiler {
             flags |= nlin << GF_NLIN_SHIFT;
             uint32_t kind;
             uint32_t dst = NONE;
-            U256 c4 = gamma_part;
+            // apply the scale: partial sums held in temporaries are already scaled, everything else is not
+            cM = sc(cM);
+            if (!y_is_acc) cY = sc(cY);
+            if (!w1_is_acc) c1 = sc(c1);
+            if (!w2_is_acc) c2 = sc(c2);
+            U256 c4 = sc(gamma_part);
             if (final_gate) {
                 kind = assign ? MK_GATE_ASSIGN : MK_GATE_CHECK;
                 if (assign) {
                     dst = out;
                     if (out_check) flags |= GF_OUT_CHECK;
                 }
-                c4 = hf::add(c4, constant);
+                c4 = hf::add(c4, sc(constant));
             } else {
                 kind = MK_GATE_ASSIGN;
                 dst = new_temp();
@@ -777,11 +788,8 @@ struct Compiler {
         U256 k = hf::neg(inv(unknown[0].c));
         plan.stats.ref_fr_mul += 1;
         plan.stats.ref_fr_inv += 1;
-        for (auto& p : prods) p.c = hf::mul(p.c, k);
-        for (auto& l : lins) l.c = hf::mul(l.c, k);
-        U256 qc = hf::mul(e.q_c, k);
         uint32_t w = unknown[0].w;
-        lower_sum(std::move(prods), std::move(lins), qc, /*assign=*/true, w, idx, false);
+        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, w, idx, false, &k);
         mark_assigned(w, idx);
         return true;
     }
