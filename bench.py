@@ -32,6 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "witnesses_per_s_2^20_gate_bn254_acir"
+# DRAM bytes per gate-instance of vm_kernel from the committed `ncu --set full` capture (profiles/r1_vm_kernel_ncu_full_v2.txt:
+# dram read 1.70 GB + write 9.26 GB for 4736 instances x 65599 micro-gates): writes are the 32 B result, operand reads hit L2.
+NCU_DRAM_BYTES_PER_GATE_INSTANCE = (1.701491e9 + 9.262512e9) / (4736 * 65599)
 UNIT = "witnesses/s"
 
 
@@ -344,7 +347,10 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "kernel": "vm_kernel", "kernel_ms_per_launch": vm_launch_ms,
+            "traffic": NCU_DRAM_BYTES_PER_GATE_INSTANCE * info["n_micro_ops"] * inst_per_launch,
+            "traffic_source": "ncu --set full capture of the same kernel on a 2^16-gate circuit (profiles/r1_vm_kernel_ncu_full_v2.txt), "
+                              "scaled by gate-instances per launch",
+            "peak_source": peak_src, "kernel": "vm_kernel", "kernel_ms_per_launch": vm_launch_ms,
             "algorithmic_bytes_per_launch": alg_bytes_launch,
             "note": "dense-coefficient gates are integer-multiply bound, not HBM bound: see imad",
             "imad": {"achieved_per_s": imad_achieved, "peak_per_s": imad["imad_wide_per_s"], "frac": imad_achieved / imad["imad_wide_per_s"],
