@@ -80,6 +80,12 @@ struct acvmb_batch {
     uint8_t* d_stage_present[2] = {nullptr, nullptr};
     size_t stage_present_bytes = 0;
     uint32_t* d_mu = nullptr;            // per-lane assignment table of value-dependent witnesses
+    // grow-only staging of the host (Brillig) segments
+    uint8_t* d_host_io = nullptr;
+    uint32_t* d_host_ids = nullptr;
+    size_t host_io_bytes = 0, host_ids_bytes = 0;
+    std::vector<uint8_t> h_in, h_out;
+    std::vector<unsigned long long> h_fail;
     // pending Brillig foreign call of instance 0 (kept for the single-instance ACVM mirror)
     bool fc_pending = false;
     std::string fc_function;
@@ -98,6 +104,8 @@ struct acvmb_batch {
         if (d_stage_present[0]) cudaFree(d_stage_present[0]);
         if (d_stage_present[1]) cudaFree(d_stage_present[1]);
         if (d_mu) cudaFree(d_mu);
+        if (d_host_io) cudaFree(d_host_io);
+        if (d_host_ids) cudaFree(d_host_ids);
         if (d_out_ids) cudaFree(d_out_ids);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -547,14 +555,29 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
     const uint32_t n = b->n_inst, n_g = (uint32_t)in_slots.size(), n_o = (uint32_t)out_w.size();
     cudaStream_t s = ctx->stream;
     // ---- D2H: status words + the input columns ----
-    std::vector<unsigned long long> fail(n);
+    std::vector<unsigned long long>& fail = b->h_fail;
+    fail.resize(n);
     CUDA_TRY(cudaMemcpyAsync(fail.data(), b->d_fail, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-    std::vector<uint8_t> in_be((size_t)n * n_g * 32);
-    uint8_t* d_io = nullptr;
-    uint32_t* d_ids = nullptr;
+    std::vector<uint8_t>& in_be = b->h_in;
+    in_be.resize((size_t)n * n_g * 32);
     size_t io_bytes = std::max<size_t>((size_t)n * std::max(n_g, n_o) * 32, 16);
-    CUDA_TRY(cudaMalloc(&d_io, io_bytes));
-    CUDA_TRY(cudaMalloc(&d_ids, std::max<size_t>((size_t)std::max(n_g, n_o) * 4, 16)));
+    size_t ids_bytes = std::max<size_t>((size_t)std::max(n_g, n_o) * 4, 16);
+    if (b->host_io_bytes < io_bytes) {
+        if (b->d_host_io) cudaFree(b->d_host_io);
+        b->d_host_io = nullptr;
+        b->host_io_bytes = 0;
+        CUDA_TRY(cudaMalloc(&b->d_host_io, io_bytes));
+        b->host_io_bytes = io_bytes;
+    }
+    if (b->host_ids_bytes < ids_bytes) {
+        if (b->d_host_ids) cudaFree(b->d_host_ids);
+        b->d_host_ids = nullptr;
+        b->host_ids_bytes = 0;
+        CUDA_TRY(cudaMalloc(&b->d_host_ids, ids_bytes));
+        b->host_ids_bytes = ids_bytes;
+    }
+    uint8_t* d_io = b->d_host_io;
+    uint32_t* d_ids = b->d_host_ids;
     if (n_g) {
         CUDA_TRY(cudaMemcpyAsync(d_ids, in_slots.data(), (size_t)n_g * 4, cudaMemcpyHostToDevice, s));
         GatherArgs g{};
@@ -574,7 +597,8 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     // ---- run the VM per instance on all host threads ----
-    std::vector<uint8_t> out_be((size_t)n * n_o * 32, 0);
+    std::vector<uint8_t>& out_be = b->h_out;
+    out_be.assign((size_t)n * n_o * 32, 0);
     unsigned n_thr = std::max(1u, std::thread::hardware_concurrency());
     n_thr = std::min<unsigned>(n_thr, n);
     auto work = [&](unsigned t) {
@@ -662,8 +686,6 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_fail, fail.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    cudaFree(d_io);
-    cudaFree(d_ids);
     return ACVMB_OK;
 }
 
