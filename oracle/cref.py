@@ -82,5 +82,26 @@ def solve_batch(circuit: oacir.Circuit, input_ids, inputs_be32: bytes, n_inst: i
     return res, outw, outp
 
 
+def solve_batch_optimized(circuit: oacir.Circuit, input_ids, inputs_be32: bytes, n_inst: int, n_witnesses: int, threads: int = 1,
+                         want_witness: bool = False, packed=None):
+    """The "optimised CPU" variant: dense witness vector, plan resolved once, inverses hoisted (ref_solver.cpp)."""
+    stream = pack_circuit(circuit) if packed is None else packed
+    n_in = len(input_ids)
+    be = np.frombuffer(inputs_be32, dtype=np.uint8).reshape(n_inst * n_in, 32)
+    limbs = np.ascontiguousarray(be[:, ::-1]).view("<u8").reshape(n_inst, n_in, 4).copy()
+    ids = np.array(list(input_ids), dtype=np.uint32)
+    res = np.zeros((n_inst, 4), dtype=np.uint32)
+    outw = np.zeros((n_inst, n_witnesses, 4), dtype=np.uint64) if want_witness else None
+    lib().ref_solve_batch_optimized.restype = C.c_int
+    rc = lib().ref_solve_batch_optimized(stream.ctypes.data_as(C.c_void_p), C.c_uint64(len(stream)), C.c_uint64(len(circuit.opcodes)),
+                                         ids.ctypes.data_as(C.c_void_p), C.c_uint32(n_in), limbs.ctypes.data_as(C.c_void_p),
+                                         C.c_uint32(n_inst), C.c_uint32(n_witnesses),
+                                         outw.ctypes.data_as(C.c_void_p) if want_witness else None,
+                                         res.ctypes.data_as(C.c_void_p), C.c_uint32(threads))
+    if rc != 0:
+        raise NotImplementedError("optimised CPU variant does not cover this circuit (value-dependent or unsolvable gate)")
+    return res, outw
+
+
 def witness_dict(outw, outp, i):
     return {w: int.from_bytes(outw[i, w].tobytes(), "little") for w in range(outw.shape[1]) if outp[i, w]}

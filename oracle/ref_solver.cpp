@@ -327,6 +327,121 @@ std::vector<Op> parse_ops(const uint64_t* s, uint64_t n_words, uint64_t n_ops) {
     return ops;
 }
 
+// ---- "optimised CPU" variant (so the GPU speed-up is not inflated by map / allocation / inversion overhead) ----
+// Same circuit, same results, but the way a careful CPU implementation of the BATCH problem would do it: the known-set is
+// resolved once per circuit, the inverse of the solved witness' coefficient is hoisted out of the per-instance loop, the
+// witness map is a dense vector in Montgomery form, no allocation in the gate loop.  Arithmetic / AND / XOR / RANGE only.
+struct OptGate {
+    std::vector<MulT> mul;
+    std::vector<LinT> lin;
+    Fr qc;
+    Fr k;            // -1/coeff of the unknown (Montgomery), valid when assign
+    uint32_t target;
+    bool assign;
+};
+
+}  // namespace
+
+extern "C" int ref_solve_batch_optimized(const uint64_t* stream, uint64_t n_words, uint64_t n_ops, const uint32_t* input_ids,
+                                         uint32_t n_inputs, const uint64_t* inputs, uint32_t n_inst, uint32_t n_witnesses,
+                                         uint64_t* out_witness, uint32_t* results, uint32_t threads) {
+    std::vector<Op> ops = parse_ops(stream, n_words, n_ops);
+    // plan: static known-set (valid for every instance of circuits without value-dependent gates)
+    std::vector<uint8_t> known(n_witnesses, 0);
+    for (uint32_t k = 0; k < n_inputs; ++k) known[input_ids[k]] = 1;
+    std::vector<OptGate> plan(ops.size());
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& o = ops[i];
+        OptGate& g = plan[i];
+        g.assign = false;
+        g.target = 0;
+        if (o.kind != 0) {
+            if (o.kind == 1 || o.kind == 2) known[o.out] = 1;
+            continue;
+        }
+        int unknowns = 0;
+        LinT unk{};
+        for (const MulT& t : o.e.mul) {
+            if (!known[t.a] || !known[t.b]) return -1;   // value-dependent / unsolvable gates: not covered by this variant
+            g.mul.push_back(t);
+        }
+        for (const LinT& t : o.e.lin) {
+            if (known[t.w]) g.lin.push_back(t);
+            else { unk = t; ++unknowns; }
+        }
+        if (unknowns > 1) return -1;
+        g.qc = o.e.qc;
+        if (unknowns == 1) {
+            g.assign = true;
+            g.target = unk.w;
+            g.k = unk.c;                 // inverted below, all gates at once (hoisted out of the per-instance loop)
+            known[unk.w] = 1;
+        }
+    }
+    {   // Montgomery's trick: one inversion for the whole circuit
+        std::vector<Fr> prefix(plan.size());
+        Fr acc = from_canonical(ONE_RAW.l);
+        for (size_t i = 0; i < plan.size(); ++i) {
+            prefix[i] = acc;
+            if (plan[i].assign) acc = mul(acc, plan[i].k);
+        }
+        Fr inv_acc = inverse(acc);
+        for (size_t i = plan.size(); i-- > 0;) {
+            if (!plan[i].assign) continue;
+            Fr c = plan[i].k;
+            plan[i].k = neg(mul(inv_acc, prefix[i]));
+            inv_acc = mul(inv_acc, c);
+        }
+    }
+    if (threads == 0) threads = 1;
+    auto work = [&](uint32_t t) {
+        std::vector<Fr> w(n_witnesses);
+        for (uint32_t i = t; i < n_inst; i += threads) {
+            for (uint32_t k = 0; k < n_inputs; ++k) w[input_ids[k]] = from_canonical(inputs + ((size_t)i * n_inputs + k) * 4);
+            Result r{ST_SOLVED, 0, (uint32_t)ops.size(), 0};
+            for (size_t ip = 0; ip < ops.size(); ++ip) {
+                const Op& o = ops[ip];
+                if (o.kind == 0) {
+                    const OptGate& g = plan[ip];
+                    Fr acc = g.qc;
+                    for (const MulT& m : g.mul) acc = add(acc, mul(mul(m.c, w[m.a]), w[m.b]));
+                    for (const LinT& l : g.lin) acc = add(acc, mul(l.c, w[l.w]));
+                    if (g.assign) w[g.target] = mul(acc, g.k);
+                    else if (acc.l[0] | acc.l[1] | acc.l[2] | acc.l[3]) { r = Result{ST_FAILURE, E_UNSAT, (uint32_t)ip, 0}; break; }
+                } else if (o.kind == 1 || o.kind == 2) {
+                    Fr x = to_canonical(w[o.a]), y = to_canonical(w[o.b]);
+                    uint64_t z[4];
+                    for (int q = 0; q < 4; ++q) {
+                        uint64_t m;
+                        int lo = 64 * q;
+                        if ((int)o.nb >= lo + 64) m = ~0ULL; else if ((int)o.nb <= lo) m = 0; else m = (1ULL << (o.nb - lo)) - 1;
+                        uint64_t a = x.l[q] & m, b = y.l[q] & m;
+                        z[q] = o.kind == 1 ? (a & b) : (a ^ b);
+                    }
+                    while (geq_p(z)) sub_p(z);
+                    w[o.out] = from_canonical(z);
+                } else {
+                    Fr x = to_canonical(w[o.a]);
+                    if ((uint32_t)nbits(x.l) > o.nb) { r = Result{ST_FAILURE, E_UNSAT, (uint32_t)ip, 0}; break; }
+                }
+            }
+            memcpy(results + (size_t)i * 4, &r, 16);
+            if (out_witness)
+                for (uint32_t k = 0; k < n_witnesses; ++k)
+                    if (known[k]) {
+                        Fr c = to_canonical(w[k]);
+                        memcpy(out_witness + ((size_t)i * n_witnesses + k) * 4, c.l, 32);
+                    }
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return 0;
+}
+
+namespace {
 }  // namespace
 
 extern "C" {

@@ -135,6 +135,13 @@ def test_cpp_restatement_matches_python_oracle():
             st, wm, _ = pwg.solve_circuit(c, iw)
             assert st == "Solved" and res[i, 0] == 0
             assert cref.witness_dict(ow, op, i) == wm
+    # the "optimised CPU" variant computes the same witnesses
+    data, inputs, nw = ab.synthetic_arith_circuit(500)
+    c = acir.decode_circuit(data)
+    inp = ab.synthetic_inputs(4)
+    res, ow, op = cref.solve_batch(c, inputs, inp, 4, nw, threads=1, want_witness=True)
+    res2, ow2 = cref.solve_batch_optimized(c, inputs, inp, 4, nw, threads=2, want_witness=True)
+    assert (res2[:, 0] == 0).all() and (ow == ow2).all()
     # failure parity: unsatisfied check at opcode 1
     b = ab.CircuitBuilder()
     b.arithmetic([], [(1, 1), (ab.P - 1, 2)], 0)
