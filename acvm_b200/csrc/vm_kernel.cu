@@ -110,12 +110,14 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
             Fe x, y, u, t;
             load_w<T>(x, cb, r->w[3]);
             load_w<T>(y, cb, r->w[4]);
+            // lazy reduction: x+alpha, y+beta < 2p stay unreduced (4p^2/R + p < 1.76p), and so does u
+            // ((1.76 + 1) p^2 / R + p < 1.52p for the second product): one conditional subtraction per gate instead of three
             lds_fe(t, r->c[1]);
-            fr::add_mod(x, x, t);
+            fr::add_raw(x, x, t);
             lds_fe(t, r->c[2]);
-            fr::add_mod(y, y, t);
+            fr::add_raw(y, y, t);
             const Fe* a1[1] = {&x};
-            fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R, < 1.19p, used unreduced
+            fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R < 1.76p
             if (nlin == 0) {
                 const Fe* a[1] = {&u};
                 fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});

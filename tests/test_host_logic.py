@@ -139,6 +139,16 @@ def test_fr_limb_algorithms_on_host(tmp_path):
             r = (ctypes.c_uint32 * 8)()
             L.t_mont_mul_split(split, arr([x]), arr([y]), r)
             assert val(r) == x * y * Rinv % P, (split, hex(x), hex(y))
+    # lazy-reduction bounds the gate kernel relies on: (x+alpha)(y+beta) with both factors < 2p, then <u, w1>.<m0, m1>
+    for it in range(3000):
+        a, b = rnd.choice([2 * P - 2, rnd.randrange(2 * P - 1)]), rnd.choice([2 * P - 2, rnd.randrange(2 * P - 1)])
+        r = (ctypes.c_uint32 * 8)()
+        L.t_mont_dot(1, arr([a]), arr([b]), r)
+        u = val(r)
+        assert u % P == a * b * Rinv % P and u < 1.76 * P + 1
+        w, m0, m1 = (rnd.choice([P - 1, rnd.randrange(P)]) for _ in range(3))
+        L.t_mont_dot(2, arr([u, w]), arr([m0, m1]), r)
+        assert val(r) % P == (u * m0 + w * m1) * Rinv % P and val(r) < 2 * P
     # carry-free 9 x 29-bit representation (fr29.cuh): conversions round-trip and the K-term dot product is exact
     Rinv261 = pow(1 << 261, -1, P)
     for it in range(3000):
