@@ -5,6 +5,6 @@ this package is the thin Python mirror of that ABI.  Importing the solver withou
 library raises ImportError -- there is no CPU implementation behind it.
 """
 from .solver import (ACVM, AcvmError, CompiledCircuit, Context, DeviceBatch, InstanceStatus, compile_plan_host,  # noqa: F401
-                     compress_witness_map, decompress_witness_map, lib)
+                     compress_witness_map, decompress_witness_map, lib, witness_checksum)
 
 __all__ = ["ACVM", "AcvmError", "CompiledCircuit", "Context", "DeviceBatch", "InstanceStatus", "compile_plan_host", "lib"]

@@ -817,9 +817,30 @@ extern "C" int acvmb_batch_download(acvmb_batch* b, uint32_t first, uint32_t n, 
 }
 
 extern "C" int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out) {
-    (void)b;
-    (void)out;
-    return set_err(ACVMB_ERR_UNSUPPORTED, "acvmb_batch_checksum: not implemented yet");
+    if (!b || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    acvmb_circuit* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    GatherArgs g{};
+    g.cols = b->d_cols;
+    g.n_slots = c->plan.n_slots;
+    g.T = (int)b->T;
+    g.n_out = c->plan.num_witnesses;
+    g.n_inst = b->n_inst;
+    g.fail = b->d_fail;
+    g.assign_opcode = c->d_assign;
+    g.mu_index_of = c->d_mu_index_of;
+    g.mu_assign = b->d_mu;
+    g.n_mu = c->plan.n_mu;
+    g.static_fail_opcode = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
+    unsigned long long* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)b->n_inst * 8));
+    cudaError_t e = launch_checksum(g, d_out, c->ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)b->n_inst * 8, cudaMemcpyDeviceToHost, c->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->ctx->stream);
+    cudaFree(d_out);
+    CUDA_TRY(e);
+    c->run.kernel_launches += 1;
+    return ACVMB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -404,6 +404,45 @@ cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// per-instance checksum of the solved witness map: sum over present witnesses of an FNV-style mix of (index, limbs)
+__device__ __forceinline__ unsigned long long mix_witness(uint32_t w, const uint4& lo, const uint4& hi) {
+    unsigned long long h = ((unsigned long long)w + 1ull) * 0x9E3779B97F4A7C15ull;
+    const uint32_t l[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h = (h ^ l[k]) * 0x100000001B3ull;
+    return h;
+}
+
+__global__ void checksum_kernel(const GatherArgs g, unsigned long long* out) {
+    // one CTA per instance, threads stride over the witnesses
+    const uint32_t inst = blockIdx.x;
+    uint32_t fail_op = (uint32_t)(g.fail[inst] >> 32);
+    if (g.static_fail_opcode < fail_op) fail_op = g.static_fail_opcode;
+    const uint32_t tile = inst / g.T, lane = inst % g.T;
+    unsigned long long acc = 0;
+    for (uint32_t w = threadIdx.x; w < g.n_out; w += blockDim.x) {
+        uint32_t ao = g.assign_opcode[w];
+        if (ao == 0xFFFFFFFDu) ao = g.mu_assign[((size_t)tile * g.n_mu + g.mu_index_of[w]) * g.T + lane];
+        if (!((ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op))) continue;
+        const uint4* p = g.cols + ((size_t)tile * g.n_slots + w) * (2 * g.T) + lane;
+        acc += mix_witness(w, p[0], p[g.T]);
+    }
+    __shared__ unsigned long long red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[inst] = red[0];
+}
+
+cudaError_t launch_checksum(const GatherArgs& g, unsigned long long* out, cudaStream_t stream) {
+    if (g.n_inst == 0) return cudaSuccess;
+    checksum_kernel<<<g.n_inst, 256, 0, stream>>>(g, out);
+    return cudaGetLastError();
+}
+
 __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

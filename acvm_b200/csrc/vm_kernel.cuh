@@ -54,6 +54,8 @@ struct GatherArgs {
     int raw;                       // 1 = witness_ids are raw column slots (temporaries allowed), no presence logic
 };
 cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream);
+// out[inst] = sum over the witnesses instance `inst` holds of mix(index, value)  (g.n_out = num_witnesses, g.n_inst instances from 0)
+cudaError_t launch_checksum(const GatherArgs& g, unsigned long long* out, cudaStream_t stream);
 cudaError_t launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t stream);
 
 // IMAD roofline micro-benchmark: returns measured multiply-accumulates per second for each variant

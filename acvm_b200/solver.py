@@ -241,6 +241,12 @@ class DeviceBatch:
         _check(lib().acvmb_batch_status(self._h, st))
         return [_status(s) for s in st]
 
+    def checksums(self):
+        """Per-instance checksum of the solved witness map, computed on the device (see witness_checksum())."""
+        out = (C.c_uint64 * self.n)()
+        _check(lib().acvmb_batch_checksum(self._h, out))
+        return list(out)
+
     def download(self, first=0, n=None, out_ids=None, out_buffer=None):
         n = self.n - first if n is None else n
         n_out = len(out_ids) if out_ids is not None else self.circuit.num_witnesses
@@ -344,6 +350,18 @@ class ACVM:
             self.close()
         except Exception:
             pass
+
+
+def witness_checksum(wm: Dict[int, int]) -> int:
+    """Host-side definition of acvmb_batch_checksum for one witness map (used by tests to cross-check the device)."""
+    M = (1 << 64) - 1
+    total = 0
+    for w, v in wm.items():
+        h = ((w + 1) * 0x9E3779B97F4A7C15) & M
+        for k in range(8):
+            h = ((h ^ ((v >> (32 * k)) & 0xFFFFFFFF)) * 0x100000001B3) & M
+        total = (total + h) & M
+    return total
 
 
 def compress_witness_map(wm: Dict[int, int]) -> bytes:

@@ -140,7 +140,9 @@ int acvmb_batch_download(acvmb_batch* b, uint32_t first_instance, uint32_t n_ins
                          uint32_t n_out_ids, uint8_t* out_witness_be32);    /* gather + D2H */
 int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first_instance, uint32_t n_instances, const uint32_t* out_ids,
                             uint32_t n_out_ids, uint8_t* out_witness_be32, uint8_t* out_present);
-/* on-device checksum of all witness columns (xor-fold), for size-independent property tests */
+/* per-instance checksum of the solved witness map, computed on the device: out[i] = sum over the witnesses w instance i holds
+ * of mix(w, value) mod 2^64, mix = FNV-style fold of the 8 little-endian 32-bit limbs seeded with (w+1)*0x9E3779B97F4A7C15.
+ * For size-independent property tests at full batch sizes (no D2H of the witness itself). out: [n_instances] */
 int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out);
 
 /* ---- single-instance mirror of the ACVM struct (acvm/src/pwg/mod.rs:129-304), batch of 1 ---- */

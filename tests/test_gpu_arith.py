@@ -193,3 +193,20 @@ def test_foreign_call_resolution_golden(ctx, golden):
     vm.resolve_pending_foreign_call([[2, 6, 12], 6, 12])
     assert vm.solve().status == "Solved"
     assert vm.finalize() == {int(k): int(v, 16) for k, v in fx["expectedWitnessMap"].items()}
+
+
+def test_device_checksum_matches_host_definition(ctx):
+    data, inputs, _ = ab.synthetic_arith_circuit(300)
+    circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+    batch = 19
+    inp = ab.synthetic_inputs(batch, seed_id=5)
+    b = acvm_b200.DeviceBatch(circ, batch)
+    b.upload(inp)
+    b.run()
+    sums = b.checksums()
+    out = b.download()
+    nw = circ.num_witnesses
+    assign = circ.assign_opcodes()
+    for i in range(batch):
+        wm = {w: int.from_bytes(out[(i * nw + w) * 32:(i * nw + w + 1) * 32], "big") for w in range(nw) if assign[w] != 0xFFFFFFFF}
+        assert acvm_b200.witness_checksum(wm) == sums[i]
