@@ -41,6 +41,7 @@ struct acvmb_ctx {
     uint32_t opt_S = 16;
     uint32_t opt_chunk_steps = 2;
     int opt_split = -1;
+    uint32_t opt_n_stage = 4;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
     uint64_t staging_bytes = 512ull << 20;
     uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
@@ -189,6 +190,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "S") ctx->opt_S = (uint32_t)value;
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
+    else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
     else if (k == "staging_bytes") ctx->staging_bytes = value;
     else return set_err(ACVMB_ERR_INVALID_ARG, "unknown option " + k);
@@ -428,6 +430,7 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     a.cols = b->d_cols;
     a.fail = b->d_fail;
     a.chunk_steps = c->plan.chunk_steps;
+    a.n_stage = c->ctx->opt_n_stage;
     a.n_slots = c->plan.n_slots;
     a.n_tiles = b->n_tiles;
     a.mu_assign = b->d_mu;

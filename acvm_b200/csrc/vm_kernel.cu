@@ -24,7 +24,7 @@ namespace acvmb {
 
 using fr::Fe;
 
-constexpr int NSTAGE = 4;
+constexpr int MAX_NSTAGE = 8;   // depth of the TMA staging ring is a launch parameter (VmArgs::n_stage)
 
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy + mbarrier (inline PTX; SASS: UBLKCP / SYNCS)
@@ -227,6 +227,7 @@ template <int T, int S, bool FULL, int SPLIT>
 __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
+    const uint32_t NSTAGE = a.n_stage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGE * chunk_bytes);
 
     const uint32_t tid = threadIdx.x;
@@ -240,13 +241,13 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
     const uint32_t n_chunks = a.n_steps / a.chunk_steps;
     const uint8_t* stream = a.stream + (size_t)a.first_step * S * sizeof(OpRec);
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        for (uint32_t s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t pre = n_chunks < (uint32_t)NSTAGE ? n_chunks : (uint32_t)NSTAGE;
+        const uint32_t pre = n_chunks < NSTAGE ? n_chunks : NSTAGE;
         for (uint32_t c = 0; c < pre; ++c) {
             mbar_expect_tx(&bars[c], chunk_bytes);
             tma_bulk_g2s(smem + (size_t)c * chunk_bytes, stream + (size_t)c * chunk_bytes, chunk_bytes, &bars[c]);
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
 
 template <int T, int S, bool FULL, int SPLIT = FR_ALU_SPLIT>
 static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
-    size_t smem = (size_t)NSTAGE * args.chunk_steps * S * sizeof(OpRec) + NSTAGE * sizeof(uint64_t);
+    if (args.n_stage < 1 || args.n_stage > MAX_NSTAGE) return cudaErrorInvalidValue;
+    size_t smem = (size_t)args.n_stage * args.chunk_steps * S * sizeof(OpRec) + args.n_stage * sizeof(uint64_t);
     auto k = vm_kernel<T, S, FULL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -301,7 +303,7 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-#define ACVMB_CONFIGS(X) X(1, 128) X(2, 64) X(4, 32) X(8, 16) X(16, 8) X(32, 4) X(4, 16) X(8, 8) X(16, 16) X(8, 32) X(32, 8) X(32, 1) X(32, 2)
+#define ACVMB_CONFIGS(X) X(1, 128) X(2, 64) X(4, 32) X(8, 16) X(16, 8) X(32, 4) X(4, 16) X(8, 8) X(16, 16) X(8, 32) X(32, 8) X(32, 1) X(32, 2) X(2, 16) X(1, 32) X(4, 8)
 
 cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pedersen) {
 #ifdef ACVMB_HEAVY_OPS

@@ -17,6 +17,7 @@ struct VmArgs {
     uint32_t first_step;          // this launch covers steps [first_step, first_step + n_steps)
     uint32_t n_steps;             // multiple of chunk_steps
     uint32_t chunk_steps;
+    uint32_t n_stage;             // depth of the shared-memory staging ring (1..8)
     uint32_t n_slots;
     uint32_t n_tiles;
     uint32_t* mu_assign;          // [tile][n_mu][T]: opcode index that assigned a value-dependent witness, ~0 = unassigned

@@ -1,22 +1,24 @@
-"""Ad-hoc GPU tuning sweep (not a test, not a bench line): pipe-split level x tile shape on a 2^16-gate circuit."""
+"""Ad-hoc GPU tuning sweep (not a test, not a bench line): tile shape / staging depth on a 2^16-gate circuit."""
 import sys, time, json, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import acvm_b200
 from acvm_b200 import acir_builder as ab
 ctx = acvm_b200.Context(0)
 print("device", ctx.device_name())
-print("imad", json.dumps(ctx.imad_microbench()))
 data, inputs, nw = ab.synthetic_arith_circuit(1 << 16)
-combos = [(16, 8, sp) for sp in (0, 1, 2, 3, 4)] + [(16, 4, sp) for sp in (0, 2, 4)]
-for S, T, split in combos:
-    ctx.set_option("S", S); ctx.set_option("T", T); ctx.set_option("split", split)
-    circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
-    for batch in (4096, 4736, 8192):
-        b = acvm_b200.DeviceBatch(circ, batch)
-        b.stage_inputs(0, ab.synthetic_inputs(16) * (batch // 16))
-        ms = [b.run_staged(0)[1] for _ in range(3)]
-        ok = all(s.status == "Solved" for s in b.status())
-        gi = (1 << 16) * batch
-        print(f"S={S} T={T} split={split} batch={batch} kernel_ms={min(ms):.3f} ok={ok} gate-inst/s={gi/(min(ms)*1e-3):.3e} imad/s={circ.info['dev_imad']*batch/(min(ms)*1e-3):.3e}", flush=True)
-        b.close()
-    circ.close()
+combos = [(16, 8, 4, 2), (16, 4, 4, 2), (16, 4, 3, 1), (16, 2, 2, 2), (16, 2, 3, 1), (16, 2, 2, 1), (16, 2, 4, 1), (8, 4, 3, 1), (32, 1, 2, 1)]
+for S, T, nst, chunk in combos:
+    ctx.set_option("S", S); ctx.set_option("T", T); ctx.set_option("n_stage", nst); ctx.set_option("chunk_steps", chunk)
+    try:
+        circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+        for batch in (4736, 5920, 8192):
+            b = acvm_b200.DeviceBatch(circ, batch)
+            b.stage_inputs(0, ab.synthetic_inputs(16) * (batch // 16))
+            ms = [b.run_staged(0)[1] for _ in range(3)]
+            ok = all(s.status == "Solved" for s in b.status())
+            gi = (1 << 16) * batch
+            print(f"S={S} T={T} n_stage={nst} chunk={chunk} batch={batch} kernel_ms={min(ms):.3f} ok={ok} gate-inst/s={gi/(min(ms)*1e-3):.3e}", flush=True)
+            b.close()
+        circ.close()
+    except Exception as e:
+        print(f"S={S} T={T} n_stage={nst} chunk={chunk}: {e}", flush=True)
