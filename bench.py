@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Rust acvm 0.27.0 cannot be built in this image (no cargo/rustc); this is the reference-algorithm restatement",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -386,13 +386,34 @@ def run_ours(args):
         line["cpu_baseline_optimized"] = {"value": n_o / dt_o, "unit": UNIT, "cores": threads, "kind": "port",
                                           "sample": f"{n_o} full solves, dense witness vector + plan-time inverses + 4x64 Montgomery "
                                                     f"({dt_o:.1f}s incl. the one-time plan; oracle/ref_solver.cpp ref_solve_batch_optimized)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+def _protect_stdout():
+    """The driver reads ONE JSON line from stdout.  Native libraries (NCCL prints its version banner there) must not be able
+    to add lines: fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real = os.fdopen(saved, "w")
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
