@@ -182,6 +182,25 @@ def workload_config(args, extra):
     return cfg
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: pin the process to the CPUs NVML reports as local to its GPU, so the pinned host buffers of the
+    end-to-end path are first-touched on the NUMA node next to the GPU's PCIe root (8 ranks x 50 GB/s of D2H otherwise
+    cross the socket interconnect)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"[bench] gpu {gpu_index}: bound to {len(cpus)} local CPUs")
+    except Exception as e:  # best effort only
+        log(f"[bench] gpu {gpu_index}: NUMA binding skipped ({e})")
+
+
 def run_ours(args):
     import acvm_b200
     from acvm_b200 import acir_builder as ab
@@ -195,6 +214,8 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     ctx = acvm_b200.Context(local_rank)
     if args.S:
         ctx.set_option("S", args.S)
