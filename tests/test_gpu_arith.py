@@ -210,3 +210,32 @@ def test_device_checksum_matches_host_definition(ctx):
     for i in range(batch):
         wm = {w: int.from_bytes(out[(i * nw + w) * 32:(i * nw + w + 1) * 32], "big") for w in range(nw) if assign[w] != 0xFFFFFFFF}
         assert acvm_b200.witness_checksum(wm) == sums[i]
+
+
+def test_forced_subbatching_and_ragged_tail(ctx):
+    # the sub-batch loop of acvmb_solve_batch (used when the witness columns do not fit in HBM) with a ragged last sub-batch
+    data, inputs, _ = ab.synthetic_arith_circuit(256, seed_id=12)
+    c2 = acvm_b200.Context(0, max_resident_bytes=(64 << 20) + 40 * 2400 * 32)   # fixed overhead + ~40 instances of columns
+    circ = acvm_b200.CompiledCircuit(c2, data, inputs)
+    batch = 103
+    inp = ab.synthetic_inputs(batch, seed_id=12)
+    out, st = circ.solve_batch(inp, batch)
+    assert circ.run_info()["n_subbatches"] >= 3
+    ref = acvm_b200.CompiledCircuit(ctx, data, inputs)
+    out_ref, st_ref = ref.solve_batch(inp, batch)
+    assert out == out_ref and [s.status for s in st] == [s.status for s in st_ref] == ["Solved"] * batch
+    c2.close()
+
+
+def test_plan_blob_roundtrip_with_host_segments(ctx):
+    # multi-GPU distribution path: rank 0 serialises the compiled plan (which embeds the ACIR bytes when Brillig opcodes need
+    # the host VM), other ranks deserialise and must produce identical results
+    from test_host_logic import _brillig_circuit, _brillig_inputs
+    rows, inp = _brillig_inputs()
+    data = _brillig_circuit()
+    a = acvm_b200.CompiledCircuit(ctx, data, [1, 2, 3])
+    blob = a.serialize()
+    b = acvm_b200.CompiledCircuit.from_blob(ctx, blob, [1, 2, 3])
+    oa, sa, pa = a.solve_batch(inp, len(rows), want_present=True)
+    ob, sb, pb = b.solve_batch(inp, len(rows), want_present=True)
+    assert (oa, pa) == (ob, pb) and [(s.status, s.error, s.opcode_index) for s in sa] == [(s.status, s.error, s.opcode_index) for s in sb]
