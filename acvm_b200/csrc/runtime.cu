@@ -397,6 +397,7 @@ extern "C" void acvmb_batch_destroy(acvmb_batch* b) {
 
 extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    cudaGetLastError();   // a stale error of an unrelated earlier call must not be attributed to this one
     acvmb_circuit* c = b->c;
     cudaStream_t s = c->ctx->stream;
     CUDA_TRY(cudaSetDevice(c->ctx->device));
@@ -421,6 +422,7 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg);
 
 extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    cudaGetLastError();   // a stale error of an unrelated earlier call must not be attributed to this one
     acvmb_circuit* c = b->c;
     cudaStream_t s = c->ctx->stream;
     CUDA_TRY(cudaSetDevice(c->ctx->device));

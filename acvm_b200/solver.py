@@ -7,6 +7,7 @@ plus the batch form this project exists for: the same circuit, many initial witn
 Everything numerical happens in libacvm_b200.so on the GPU; this file only marshals buffers.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -56,6 +57,7 @@ class Context:
 
     def __init__(self, device: int = 0, **options):
         self._h = C.c_void_p()
+        self._children = weakref.WeakSet()   # circuits / VMs created on this context: closed before the context itself
         _check(lib().acvmb_ctx_create(device, C.byref(self._h)))
         for k, v in options.items():
             self.set_option(k, v)
@@ -78,6 +80,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):   # the C objects hold a pointer to the context: they must go first
+                child.close()
             lib().acvmb_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -146,6 +150,8 @@ class CompiledCircuit:
         _check(lib().acvmb_circuit_info(self._h, C.byref(info)))
         self.info = info.as_dict()
         self.num_witnesses = self.info["num_witnesses"]
+        self._batches = weakref.WeakSet()
+        ctx._children.add(self)
 
     @classmethod
     def from_blob(cls, ctx, blob: bytes, input_witnesses: Sequence[int]):
@@ -194,6 +200,8 @@ class CompiledCircuit:
 
     def close(self):
         if self._h:
+            for b in list(self._batches):
+                b.close()
             lib().acvmb_circuit_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -212,6 +220,7 @@ class DeviceBatch:
         self.n = n
         self._h = C.c_void_p()
         _check(lib().acvmb_batch_create(circuit._h, n, C.byref(self._h)))
+        circuit._batches.add(self)
 
     def resize(self, n: int):
         _check(lib().acvmb_batch_resize(self._h, n))
@@ -276,6 +285,7 @@ class ACVM:
         keys = sorted(initial_witness)
         vals = b"".join(int(initial_witness[k]).to_bytes(32, "big") for k in keys)
         _check(lib().acvmb_vm_new(ctx._h, acir_bytes, len(acir_bytes), _u32_array(keys), vals, len(keys), C.byref(self._h)))
+        ctx._children.add(self)
 
     def solve(self) -> InstanceStatus:
         st = _lib.Status()

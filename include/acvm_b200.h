@@ -89,6 +89,7 @@ typedef struct {
 
 /* ---- context ---------------------------------------------------------------------------- */
 int acvmb_ctx_create(int device, acvmb_ctx** out);
+/* destroy every circuit / batch / vm created on a context BEFORE the context itself (they keep a pointer to it) */
 void acvmb_ctx_destroy(acvmb_ctx* ctx);
 const char* acvmb_last_error(void);           /* thread-local message of the last failing call */
 int acvmb_device_name(acvmb_ctx* ctx, char* buf, size_t len);
