@@ -223,8 +223,11 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
     if (fr::num_bits(x) > r->w[7]) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
 }
 
+// FULL variant: the curve / hash code wants ~128 registers, which would allow only 4 CTAs of 128 threads per SM; the
+// plan serialises heavy ops along each instance's dependency chain, so run time is (number of CTA waves) x (sum of heavy-op
+// latencies) and keeping the whole sub-batch in ONE wave matters more than spill-free heavy ops: cap at 7 CTAs/SM.
 template <int T, int S, bool FULL, int SPLIT>
-__global__ void __launch_bounds__(T* S) vm_kernel(const VmArgs a) {
+__global__ void __launch_bounds__(T* S, (FULL && T * S <= 128) ? (896 / (T * S)) : 1) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
     const uint32_t NSTAGE = a.n_stage;
