@@ -226,8 +226,10 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
 // FULL variant: the curve / hash code wants ~128 registers, which would allow only 4 CTAs of 128 threads per SM; the
 // plan serialises heavy ops along each instance's dependency chain, so run time is (number of CTA waves) x (sum of heavy-op
 // latencies) and keeping the whole sub-batch in ONE wave matters more than spill-free heavy ops: cap at 7 CTAs/SM.
-template <int T, int S, bool FULL, int SPLIT>
-__global__ void __launch_bounds__(T* S, (FULL && T * S <= 128) ? (896 / (T * S)) : 1) vm_kernel(const VmArgs a) {
+// CAP selects the register-capped build; the launcher uses it only when the uncapped one could not hold the sub-batch in a
+// single wave (it costs ~30 % on Keccak, whose state then spills).
+template <int T, int S, bool FULL, int SPLIT, bool CAP = false>
+__global__ void __launch_bounds__(T* S, (CAP && T * S <= 128) ? (896 / (T * S)) : 1) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
     const uint32_t NSTAGE = a.n_stage;
@@ -299,7 +301,14 @@ template <int T, int S, bool FULL, int SPLIT = FR_ALU_SPLIT>
 static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     if (args.n_stage < 1 || args.n_stage > MAX_NSTAGE) return cudaErrorInvalidValue;
     size_t smem = (size_t)args.n_stage * args.chunk_steps * S * sizeof(OpRec) + args.n_stage * sizeof(uint64_t);
-    auto k = vm_kernel<T, S, FULL, SPLIT>;
+    auto k = vm_kernel<T, S, FULL, SPLIT, false>;
+    if (FULL && T * S <= 128) {
+        // uncapped FULL build: ~128 registers -> 65536 / (128 * threads) CTAs per SM
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const uint32_t one_wave = (uint32_t)sms * (65536u / (128u * T * S));
+        if (args.n_tiles > one_wave) k = vm_kernel<T, S, FULL, SPLIT, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<args.n_tiles, T * S, smem, stream>>>(args);
