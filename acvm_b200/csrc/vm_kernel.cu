@@ -302,7 +302,7 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     if (args.n_stage < 1 || args.n_stage > MAX_NSTAGE) return cudaErrorInvalidValue;
     size_t smem = (size_t)args.n_stage * args.chunk_steps * S * sizeof(OpRec) + args.n_stage * sizeof(uint64_t);
     auto k = vm_kernel<T, S, FULL, SPLIT, false>;
-    if (FULL && T * S <= 128) {
+    if constexpr (FULL && T * S <= 128) {
         // uncapped FULL build: ~128 registers -> 65536 / (128 * threads) CTAs per SM
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
