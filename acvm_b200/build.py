@@ -55,7 +55,9 @@ def build(force=False, verbose=False):
         with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
             f.write(log)
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lz", "-gencode", "arch=compute_100a,code=sm_100a"]
+        # --no-undefined: a symbol missing from the objects must fail HERE, not at the first call on the GPU box
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lz", "-lpthread", "-ldl", "-lrt", "-Xlinker", "--no-undefined",
+                                                      "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -350,7 +350,7 @@ extern "C" int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, si
 static uint32_t pick_T(const acvmb_ctx* ctx, const Plan& p) {
     uint32_t T = ctx->opt_T ? ctx->opt_T : std::max(1u, 128u / p.S);
     if (T > 32) T = 32;
-    while (T > 1 && !vm_config_supported((int)T, (int)p.S)) T /= 2;
+    while (T > 1 && !vm_config_supported((int)T, (int)p.S, p.needs_full_kernel)) T /= 2;
     return T;
 }
 
@@ -361,7 +361,7 @@ extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_
     b->c = c;
     b->n_inst = n_instances;
     b->T = pick_T(c->ctx, c->plan);
-    if (!vm_config_supported((int)b->T, (int)c->plan.S))
+    if (!vm_config_supported((int)b->T, (int)c->plan.S, c->plan.needs_full_kernel))
         return set_err(ACVMB_ERR_INVALID_ARG, "no kernel instantiation for T=" + std::to_string(b->T) + " S=" + std::to_string(c->plan.S));
     b->capacity = n_instances;
     b->n_tiles = (n_instances + b->T - 1) / b->T;

@@ -315,7 +315,10 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-#define ACVMB_CONFIGS(X) X(1, 128) X(2, 64) X(4, 32) X(8, 16) X(16, 8) X(32, 4) X(4, 16) X(8, 8) X(16, 16) X(8, 32) X(32, 8) X(32, 1) X(32, 2) X(2, 16) X(1, 32) X(4, 8)
+// tile shapes (T instances x S slots).  The FULL variant (hash / curve / general ops) is instantiated for fewer shapes:
+// it dominates compile time.
+#define ACVMB_CONFIGS_LIGHT(X) X(8, 16) X(4, 16) X(2, 16) X(16, 16) X(16, 8) X(32, 4) X(32, 2) X(32, 1) X(4, 32) X(2, 64)
+#define ACVMB_CONFIGS_FULL(X) X(8, 16) X(4, 16) X(16, 8) X(32, 4) X(32, 2) X(32, 1) X(4, 32) X(2, 64)
 
 cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pedersen) {
 #ifdef ACVMB_HEAVY_OPS
@@ -327,26 +330,29 @@ cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pederse
 #endif
 }
 
-bool vm_config_supported(int T, int S) {
+bool vm_config_supported(int T, int S, bool full) {
 #define X(t, s) if (T == t && S == s) return true;
-    ACVMB_CONFIGS(X)
+    if (full) { ACVMB_CONFIGS_FULL(X) } else { ACVMB_CONFIGS_LIGHT(X) }
 #undef X
     return false;
 }
 
 cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream) {
-    // tuning hook: explicit FMA/ALU pipe-split level for the two production tile shapes of the arithmetic kernel
-    if (cfg.split >= 0 && !cfg.full && cfg.S == 16 && (cfg.T == 8 || cfg.T == 4)) {
-#define Y(t, sp) if (cfg.T == t && cfg.split == sp) return launch_one<t, 16, false, sp>(args, stream);
-        Y(8, 0) Y(8, 1) Y(8, 2) Y(8, 3) Y(8, 4) Y(4, 0) Y(4, 2) Y(4, 4)
+    // tuning hook: explicit FMA/ALU pipe-split level for the production tile shape of the arithmetic kernel
+    if (cfg.split >= 0 && !cfg.full && cfg.S == 16 && cfg.T == 8) {
+#define Y(sp) if (cfg.split == sp) return launch_one<8, 16, false, sp>(args, stream);
+        Y(0) Y(1) Y(2) Y(3) Y(4)
 #undef Y
     }
-#define X(t, s)                                                                        \
-    if (cfg.T == t && cfg.S == s) {                                                    \
-        return cfg.full ? launch_one<t, s, true>(args, stream) : launch_one<t, s, false>(args, stream); \
-    }
-    ACVMB_CONFIGS(X)
+    if (cfg.full) {
+#define X(t, s) if (cfg.T == t && cfg.S == s) return launch_one<t, s, true>(args, stream);
+        ACVMB_CONFIGS_FULL(X)
 #undef X
+    } else {
+#define X(t, s) if (cfg.T == t && cfg.S == s) return launch_one<t, s, false>(args, stream);
+        ACVMB_CONFIGS_LIGHT(X)
+#undef X
+    }
     return cudaErrorInvalidConfiguration;
 }
 

@@ -32,7 +32,7 @@ struct KernelConfig {
 
 // returns cudaSuccess or the launch error; smem_bytes/regs reported for the run record
 cudaError_t launch_vm(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream);
-bool vm_config_supported(int T, int S);
+bool vm_config_supported(int T, int S, bool full);
 // device pointers of the Grumpkin lookup tables (built by the host once per context)
 cudaError_t set_curve_tables(const uint32_t* fixed_base, const uint32_t* pedersen);
 
