@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libacvm_b200.so")
-SOURCES = ["runtime.cu", "vm_kernel.cu", "acir.cpp", "plan.cpp"]
+SOURCES = ["vm_kernel_full.cu", "vm_kernel.cu", "runtime.cu", "acir.cpp", "plan.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-DACVMB_HEAVY_OPS"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
 
 
 def _deps_mtime():
