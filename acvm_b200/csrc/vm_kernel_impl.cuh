@@ -233,7 +233,7 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
 // CAP selects the register-capped build; the launcher uses it only when the uncapped one could not hold the sub-batch in a
 // single wave (it costs ~30 % on Keccak, whose state then spills).
 template <int T, int S, bool FULL, int SPLIT, bool CAP = false>
-__global__ void __launch_bounds__(T* S, (CAP && T * S <= 128) ? (896 / (T * S)) : 1) vm_kernel(const VmArgs a) {
+__global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : (FULL ? 512 / (T * S) : 1)) : 1) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
     const uint32_t NSTAGE = a.n_stage;
