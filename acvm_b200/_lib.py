@@ -81,6 +81,8 @@ def load():
         "acvmb_pedersen": (C.c_int, [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_sha256": (C.c_int, [vp, C.c_char_p, C.c_uint32, C.c_uint32, vp]),
         "acvmb_keccak256": (C.c_int, [vp, C.c_char_p, C.c_uint32, C.c_uint32, vp]),
+        "acvmb_ecdsa_secp256k1_verify": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, vp, C.POINTER(Status)]),
+        "acvmb_ecdsa_secp256r1_verify": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_plan_compile_host": (C.c_int, [C.c_char_p, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.POINTER(PlanInfo), vp,
                                               C.c_size_t, C.POINTER(C.c_size_t)]),
         "acvmb_pedersen_generator_host": (C.c_int, [C.c_uint32, C.c_char_p]),

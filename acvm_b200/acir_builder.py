@@ -188,6 +188,35 @@ class CircuitBuilder:
         self._see(*outputs)
         self.n_opcodes += 1
 
+    def ecdsa(self, name, public_key_x, public_key_y, signature, hashed_message, output):
+        """name: EcdsaSecp256k1 | EcdsaSecp256r1; field order of black_box_function_call.rs:60-75"""
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS[name])
+        self._vfi(public_key_x)
+        self._vfi(public_key_y)
+        self._vfi(signature)
+        self._vfi(hashed_message)
+        self.w.u32(output)
+        self._see(output)
+        self.n_opcodes += 1
+
+    def recursive_aggregation(self, verification_key, proof, public_inputs, key_hash, input_aggregation_object,
+                              output_aggregation_object):
+        """black_box_function_call.rs:84-112; input_aggregation_object is an Option<Vec<FunctionInput>>"""
+        self.w.u32(1)
+        self.w.u32(BLACKBOX_TAGS["RecursiveAggregation"])
+        self._vfi(verification_key)
+        self._vfi(proof)
+        self._vfi(public_inputs)
+        self._fi(key_hash)
+        if input_aggregation_object is None:
+            self.w.u8(0)
+        else:
+            self.w.u8(1)
+            self._vfi(input_aggregation_object)
+        self._vw(output_aggregation_object)
+        self.n_opcodes += 1
+
     def _expr(self, e):
         """e = (mul_terms, lin, q_c)"""
         w_expression(self.w, e[0], e[1], e[2])

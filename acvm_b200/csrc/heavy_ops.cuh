@@ -12,6 +12,7 @@
 // columns (each message byte is its own 32-byte witness, hash.rs:51-66) and the 32 digest bytes
 // are scattered to 32 output columns.
 #pragma once
+#include "ecdsa.cuh"
 #include "fr.cuh"
 #include "plan.hpp"
 
@@ -869,6 +870,37 @@ __device__ __noinline__ void exec_mem(const OpRec* r, uint32_t kind, uint4* cb, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ECDSA secp256k1 / secp256r1 (signature/ecdsa.rs:12-97): every input is one byte = the low byte of its witness
+// (signature/mod.rs:5-18, to_be_bytes().last()); out := 1 / 0; reference panics -> EK_REFERENCE_PANIC.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int ecdsa_verify_dev(int curve, const uint8_t* bytes) {
+    return ec::ecdsa_verify(curve, bytes + 128, bytes, bytes + 32, bytes + 64);
+}
+template <int T>
+__device__ __noinline__ void exec_ecdsa(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    uint8_t bytes[160];   // pkx | pky | sig | hashed message
+#pragma unroll 1
+    for (int k0 = 0; k0 < 160; k0 += 8) {
+        uint32_t low[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) low[g] = reinterpret_cast<const uint32_t*>(cb + (size_t)pl[1 + k0 + g] * (2 * T))[0];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) bytes[k0 + g] = (uint8_t)low[g];
+    }
+    const int res = ecdsa_verify_dev((int)pl[0], bytes);
+    if (res == ec::EC_PANIC) {
+        hv_fail(fail, r->w[1], EK_REFERENCE_PANIC, 0);
+        return;
+    }
+    Fe v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.l[k] = 0;
+    v.l[0] = res == ec::EC_TRUE;
+    insert_value_dev<T>(r, flags & GF_OUT_CHECK, r->w[2], v, cb, fail);
+}
+
 template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
                                            const uint32_t* payload, uint32_t* mu) {
@@ -890,6 +922,9 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_PEDERSEN:
             exec_pedersen<T>(r, flags, cb, fail, payload);
+            break;
+        case MK_ECDSA:
+            exec_ecdsa<T>(r, flags, cb, fail, payload);
             break;
         case MK_GATE_GENERAL:
             exec_general<T>(r, cb, fail, payload, mu);

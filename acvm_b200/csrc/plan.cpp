@@ -796,7 +796,7 @@ struct Compiler {
 
     bool blackbox(uint32_t idx, const BlackBoxCall& b) {
         for (uint32_t w : b.outputs)
-            if (known[w] == W_MAYBE)
+            if (known[w] == W_MAYBE && b.func != BB_RecursiveAggregation)
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": blackbox output witness " + std::to_string(w) +
                                          " is only conditionally assigned by an earlier value-dependent gate; not supported yet");
         for (auto& in : b.inputs)
@@ -986,6 +986,58 @@ struct Compiler {
                 ++plan.stats.n_micro;
                 ++plan.stats.n_curve;
                 plan.stats.alg_bytes += 32 * b.inputs.size() + 64;
+                return true;
+            }
+            case BB_EcdsaSecp256k1:
+            case BB_EcdsaSecp256r1: {
+                // signature/ecdsa.rs:12-97.  seg[] = sizes of public_key_x, public_key_y, signature, hashed_message.
+                static const char* label[3] = {"pubkey_x", "pubkey_y", "signature"};
+                static const uint32_t want[3] = {32, 32, 64};
+                for (int k = 0; k < 3; ++k)
+                    if (b.seg[k] != want[k]) {
+                        fail_static(idx, EK_BLACKBOX_FAILED, b.func,
+                                    std::string("expected ") + label[k] + " size " + std::to_string(want[k]) + " but received " +
+                                        std::to_string(b.seg[k]));
+                        return false;
+                    }
+                if (b.seg[3] != 32) {  // GenericArray::from_slice(hashed_msg) asserts the length (blackbox_solver/src/lib.rs:127)
+                    fail_static(idx, EK_REFERENCE_PANIC, 0, "hashed message is not 32 bytes");
+                    return false;
+                }
+                uint32_t out = b.outputs[0];
+                uint32_t flags = GF_HEAVY;
+                std::vector<uint32_t> rd, wr;
+                uint32_t off = (uint32_t)plan.payload.size();
+                plan.payload.push_back(b.func == BB_EcdsaSecp256k1 ? 0u : 1u);
+                for (auto& in : b.inputs) {   // pkx[32] pky[32] sig[64] hashed_message[32]; num_bits unused (signature/mod.rs:5-18)
+                    plan.payload.push_back(in.witness);
+                    rd.push_back(in.witness);
+                }
+                if (known[out]) { flags |= GF_OUT_CHECK; rd.push_back(out); }
+                wr.push_back(out);
+                r.w[0] = MK_ECDSA | (flags << 8);
+                r.w[1] = idx;
+                r.w[2] = out;
+                r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+                r.w[7] = off;
+                place_heavy(r, rd, wr);
+                if (!known[out]) mark_assigned(out, idx);
+                ++plan.stats.n_curve;
+                plan.stats.alg_bytes += 32 * b.inputs.size() + 32;
+                return true;
+            }
+            case BB_RecursiveAggregation: {
+                // blackbox/mod.rs:154-161: every output witness := 0 (insert_value semantics); the proof is the backend's job
+                for (uint32_t w : b.outputs) {
+                    if (known[w] == W_MAYBE) {   // per-lane presence: same rule as the gate `w = 0`
+                        Expression e;
+                        e.linear_combinations.push_back({hf::from_u64(1), w});
+                        if (!arithmetic(idx, e)) return false;
+                        continue;
+                    }
+                    lower_sum({}, {}, U256{}, /*assign=*/true, w, idx, /*out_check=*/known[w] != 0);
+                    if (!known[w]) mark_assigned(w, idx);
+                }
                 return true;
             }
             default:

@@ -48,6 +48,7 @@ enum MicroKind : uint32_t {
     MK_MEM_WRITE = 17,    // x = index, y = value, w1 = predicate|NONE;     payload[aux..]: base, len  (memory_op.rs:111-123)
     MK_BLAKE2S = 18,      // same payload as MK_SHA256                                  (hash.rs:28-48 -> blake2 0.10.6)
     MK_HASH_TO_FIELD = 19,// payload: n_in, check, NONE, 0, (witness,num_bits)*, 1 output: blake2s digest reduced mod p (hash.rs:13-24)
+    MK_ECDSA = 20,        // out := verify; payload[aux..]: curve (0 k1, 1 r1), 32 pkx, 32 pky, 64 sig, 32 hashed-message witnesses (signature/ecdsa.rs)
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
 };
 

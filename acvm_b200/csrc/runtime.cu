@@ -1111,6 +1111,43 @@ extern "C" int acvmb_keccak256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg
     return hash_bytes(ctx, BB_Keccak256, msgs, msg_len, batch, digests);
 }
 
+static int ecdsa_bytes(acvmb_ctx* ctx, uint32_t func, const uint8_t* hashed, const uint8_t* pkx, const uint8_t* pky, const uint8_t* sig,
+                       uint32_t batch, uint8_t* out_valid, acvmb_status* st) {
+    if (!ctx || !hashed || !pkx || !pky || !sig || !out_valid || !st) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    Opcode op;
+    op.kind = OP_BlackBox;
+    op.bb.func = func;
+    std::vector<uint32_t> in_ids;
+    for (uint32_t i = 0; i < 160; ++i) {   // get_inputs_vec order: pkx, pky, signature, hashed message
+        op.bb.inputs.push_back({i + 1, 8});
+        in_ids.push_back(i + 1);
+    }
+    op.bb.seg[0] = op.bb.seg[1] = op.bb.seg[3] = 32;
+    op.bb.seg[2] = 64;
+    op.bb.outputs = {161};
+    std::vector<uint8_t> in((size_t)batch * 160 * 32, 0);
+    for (size_t i = 0; i < batch; ++i) {
+        uint8_t* row = &in[i * 160 * 32];
+        for (int k = 0; k < 32; ++k) row[(size_t)k * 32 + 31] = pkx[i * 32 + k];
+        for (int k = 0; k < 32; ++k) row[(size_t)(32 + k) * 32 + 31] = pky[i * 32 + k];
+        for (int k = 0; k < 64; ++k) row[(size_t)(64 + k) * 32 + 31] = sig[i * 64 + k];
+        for (int k = 0; k < 32; ++k) row[(size_t)(128 + k) * 32 + 31] = hashed[i * 32 + k];
+    }
+    std::vector<uint8_t> out((size_t)batch * 32);
+    int rc = run_single_opcode(ctx, op, 162, in_ids, {161}, in.data(), batch, out.data(), st);
+    if (rc) return rc;
+    for (size_t i = 0; i < batch; ++i) out_valid[i] = st[i].code == ACVMB_SOLVED ? out[i * 32 + 31] : 0;
+    return ACVMB_OK;
+}
+extern "C" int acvmb_ecdsa_secp256k1_verify(acvmb_ctx* ctx, const uint8_t* hashed, const uint8_t* pkx, const uint8_t* pky,
+                                            const uint8_t* sig, uint32_t batch, uint8_t* out_valid, acvmb_status* st) {
+    return ecdsa_bytes(ctx, BB_EcdsaSecp256k1, hashed, pkx, pky, sig, batch, out_valid, st);
+}
+extern "C" int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed, const uint8_t* pkx, const uint8_t* pky,
+                                            const uint8_t* sig, uint32_t batch, uint8_t* out_valid, acvmb_status* st) {
+    return ecdsa_bytes(ctx, BB_EcdsaSecp256r1, hashed, pkx, pky, sig, batch, out_valid, st);
+}
+
 extern "C" int acvmb_imad_microbench(acvmb_ctx* ctx, double* a, double* b, double* c, double* mhz) {
     if (!ctx) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));

@@ -120,6 +120,18 @@ class Context:
     def keccak256(self, msgs: Sequence[bytes]):
         return self._hash("acvmb_keccak256", msgs)
 
+    def ecdsa_verify(self, curve: str, hashed_msgs: Sequence[bytes], public_keys_x: Sequence[bytes], public_keys_y: Sequence[bytes],
+                     signatures: Sequence[bytes]):
+        """ecdsa_secp256k1_verify / ecdsa_secp256r1_verify (blackbox_solver/src/lib.rs:67-83), batched.
+        curve: "secp256k1" | "secp256r1".  Returns ([bool], [InstanceStatus]); reference panics show up in the status."""
+        n = len(hashed_msgs)
+        assert all(len(x) == 32 for x in list(hashed_msgs) + list(public_keys_x) + list(public_keys_y)) and all(len(x) == 64 for x in signatures)
+        out = C.create_string_buffer(n)
+        st = (_lib.Status * n)()
+        fn = {"secp256k1": lib().acvmb_ecdsa_secp256k1_verify, "secp256r1": lib().acvmb_ecdsa_secp256r1_verify}[curve]
+        _check(fn(self._h, b"".join(hashed_msgs), b"".join(public_keys_x), b"".join(public_keys_y), b"".join(signatures), n, out, st))
+        return [bool(b) for b in out.raw], [_status(s) for s in st]
+
     def _hash(self, fn, msgs):
         n = len(msgs)
         ln = len(msgs[0]) if n else 0

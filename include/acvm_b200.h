@@ -181,6 +181,15 @@ int acvmb_pedersen(acvmb_ctx* ctx, const uint8_t* inputs_be32 /*[batch][n_inputs
 int acvmb_sha256(acvmb_ctx* ctx, const uint8_t* msgs /*[batch][msg_len]*/, uint32_t msg_len, uint32_t batch,
                  uint8_t* digests /*[batch][32]*/);
 int acvmb_keccak256(acvmb_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint32_t batch, uint8_t* digests);
+/* acvm_blackbox_solver::ecdsa_secp256k1_verify / ecdsa_secp256r1_verify (blackbox_solver/src/lib.rs:67-83,101-210), batched.
+ * out_valid[i] = 1 / 0.  Inputs on which the reference panics (r or s outside [1, n-1], x not on the curve, hash >= n,
+ * R at infinity) give out_status[i] = {ACVMB_FAILURE, ACVMB_E_REFERENCE_PANIC} and out_valid[i] = 0.  As in the reference,
+ * only the parity of public_key_y is used (the key is rebuilt from its compressed encoding). */
+int acvmb_ecdsa_secp256k1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg /*[batch][32]*/, const uint8_t* public_key_x /*[batch][32]*/,
+                                 const uint8_t* public_key_y /*[batch][32]*/, const uint8_t* signature /*[batch][64]*/, uint32_t batch,
+                                 uint8_t* out_valid /*[batch]*/, acvmb_status* out_status);
+int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg, const uint8_t* public_key_x, const uint8_t* public_key_y,
+                                 const uint8_t* signature, uint32_t batch, uint8_t* out_valid, acvmb_status* out_status);
 
 /* ---- host-only: decode + compile without a device (CPU tests of the decoder / plan compiler) ---- */
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,

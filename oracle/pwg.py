@@ -279,6 +279,19 @@ def solve_blackbox(backend, wm, bb):  # blackbox/mod.rs:50-163
             raise ResolutionError("BlackBoxFunctionFailed", func=e.func, message=e.reason)
         insert_value(bb["outputs"][0], x, wm)
         insert_value(bb["outputs"][1], y, wm)
+    elif n in ("EcdsaSecp256k1", "EcdsaSecp256r1"):  # signature/ecdsa.rs:12-97, signature/mod.rs:5-18
+        from . import ecdsa
+        low_bytes = lambda ins: bytes(witness_to_value(wm, w) & 0xFF for (w, _) in ins)   # to_be_bytes().last()
+        hashed = low_bytes(bb["hashed_message"])
+        for key, size, label in (("public_key_x", 32, "pubkey_x"), ("public_key_y", 32, "pubkey_y"), ("signature", 64, "signature")):
+            if len(bb[key]) != size:
+                raise ResolutionError("BlackBoxFunctionFailed", func=n,
+                                      message=f"expected {label} size {size} but received {len(bb[key])}")
+        try:
+            valid = ecdsa.verify(n, hashed, low_bytes(bb["public_key_x"]), low_bytes(bb["public_key_y"]), low_bytes(bb["signature"]))
+        except ecdsa.ReferencePanic as e:
+            raise ReferencePanic(str(e))
+        insert_value(bb["output"], 1 if valid else 0, wm)
     elif n == "RecursiveAggregation":  # mod.rs:154-161
         for w in bb["output_aggregation_object"]:
             insert_value(w, 0, wm)

@@ -11,6 +11,7 @@ Sources (all under /root/reference):
   acir_field/src/generic_ark.rs:424-438          hex of 0,-1,-2,-3
   barretenberg_blackbox_solver/src/wasm/*.rs     Pedersen / fixed-base KATs
   brillig_vm/src/black_box.rs:203-209            SHA-256("hello world")
+  blackbox_solver/src/lib.rs:216-290             ECDSA secp256k1 / secp256r1 valid-signature KATs
 """
 import json, os, re, sys
 
@@ -42,6 +43,20 @@ def ts_fixture(path):
     for m in re.finditer(r"export const (\w+)\s*=\s*\n?\s*\"(0x[0-9a-fA-F]+)\";", src):
         fx[m.group(1)] = m.group(2)
     return fx
+
+
+def ecdsa_kats(path):
+    """blackbox_solver/src/lib.rs:216-290: the two `verifies_valid_*_signature_with_low_s_value` tests."""
+    src = open(path).read()
+    out = {}
+    for m in re.finditer(r"fn verifies_valid_(k1|r1)_signature_with_low_s_value\(\) \{(.*?)assert!\(valid\)", src, re.S):
+        kat = {}
+        for a in re.finditer(r"let (\w+)(?::\s*\[u8; \d+\])?\s*=\s*\[(.*?)\];", m.group(2), re.S):
+            kat[a.group(1)] = bytes(int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", a.group(2))).hex()
+        assert {len(bytes.fromhex(v)) for v in kat.values()} == {32, 64}, kat
+        out["EcdsaSecp256" + m.group(1)] = kat
+    assert set(out) == {"EcdsaSecp256k1", "EcdsaSecp256r1"}
+    return out
 
 
 def main():
@@ -80,6 +95,7 @@ def main():
              "x": "09489945604c9686e698cb69d7bd6fc0cdb02e9faae3e1a433f1c342c1a5ecc4",
              "y": "24f50d25508b4dfb1e8a834e39565f646e217b24cb3a475c2e4991d1bb07a9d8"},
         ],
+        "ecdsa_valid": ecdsa_kats(f"{REF}/blackbox_solver/src/lib.rs"),  # expected result: true
         "grumpkin_order": "30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47",  # scalar_mul.rs:42-45
     }
     # sanity: the rust and ts byte vectors must agree where both exist

@@ -12,7 +12,7 @@ NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
           GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17,
-          BLAKE2S=18, HASH_TO_FIELD=19)
+          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20)
 EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
@@ -147,7 +147,24 @@ def default_hooks():
                 w.append((slot, v))
         return w
 
-    return {MK["BLAKE2S"]: hash_hook(hashes.blake2s), MK["HASH_TO_FIELD"]: hash_to_field, MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
+    def ecdsa_hook(cols, hdr, payload, record_fail):
+        from oracle import ecdsa
+        flags = hdr[0] >> 8
+        opcode, out, off = hdr[1], hdr[2], hdr[7]
+        b = bytes(cols[w] & 0xFF for w in payload[off + 1: off + 161])
+        try:
+            v = 1 if ecdsa.verify(["EcdsaSecp256k1", "EcdsaSecp256r1"][payload[off]], b[128:160], b[0:32], b[32:64], b[64:128]) else 0
+        except ecdsa.ReferencePanic:
+            record_fail(opcode, EK_PANIC)
+            return []
+        if flags & GF_OUT_CHECK_:
+            if cols[out] != v:
+                record_fail(opcode, EK_UNSAT)
+                return [(out, v)]
+            return []
+        return [(out, v)]
+
+    return {MK["ECDSA"]: ecdsa_hook, MK["BLAKE2S"]: hash_hook(hashes.blake2s), MK["HASH_TO_FIELD"]: hash_to_field, MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
 
 
 def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):

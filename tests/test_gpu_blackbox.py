@@ -206,3 +206,39 @@ def test_blake2s_and_hash_to_field(ctx):
     data = b.to_bytes()
     batch = 6
     _check_circuit(ctx, data, [1, 2, 3, 4, 5], batch, ab.synthetic_inputs(batch, n_inputs=5, seed_id=77))
+
+
+@pytest.mark.parametrize("name,curve", [("EcdsaSecp256k1", "secp256k1"), ("EcdsaSecp256r1", "secp256r1")])
+def test_ecdsa_kats_and_trait_call(ctx, golden, name, curve):  # blackbox_solver/src/lib.rs:216-290
+    import ecdsa_cases
+    k = golden["kats"]["ecdsa_valid"][name]
+    kat = [bytes.fromhex(k[a]) for a in ("hashed_message", "pub_key_x", "pub_key_y", "signature")]
+    cs = ecdsa_cases.cases(name, seed=5, n_random=2)
+    hm = [kat[0]] + [c[1] for c in cs]
+    px = [kat[1]] + [c[2] for c in cs]
+    py = [kat[2]] + [c[3] for c in cs]
+    sg = [kat[3]] + [c[4] for c in cs]
+    valid, st = ctx.ecdsa_verify(curve, hm, px, py, sg)
+    assert valid[0] is True and st[0].status == "Solved"
+    for i, c in enumerate(cs, start=1):
+        if c[5] == "panic":
+            assert st[i].status == "Failure" and st[i].error == "ReferencePanic" and valid[i] is False, c[0]
+        else:
+            assert st[i].status == "Solved" and valid[i] is c[5], c[0]
+
+
+@pytest.mark.parametrize("name", ["EcdsaSecp256k1", "EcdsaSecp256r1"])
+def test_ecdsa_circuit_with_recursive_aggregation(ctx, name):
+    import ecdsa_cases
+    rnd = random.Random(17)
+    cs = ecdsa_cases.cases(name, seed=7, n_random=2)
+    inp = b"".join(ecdsa_cases.input_row(c, rnd) for c in cs)
+    st = _check_circuit(ctx, ecdsa_cases.circuit(name), ecdsa_cases.INPUTS, len(cs), inp)
+    assert {s.status for s in st} == {"Solved", "Failure"}
+    # an aggregation-object output that an earlier opcode assigned a non-zero value: UnsatisfiedConstrain at that opcode
+    st = _check_circuit(ctx, ecdsa_cases.circuit(name, preassigned_out=True), ecdsa_cases.INPUTS, 4, inp)
+    assert st[0].error == "UnsatisfiedConstrain" and st[0].opcode_index == 2
+    # malformed opcodes fail every instance the way the reference does
+    for kw, err in ((dict(n_pkx=31), "BlackBoxFunctionFailed"), (dict(n_hm=31), "ReferencePanic")):
+        st = _check_circuit(ctx, ecdsa_cases.circuit(name, **kw), ecdsa_cases.INPUTS, 2, inp)
+        assert all(s.error == err and s.opcode_index == 0 for s in st)

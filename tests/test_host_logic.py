@@ -435,3 +435,37 @@ def test_witness_map_compression_golden(golden):  # acvm_js/test/shared/witness_
     ours = acvm_b200.compress_witness_map(expected)
     assert acvm_b200.decompress_witness_map(ours) == expected
     assert acir.decode_witness_map(ours) == expected        # the oracle's independent decoder accepts our bytes
+
+
+def test_ecdsa_device_routine_on_host(tmp_path, golden):
+    """acvm_b200/csrc/ecdsa.cuh is plain C++: the routine each GPU lane runs, compiled for the host, against the oracle."""
+    import ecdsa_cases
+    from oracle import ecdsa
+    so = tmp_path / "ecdsa_host_shim.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "host", "ecdsa_host_shim.cpp")], check=True)
+    L = ctypes.CDLL(str(so))
+    for ci, name in enumerate(("EcdsaSecp256k1", "EcdsaSecp256r1")):
+        k = golden["kats"]["ecdsa_valid"][name]
+        assert L.t_ecdsa_verify(ci, *[bytes.fromhex(k[a]) for a in ("hashed_message", "pub_key_x", "pub_key_y", "signature")]) == 1
+        seen = set()
+        for (label, hm, px, py, sig, exp) in ecdsa_cases.cases(name, seed=2, n_random=6):
+            assert L.t_ecdsa_verify(ci, hm, px, py, sig) == {True: 1, False: 0, "panic": 2}[exp], (name, label)
+            seen.add(exp)
+        assert seen == {True, False, "panic"}
+
+
+@pytest.mark.parametrize("name", ["EcdsaSecp256k1", "EcdsaSecp256r1"])
+def test_ecdsa_and_recursive_aggregation_plan_vs_oracle(name):
+    import ecdsa_cases
+    rnd = random.Random(9)
+    cs = ecdsa_cases.cases(name, seed=3, n_random=1)
+    inp = b"".join(ecdsa_cases.input_row(c, rnd) for c in cs)
+    info = _interp_vs_oracle(ecdsa_cases.circuit(name), ecdsa_cases.INPUTS, inp, len(cs))
+    assert info["needs_full_kernel"] == 1 and info["n_curve"] == 1 and not info["static_fail_present"]
+    # RecursiveAggregation output that an earlier opcode already assigned: insert_value compares with 0 (mod.rs:154-161)
+    _interp_vs_oracle(ecdsa_cases.circuit(name, preassigned_out=True), ecdsa_cases.INPUTS, inp, 3)
+    # malformed opcodes: size errors are BlackBoxFunctionFailed, a short hash panics in GenericArray::from_slice
+    info = _interp_vs_oracle(ecdsa_cases.circuit(name, n_pkx=31), ecdsa_cases.INPUTS, inp, 1)
+    assert info["static_fail_present"] and acvm_b200.solver.ERR_NAMES[info["static_fail_kind"]] == "BlackBoxFunctionFailed"
+    info = _interp_vs_oracle(ecdsa_cases.circuit(name, n_hm=31), ecdsa_cases.INPUTS, inp, 1)
+    assert info["static_fail_present"] and acvm_b200.solver.ERR_NAMES[info["static_fail_kind"]] == "ReferencePanic"

@@ -168,3 +168,53 @@ def test_pedersen_structure():
     a = pedersen.commit_native([5, 6], 0)
     assert a != pedersen.commit_native([6, 5], 0) and a != pedersen.commit_native([5, 6], 1)
     assert pedersen.commit_native([], 3) == (0, 0)
+
+
+def test_ecdsa_reference_kats(golden):  # blackbox_solver/src/lib.rs:216-290
+    from oracle import ecdsa
+    assert set(golden["kats"]["ecdsa_valid"]) == {"EcdsaSecp256k1", "EcdsaSecp256r1"}
+    for name, k in golden["kats"]["ecdsa_valid"].items():
+        args = [bytes.fromhex(k[a]) for a in ("hashed_message", "pub_key_x", "pub_key_y", "signature")]
+        assert ecdsa.verify(name, *args) is True
+        bad = bytearray(args[0]); bad[5] ^= 1
+        assert ecdsa.verify(name, bytes(bad), *args[1:]) is False
+
+
+def test_ecdsa_oracle_against_openssl():
+    """Independent pin of the third-party arithmetic (k256 / p256 are not in the tree): OpenSSL, through `cryptography`,
+    must agree with oracle/ecdsa.py on signatures made by either side.  OpenSSL accepts high-S signatures, so the
+    comparison is on low-S ones; the low-S rule itself is the reference's (lib.rs:133-136)."""
+    import random
+    crypto = pytest.importorskip("cryptography")
+    from cryptography.exceptions import InvalidSignature
+    from cryptography.hazmat.primitives import hashes as chashes
+    from cryptography.hazmat.primitives.asymmetric import ec as cec, utils as cutils
+    from oracle import ecdsa
+    rnd = random.Random(11)
+    for name, curve in (("EcdsaSecp256k1", cec.SECP256K1()), ("EcdsaSecp256r1", cec.SECP256R1())):
+        c = ecdsa.CURVES[name]
+        for it in range(6):
+            digest = bytes(rnd.randrange(256) for _ in range(32))
+            if int.from_bytes(digest, "big") >= c.n:
+                continue
+            # signed by OpenSSL, verified by the oracle
+            key = cec.generate_private_key(curve)
+            pub = key.public_key().public_numbers()
+            r, s = cutils.decode_dss_signature(key.sign(digest, cec.ECDSA(cutils.Prehashed(chashes.SHA256()))))
+            sig = r.to_bytes(32, "big") + s.to_bytes(32, "big")
+            px, py = pub.x.to_bytes(32, "big"), pub.y.to_bytes(32, "big")
+            assert ecdsa.verify(name, digest, px, py, sig) is (s <= (c.n - 1) // 2)
+            low = r.to_bytes(32, "big") + min(s, c.n - s).to_bytes(32, "big")
+            assert ecdsa.verify(name, digest, px, py, low) is True
+            # signed by the oracle's helper, verified by OpenSSL; and a corrupted copy rejected by both
+            d = rnd.randrange(1, c.n)
+            P = ecdsa.public_key(name, d)
+            r2, s2 = ecdsa.sign(name, d, int.from_bytes(digest, "big"), rnd.randrange(1, c.n))
+            opub = cec.EllipticCurvePublicNumbers(P[0], P[1], curve).public_key()
+            opub.verify(cutils.encode_dss_signature(r2, s2), digest, cec.ECDSA(cutils.Prehashed(chashes.SHA256())))
+            wrong = bytes([digest[0] ^ 0x40]) + digest[1:]
+            with pytest.raises(InvalidSignature):
+                opub.verify(cutils.encode_dss_signature(r2, s2), wrong, cec.ECDSA(cutils.Prehashed(chashes.SHA256())))
+            if int.from_bytes(wrong, "big") < c.n:
+                assert ecdsa.verify(name, wrong, P[0].to_bytes(32, "big"), P[1].to_bytes(32, "big"),
+                                    r2.to_bytes(32, "big") + s2.to_bytes(32, "big")) is False
