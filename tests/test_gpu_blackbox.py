@@ -236,9 +236,9 @@ def test_ecdsa_circuit_with_recursive_aggregation(ctx, name):
     st = _check_circuit(ctx, ecdsa_cases.circuit(name), ecdsa_cases.INPUTS, len(cs), inp)
     assert {s.status for s in st} == {"Solved", "Failure"}
     # an aggregation-object output that an earlier opcode assigned a non-zero value: UnsatisfiedConstrain at that opcode
-    st = _check_circuit(ctx, ecdsa_cases.circuit(name, preassigned_out=True), ecdsa_cases.INPUTS, 4, inp)
+    st = _check_circuit(ctx, ecdsa_cases.circuit(name, preassigned_out=True), ecdsa_cases.INPUTS, 4, inp[:4 * 160 * 32])
     assert st[0].error == "UnsatisfiedConstrain" and st[0].opcode_index == 2
     # malformed opcodes fail every instance the way the reference does
     for kw, err in ((dict(n_pkx=31), "BlackBoxFunctionFailed"), (dict(n_hm=31), "ReferencePanic")):
-        st = _check_circuit(ctx, ecdsa_cases.circuit(name, **kw), ecdsa_cases.INPUTS, 2, inp)
+        st = _check_circuit(ctx, ecdsa_cases.circuit(name, **kw), ecdsa_cases.INPUTS, 2, inp[:2 * 160 * 32])
         assert all(s.error == err and s.opcode_index == 0 for s in st)
