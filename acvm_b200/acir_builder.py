@@ -252,6 +252,22 @@ class CircuitBuilder:
         self.w.u32(radix)
         self.n_opcodes += 1
 
+    def directive_permutation_sort(self, inputs, tuple_, bits, sort_by):
+        """Directive::PermutationSort (acir/src/circuit/directives.rs:24-35); inputs: list of lists of expressions."""
+        self.w.u32(2)
+        self.w.u32(2)
+        self.w.u64(len(inputs))
+        for element in inputs:
+            self.w.u64(len(element))
+            for e in element:
+                self._expr(e)
+        self.w.u32(tuple_)
+        self._vw(bits)
+        self.w.u64(len(sort_by))
+        for i in sort_by:
+            self.w.u32(i)
+        self.n_opcodes += 1
+
     def memory_init(self, block_id, init):
         self.w.u32(5)
         self.w.u32(block_id)

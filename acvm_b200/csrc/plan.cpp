@@ -562,7 +562,50 @@ struct Compiler {
             plan.stats.alg_bytes += 32 * (1 + n_b);
             return true;
         }
-        throw std::runtime_error("opcode " + std::to_string(idx) + ": Directive::PermutationSort is out of scope (SURVEY 2)");
+        // Directive::PermutationSort (directives/mod.rs:88-121): tuples are evaluated into slots on the device, the sort and
+        // the switch routing run on the host between two device segments (sort_host.hpp), like Brillig.
+        const uint32_t n = (uint32_t)d.sort_inputs.size();
+        std::vector<uint32_t> slots;
+        for (auto& element : d.sort_inputs) {
+            if (element.size() != d.tuple) {
+                fail_static(idx, EK_REFERENCE_PANIC, 0, "PermutationSort element does not have `tuple` entries");
+                return false;
+            }
+            for (auto& e : element) {
+                uint32_t s;
+                if (!expr_to_slot(idx, e, s)) return false;
+                slots.push_back(s);
+            }
+        }
+        if (n >= 2)
+            for (uint32_t k : d.sort_by)
+                if (k > d.tuple)
+                    throw std::runtime_error("opcode " + std::to_string(idx) + ": PermutationSort sort_by index outside the tuple is not supported");
+        uint32_t n_control = 0;   // switches of the network on n wires: sum of ceil(log2(i + 1))
+        for (uint32_t i = 1; i < n; ++i) n_control += 32 - __builtin_clz(i);
+        const uint32_t n_bits = std::min<uint32_t>(n_control, (uint32_t)d.out.size());   // bits.iter().zip(control)
+        std::vector<uint32_t> desc = {n, d.tuple, (uint32_t)d.sort_by.size()};
+        desc.insert(desc.end(), d.sort_by.begin(), d.sort_by.end());
+        desc.insert(desc.end(), slots.begin(), slots.end());
+        desc.push_back(n_bits);
+        std::vector<uint32_t> outs;
+        for (uint32_t k = 0; k < n_bits; ++k) {
+            uint32_t w = d.out[k];
+            if (known[w] == W_MAYBE)
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": PermutationSort output is conditionally assigned; not supported yet");
+            bool dup = std::find(outs.begin(), outs.end(), w) != outs.end();
+            desc.push_back(w);
+            desc.push_back((known[w] || dup) ? 1u : 0u);
+            outs.push_back(w);
+        }
+        close_device_segment();
+        uint32_t off = (uint32_t)plan.host_desc.size();
+        plan.host_desc.insert(plan.host_desc.end(), desc.begin(), desc.end());
+        plan.segments.push_back(Segment{2, idx, off, 0});
+        for (uint32_t w : outs)
+            if (!known[w]) mark_assigned(w, idx);
+        ++plan.stats.n_directive;
+        return true;
     }
 
     // MemoryInit / MemoryOp (acvm/src/pwg/memory_op.rs:16-123).  A block is a run of extra columns; the dynamic index of

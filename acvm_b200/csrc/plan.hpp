@@ -102,7 +102,7 @@ struct PlanStats {
 // Brillig opcode executed by the host VM on columns copied out of / back into HBM (north star: "Brillig opcodes
 // execute on the host brillig_vm with results DMA'd back into the device WitnessMap").
 struct Segment {
-    uint32_t kind;   // 0 = device, 1 = host Brillig
+    uint32_t kind;   // 0 = device, 1 = host Brillig, 2 = host PermutationSort (descriptor: n, tuple, n_sort_by, sort_by*, slots, n_bits, {witness, known}*)
     uint32_t a;      // device: first step        host: ACIR opcode index
     uint32_t b;      // device: number of steps   host: offset into Plan::host_desc
     uint32_t c;

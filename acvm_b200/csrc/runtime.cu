@@ -14,6 +14,7 @@
 #include "../../include/acvm_b200.h"
 #include "acir.hpp"
 #include "brillig_host.hpp"
+#include "sort_host.hpp"
 #include "curve_host.hpp"
 #include "plan.hpp"
 #include "vm_kernel.cuh"
@@ -419,6 +420,7 @@ extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
 }
 
 static int run_host_brillig(acvmb_batch* b, const Segment& sg);
+static int run_host_permutation_sort(acvmb_batch* b, const Segment& sg);
 
 extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
@@ -452,7 +454,7 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
             total += ms;
             c->run.kernel_launches += 1;
         } else {
-            int rc = run_host_brillig(b, sg);
+            int rc = sg.kind == 2 ? run_host_permutation_sort(b, sg) : run_host_brillig(b, sg);
             if (rc) return rc;
         }
     }
@@ -516,47 +518,20 @@ static inline unsigned long long fail_key(uint32_t opcode, uint32_t kind, uint32
     return ((unsigned long long)opcode << 32) | ((unsigned long long)(kind & 0xF) << 28) | (aux & 0x0FFFFFFFu);
 }
 
-static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
+// Shared I/O of a host segment: gather `in_slots` (+ already-assigned outputs), call per_instance(i, val, result) on all
+// host threads for the instances that are still live at `opcode`, then insert_value the results and merge failures.
+// per_instance returns ~0ull when the outputs are to be inserted, else the failure key to record.
+template <class F>
+static int run_host_io(acvmb_batch* b, uint32_t opcode, std::vector<uint32_t> in_slots, const std::vector<uint32_t>& out_w,
+                       const std::vector<uint32_t>& out_known, F&& per_instance) {
     acvmb_circuit* c = b->c;
     acvmb_ctx* ctx = c->ctx;
-    if (!c->has_circuit) return set_err(ACVMB_ERR_STATE, "plan has a host segment but the circuit bytes are not attached");
-    const Brillig& br = c->circuit.opcodes[sg.a].brillig;
-    const uint32_t* d = c->plan.host_desc.data() + sg.b;
-    const uint32_t opcode = sg.a;
-    // ---- unpack the descriptor ----
-    std::vector<uint32_t> in_slots;          // gathered columns, in order
-    uint32_t pred_slot = *d++;
-    if (pred_slot != 0xFFFFFFFFu) in_slots.push_back(pred_slot);
-    struct In { bool arr; uint32_t first, count; };
-    std::vector<In> ins;
-    uint32_t n_in = *d++;
-    for (uint32_t i = 0; i < n_in; ++i) {
-        bool arr = *d++ != 0;
-        uint32_t cnt = *d++;
-        ins.push_back({arr, (uint32_t)in_slots.size(), cnt});
-        for (uint32_t k = 0; k < cnt; ++k) in_slots.push_back(*d++);
-    }
-    struct Out { bool arr; uint32_t first, count; };
-    std::vector<Out> outs;
-    std::vector<uint32_t> out_w, out_known;
-    uint32_t n_out = *d++;
-    for (uint32_t i = 0; i < n_out; ++i) {
-        bool arr = *d++ != 0;
-        uint32_t cnt = *d++;
-        outs.push_back({arr, (uint32_t)out_w.size(), cnt});
-        for (uint32_t k = 0; k < cnt; ++k) {
-            out_w.push_back(*d++);
-            out_known.push_back(*d++);
-        }
-    }
-    const uint32_t known_first = (uint32_t)in_slots.size();   // already-assigned outputs are read too (insert_value compares)
-    std::vector<int> known_pos(out_w.size(), -1);
+    std::vector<int> known_pos(out_w.size(), -1);   // already-assigned outputs are read too (insert_value compares)
     for (size_t k = 0; k < out_w.size(); ++k)
         if (out_known[k]) {
             known_pos[k] = (int)in_slots.size();
             in_slots.push_back(out_w[k]);
         }
-    (void)known_first;
     const uint32_t n = b->n_inst, n_g = (uint32_t)in_slots.size(), n_o = (uint32_t)out_w.size();
     cudaStream_t s = ctx->stream;
     // ---- D2H: status words + the input columns ----
@@ -601,7 +576,7 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
         c->run.kernel_launches += 1;
     }
     CUDA_TRY(cudaStreamSynchronize(s));
-    // ---- run the VM per instance on all host threads ----
+    // ---- per instance on all host threads ----
     std::vector<uint8_t>& out_be = b->h_out;
     out_be.assign((size_t)n * n_o * 32, 0);
     unsigned n_thr = std::max(1u, std::thread::hardware_concurrency());
@@ -611,57 +586,11 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
             if ((uint32_t)(fail[i] >> 32) < opcode) continue;   // this instance stopped at an earlier opcode
             auto val = [&](uint32_t pos) { return hf::from_be_bytes_reduce(&in_be[((size_t)i * n_g + pos) * 32], 32); };
             std::vector<U256> result(n_o);
-            bool ran = true;
-            if (pred_slot != 0xFFFFFFFFu && val(0).is_zero()) {
-                ran = false;   // zero predicate: outputs are zeroed (brillig.rs:34-37,133-150)
-            } else {
-                bvm::VM vm;
-                for (auto& in : ins) {
-                    if (!in.arr) {
-                        vm.regs.push_back(val(in.first));
-                    } else {
-                        vm.regs.push_back(hf::from_u64(vm.mem.size()));
-                        for (uint32_t k = 0; k < in.count; ++k) vm.mem.push_back(val(in.first + k));
-                    }
-                }
-                bvm::Result r = vm.run(br);
-                if (r.status == bvm::Status::Failure) {
-                    fail[i] = std::min(fail[i], fail_key(opcode, EK_BRILLIG_FAILED, r.call_stack.empty() ? 0 : (uint32_t)r.call_stack.back()));
-                    continue;
-                }
-                if (r.status == bvm::Status::Panic) {
-                    fail[i] = std::min(fail[i], fail_key(opcode, EK_REFERENCE_PANIC, 0));
-                    continue;
-                }
-                if (r.status == bvm::Status::ForeignCallWait) {
-                    fail[i] = std::min(fail[i], fail_key(opcode, 0xF, 0));   // decoded as ACVMB_REQUIRES_FOREIGN_CALL
-                    if (i == 0) {
-                        b->fc_pending = true;
-                        b->fc_function = r.message;
-                        b->fc_inputs = std::move(r.fc_inputs);
-                    }
-                    continue;
-                }
-                bool bad = false;
-                for (size_t oi = 0; oi < outs.size() && !bad; ++oi) {
-                    U256 reg = oi < vm.regs.size() ? vm.regs[oi] : U256{};
-                    if (!outs[oi].arr) {
-                        result[outs[oi].first] = reg;
-                    } else {
-                        if (reg.l[1] | reg.l[2] | reg.l[3]) { bad = true; break; }
-                        for (uint32_t k = 0; k < outs[oi].count; ++k) {
-                            size_t p = (size_t)reg.l[0] + k;
-                            if (p >= vm.mem.size()) { bad = true; break; }   // Vec index out of bounds panics
-                            result[outs[oi].first + k] = vm.mem[p];
-                        }
-                    }
-                }
-                if (bad) {
-                    fail[i] = std::min(fail[i], fail_key(opcode, EK_REFERENCE_PANIC, 0));
-                    continue;
-                }
+            unsigned long long key = per_instance(i, val, result);
+            if (key != ~0ull) {
+                fail[i] = std::min(fail[i], key);
+                continue;
             }
-            (void)ran;
             // insert_value in output order: an already-assigned witness is replaced, a mismatch is UnsatisfiedConstrain
             std::vector<std::pair<uint32_t, U256>> seen;
             for (uint32_t k = 0; k < n_o; ++k) {
@@ -692,6 +621,106 @@ static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
     CUDA_TRY(cudaMemcpyAsync(b->d_fail, fail.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return ACVMB_OK;
+}
+
+static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
+    acvmb_circuit* c = b->c;
+    if (!c->has_circuit) return set_err(ACVMB_ERR_STATE, "plan has a host segment but the circuit bytes are not attached");
+    const Brillig& br = c->circuit.opcodes[sg.a].brillig;
+    const uint32_t* d = c->plan.host_desc.data() + sg.b;
+    const uint32_t opcode = sg.a;
+    // ---- unpack the descriptor ----
+    std::vector<uint32_t> in_slots;          // gathered columns, in order
+    uint32_t pred_slot = *d++;
+    if (pred_slot != 0xFFFFFFFFu) in_slots.push_back(pred_slot);
+    struct In { bool arr; uint32_t first, count; };
+    std::vector<In> ins;
+    uint32_t n_in = *d++;
+    for (uint32_t i = 0; i < n_in; ++i) {
+        bool arr = *d++ != 0;
+        uint32_t cnt = *d++;
+        ins.push_back({arr, (uint32_t)in_slots.size(), cnt});
+        for (uint32_t k = 0; k < cnt; ++k) in_slots.push_back(*d++);
+    }
+    struct Out { bool arr; uint32_t first, count; };
+    std::vector<Out> outs;
+    std::vector<uint32_t> out_w, out_known;
+    uint32_t n_out = *d++;
+    for (uint32_t i = 0; i < n_out; ++i) {
+        bool arr = *d++ != 0;
+        uint32_t cnt = *d++;
+        outs.push_back({arr, (uint32_t)out_w.size(), cnt});
+        for (uint32_t k = 0; k < cnt; ++k) {
+            out_w.push_back(*d++);
+            out_known.push_back(*d++);
+        }
+    }
+    auto per_instance = [&](uint32_t i, auto& val, std::vector<U256>& result) -> unsigned long long {
+        if (pred_slot != 0xFFFFFFFFu && val(0).is_zero()) return ~0ull;   // zero predicate: outputs are zeroed (brillig.rs:34-37,133-150)
+        bvm::VM vm;
+        for (auto& in : ins) {
+            if (!in.arr) {
+                vm.regs.push_back(val(in.first));
+            } else {
+                vm.regs.push_back(hf::from_u64(vm.mem.size()));
+                for (uint32_t k = 0; k < in.count; ++k) vm.mem.push_back(val(in.first + k));
+            }
+        }
+        bvm::Result r = vm.run(br);
+        if (r.status == bvm::Status::Failure)
+            return fail_key(opcode, EK_BRILLIG_FAILED, r.call_stack.empty() ? 0 : (uint32_t)r.call_stack.back());
+        if (r.status == bvm::Status::Panic) return fail_key(opcode, EK_REFERENCE_PANIC, 0);
+        if (r.status == bvm::Status::ForeignCallWait) {
+            if (i == 0) {
+                b->fc_pending = true;
+                b->fc_function = r.message;
+                b->fc_inputs = std::move(r.fc_inputs);
+            }
+            return fail_key(opcode, 0xF, 0);   // decoded as ACVMB_REQUIRES_FOREIGN_CALL
+        }
+        for (size_t oi = 0; oi < outs.size(); ++oi) {
+            U256 reg = oi < vm.regs.size() ? vm.regs[oi] : U256{};
+            if (!outs[oi].arr) {
+                result[outs[oi].first] = reg;
+            } else {
+                if (reg.l[1] | reg.l[2] | reg.l[3]) return fail_key(opcode, EK_REFERENCE_PANIC, 0);
+                for (uint32_t k = 0; k < outs[oi].count; ++k) {
+                    size_t p = (size_t)reg.l[0] + k;
+                    if (p >= vm.mem.size()) return fail_key(opcode, EK_REFERENCE_PANIC, 0);   // Vec index out of bounds panics
+                    result[outs[oi].first + k] = vm.mem[p];
+                }
+            }
+        }
+        return ~0ull;
+    };
+    return run_host_io(b, opcode, std::move(in_slots), out_w, out_known, per_instance);
+}
+
+// Host segment kind 2: Directive::PermutationSort (directives/mod.rs:88-121).  Self-contained descriptor:
+// n, tuple, n_sort_by, sort_by*, n*tuple value slots, n_bits, {witness, known}*.
+static int run_host_permutation_sort(acvmb_batch* b, const Segment& sg) {
+    const uint32_t* d = b->c->plan.host_desc.data() + sg.b;
+    const uint32_t opcode = sg.a;
+    const uint32_t n = *d++, tuple = *d++, n_sort = *d++;
+    std::vector<uint32_t> sort_by(d, d + n_sort);
+    d += n_sort;
+    std::vector<uint32_t> in_slots(d, d + (size_t)n * tuple);
+    d += (size_t)n * tuple;
+    const uint32_t n_bits = *d++;
+    std::vector<uint32_t> out_w, out_known;
+    for (uint32_t k = 0; k < n_bits; ++k) {
+        out_w.push_back(*d++);
+        out_known.push_back(*d++);
+    }
+    auto per_instance = [&](uint32_t, auto& val, std::vector<U256>& result) -> unsigned long long {
+        std::vector<U256> values((size_t)n * tuple);
+        for (size_t k = 0; k < values.size(); ++k) values[k] = val((uint32_t)k);
+        std::vector<uint8_t> bits;
+        if (!psort::permutation_sort_bits(values, n, tuple, sort_by, bits)) return fail_key(opcode, EK_REFERENCE_PANIC, 0);
+        for (uint32_t k = 0; k < n_bits; ++k) result[k] = hf::from_u64(k < bits.size() ? bits[k] : 0);
+        return ~0ull;
+    };
+    return run_host_io(b, opcode, std::move(in_slots), out_w, out_known, per_instance);
 }
 
 static void decode_status(const Plan& p, unsigned long long word, acvmb_status* st) {
@@ -1202,6 +1231,18 @@ extern "C" int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32
     gk::Pt p = gk::derive_pedersen_generator(index);
     hf::to_be_bytes(p.x, out_xy_be32);
     hf::to_be_bytes(p.y, out_xy_be32 + 32);
+    return ACVMB_OK;
+}
+
+// host-only test hook: control bits of the permutation network that maps 0..n-1 onto `outputs` (sorting.rs:164-235)
+extern "C" int acvmb_permutation_route_host(const uint32_t* outputs, uint32_t n, uint8_t* bits, uint32_t cap, uint32_t* n_bits) {
+    if ((!outputs && n) || !n_bits) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    std::vector<uint32_t> base(n), out(outputs, outputs + n);
+    for (uint32_t i = 0; i < n; ++i) base[i] = i;
+    std::vector<uint8_t> b;
+    if (!psort::route(base, out, n, b)) return set_err(ACVMB_ERR_STATE, "outputs are not a permutation of 0..n-1 (the reference panics)");
+    *n_bits = (uint32_t)b.size();
+    if (bits) memcpy(bits, b.data(), std::min<size_t>(cap, b.size()));
     return ACVMB_OK;
 }
 

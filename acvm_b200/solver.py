@@ -415,3 +415,14 @@ def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int 
     buf = (C.c_uint8 * need.value)()
     _check(lib().acvmb_plan_compile_host(acir_bytes, len(acir_bytes), ids, len(input_witnesses), S, None, buf, need.value, C.byref(need)))
     return info.as_dict(), bytes(buf)
+
+
+def permutation_route_host(outputs: Sequence[int]):
+    """sorting::route(0..n-1, outputs) on the host (acvm/src/pwg/directives/sorting.rs:164-235): list of switch bits."""
+    n = len(outputs)
+    arr = _u32_array(list(outputs))
+    nb = C.c_uint32()
+    _check(lib().acvmb_permutation_route_host(arr, n, None, 0, C.byref(nb)))
+    buf = (C.c_uint8 * max(1, nb.value))()
+    _check(lib().acvmb_permutation_route_host(arr, n, buf, nb.value, C.byref(nb)))
+    return [bool(b) for b in buf[:nb.value]]

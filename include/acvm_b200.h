@@ -196,6 +196,11 @@ int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
 int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]);
+
+/* host-only: switch settings of the permutation network mapping 0..n-1 onto `outputs`, i.e. sorting::route
+ * (acvm/src/pwg/directives/sorting.rs:164-235) as Directive::PermutationSort calls it (directives/mod.rs:113-114).
+ * bits (one byte per switch) may be NULL to query *n_bits. */
+int acvmb_permutation_route_host(const uint32_t* outputs, uint32_t n, uint8_t* bits, uint32_t cap, uint32_t* n_bits);
 /* run one Brillig opcode of a circuit on the host VM (status: 0 finished, 1 failure, 2 foreign-call wait, 3 reference panic) */
 int acvmb_brillig_run_host(const uint8_t* gz_bincode, size_t len, uint32_t opcode_index, const uint8_t* in_values_be32,
                            uint32_t n_in_values, uint8_t* out_values_be32, uint32_t n_out_values, uint32_t* status,

@@ -327,8 +327,24 @@ def solve_directive(wm, d):
             raise ResolutionError("UnsatisfiedConstrain")
         for i, w in enumerate(d["b"]):
             insert_value(w, (digits[i] & 0xFF) if i < len(digits) else 0, wm)  # from_be_bytes_reduce(&[digit as u8])
+    elif d["name"] == "PermutationSort":  # directives/mod.rs:88-121
+        from . import sorting
+        rows = []
+        for element in d["inputs"]:
+            if len(element) != d["tuple"]:
+                raise ReferencePanic("assert_eq!(element.len(), *tuple as usize)")
+            rows.append([get_value(e, wm) for e in element])
+        if len(rows) >= 2 and any(i > d["tuple"] for i in d["sort_by"]):
+            # the reference panics only if a comparison reaches the index, which depends on slice::sort_by's internals
+            raise NotImplementedError("oracle: sort_by index outside the tuple")
+        try:
+            control = sorting.permutation_sort_bits(rows, d["sort_by"])
+        except sorting.ReferencePanic as e:
+            raise ReferencePanic(str(e))
+        for w, bit in zip(d["bits"], control):
+            insert_value(w, 1 if bit else 0, wm)
     else:
-        raise NotImplementedError("oracle: PermutationSort is out of scope (SURVEY 2)")
+        raise ValueError(d["name"])
 
 
 # ---- memory (acvm/src/pwg/memory_op.rs) ------------------------------------------------------

@@ -12,6 +12,7 @@ Sources (all under /root/reference):
   barretenberg_blackbox_solver/src/wasm/*.rs     Pedersen / fixed-base KATs
   brillig_vm/src/black_box.rs:203-209            SHA-256("hello world")
   blackbox_solver/src/lib.rs:216-290             ECDSA secp256k1 / secp256r1 valid-signature KATs
+  acvm/src/pwg/directives/sorting.rs:298-372     permutation-network routing literals
 """
 import json, os, re, sys
 
@@ -96,6 +97,13 @@ def main():
              "y": "24f50d25508b4dfb1e8a834e39565f646e217b24cb3a475c2e4991d1bb07a9d8"},
         ],
         "ecdsa_valid": ecdsa_kats(f"{REF}/blackbox_solver/src/lib.rs"),  # expected result: true
+        "permutation_route": [  # acvm/src/pwg/directives/sorting.rs:298-372 (test_route literals): inputs, outputs, control bits
+            {"inputs": [1, 2, 3], "outputs": [1, 2, 3], "bits": [0, 0, 0]},
+            {"inputs": [1, 2, 3], "outputs": [1, 3, 2], "bits": [0, 0, 1]},
+            {"inputs": [1, 2, 3], "outputs": [3, 2, 1], "bits": [1, 1, 1]},
+            {"inputs": [0, 1, 2, 3], "outputs": [2, 3, 0, 1], "bits": [0, 1, 1, 1, 1]},
+            {"inputs": [0, 1, 2, 3, 4], "outputs": [0, 3, 4, 2, 1], "bits": [0, 0, 0, 1, 0, 1, 0, 1]},
+        ],
         "grumpkin_order": "30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47",  # scalar_mul.rs:42-45
     }
     # sanity: the rust and ts byte vectors must agree where both exist

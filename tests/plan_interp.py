@@ -246,18 +246,45 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 record_fail(opcode, EK_UNSAT)
             cols[w_] = v
 
+    def sort_segment(opcode, off):
+        """PermutationSort host segment (kind 2): self-contained descriptor, oracle/sorting.py does the routing."""
+        from oracle import sorting
+        nonlocal fail
+        if fail is not None and fail[0] < opcode:
+            return
+        d = plan.host_desc
+        n, tup, n_sort = d[off:off + 3]
+        p_ = off + 3
+        sort_by = list(d[p_:p_ + n_sort]); p_ += n_sort
+        vals = [cols[s_] for s_ in d[p_:p_ + n * tup]]; p_ += n * tup
+        n_bits = d[p_]; p_ += 1
+        outs = [(d[p_ + 2 * k], d[p_ + 2 * k + 1]) for k in range(n_bits)]
+        try:
+            bits = sorting.permutation_sort_bits([vals[i * tup:(i + 1) * tup] for i in range(n)], sort_by)
+        except sorting.ReferencePanic:
+            record_fail(opcode, EK_PANIC)
+            return
+        for (w_, known_), v in zip(outs, bits):
+            v = int(v)
+            if known_ and cols[w_] != v:
+                record_fail(opcode, EK_UNSAT)
+            cols[w_] = v
+
     step_plan = []
     if plan.segments:
         for (kind_, a_, b_, _c) in plan.segments:
             if kind_ == 0:
                 step_plan += [("step", s_) for s_ in range(a_, a_ + b_)]
             else:
-                step_plan.append(("host", a_, b_))
+                step_plan.append(("host" if kind_ == 1 else "sort", a_, b_))
     else:
         step_plan = [("step", s_) for s_ in range(plan.n_steps)]
     for item in step_plan:
         if item[0] == "host":
             host_segment(item[1], item[2])
+            continue
+        if item[0] == "sort":
+            sort_segment(item[1], item[2])
             continue
         step = item[1]
         writes = []

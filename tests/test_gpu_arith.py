@@ -239,3 +239,16 @@ def test_plan_blob_roundtrip_with_host_segments(ctx):
     oa, sa, pa = a.solve_batch(inp, len(rows), want_present=True)
     ob, sb, pb = b.solve_batch(inp, len(rows), want_present=True)
     assert (oa, pa) == (ob, pb) and [(s.status, s.error, s.opcode_index) for s in sa] == [(s.status, s.error, s.opcode_index) for s in sb]
+
+
+@pytest.mark.parametrize("n,tup,sort_by", [(5, 1, [0]), (8, 2, [1, 0]), (33, 2, [0]), (2, 1, [0]), (1, 1, [0])])
+def test_permutation_sort_directive(ctx, n, tup, sort_by):
+    """Directive::PermutationSort runs as a host segment between two device segments (directives/mod.rs:88-121)."""
+    from sort_cases import sort_circuit, sort_rows
+    from test_gpu_blackbox import _check_circuit
+    data, inputs = sort_circuit(n, tup, sort_by)
+    batch = 37
+    st = _check_circuit(ctx, data, inputs, batch, sort_rows(n, tup, batch))
+    assert all(s.status == "Solved" for s in st)
+    data, _ = sort_circuit(n, tup, sort_by, preassign_bit=True)
+    _check_circuit(ctx, data, inputs, batch, sort_rows(n, tup, batch))

@@ -469,3 +469,36 @@ def test_ecdsa_and_recursive_aggregation_plan_vs_oracle(name):
     assert info["static_fail_present"] and acvm_b200.solver.ERR_NAMES[info["static_fail_kind"]] == "BlackBoxFunctionFailed"
     info = _interp_vs_oracle(ecdsa_cases.circuit(name, n_hm=31), ecdsa_cases.INPUTS, inp, 1)
     assert info["static_fail_present"] and acvm_b200.solver.ERR_NAMES[info["static_fail_kind"]] == "ReferencePanic"
+
+
+def test_permutation_route_host_matches_oracle(golden):
+    from oracle import sorting
+    for k in golden["kats"]["permutation_route"]:
+        base = sorted(k["inputs"])
+        assert acvm_b200.solver.permutation_route_host([base.index(v) for v in k["outputs"]]) == [bool(b) for b in k["bits"]]
+    rnd = random.Random(8)
+    assert acvm_b200.solver.permutation_route_host([]) == [] and acvm_b200.solver.permutation_route_host([0]) == []
+    for n in list(range(2, 40)) + [63, 64, 65, 200, 1000]:
+        for _ in range(3):
+            b = list(range(n))
+            rnd.shuffle(b)
+            assert acvm_b200.solver.permutation_route_host(b) == sorting.route(list(range(n)), b), n
+    with pytest.raises(acvm_b200.AcvmError):
+        acvm_b200.solver.permutation_route_host([0, 0, 1])
+
+
+from sort_cases import sort_circuit as _sort_circuit, sort_rows as _sort_rows  # noqa: E402
+
+
+@pytest.mark.parametrize("n,tup,sort_by", [(5, 1, [0]), (8, 2, [1, 0]), (7, 2, [0]), (2, 1, [0]), (1, 1, [0]), (12, 3, [2, 3]), (6, 1, [1])])
+def test_permutation_sort_plan_vs_oracle(n, tup, sort_by):
+    data, inputs = _sort_circuit(n, tup, sort_by)
+    batch = 6
+    inp = _sort_rows(n, tup, batch)
+    _interp_vs_oracle(data, inputs, inp, batch)
+    # fewer / more bit witnesses than switches: zip() truncates (directives/mod.rs:115)
+    for nb in (0, 1, 40):
+        data2, _ = _sort_circuit(n, tup, sort_by, n_bits=nb)
+        _interp_vs_oracle(data2, inputs, inp, 2)
+    data3, _ = _sort_circuit(n, tup, sort_by, preassign_bit=True)
+    _interp_vs_oracle(data3, inputs, inp, batch)

@@ -218,3 +218,17 @@ def test_ecdsa_oracle_against_openssl():
             if int.from_bytes(wrong, "big") < c.n:
                 assert ecdsa.verify(name, wrong, P[0].to_bytes(32, "big"), P[1].to_bytes(32, "big"),
                                     r2.to_bytes(32, "big") + s2.to_bytes(32, "big")) is False
+
+
+def test_permutation_route_reference_literals(golden):  # acvm/src/pwg/directives/sorting.rs:298-372
+    import random
+    from oracle import sorting
+    for k in golden["kats"]["permutation_route"]:
+        assert sorting.route(k["inputs"], k["outputs"]) == [bool(b) for b in k["bits"]]
+    rnd = random.Random(3)
+    for n in list(range(2, 50)) + [64, 100, 257]:     # the reference's own property test (sorting.rs:374-386)
+        a = list(range(n))
+        b = a[:]
+        rnd.shuffle(b)
+        c = sorting.route(a, b)
+        assert len(c) == sorting.switch_count(n) and sorting.execute_network(c, a) == b
