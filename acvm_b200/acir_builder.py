@@ -331,6 +331,12 @@ class CircuitBuilder:
             if bb["name"] in ("Sha256", "Blake2s", "Keccak256"):
                 for v in (*bb["message"], *bb["output"]):
                     w.u64(v)
+            elif bb["name"] == "HashToField128Security":
+                for v in (*bb["message"], bb["output"]):
+                    w.u64(v)
+            elif bb["name"] in ("EcdsaSecp256k1", "EcdsaSecp256r1"):
+                for v in (*bb["hashed_msg"], *bb["public_key_x"], *bb["public_key_y"], *bb["signature"], bb["result"]):
+                    w.u64(v)
             elif bb["name"] == "FixedBaseScalarMul":
                 for v in (bb["low"], bb["high"], *bb["result"]):
                     w.u64(v)

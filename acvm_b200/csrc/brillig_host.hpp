@@ -9,6 +9,7 @@
 // 2^16, pointer that does not fit usize, out-of-range memory read, bigint underflow, division by zero ...) ends the
 // run with Status::Panic, which the caller reports as ACVMB_E_REFERENCE_PANIC.
 #pragma once
+#include "ecdsa.cuh"
 #include <string>
 #include <vector>
 
@@ -69,6 +70,52 @@ inline void sha256_host(const uint8_t* msg, size_t n, uint8_t out[32]) {
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
     for (int i = 0; i < 32; ++i) out[i] = (uint8_t)(h[i >> 2] >> (24 - 8 * (i & 3)));
+}
+
+// BLAKE2s-256, unkeyed (RFC 7693) -- blackbox_solver/src/lib.rs:52-55 -> blake2 0.10.6
+inline void blake2s_host(const uint8_t* msg, size_t n, uint8_t out[32]) {
+    static const uint32_t IV[8] = {0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19};
+    static const uint8_t SIGMA[10][16] = {
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+        {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+        {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+        {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+        {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+    uint32_t h[8];
+    for (int i = 0; i < 8; ++i) h[i] = IV[i];
+    h[0] ^= 0x01010020u;   // digest length 32, no key, fanout = depth = 1
+    auto rotr = [](uint32_t x, int r) { return (x >> r) | (x << (32 - r)); };
+    size_t off = 0;
+    do {
+        const size_t take = n - off > 64 ? 64 : n - off;
+        const bool last = off + take == n;
+        uint8_t blk[64] = {0};
+        for (size_t i = 0; i < take; ++i) blk[i] = msg[off + i];
+        off += take;
+        uint32_t m[16], v[16];
+        for (int i = 0; i < 16; ++i)
+            m[i] = (uint32_t)blk[4 * i] | ((uint32_t)blk[4 * i + 1] << 8) | ((uint32_t)blk[4 * i + 2] << 16) | ((uint32_t)blk[4 * i + 3] << 24);
+        for (int i = 0; i < 8; ++i) { v[i] = h[i]; v[8 + i] = IV[i]; }
+        const uint64_t t = off;
+        v[12] ^= (uint32_t)t;
+        v[13] ^= (uint32_t)(t >> 32);
+        if (last) v[14] = ~v[14];
+        auto G = [&](int a, int b, int c, int d, uint32_t x, uint32_t y) {
+            v[a] = v[a] + v[b] + x; v[d] = rotr(v[d] ^ v[a], 16);
+            v[c] = v[c] + v[d];     v[b] = rotr(v[b] ^ v[c], 12);
+            v[a] = v[a] + v[b] + y; v[d] = rotr(v[d] ^ v[a], 8);
+            v[c] = v[c] + v[d];     v[b] = rotr(v[b] ^ v[c], 7);
+        };
+        for (int r = 0; r < 10; ++r) {
+            const uint8_t* sg = SIGMA[r];
+            G(0, 4, 8, 12, m[sg[0]], m[sg[1]]);   G(1, 5, 9, 13, m[sg[2]], m[sg[3]]);
+            G(2, 6, 10, 14, m[sg[4]], m[sg[5]]);  G(3, 7, 11, 15, m[sg[6]], m[sg[7]]);
+            G(0, 5, 10, 15, m[sg[8]], m[sg[9]]);  G(1, 6, 11, 12, m[sg[10]], m[sg[11]]);
+            G(2, 7, 8, 13, m[sg[12]], m[sg[13]]); G(3, 4, 9, 14, m[sg[14]], m[sg[15]]);
+        }
+        for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[8 + i];
+    } while (off < n);
+    for (int i = 0; i < 32; ++i) out[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
 }
 
 // ---- 256-bit unsigned helpers (values are < 2^254, bit sizes <= 256) ----
@@ -383,15 +430,38 @@ struct VM {
                         break;
                     }
                     case 12: {  // BlackBox (black_box.rs:42-165)
-                        if (o.bb_tag == 0 || o.bb_tag == 2) {   // Sha256 / Keccak256 {message: HeapVector, output: HeapArray}
+                        if (o.bb_tag <= 3) {   // Sha256 / Blake2s / Keccak256 {message: HeapVector, output: HeapArray}; HashToField {.., output: register}
                             size_t p = to_usize(get(o.bb[0])), n = to_usize(get(o.bb[1]));
                             if (p + n > mem.size()) throw PanicEx{"memory read out of bounds"};
                             std::vector<uint8_t> msg = bytes_of(p, n);
                             uint8_t d[32];
-                            if (o.bb_tag == 0) sha256_host(msg.data(), msg.size(), d); else gk::keccak256_host(msg.data(), msg.size(), d);
-                            U256 vals[32];
-                            for (int i = 0; i < 32; ++i) vals[i] = hf::from_u64(d[i]);
-                            mwrite(to_usize(get(o.bb[2])), vals, 32);
+                            if (o.bb_tag == 0) sha256_host(msg.data(), msg.size(), d);
+                            else if (o.bb_tag == 2) gk::keccak256_host(msg.data(), msg.size(), d);
+                            else blake2s_host(msg.data(), msg.size(), d);
+                            if (o.bb_tag == 3) {   // digest as a big-endian integer, reduced mod p (blackbox_solver/src/lib.rs:62-65,94-99)
+                                set(o.bb[2], hf::from_be_bytes_reduce(d, 32));
+                            } else {
+                                U256 vals[32];
+                                for (int i = 0; i < 32; ++i) vals[i] = hf::from_u64(d[i]);
+                                mwrite(to_usize(get(o.bb[2])), vals, 32);
+                            }
+                        } else if (o.bb_tag == 4 || o.bb_tag == 5) {   // EcdsaSecp256k1 / r1 (black_box.rs:73-127)
+                            static const char* what[3] = {"Invalid public key x length", "Invalid public key y length", "Invalid signature length"};
+                            static const size_t want[3] = {32, 32, 64};
+                            std::vector<uint8_t> part[3];
+                            for (int k = 0; k < 3; ++k) {
+                                size_t p = to_usize(get(o.bb[2 + 2 * k])), n = (size_t)o.bb[3 + 2 * k];
+                                if (p + n > mem.size()) throw PanicEx{"memory read out of bounds"};
+                                if (n != want[k]) return fail(std::string("Failed to solve blackbox function: ecdsa, reason: ") + what[k]);
+                                part[k] = bytes_of(p, n);
+                            }
+                            size_t p = to_usize(get(o.bb[0])), n = to_usize(get(o.bb[1]));
+                            if (p + n > mem.size()) throw PanicEx{"memory read out of bounds"};
+                            std::vector<uint8_t> hashed = bytes_of(p, n);
+                            if (hashed.size() != 32) throw PanicEx{"GenericArray::from_slice: hashed message is not 32 bytes"};
+                            int res = ec::ecdsa_verify(o.bb_tag == 4 ? 0 : 1, hashed.data(), part[0].data(), part[1].data(), part[2].data());
+                            if (res == ec::EC_PANIC) throw PanicEx{"ecdsa verification panics in the reference"};
+                            set(o.bb[8], hf::from_u64(res == ec::EC_TRUE));
                         } else if (o.bb_tag == 8) {               // FixedBaseScalarMul {low, high, result: HeapArray}
                             U256 lo = get(o.bb[0]), hi = get(o.bb[1]);
                             if (lo.l[2] | lo.l[3] | hi.l[2] | hi.l[3])

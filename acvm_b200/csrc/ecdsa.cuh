@@ -40,7 +40,7 @@ struct EcCurve {
 
 #if defined(__CUDACC__)
 // seen identically by the host and device passes of nvcc; host code (EC_HD functions called on the CPU) uses the copy below
-__constant__ EcCurve g_ec_curves[2] = {
+static __constant__ EcCurve g_ec_curves[2] = {
 #include "ecdsa_consts.inc"
 };
 #endif

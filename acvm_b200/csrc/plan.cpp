@@ -727,7 +727,7 @@ struct Compiler {
     // slots; the VM itself runs on the host between two device segments.
     bool brillig(uint32_t idx, const Brillig& br) {
         for (auto& o : br.bytecode)
-            if (o.tag == 12 && !(o.bb_tag == 0 || o.bb_tag == 2 || o.bb_tag == 8))
+            if (o.tag == 12 && (o.bb_tag == 6 || o.bb_tag == 7))   // SchnorrVerify / Pedersen need barretenberg (parity unpinned)
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": Brillig BlackBox op " + std::to_string(o.bb_tag) +
                                          " is not supported by the host VM yet");
         uint32_t sp = NONE;

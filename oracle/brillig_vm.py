@@ -151,6 +151,31 @@ class VM:
                 msg = bytes(v & 0xFF for v in self.memory[p:p + ln])
                 d = {"Sha256": hashes.sha256, "Keccak256": hashes.keccak256, "Blake2s": hashes.blake2s}[n](msg)
                 self.mwrite(self.to_usize(self.get(bb["output"][0])), list(d))
+            elif n == "HashToField128Security":  # black_box.rs:66-72
+                p, ln = self.to_usize(self.get(bb["message"][0])), self.to_usize(self.get(bb["message"][1]))
+                if p + ln > len(self.memory):
+                    raise ReferencePanic("memory slice out of range")
+                d = hashes.blake2s(bytes(v & 0xFF for v in self.memory[p:p + ln]))
+                self.set(bb["output"], int.from_bytes(d, "big") % F.P)
+            elif n in ("EcdsaSecp256k1", "EcdsaSecp256r1"):  # black_box.rs:73-127
+                from . import ecdsa
+                parts = []
+                for key, size, label in (("public_key_x", 32, "public key x"), ("public_key_y", 32, "public key y"), ("signature", 64, "signature")):
+                    p, ln = self.to_usize(self.get(bb[key][0])), bb[key][1]
+                    if p + ln > len(self.memory):
+                        raise ReferencePanic("memory slice out of range")
+                    if ln != size:
+                        return self._fail(f"Invalid {label} length")
+                    parts.append(bytes(v & 0xFF for v in self.memory[p:p + ln]))
+                p, ln = self.to_usize(self.get(bb["hashed_msg"][0])), self.to_usize(self.get(bb["hashed_msg"][1]))
+                if p + ln > len(self.memory):
+                    raise ReferencePanic("memory slice out of range")
+                hashed = bytes(v & 0xFF for v in self.memory[p:p + ln])
+                try:
+                    ok = ecdsa.verify(n, hashed, *parts)
+                except ecdsa.ReferencePanic as e:
+                    raise ReferencePanic(str(e))
+                self.set(bb["result"], 1 if ok else 0)
             elif n == "FixedBaseScalarMul":
                 try:
                     x, y = self.backend.fixed_base_scalar_mul(self.get(bb["low"]), self.get(bb["high"]))

@@ -347,48 +347,49 @@ def test_oracle_brillig_foreign_call_fixtures(golden):
     assert vm.finalize() == {int(k): int(v, 16) for k, v in sh["complex_foreign_call"]["expectedWitnessMap"].items()}
 
 
+def _brillig_run_cpp(data, idx, in_vals, n_out):
+    import ctypes as C
+    buf = b"".join(int(v).to_bytes(32, "big") for v in in_vals)
+    out = C.create_string_buffer(max(1, n_out) * 32)
+    st, pc = C.c_uint32(), C.c_uint32()
+    lib = acvm_b200.lib()
+    rc = lib.acvmb_brillig_run_host(data, len(data), idx, buf, len(in_vals), out, n_out, C.byref(st), C.byref(pc))
+    assert rc == 0, lib.acvmb_last_error()
+    return st.value, pc.value, [int.from_bytes(out.raw[i * 32:(i + 1) * 32], "big") for i in range(n_out)]
+
+def _brillig_run_oracle(br, in_vals):
+    from oracle import brillig_vm as obv
+    regs, mem, pos = [], [], 0
+    for kind, e in br["inputs"]:
+        if kind == "Single":
+            regs.append(in_vals[pos]); pos += 1
+        else:
+            regs.append(len(mem)); mem += in_vals[pos:pos + len(e)]; pos += len(e)
+    vm = obv.VM(regs, mem, br["bytecode"], br["foreign_call_results"], pwg.OracleBackend())
+    try:
+        st = vm.process_opcodes()
+    except pwg.ReferencePanic:
+        return 3, 0, None
+    if st[0] == "Failure":
+        return 1, st[2][-1], None
+    if st[0] == "ForeignCallWait":
+        return 2, 0, None
+    outs = []
+    for i, (kind, o) in enumerate(br["outputs"]):
+        reg = vm.get(i)
+        if kind == "Simple":
+            outs.append(reg)
+        else:
+            if reg.bit_length() > 64 or reg + len(o) > len(vm.memory):
+                return 3, 0, None
+            outs += vm.memory[reg:reg + len(o)]
+    return 0, 0, outs
+
+
 def test_cpp_brillig_vm_matches_oracle_vm():
     """The C++ host VM (csrc/brillig_host.hpp) against the oracle's VM on every Brillig opcode of the test circuit and on
     randomly generated integer/field programs (all BinaryIntOp kinds, several bit sizes)."""
-    import ctypes as C
-    from oracle import brillig_vm as obv
-    lib = acvm_b200.lib()
-
-    def run_cpp(data, idx, in_vals, n_out):
-        buf = b"".join(int(v).to_bytes(32, "big") for v in in_vals)
-        out = C.create_string_buffer(max(1, n_out) * 32)
-        st, pc = C.c_uint32(), C.c_uint32()
-        rc = lib.acvmb_brillig_run_host(data, len(data), idx, buf, len(in_vals), out, n_out, C.byref(st), C.byref(pc))
-        assert rc == 0, lib.acvmb_last_error()
-        return st.value, pc.value, [int.from_bytes(out.raw[i * 32:(i + 1) * 32], "big") for i in range(n_out)]
-
-    def run_oracle(br, in_vals):
-        regs, mem, pos = [], [], 0
-        for kind, e in br["inputs"]:
-            if kind == "Single":
-                regs.append(in_vals[pos]); pos += 1
-            else:
-                regs.append(len(mem)); mem += in_vals[pos:pos + len(e)]; pos += len(e)
-        vm = obv.VM(regs, mem, br["bytecode"], br["foreign_call_results"], pwg.OracleBackend())
-        try:
-            st = vm.process_opcodes()
-        except pwg.ReferencePanic:
-            return 3, 0, None
-        if st[0] == "Failure":
-            return 1, st[2][-1], None
-        if st[0] == "ForeignCallWait":
-            return 2, 0, None
-        outs = []
-        for i, (kind, o) in enumerate(br["outputs"]):
-            reg = vm.get(i)
-            if kind == "Simple":
-                outs.append(reg)
-            else:
-                if reg.bit_length() > 64 or reg + len(o) > len(vm.memory):
-                    return 3, 0, None
-                outs += vm.memory[reg:reg + len(o)]
-        return 0, 0, outs
-
+    run_cpp, run_oracle = _brillig_run_cpp, _brillig_run_oracle
     rnd = random.Random(3)
     P = ab.P
     # random straight-line programs over 6 registers
@@ -502,3 +503,58 @@ def test_permutation_sort_plan_vs_oracle(n, tup, sort_by):
         _interp_vs_oracle(data2, inputs, inp, 2)
     data3, _ = _sort_circuit(n, tup, sort_by, preassign_bit=True)
     _interp_vs_oracle(data3, inputs, inp, batch)
+
+
+def test_cpp_brillig_vm_blackbox_ops(golden):
+    """Brillig BlackBox ops on the host VM (brillig_vm/src/black_box.rs:42-165): the three hashes, HashToField128Security
+    and both ECDSA curves, against the oracle's VM."""
+    import ecdsa_cases
+    rnd = random.Random(21)
+    # message in memory[0..n), digest to memory[100..132), field hash to a register
+    for n in (0, 1, 55, 64, 65, 130):
+        msg = [rnd.randrange(1 << 20) for _ in range(n)]     # only the low byte of each value is hashed
+        code = [dict(op="Const", destination=1, value=n), dict(op="Const", destination=2, value=200)]
+        for k, name in enumerate(("Sha256", "Blake2s", "Keccak256")):
+            code.append(dict(op="Const", destination=3 + k, value=200 + 32 * k))
+            code.append(dict(op="BlackBox", bb=dict(name=name, message=(0, 1), output=(3 + k, 32))))
+        code.append(dict(op="BlackBox", bb=dict(name="HashToField128Security", message=(0, 1), output=7)))
+        code.append(dict(op="Mov", destination=0, source=2))
+        code.append(dict(op="Mov", destination=1, source=7))
+        code.append(dict(op="Stop"))
+        b = ab.CircuitBuilder()
+        # memory must exist up to 296: pass a 300-element array as the first input (register 0 = pointer 0)
+        b.brillig([("Array", [ab.wexpr(k + 1) for k in range(300)])], [("Array", list(range(400, 496))), ("Simple", 500)], code)
+        data = b.to_bytes()
+        br = acir.decode_circuit(data).opcodes[0].body
+        ins = msg + [0] * (300 - n)
+        so, _, oo = _brillig_run_oracle(br, ins)
+        sc, _, oc_ = _brillig_run_cpp(data, 0, ins, 97)
+        assert (so, sc) == (0, 0) and oc_ == oo, n
+    # ECDSA: memory = pkx | pky | sig | hashed
+    for name in ("EcdsaSecp256k1", "EcdsaSecp256r1"):
+        code = [dict(op="Const", destination=1, value=32), dict(op="Const", destination=2, value=64), dict(op="Const", destination=3, value=128),
+                dict(op="Const", destination=4, value=32),
+                dict(op="BlackBox", bb=dict(name=name, hashed_msg=(3, 4), public_key_x=(0, 32), public_key_y=(1, 32), signature=(2, 64), result=5)),
+                dict(op="Mov", destination=0, source=5), dict(op="Stop")]
+        b = ab.CircuitBuilder()
+        b.brillig([("Array", [ab.wexpr(k + 1) for k in range(160)])], [("Simple", 300)], code)
+        data = b.to_bytes()
+        br = acir.decode_circuit(data).opcodes[0].body
+        seen = set()
+        for c in ecdsa_cases.cases(name, seed=13, n_random=1):
+            ins = list(c[2]) + list(c[3]) + list(c[4]) + list(c[1])
+            so, _, oo = _brillig_run_oracle(br, ins)
+            sc, _, oc_ = _brillig_run_cpp(data, 0, ins, 1)
+            assert sc == so == (3 if c[5] == "panic" else 0), c[0]
+            if so == 0:
+                assert oc_ == oo == [1 if c[5] else 0], c[0]
+            seen.add(c[5])
+        assert seen == {True, False, "panic"}
+        # wrong array size: BlackBoxResolutionError::Failed -> VM failure, not a panic
+        code[4] = dict(op="BlackBox", bb=dict(name=name, hashed_msg=(3, 4), public_key_x=(0, 31), public_key_y=(1, 32), signature=(2, 64), result=5))
+        b = ab.CircuitBuilder()
+        b.brillig([("Array", [ab.wexpr(k + 1) for k in range(160)])], [("Simple", 300)], code)
+        data = b.to_bytes()
+        so, pco, _ = _brillig_run_oracle(acir.decode_circuit(data).opcodes[0].body, ins)
+        sc, pcc, _ = _brillig_run_cpp(data, 0, ins, 1)
+        assert (so, pco) == (sc, pcc) == (1, 4)
