@@ -367,6 +367,100 @@ FR_PRIM void mont_mul_s(Fe& r, const Fe& a, const Fe& b) {
 }
 FR_PRIM void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_s<FR_ALU_SPLIT>(r, a, b); }
 
+// ---------------------------------------------------------------------------------------------
+// Modular inverse by the binary extended Euclid, shaped for SIMT: every iteration is the SAME straight-line code for
+// all lanes (conditional swap so that u > v, u -= v, x1 -= x2, then strip ALL trailing zeros of u at once: u >>= k and
+// x1 := x1 / 2^k mod p through one Montgomery-style correction x1 + ((-x1 / p) mod 2^k) * p, exact for k <= 32).
+// ~190 iterations of ~110 instructions instead of the ~380 Montgomery products of a Fermat ladder; lanes only differ
+// in their trip count.  Plain C++ (no carry asm) so the host test build runs the same code.
+// a: 0 < a < p, any representation (the value is inverted as an integer mod p); r = a^-1 mod p, canonical.
+// ---------------------------------------------------------------------------------------------
+FR_HD void bea_shr(uint32_t* x, uint32_t top, int k) {   // (top:x) >>= k, 1 <= k <= 32
+    if (k == 32) {
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) x[i] = x[i + 1];
+        x[N - 1] = top;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) x[i] = (x[i] >> k) | (x[i + 1] << (32 - k));
+        x[N - 1] = (x[N - 1] >> k) | (top << (32 - k));
+    }
+}
+FR_HD int bea_ctz32(uint32_t v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+// u even, u != 0: u >>= ctz(u), x := x / 2^ctz(u) mod p
+FR_HD void bea_strip(uint32_t* u, uint32_t* x) {
+    while (!(u[0] & 1u)) {
+        const int k = u[0] ? bea_ctz32(u[0]) : 32;
+        bea_shr(u, 0u, k);
+        const uint32_t m = (x[0] * FR_M0) & (k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u));
+        unsigned long long c = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            c += (unsigned long long)m * p_limb(i) + x[i];
+            x[i] = (uint32_t)c;
+            c >>= 32;
+        }
+        bea_shr(x, (uint32_t)c, k);
+    }
+}
+FR_HD void inv_bea(Fe& r, const Fe& a) {
+    uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { u[i] = a.l[i]; v[i] = p_limb(i); x1[i] = i == 0; x2[i] = 0; }
+    bea_strip(u, x1);
+    while (true) {
+        // make u > v (both odd, never equal unless both are 1)
+        bool lt = false;
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            if (u[i] != v[i]) { lt = u[i] < v[i]; break; }
+        }
+        if (lt) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                uint32_t t = u[i]; u[i] = v[i]; v[i] = t;
+                t = x1[i]; x1[i] = x2[i]; x2[i] = t;
+            }
+        }
+        uint32_t rest = v[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; ++i) rest |= v[i];
+        if (rest == 0) break;   // v == 1: x2 * a == 1
+        long long br = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            long long d = (long long)u[i] - v[i] + br;
+            u[i] = (uint32_t)d;
+            br = d >> 32;
+        }
+        br = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            long long d = (long long)x1[i] - x2[i] + br;
+            x1[i] = (uint32_t)d;
+            br = d >> 32;
+        }
+        if (br) {
+            unsigned long long c = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                c += (unsigned long long)x1[i] + p_limb(i);
+                x1[i] = (uint32_t)c;
+                c >>= 32;
+            }
+        }
+        bea_strip(u, x1);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = x2[i];
+}
+
 // number of significant bits of a canonical value (acir_field/src/generic_ark.rs:214-221)
 FR_PRIM uint32_t num_bits(const Fe& a) {
     uint32_t nb = 0;

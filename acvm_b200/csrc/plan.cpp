@@ -31,23 +31,98 @@ struct Lin {
 
 class Scheduler {
    public:
-    Scheduler(uint32_t S, uint32_t n_slots) : S_(S), ready_(n_slots, 0), war_(n_slots, 0) {}
+    Scheduler(uint32_t S, uint32_t n_slots) : S_(S), ready_(n_slots, 0), war_(n_slots, 0), lvl_w_(n_slots, 0), lvl_r_(n_slots, 0) {}
 
     void grow_slots(uint32_t n) {
         if (n > ready_.size()) {
             ready_.resize(n, 0);
             war_.resize(n, 0);
+            lvl_w_.resize(n, 0);
+            lvl_r_.resize(n, 0);
         }
     }
 
     // everything placed so far completes before anything placed later starts (segment boundary)
     uint32_t barrier(uint32_t chunk_steps) {
+        flush();
         floor_ = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
         n_steps_ = floor_;
         return floor_;
     }
 
+    // Micro-ops whose single-lane latency is ~1000x an arithmetic gate (curve operations).  A step costs as much as its
+    // slowest slot, so a program-order list schedule that drops each of them into its own step serialises them.  From
+    // the first such op of a segment on, placement is deferred: flush() computes for every buffered op its "curve depth"
+    // (number of curve ops on the longest slot-hazard chain RAW/WAR/WAW that ends in it), orders the segment as
+    // [cheap depth 0] [curve depth 1] [cheap depth 1] [curve depth 2] ... and list-schedules that order.  Curve ops of
+    // one depth are mutually independent, so they pack S per step and their latencies overlap.  Any order that respects
+    // the slot hazards computes the same values, and failures are reported by lowest opcode index, not by step.
+    static bool is_costly(uint32_t kind) { return kind == MK_FIXED_BASE || kind == MK_PEDERSEN || kind == MK_ECDSA; }
+
     void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
+        const bool costly = is_costly(rec.w[0] & 0xFF);
+        if (!buffering_ && !costly) {
+            place_now(rec, reads, nr, writes, nw);
+            return;
+        }
+        buffering_ = true;
+        Pending p;
+        p.rec = rec;
+        p.off = (uint32_t)pool_.size();
+        p.nr = (uint32_t)nr;
+        p.nw = (uint32_t)nw;
+        p.costly = costly;
+        pool_.insert(pool_.end(), reads, reads + nr);
+        pool_.insert(pool_.end(), writes, writes + nw);
+        pend_.push_back(p);
+    }
+
+    void flush() {
+        if (!buffering_) return;
+        buffering_ = false;
+        std::vector<uint32_t> touched;
+        auto touch = [&](uint32_t slot) {
+            if (!lvl_w_[slot] && !lvl_r_[slot]) touched.push_back(slot);
+        };
+        std::vector<uint32_t> key(pend_.size());
+        for (size_t i = 0; i < pend_.size(); ++i) {
+            const Pending& p = pend_[i];
+            const uint32_t* rd = pool_.data() + p.off;
+            const uint32_t* wr = rd + p.nr;
+            uint32_t d = 0;
+            for (uint32_t k = 0; k < p.nr; ++k) d = std::max(d, lvl_w_[rd[k]]);
+            for (uint32_t k = 0; k < p.nw; ++k) d = std::max(d, std::max(lvl_w_[wr[k]], lvl_r_[wr[k]]));
+            if (p.costly) ++d;
+            for (uint32_t k = 0; k < p.nr; ++k) {
+                touch(rd[k]);
+                lvl_r_[rd[k]] = std::max(lvl_r_[rd[k]], d);
+            }
+            for (uint32_t k = 0; k < p.nw; ++k) {
+                touch(wr[k]);
+                lvl_w_[wr[k]] = d;
+                lvl_r_[wr[k]] = d;   // readers-since-last-write restarts; d keeps the slot marked as touched when d > 0
+            }
+            key[i] = 2 * d + (p.costly ? 0u : 1u);
+        }
+        for (uint32_t slot : touched) lvl_w_[slot] = lvl_r_[slot] = 0;
+        std::vector<uint32_t> order(pend_.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        uint32_t prev = 1;   // ops placed before buffering began are cheap, depth 0
+        for (uint32_t i : order) {
+            if (key[i] != prev) {
+                floor_ = n_steps_;   // curve steps hold curve ops only
+                prev = key[i];
+            }
+            const Pending& p = pend_[i];
+            const uint32_t* rd = pool_.data() + p.off;
+            place_now(p.rec, rd, p.nr, rd + p.nr, p.nw);
+        }
+        pend_.clear();
+        pool_.clear();
+    }
+
+    void place_now(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
         uint32_t e = floor_;
         for (size_t i = 0; i < nr; ++i) e = std::max(e, ready_[reads[i]]);
         for (size_t i = 0; i < nw; ++i) e = std::max(e, std::max(ready_[writes[i]], war_[writes[i]]));
@@ -60,11 +135,12 @@ class Scheduler {
         n_steps_ = std::max(n_steps_, s + 1);
     }
 
-    uint32_t n_steps() const { return n_steps_; }
-    size_t n_ops() const { return ops_.size(); }
+    uint32_t n_steps() { flush(); return n_steps_; }
+    size_t n_ops() { flush(); return ops_.size(); }
 
     // emit the dense [n_steps_padded][S] record array
-    void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps) const {
+    void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps) {
+        flush();
         n_steps_padded = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
         if (n_steps_padded == 0) n_steps_padded = chunk_steps;
         stream.assign((size_t)n_steps_padded * S_, OpRec{});
@@ -104,6 +180,15 @@ class Scheduler {
             fill_.push_back(0);
         }
     }
+    struct Pending {
+        OpRec rec;
+        uint32_t off, nr, nw;
+        bool costly;
+    };
+    std::vector<Pending> pend_;
+    std::vector<uint32_t> pool_;            // reads then writes of every pending op
+    std::vector<uint32_t> lvl_w_, lvl_r_;   // flush(): curve depth of the last writer / of the readers since
+    bool buffering_ = false;
     uint32_t S_;
     std::vector<uint32_t> ready_, war_;
     std::vector<uint32_t> fill_, next_;

@@ -27,6 +27,7 @@ void t_mont_mul_split(int split, const uint32_t* a, const uint32_t* b, uint32_t*
 void t_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); add_mod(R, A, B); memcpy(r, R.l, 32); }
 void t_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32); sub_mod(R, A, B); memcpy(r, R.l, 32); }
 void t_reduce(uint32_t* a) { Fe A; memcpy(A.l, a, 32); reduce_256(A); memcpy(a, A.l, 32); }
+void t_inv_bea(const uint32_t* a, uint32_t* r) { Fe A, R; memcpy(A.l, a, 32); inv_bea(R, A); memcpy(r, R.l, 32); }
 uint32_t t_num_bits(const uint32_t* a) { Fe A; memcpy(A.l, a, 32); return num_bits(A); }
 }
 
