@@ -599,6 +599,200 @@ __device__ __noinline__ void exec_pedersen(const OpRec* r, uint32_t flags, uint4
 }
 
 // ---------------------------------------------------------------------------------------------
+// Curve micro-ops for plan-level parallelism.  A fixed-base multiplication or a Pedersen chaining round is a sum of
+// table points; one lane doing all of it serially (exec_fixed_base / exec_pedersen above) leaves the other S-1 slot
+// threads of the instance idle for ~1 ms.  The plan compiler (plan.cpp: curve_sum_*) instead emits
+//   MK_CURVE_PART  partial sum of a few table points selected by windows of one scalar  -> Jacobian point in 3 slots
+//   MK_JAC_ADD     point + point                                                       -> Jacobian point in 3 slots
+//   MK_JAC_FINAL   point (+ point) -> affine canonical (x, y) with insert_value semantics (one inversion)
+// and the list scheduler runs the independent ones in the same step.  Jacobian coordinates travel through temporary
+// columns in Montgomery form; Z = 0 encodes the point at infinity.
+// MK_CURVE_PART parameters (r->c[0]): [0] scalar source: 0 = slot w[3], 1 = Pedersen IV table entry c[0][5], 2 = immediate
+// c[0][5];  [1] table: 0 = fixed-base (8-bit windows, digit 0 skipped), 1 = Pedersen (9-bit windows);  [2] first window
+// of the scalar;  [3] number of windows;  [4] table window offset (fixed-base high limb: 16; Pedersen parity 1: 29).
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void jac_dbl(Jac& acc) {   // "dbl-2009-l", a = 0
+    if (acc.inf) return;
+    if (fr::is_zero(acc.Y)) { acc.inf = true; return; }
+    Fe A, B, C, D, E, F, t, X3, Y3, Z3;
+    fe_sqr(A, acc.X);
+    fe_sqr(B, acc.Y);
+    fe_sqr(C, B);
+    fr::add_mod(D, acc.X, B);
+    fe_sqr(D, D);
+    fr::sub_mod(D, D, A);
+    fr::sub_mod(D, D, C);
+    fe_dbl(D, D);
+    fe_dbl(E, A);
+    fr::add_mod(E, E, A);
+    fe_sqr(F, E);
+    fe_dbl(t, D);
+    fr::sub_mod(X3, F, t);
+    fr::sub_mod(t, D, X3);
+    fe_mul(Y3, E, t);
+    fe_dbl(C, C); fe_dbl(C, C); fe_dbl(C, C);
+    fr::sub_mod(Y3, Y3, C);
+    fe_mul(Z3, acc.Y, acc.Z);
+    fe_dbl(Z3, Z3);
+    acc.X = X3; acc.Y = Y3; acc.Z = Z3;
+}
+
+// a += b, both Jacobian ("add-2007-bl": 11M + 5S), every special case handled
+__device__ __noinline__ void jac_add_full(Jac& a, const Jac& b) {
+    if (b.inf) return;
+    if (a.inf) { a = b; return; }
+    Fe z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+    fe_sqr(z1z1, a.Z);
+    fe_sqr(z2z2, b.Z);
+    fe_mul(u1, a.X, z2z2);
+    fe_mul(u2, b.X, z1z1);
+    fe_mul(s1, a.Y, b.Z);
+    fe_mul(s1, s1, z2z2);
+    fe_mul(s2, b.Y, a.Z);
+    fe_mul(s2, s2, z1z1);
+    fr::sub_mod(h, u2, u1);
+    fr::sub_mod(rr, s2, s1);
+    if (fr::is_zero(h)) {
+        if (fr::is_zero(rr)) jac_dbl(a); else a.inf = true;
+        return;
+    }
+    fe_dbl(i, h);
+    fe_sqr(i, i);             // I = (2H)^2
+    fe_mul(j, h, i);          // J = H*I
+    fe_dbl(rr, rr);           // r = 2*(S2-S1)
+    fe_mul(v, u1, i);         // V = U1*I
+    Fe X3, Y3, Z3;
+    fe_sqr(X3, rr);
+    fr::sub_mod(X3, X3, j);
+    fe_dbl(t, v);
+    fr::sub_mod(X3, X3, t);
+    fr::sub_mod(t, v, X3);
+    fe_mul(Y3, rr, t);
+    fe_mul(t, s1, j);
+    fe_dbl(t, t);
+    fr::sub_mod(Y3, Y3, t);
+    fr::add_mod(Z3, a.Z, b.Z);
+    fe_sqr(Z3, Z3);
+    fr::sub_mod(Z3, Z3, z1z1);
+    fr::sub_mod(Z3, Z3, z2z2);
+    fe_mul(Z3, Z3, h);
+    a.X = X3; a.Y = Y3; a.Z = Z3;
+}
+
+template <int T>
+__device__ __forceinline__ void load_jac(Jac& p, const uint4* cb, uint32_t base) {
+    hv_load<T>(p.X, cb, base);
+    hv_load<T>(p.Y, cb, base + 1);
+    hv_load<T>(p.Z, cb, base + 2);
+    p.inf = fr::is_zero(p.Z);
+}
+template <int T>
+__device__ __forceinline__ void store_jac(uint4* cb, uint32_t base, const Jac& p) {
+    if (p.inf) {
+        Fe z;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z.l[k] = 0;
+        hv_store<T>(cb, base, z);
+        hv_store<T>(cb, base + 1, z);
+        hv_store<T>(cb, base + 2, z);
+    } else {
+        hv_store<T>(cb, base, p.X);
+        hv_store<T>(cb, base + 1, p.Y);
+        hv_store<T>(cb, base + 2, p.Z);
+    }
+}
+__device__ __forceinline__ void load_table_point(Fe& px, Fe& py, const uint32_t* table, size_t row) {
+    const uint4* tp = reinterpret_cast<const uint4*>(table + row * 16);
+    uint4 a = tp[0], b = tp[1], c = tp[2], e = tp[3];
+    px.l[0] = a.x; px.l[1] = a.y; px.l[2] = a.z; px.l[3] = a.w; px.l[4] = b.x; px.l[5] = b.y; px.l[6] = b.z; px.l[7] = b.w;
+    py.l[0] = c.x; py.l[1] = c.y; py.l[2] = c.z; py.l[3] = c.w; py.l[4] = e.x; py.l[5] = e.y; py.l[6] = e.z; py.l[7] = e.w;
+}
+
+template <int T>
+__device__ __noinline__ void exec_curve_part(const OpRec* r, uint4* cb) {
+    const uint32_t mode = r->c[0][0], table = r->c[0][1], first = r->c[0][2], count = r->c[0][3], toff = r->c[0][4], imm = r->c[0][5];
+    uint32_t l[9];
+    if (mode == 0) {
+        Fe v;
+        hv_load<T>(v, cb, r->w[3]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = v.l[k];
+    } else if (mode == 1) {
+        const uint32_t* ivp = g_curve_tables.pedersen + (size_t)2 * PED_WINDOWS * PED_TABLE_SIZE * 16 + (size_t)(imm % PED_IV_SIZE) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = ivp[k];
+    } else {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) l[k] = 0;
+        l[0] = imm;
+    }
+    l[8] = 0;
+    Jac acc;
+    acc.inf = true;
+#pragma unroll 1
+    for (uint32_t w = first; w < first + count; ++w) {
+        Fe px, py;
+        if (table == 0) {
+            const uint32_t d = (l[w >> 2] >> (8 * (w & 3))) & 0xFF;
+            if (d == 0) continue;
+            load_table_point(px, py, g_curve_tables.fixed_base, (size_t)(toff + w) * 255 + (d - 1));
+        } else {
+            const uint32_t o = 9 * w, limb = o >> 5, sh = o & 31;
+            const uint32_t s9 = __funnelshift_r(l[limb], l[limb + 1], sh) & 0x1FF;
+            load_table_point(px, py, g_curve_tables.pedersen, (size_t)(toff + w) * PED_TABLE_SIZE + s9);
+        }
+        jac_madd(acc, px, py);
+    }
+    store_jac<T>(cb, r->w[2], acc);
+}
+
+template <int T>
+__device__ __noinline__ void exec_jac_add(const OpRec* r, uint4* cb) {
+    Jac a, b;
+    load_jac<T>(a, cb, r->w[3]);
+    load_jac<T>(b, cb, r->w[4]);
+    jac_add_full(a, b);
+    store_jac<T>(cb, r->w[2], a);
+}
+
+// w[3] (+ w[4]) -> affine; out x = w[2], out y = w[5] (NONE: x only, the Pedersen chaining value).
+// c[0][0] != 0: FixedBaseScalarMul input validation on w[6] = low, w[7] = high first (scalar_mul.rs:25-51).
+template <int T>
+__device__ __noinline__ void exec_jac_final(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    if (r->c[0][0]) {
+        Fe lo, hi;
+        hv_load<T>(lo, cb, r->w[6]);
+        hv_load<T>(hi, cb, r->w[7]);
+        bool bad = (lo.l[4] | lo.l[5] | lo.l[6] | lo.l[7]) || (hi.l[4] | hi.l[5] | hi.l[6] | hi.l[7]);
+        if (!bad) {
+            const uint32_t s[8] = {lo.l[0], lo.l[1], lo.l[2], lo.l[3], hi.l[0], hi.l[1], hi.l[2], hi.l[3]};
+            const uint32_t n[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+            bool lt = false;
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                if (s[i] != n[i]) { lt = s[i] < n[i]; break; }
+            }
+            bad = !lt;
+        }
+        if (bad) {
+            hv_fail(fail, r->w[1], EK_BLACKBOX_FAILED, BB_FixedBaseScalarMul);
+            return;
+        }
+    }
+    Jac a;
+    load_jac<T>(a, cb, r->w[3]);
+    if (r->w[4] != 0xFFFFFFFFu) {
+        Jac b;
+        load_jac<T>(b, cb, r->w[4]);
+        jac_add_full(a, b);
+    }
+    Fe x, y;
+    jac_to_affine_canonical(x, y, a);
+    if (r->w[5] == 0xFFFFFFFFu) hv_store<T>(cb, r->w[2], x);
+    else write_point<T>(r, flags, x, y, r->w[2], r->w[5], cb, fail);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Value-dependent arithmetic gate: the reference's evaluate() + solve() run per lane
 // (acvm/src/pwg/arithmetic.rs:27-127,212-239).  `mu` is this lane's "assigned by opcode" table for the witnesses
 // whose assignment depends on instance values (entry = opcode index that assigned it, NONE = unassigned).
@@ -923,6 +1117,15 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_ECDSA:
             exec_ecdsa<T>(r, flags, cb, fail, payload);
+            break;
+        case MK_CURVE_PART:
+            exec_curve_part<T>(r, cb);
+            break;
+        case MK_JAC_ADD:
+            exec_jac_add<T>(r, cb);
+            break;
+        case MK_JAC_FINAL:
+            exec_jac_final<T>(r, flags, cb, fail);
             break;
         case MK_GATE_GENERAL:
             exec_general<T>(r, cb, fail, payload, mu);

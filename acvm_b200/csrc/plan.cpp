@@ -231,6 +231,14 @@ struct Compiler {
         return t;
     }
 
+    // three consecutive temporaries: one Jacobian point
+    uint32_t new_temp3() {
+        if ((temp_next % opt.temp_pool) + 3 > opt.temp_pool) temp_next += opt.temp_pool - (temp_next % opt.temp_pool);
+        uint32_t t = temp_base + (temp_next % opt.temp_pool);
+        temp_next += 3;
+        return t;
+    }
+
     static void put(uint32_t dst[8], const U256& v) { hf::to_limbs32(v, dst); }
 
     void fail_static(uint32_t opcode, uint32_t kind, uint32_t aux, const std::string& detail) {
@@ -922,6 +930,78 @@ struct Compiler {
         return true;
     }
 
+    // ---- plan-level parallel curve sums (device side: heavy_ops.cuh, MK_CURVE_PART / MK_JAC_ADD / MK_JAC_FINAL) ----
+    bool split_curve_ops() const { return opt.split_curve && opt.S >= 8; }
+
+    // partial sums over `n_windows` windows of one scalar, `per` windows per micro-op; returns the point slots
+    void curve_parts(uint32_t idx, uint32_t mode, uint32_t src_slot, uint32_t imm, uint32_t table, uint32_t n_windows, uint32_t per,
+                     uint32_t toff, std::vector<uint32_t>& points) {
+        for (uint32_t first = 0; first < n_windows; first += per) {
+            OpRec r{};
+            uint32_t out = new_temp3();
+            r.w[0] = MK_CURVE_PART;
+            r.w[1] = idx;
+            r.w[2] = out;
+            r.w[3] = mode == 0 ? src_slot : NONE;
+            r.w[4] = r.w[5] = r.w[6] = r.w[7] = NONE;
+            r.c[0][0] = mode;
+            r.c[0][1] = table;
+            r.c[0][2] = first;
+            r.c[0][3] = std::min(per, n_windows - first);
+            r.c[0][4] = toff;
+            r.c[0][5] = imm;
+            std::vector<uint32_t> rd, wr = {out, out + 1, out + 2};
+            if (mode == 0) rd.push_back(src_slot);
+            place_heavy(r, rd, wr);
+            points.push_back(out);
+        }
+    }
+    // pairwise tree of Jacobian additions until at most `keep` points remain
+    void curve_reduce(uint32_t idx, std::vector<uint32_t>& points, size_t keep) {
+        while (points.size() > keep) {
+            std::vector<uint32_t> next;
+            size_t n_pairs = std::min(points.size() / 2, points.size() - keep);
+            for (size_t i = 0; i < n_pairs; ++i) {
+                OpRec r{};
+                uint32_t a = points[2 * i], b = points[2 * i + 1], out = new_temp3();
+                r.w[0] = MK_JAC_ADD;
+                r.w[1] = idx;
+                r.w[2] = out;
+                r.w[3] = a;
+                r.w[4] = b;
+                r.w[5] = r.w[6] = r.w[7] = NONE;
+                std::vector<uint32_t> rd = {a, a + 1, a + 2, b, b + 1, b + 2}, wr = {out, out + 1, out + 2};
+                place_heavy(r, rd, wr);
+                next.push_back(out);
+            }
+            for (size_t i = 2 * n_pairs; i < points.size(); ++i) next.push_back(points[i]);
+            points.swap(next);
+        }
+    }
+    // affine(points[0] (+ points[1])) -> out_x (, out_y); flags carry GF_OUT_CHECK / GF_OUT2_CHECK for witness outputs
+    void curve_final(uint32_t idx, const std::vector<uint32_t>& points, uint32_t out_x, uint32_t out_y, uint32_t flags,
+                     bool validate_fixed_base, uint32_t lo, uint32_t hi) {
+        OpRec r{};
+        r.w[0] = MK_JAC_FINAL | (flags << 8);
+        r.w[1] = idx;
+        r.w[2] = out_x;
+        r.w[3] = points[0];
+        r.w[4] = points.size() > 1 ? points[1] : NONE;
+        r.w[5] = out_y;
+        r.w[6] = validate_fixed_base ? lo : NONE;
+        r.w[7] = validate_fixed_base ? hi : NONE;
+        r.c[0][0] = validate_fixed_base ? 1u : 0u;
+        std::vector<uint32_t> rd, wr = {out_x};
+        for (uint32_t pt : points) { rd.push_back(pt); rd.push_back(pt + 1); rd.push_back(pt + 2); }
+        if (validate_fixed_base) { rd.push_back(lo); rd.push_back(hi); }
+        if (flags & GF_OUT_CHECK) rd.push_back(out_x);
+        if (out_y != NONE) {
+            if (flags & GF_OUT2_CHECK) rd.push_back(out_y);
+            wr.push_back(out_y);
+        }
+        place_heavy(r, rd, wr);
+    }
+
     bool blackbox(uint32_t idx, const BlackBoxCall& b) {
         for (uint32_t w : b.outputs)
             if (known[w] == W_MAYBE && b.func != BB_RecursiveAggregation)
@@ -1064,6 +1144,22 @@ struct Compiler {
             case BB_FixedBaseScalarMul: {
                 uint32_t ox = b.outputs[0], oy = b.outputs[1];
                 uint32_t flags = GF_HEAVY;
+                if (split_curve_ops()) {
+                    // s*G = sum over 32 8-bit windows of table points: 8 partial sums of 4 windows, a 3-level addition tree
+                    // whose last addition rides in the finaliser (which also validates the limbs, scalar_mul.rs:25-51)
+                    if (known[ox]) flags |= GF_OUT_CHECK;
+                    if (known[oy] || oy == ox) flags |= GF_OUT2_CHECK;
+                    std::vector<uint32_t> pts;
+                    curve_parts(idx, 0, b.inputs[0].witness, 0, 0, 16, 4, 0, pts);
+                    curve_parts(idx, 0, b.inputs[1].witness, 0, 0, 16, 4, 16, pts);
+                    curve_reduce(idx, pts, 2);
+                    curve_final(idx, pts, ox, oy, flags, true, b.inputs[0].witness, b.inputs[1].witness);
+                    if (!known[ox]) mark_assigned(ox, idx);
+                    if (!known[oy]) mark_assigned(oy, idx);
+                    ++plan.stats.n_curve;
+                    plan.stats.alg_bytes += 128;
+                    return true;
+                }
                 std::vector<uint32_t> rd = {b.inputs[0].witness, b.inputs[1].witness}, wr;
                 if (known[ox]) { flags |= GF_OUT_CHECK; rd.push_back(ox); }
                 wr.push_back(ox);
@@ -1089,6 +1185,41 @@ struct Compiler {
             case BB_Pedersen: {
                 uint32_t ox = b.outputs[0], oy = b.outputs[1];
                 uint32_t flags = GF_HEAVY;
+                if (split_curve_ops() && !b.inputs.empty()) {
+                    // r_0 = IV; r_{k+1} = (H0(r_k) + H1(v_k)).x; out = H0(r_n) + H1(n)   (oracle/pedersen.py).  Each H is a sum of
+                    // 29 table points -> 8 partial sums.  Every H1 is independent of the chain and is reduced to one point ahead
+                    // of it; a chaining round is then 8 partial sums, a 3-level addition tree and one finaliser.
+                    if (known[ox]) flags |= GF_OUT_CHECK;
+                    if (known[oy] || oy == ox) flags |= GF_OUT2_CHECK;
+                    const uint32_t n_in = (uint32_t)b.inputs.size();
+                    std::vector<uint32_t> h1(n_in + 1);
+                    for (uint32_t k = 0; k <= n_in; ++k) {
+                        std::vector<uint32_t> pts;
+                        if (k < n_in) curve_parts(idx, 0, b.inputs[k].witness, 0, 1, 29, 4, 29, pts);   // num_bits is ignored (pedersen.rs:18-20)
+                        else curve_parts(idx, 2, NONE, n_in, 1, 29, 4, 29, pts);                          // the length block: an immediate scalar
+                        curve_reduce(idx, pts, 1);
+                        h1[k] = pts[0];
+                    }
+                    uint32_t chain = NONE;   // slot holding r_k (canonical x of the previous round)
+                    for (uint32_t k = 0; k <= n_in; ++k) {
+                        std::vector<uint32_t> pts;
+                        if (k == 0) curve_parts(idx, 1, NONE, b.domain_separator, 1, 29, 4, 0, pts);
+                        else curve_parts(idx, 0, chain, 0, 1, 29, 4, 0, pts);
+                        pts.push_back(h1[k]);
+                        curve_reduce(idx, pts, 2);
+                        if (k < n_in) {
+                            chain = new_temp();
+                            curve_final(idx, pts, chain, NONE, GF_HEAVY, false, NONE, NONE);
+                        } else {
+                            curve_final(idx, pts, ox, oy, flags, false, NONE, NONE);
+                        }
+                    }
+                    if (!known[ox]) mark_assigned(ox, idx);
+                    if (!known[oy]) mark_assigned(oy, idx);
+                    ++plan.stats.n_curve;
+                    plan.stats.alg_bytes += 32 * b.inputs.size() + 64;
+                    return true;
+                }
                 std::vector<uint32_t> rd, wr;
                 uint32_t off = (uint32_t)plan.payload.size();
                 plan.payload.push_back((uint32_t)b.inputs.size());
@@ -1304,9 +1435,18 @@ static std::vector<U256> batch_inverse(const std::vector<U256>& v) {
     return out;
 }
 
-Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt) {
+Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt_in) {
+    PlanOptions opt = opt_in;
     if (opt.S == 0 || opt.S > 64) throw std::runtime_error("plan: S must be in 1..64");
     uint32_t nw = witness_span(c, input_witnesses);
+    // Jacobian points of the split curve micro-ops travel through temporaries (3 slots each, ~270 per Pedersen): a larger
+    // round-robin pool keeps slot reuse (a false WAR dependency) from serialising independent curve operations
+    if (opt.split_curve && opt.S >= 8)
+        for (auto& op : c.opcodes)
+            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul)) {
+                opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 8192);
+                break;
+            }
     if (c.opcodes.size() < 2048) {   // small circuits: direct inversions
         Compiler comp(c, opt, nw);
         comp.run(input_witnesses);

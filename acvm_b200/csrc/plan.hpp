@@ -49,6 +49,9 @@ enum MicroKind : uint32_t {
     MK_BLAKE2S = 18,      // same payload as MK_SHA256                                  (hash.rs:28-48 -> blake2 0.10.6)
     MK_HASH_TO_FIELD = 19,// payload: n_in, check, NONE, 0, (witness,num_bits)*, 1 output: blake2s digest reduced mod p (hash.rs:13-24)
     MK_ECDSA = 20,        // out := verify; payload[aux..]: curve (0 k1, 1 r1), 32 pkx, 32 pky, 64 sig, 32 hashed-message witnesses (signature/ecdsa.rs)
+    MK_CURVE_PART = 21,   // out (3 slots from w[2]) := sum of table points picked by windows of one scalar; parameters in c[0] (heavy_ops.cuh)
+    MK_JAC_ADD = 22,      // out (3 slots from w[2]) := point at w[3] + point at w[4]   (Jacobian, Montgomery form, Z = 0 is infinity)
+    MK_JAC_FINAL = 23,    // (x, y) at w[2], w[5] := affine(point at w[3] [+ point at w[4]]); c[0][0]: validate fixed-base scalar w[6], w[7]
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
 };
 
@@ -135,6 +138,7 @@ struct PlanOptions {
     uint32_t S = 16;
     uint32_t chunk_steps = 2;
     uint32_t temp_pool = 2048;
+    bool split_curve = true;   // lower FixedBaseScalarMul / Pedersen into parallel partial-sum micro-ops when S >= 8
 };
 
 // Throws std::runtime_error for opcodes outside the device scope.

@@ -12,7 +12,7 @@ NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
           GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17,
-          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20)
+          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20, CURVE_PART=21, JAC_ADD=22, JAC_FINAL=23)
 EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
@@ -164,7 +164,65 @@ def default_hooks():
             return []
         return [(out, v)]
 
-    return {MK["ECDSA"]: ecdsa_hook, MK["BLAKE2S"]: hash_hook(hashes.blake2s), MK["HASH_TO_FIELD"]: hash_to_field, MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
+    # Split curve micro-ops.  The interpreter keeps a point in its three temporary slots as (x, y, 1) affine or (0, 0, 0):
+    # the device's Jacobian/Montgomery encoding is not observable (temporaries never leave the device), only the
+    # finaliser's canonical affine output is.
+    def _pt_load(cols, base):
+        return grumpkin.INF if cols[base + 2] == 0 else (cols[base], cols[base + 1])
+
+    def _pt_store(base, pt):
+        return [(base, 0), (base + 1, 0), (base + 2, 0)] if pt is grumpkin.INF else [(base, pt[0]), (base + 1, pt[1]), (base + 2, 1)]
+
+    def curve_part(cols, hdr, payload, record_fail, consts=None):
+        from oracle import pedersen
+        mode, table, first, count, toff, imm = consts[0][:6]
+        if mode == 0:
+            v = cols[hdr[3]]
+        elif mode == 1:
+            v = pedersen.iv_point_x(imm)
+        else:
+            v = imm
+        acc = grumpkin.INF
+        for w in range(first, first + count):
+            if table == 0:
+                d = (v >> (8 * w)) & 0xFF
+                if d:
+                    acc = grumpkin.add(acc, grumpkin.mul(d << (8 * (toff + w)), grumpkin.G))
+            else:
+                s9 = (v >> (9 * w)) & 0x1FF
+                par, i = divmod(toff + w, pedersen.NUM_WINDOWS)
+                acc = grumpkin.add(acc, grumpkin.mul(s9 + 1, pedersen.generators()[par][i]))
+        return _pt_store(hdr[2], acc)
+
+    def jac_add(cols, hdr, payload, record_fail, consts=None):
+        return _pt_store(hdr[2], grumpkin.add(_pt_load(cols, hdr[3]), _pt_load(cols, hdr[4])))
+
+    def jac_final(cols, hdr, payload, record_fail, consts=None):
+        flags = hdr[0] >> 8
+        opcode = hdr[1]
+        if consts[0][0]:
+            try:
+                grumpkin.fixed_base_scalar_mul(cols[hdr[6]], cols[hdr[7]])
+            except grumpkin.BlackBoxFailed:
+                record_fail(opcode, EK_BB_FAILED, 10)
+                return []
+        pt = _pt_load(cols, hdr[3])
+        if hdr[4] != NONE:
+            pt = grumpkin.add(pt, _pt_load(cols, hdr[4]))
+        x, y = (0, 0) if pt is grumpkin.INF else pt
+        if hdr[5] == NONE:
+            return [(hdr[2], x)]
+        w = []
+        for (slot, v, chk) in ((hdr[2], x, flags & GF_OUT_CHECK_), (hdr[5], y, flags & GF_OUT2_CHECK_)):
+            if chk:
+                if cols[slot] != v:
+                    record_fail(opcode, EK_UNSAT)
+                    w.append((slot, v))
+            else:
+                w.append((slot, v))
+        return w
+
+    return {MK["CURVE_PART"]: curve_part, MK["JAC_ADD"]: jac_add, MK["JAC_FINAL"]: jac_final, MK["ECDSA"]: ecdsa_hook, MK["BLAKE2S"]: hash_hook(hashes.blake2s), MK["HASH_TO_FIELD"]: hash_to_field, MK["PEDERSEN"]: pedersen_hook, MK["SHA256"]: hash_hook(hashes.sha256), MK["KECCAK256"]: hash_hook(hashes.keccak256), MK["FIXED_BASE"]: fixed_base}
 
 
 def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
@@ -438,6 +496,9 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                     if pl[aux + 2 + 2 * i] not in mu:
                         record_fail(opcode, EK_MISSING, pl[aux + 1 + 2 * i])
                         break
+            elif hooks and kind in hooks and kind in (MK["CURVE_PART"], MK["JAC_ADD"], MK["JAC_FINAL"]):
+                words = [[(cv >> (32 * j)) & 0xFFFFFFFF for j in range(8)] for cv in c]
+                writes.extend(hooks[kind](cols, hdr, plan.payload, record_fail, consts=words))
             elif hooks and kind in hooks:
                 writes.extend(hooks[kind](cols, hdr, plan.payload, record_fail))
             else:

@@ -558,3 +558,30 @@ def test_cpp_brillig_vm_blackbox_ops(golden):
         so, pco, _ = _brillig_run_oracle(acir.decode_circuit(data).opcodes[0].body, ins)
         sc, pcc, _ = _brillig_run_cpp(data, 0, ins, 1)
         assert (so, pco) == (sc, pcc) == (1, 4)
+
+
+@pytest.mark.parametrize("S", [4, 8, 16, 32])
+def test_curve_ops_monolithic_and_split_plans_vs_oracle(S):
+    """FixedBaseScalarMul / Pedersen: one micro-op per call at S < 8, partial-sum / addition-tree / finaliser micro-ops at
+    S >= 8 (plan.cpp curve_parts / curve_reduce / curve_final) -- both against the oracle, including chained calls, an
+    empty Pedersen, limbs that fail validation, the zero scalar and a pre-assigned output."""
+    from oracle import grumpkin
+    b = ab.CircuitBuilder()
+    b.pedersen([(1, 254), (2, 254)], 0, (10, 11))
+    b.pedersen([(10, 254)], 5, (12, 13))
+    b.pedersen([], 1, (14, 15))
+    b.pedersen([(1, 254), (11, 254), (3, 254)], 1023, (16, 17))
+    b.logic("AND", (1, 100), (2, 100), 18)
+    b.logic("AND", (3, 100), (2, 100), 19)
+    b.fixed_base_scalar_mul((18, 128), (19, 128), (20, 21))
+    b.arithmetic([(1, 20, 21)], [(1, 16), (ab.P - 1, 24)], 0)
+    b.fixed_base_scalar_mul((1, 254), (19, 128), (22, 23))   # low limb >= 2^128 in the random rows: BlackBoxFunctionFailed
+    data = b.to_bytes()
+    info = _interp_vs_oracle(data, [1, 2, 3], ab.synthetic_inputs(3, n_inputs=3, seed_id=9), 3, S=S)
+    assert info["n_curve"] == 6 and (info["n_micro_ops"] > 100) == (S >= 8)
+    b = ab.CircuitBuilder()
+    b.fixed_base_scalar_mul((1, 128), (2, 128), (4, 3))      # y is pre-assigned: insert_value compares
+    b.arithmetic([], [(1, 4), (ab.P - 1, 6)], 1)
+    g5 = grumpkin.fixed_base_scalar_mul(5, 0)
+    rows = [[0, 0, 0], [5, 0, g5[1]], [1 << 128, 0, 7]]
+    _interp_vs_oracle(b.to_bytes(), [1, 2, 3], b"".join(int(v).to_bytes(32, "big") for r in rows for v in r), 3, S=S)
