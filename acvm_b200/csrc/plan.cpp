@@ -31,7 +31,9 @@ struct Lin {
 
 class Scheduler {
    public:
-    Scheduler(uint32_t S, uint32_t n_slots) : S_(S), ready_(n_slots, 0), war_(n_slots, 0), lvl_w_(n_slots, 0), lvl_r_(n_slots, 0) {}
+    Scheduler(uint32_t S, uint32_t n_slots)
+        : S_(S), ready_(n_slots, 0), war_(n_slots, 0), lvl_w_(n_slots, 0), lvl_r_(n_slots, 0), own_w_(n_slots, 0xFFFFFFFFu),
+          own_r_(n_slots, 0xFFFFFFFFu), seen_(n_slots, 0) {}
 
     void grow_slots(uint32_t n) {
         if (n > ready_.size()) {
@@ -39,6 +41,9 @@ class Scheduler {
             war_.resize(n, 0);
             lvl_w_.resize(n, 0);
             lvl_r_.resize(n, 0);
+            own_w_.resize(n, 0xFFFFFFFFu);
+            own_r_.resize(n, 0xFFFFFFFFu);
+            seen_.resize(n, 0);
         }
     }
 
@@ -50,14 +55,19 @@ class Scheduler {
         return floor_;
     }
 
-    // Micro-ops whose single-lane latency is ~1000x an arithmetic gate (curve operations).  A step costs as much as its
-    // slowest slot, so a program-order list schedule that drops each of them into its own step serialises them.  From
-    // the first such op of a segment on, placement is deferred: flush() computes for every buffered op its "curve depth"
-    // (number of curve ops on the longest slot-hazard chain RAW/WAR/WAW that ends in it), orders the segment as
-    // [cheap depth 0] [curve depth 1] [cheap depth 1] [curve depth 2] ... and list-schedules that order.  Curve ops of
-    // one depth are mutually independent, so they pack S per step and their latencies overlap.  Any order that respects
-    // the slot hazards computes the same values, and failures are reported by lowest opcode index, not by step.
-    static bool is_costly(uint32_t kind) { return kind == MK_FIXED_BASE || kind == MK_PEDERSEN || kind == MK_ECDSA; }
+    // Curve micro-ops are 10..1000x slower than an arithmetic gate and a step costs as much as its slowest slot, so a
+    // program-order list schedule that lets each curve call start wherever its operands happen to be ready scatters the slow
+    // steps all over the stream.  From the first curve micro-op of a segment on, placement is deferred: flush() computes for
+    // every buffered op its "curve depth" -- the number of curve CALLS (ACIR opcodes; a call may be many micro-ops) on the
+    // longest slot-hazard chain (RAW/WAR/WAW) that ends in it -- orders the segment as
+    //   [cheap depth 0] [curve depth 1] [cheap depth 1] [curve depth 2] ...
+    // and list-schedules that order.  Curve calls of one depth are mutually independent and start on the same step, so
+    // their partial sums, addition trees and finalisers line up in shared steps and the latencies overlap.  Any order
+    // that respects the slot hazards computes the same values; failures are reported by lowest opcode index, not by step.
+    static bool is_costly(uint32_t kind) {
+        return kind == MK_FIXED_BASE || kind == MK_PEDERSEN || kind == MK_ECDSA || kind == MK_CURVE_PART || kind == MK_JAC_ADD ||
+               kind == MK_JAC_FINAL;
+    }
 
     void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
         const bool costly = is_costly(rec.w[0] & 0xFF);
@@ -80,38 +90,47 @@ class Scheduler {
     void flush() {
         if (!buffering_) return;
         buffering_ = false;
+        constexpr uint32_t NO_CALL = 0xFFFFFFFFu, MIXED = 0xFFFFFFFEu;
         std::vector<uint32_t> touched;
-        auto touch = [&](uint32_t slot) {
-            if (!lvl_w_[slot] && !lvl_r_[slot]) touched.push_back(slot);
-        };
         std::vector<uint32_t> key(pend_.size());
         for (size_t i = 0; i < pend_.size(); ++i) {
             const Pending& p = pend_[i];
             const uint32_t* rd = pool_.data() + p.off;
             const uint32_t* wr = rd + p.nr;
-            uint32_t d = 0;
-            for (uint32_t k = 0; k < p.nr; ++k) d = std::max(d, lvl_w_[rd[k]]);
-            for (uint32_t k = 0; k < p.nw; ++k) d = std::max(d, std::max(lvl_w_[wr[k]], lvl_r_[wr[k]]));
-            if (p.costly) ++d;
+            const uint32_t call = p.costly ? p.rec.w[1] : NO_CALL;   // ACIR opcode index of the curve call
+            // a hazard on an op of another call (or on a cheap op) puts a curve micro-op one level deeper; hazards inside
+            // its own call, and every hazard of a cheap op, keep the level
+            auto via = [&](uint32_t lvl, uint32_t owner) { return (p.costly && owner != call) ? lvl + 1 : lvl; };
+            uint32_t d = p.costly ? 1u : 0u;
+            for (uint32_t k = 0; k < p.nr; ++k) d = std::max(d, via(lvl_w_[rd[k]], own_w_[rd[k]]));
+            for (uint32_t k = 0; k < p.nw; ++k)
+                d = std::max(d, std::max(via(lvl_w_[wr[k]], own_w_[wr[k]]), via(lvl_r_[wr[k]], own_r_[wr[k]])));
             for (uint32_t k = 0; k < p.nr; ++k) {
-                touch(rd[k]);
-                lvl_r_[rd[k]] = std::max(lvl_r_[rd[k]], d);
+                const uint32_t s = rd[k];
+                if (!seen_[s]) { seen_[s] = 1; touched.push_back(s); }
+                if (d > lvl_r_[s]) { lvl_r_[s] = d; own_r_[s] = call; }
+                else if (d == lvl_r_[s] && own_r_[s] != call) own_r_[s] = MIXED;
             }
             for (uint32_t k = 0; k < p.nw; ++k) {
-                touch(wr[k]);
-                lvl_w_[wr[k]] = d;
-                lvl_r_[wr[k]] = d;   // readers-since-last-write restarts; d keeps the slot marked as touched when d > 0
+                const uint32_t s = wr[k];
+                if (!seen_[s]) { seen_[s] = 1; touched.push_back(s); }
+                lvl_w_[s] = d; own_w_[s] = call;
+                lvl_r_[s] = d; own_r_[s] = call;   // readers-since-last-write restarts
             }
             key[i] = 2 * d + (p.costly ? 0u : 1u);
         }
-        for (uint32_t slot : touched) lvl_w_[slot] = lvl_r_[slot] = 0;
+        for (uint32_t s : touched) {
+            lvl_w_[s] = lvl_r_[s] = 0;
+            own_w_[s] = own_r_[s] = NO_CALL;
+            seen_[s] = 0;
+        }
         std::vector<uint32_t> order(pend_.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         uint32_t prev = 1;   // ops placed before buffering began are cheap, depth 0
         for (uint32_t i : order) {
             if (key[i] != prev) {
-                floor_ = n_steps_;   // curve steps hold curve ops only
+                floor_ = n_steps_;   // curve steps hold curve micro-ops only
                 prev = key[i];
             }
             const Pending& p = pend_[i];
@@ -188,6 +207,8 @@ class Scheduler {
     std::vector<Pending> pend_;
     std::vector<uint32_t> pool_;            // reads then writes of every pending op
     std::vector<uint32_t> lvl_w_, lvl_r_;   // flush(): curve depth of the last writer / of the readers since
+    std::vector<uint32_t> own_w_, own_r_;   // ... and the curve call they belong to
+    std::vector<uint8_t> seen_;
     bool buffering_ = false;
     uint32_t S_;
     std::vector<uint32_t> ready_, war_;
@@ -1444,7 +1465,7 @@ Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses
     if (opt.split_curve && opt.S >= 8)
         for (auto& op : c.opcodes)
             if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul)) {
-                opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 8192);
+                opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 32768);
                 break;
             }
     if (c.opcodes.size() < 2048) {   // small circuits: direct inversions

@@ -39,8 +39,9 @@ struct acvmb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaDeviceProp prop{};
     uint32_t opt_T = 0;   // 0 = auto
-    uint32_t opt_S = 16;
+    uint32_t opt_S = 0;   // 0 = auto: 16, or 8 for circuits with curve calls (see circuit_from_struct)
     uint32_t opt_chunk_steps = 2;
+    uint32_t opt_split_curve = 1, opt_temp_pool = 0;
     int opt_split = -1;
     uint32_t opt_n_stage = 4;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
@@ -190,6 +191,8 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     if (k == "T") ctx->opt_T = (uint32_t)value;
     else if (k == "S") ctx->opt_S = (uint32_t)value;
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
+    else if (k == "split_curve") ctx->opt_split_curve = (uint32_t)value;
+    else if (k == "temp_pool") ctx->opt_temp_pool = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
@@ -241,7 +244,22 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     c->ctx = ctx;
     PlanOptions opt;
     opt.S = ctx->opt_S;
+    if (!opt.S) {
+        // Curve calls are the slow micro-ops by three orders of magnitude.  They want every lane of a warp busy (T = 32
+        // instances per slot, pick_T) and their partial sums spread over slot threads (split lowering needs S >= 8);
+        // measured on B200 (profiles/r1_curve_tile_shapes.txt) T=32,S=8 is ~2x the arithmetic-tuned T=8,S=16 on both the
+        // Pedersen chain and the mixed circuit.
+        opt.S = 16;
+        for (auto& op : circ.opcodes)
+            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul || op.bb.func == BB_EcdsaSecp256k1 ||
+                                           op.bb.func == BB_EcdsaSecp256r1)) {
+                opt.S = 8;
+                break;
+            }
+    }
     opt.chunk_steps = ctx->opt_chunk_steps;
+    opt.split_curve = ctx->opt_split_curve != 0;
+    if (ctx->opt_temp_pool) opt.temp_pool = ctx->opt_temp_pool;
     std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
     try {
         c->plan = compile_plan(circ, inputs, opt);
@@ -350,6 +368,7 @@ extern "C" int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, si
 // ---------------------------------------------------------------------------------------------
 static uint32_t pick_T(const acvmb_ctx* ctx, const Plan& p) {
     uint32_t T = ctx->opt_T ? ctx->opt_T : std::max(1u, 128u / p.S);
+    if (!ctx->opt_T && p.stats.n_curve && vm_config_supported(32, (int)p.S, p.needs_full_kernel)) T = 32;   // full warps per curve micro-op
     if (T > 32) T = 32;
     while (T > 1 && !vm_config_supported((int)T, (int)p.S, p.needs_full_kernel)) T /= 2;
     return T;

@@ -233,7 +233,7 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
 // CAP selects the register-capped build; the launcher uses it only when the uncapped one could not hold the sub-batch in a
 // single wave (it costs ~30 % on Keccak, whose state then spills).
 template <int T, int S, bool FULL, int SPLIT, bool CAP = false>
-__global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : (FULL ? 512 / (T * S) : 1)) : 1) vm_kernel(const VmArgs a) {
+__global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : (FULL ? 512 / (T * S) : 1)) : ((FULL && T * S <= 512) ? 512 / (T * S) : 1)) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
     const uint32_t NSTAGE = a.n_stage;
@@ -322,8 +322,8 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
 
 // tile shapes (T instances x S slots).  The FULL variant (hash / curve / general ops) is instantiated for fewer shapes:
 // it dominates compile time.
-#define ACVMB_CONFIGS_LIGHT(X) X(8, 16) X(4, 16) X(2, 16) X(16, 16) X(16, 8) X(32, 4) X(32, 2) X(32, 1) X(4, 32) X(2, 64)
-#define ACVMB_CONFIGS_FULL(X) X(8, 16) X(4, 16) X(16, 8) X(32, 4) X(32, 1)
+#define ACVMB_CONFIGS_LIGHT(X) X(8, 16) X(4, 16) X(2, 16) X(16, 16) X(16, 8) X(32, 4) X(32, 2) X(32, 1) X(4, 32) X(2, 64) X(32, 8)
+#define ACVMB_CONFIGS_FULL(X) X(8, 16) X(4, 16) X(16, 8) X(32, 4) X(32, 1) X(32, 8)
 
 cudaError_t launch_vm_full(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream);   // vm_kernel_full.cu
 

@@ -59,10 +59,15 @@ def main():
     ap.add_argument("--hash-calls", type=int, default=1 << 12)
     ap.add_argument("--mixed-ops", type=int, default=1 << 16)
     ap.add_argument("--S", type=int, default=0)
+    ap.add_argument("--mixed-batch", type=int, default=8192)
+    ap.add_argument("--opt", action="append", default=[], help="context option key=value (e.g. split_curve=0, temp_pool=65536)")
     args = ap.parse_args()
     ctx = acvm_b200.Context(0)
     if args.S:
         ctx.set_option("S", args.S)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     which = args.which.split(",")
     if "modes" in which:   # config 1 shape at 2^16 gates: operand locality x coefficient distribution
         for mode in ("local", "global"):
@@ -85,7 +90,7 @@ def main():
         print(json.dumps(dict(config="pedersen_chain derived", pedersen_per_s=args.pedersen_calls * batch / (line["ms"] * 1e-3))), flush=True)
     if "mixed" in which:   # config 4
         data, inputs, nw, counts = ab.mixed_circuit(args.mixed_ops)
-        batch = 8192
+        batch = args.mixed_batch
         measure(ctx, "mixed_93_4_2_1", data, inputs, batch, ab.synthetic_inputs(64, seed_id=4) * (batch // 64), args.reps,
                 dict(ops=args.mixed_ops, counts=counts, n_witnesses=nw))
 

@@ -212,7 +212,9 @@ int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wid
 /* register-resident Montgomery multiplications per second for the 5 FMA/ALU pipe-split levels of the K0 field
  * library (fr_mul_per_s[0..4]): the practical Fr-mul ceiling */
 int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
-/* tuning knobs: "T" (instances per CTA), "S" (slots per step; recompile plan), "max_resident_bytes" */
+/* tuning knobs: "T" (instances per CTA), "S" (slots per step), "chunk_steps", "n_stage", "split", "max_resident_bytes",
+ * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns); plan options apply to
+ * circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);
 
 #ifdef __cplusplus

@@ -242,3 +242,27 @@ def test_ecdsa_circuit_with_recursive_aggregation(ctx, name):
     for kw, err in ((dict(n_pkx=31), "BlackBoxFunctionFailed"), (dict(n_hm=31), "ReferencePanic")):
         st = _check_circuit(ctx, ecdsa_cases.circuit(name, **kw), ecdsa_cases.INPUTS, 2, inp[:2 * 160 * 32])
         assert all(s.error == err and s.opcode_index == 0 for s in st)
+
+
+@pytest.mark.parametrize("T,S,split", [(8, 16, 0), (8, 16, 1), (16, 8, 1), (32, 4, 0), (32, 8, 1), (32, 1, 0)])
+def test_curve_ops_every_tile_shape_and_lowering(T, S, split):
+    """FixedBaseScalarMul + chained Pedersen under the monolithic (one micro-op per call) and the split (partial sums /
+    addition tree / finaliser) lowerings and the tile shapes the FULL kernel is built for; the default context picks
+    T=32, S=8, split (runtime.cu circuit_from_struct / pick_T), which the other tests of this file exercise."""
+    ctx = acvm_b200.Context(0)
+    try:
+        ctx.set_option("T", T); ctx.set_option("S", S); ctx.set_option("split_curve", split)
+        b = ab.CircuitBuilder()
+        b.pedersen([(1, 254), (2, 254)], 0, (10, 11))
+        b.pedersen([(10, 254), (3, 254)], 7, (12, 13))
+        b.pedersen([], 1, (14, 15))
+        b.logic("AND", (1, 100), (2, 100), 18)
+        b.logic("AND", (3, 100), (12, 100), 19)
+        b.fixed_base_scalar_mul((18, 128), (19, 128), (20, 21))
+        b.arithmetic([(1, 20, 21)], [(1, 13), (ab.P - 1, 24)], 0)
+        b.fixed_base_scalar_mul((1, 254), (19, 128), (22, 23))   # low limb >= 2^128 for random inputs: BlackBoxFunctionFailed
+        batch = 41
+        st = _check_circuit(ctx, b.to_bytes(), [1, 2, 3], batch, ab.synthetic_inputs(batch, n_inputs=3, seed_id=5))
+        assert all(s.error == "BlackBoxFunctionFailed" and s.opcode_index == 7 for s in st)
+    finally:
+        ctx.close()
