@@ -375,87 +375,85 @@ FR_PRIM void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_s<FR_ALU_SPLIT
 // in their trip count.  Plain C++ (no carry asm) so the host test build runs the same code.
 // a: 0 < a < p, any representation (the value is inverted as an integer mod p); r = a^-1 mod p, canonical.
 // ---------------------------------------------------------------------------------------------
-FR_HD void bea_shr(uint32_t* x, uint32_t top, int k) {   // (top:x) >>= k, 1 <= k <= 32
-    if (k == 32) {
-#pragma unroll
-        for (int i = 0; i < N - 1; ++i) x[i] = x[i + 1];
-        x[N - 1] = top;
-    } else {
-#pragma unroll
-        for (int i = 0; i < N - 1; ++i) x[i] = (x[i] >> k) | (x[i + 1] << (32 - k));
-        x[N - 1] = (x[N - 1] >> k) | (top << (32 - k));
-    }
-}
-FR_HD int bea_ctz32(uint32_t v) {   // v != 0
+FR_PRIM uint32_t bea_funnel_r(uint32_t lo, uint32_t hi, uint32_t k) {   // (hi:lo) >> k, 0 <= k <= 32
 #if defined(__CUDA_ARCH__)
-    return __ffs((int)v) - 1;
+    return __funnelshift_rc(lo, hi, k);
 #else
-    return __builtin_ctz(v);
+    return k == 0 ? lo : (k >= 32 ? hi : ((lo >> k) | (hi << (32 - k))));
 #endif
 }
-// u even, u != 0: u >>= ctz(u), x := x / 2^ctz(u) mod p
-FR_HD void bea_strip(uint32_t* u, uint32_t* x) {
-    while (!(u[0] & 1u)) {
-        const int k = u[0] ? bea_ctz32(u[0]) : 32;
-        bea_shr(u, 0u, k);
-        const uint32_t m = (x[0] * FR_M0) & (k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u));
-        unsigned long long c = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            c += (unsigned long long)m * p_limb(i) + x[i];
-            x[i] = (uint32_t)c;
-            c >>= 32;
-        }
-        bea_shr(x, (uint32_t)c, k);
-    }
+FR_PRIM uint32_t bea_ctz32(uint32_t v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
 }
-FR_HD void inv_bea(Fe& r, const Fe& a) {
+// u even, u != 0: u >>= ctz(u), x := x / 2^ctz(u) mod p   (k <= 32 bits per pass; a second pass needs u[0] == 0)
+FR_PRIM void bea_strip(uint32_t* u, uint32_t* x) {
+    do {
+        const uint32_t k = u[0] ? bea_ctz32(u[0]) : 32u;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) u[i] = bea_funnel_r(u[i], u[i + 1], k);
+        u[N - 1] = bea_funnel_r(u[N - 1], 0u, k);
+        // x + m*p is divisible by 2^k for m = (-x / p) mod 2^k; the sum has 9 limbs and is < 2^k * p
+        const uint32_t m = (x[0] * FR_M0) & (k == 32u ? 0xFFFFFFFFu : ((1u << k) - 1u));
+        uint32_t t[N + 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) t[i] = x[i];
+        cmad_p<0>(t, m);          // columns (0,1) (2,3) (4,5) (6,7) += m * p0, p2, p4, p6
+        addc(t[N], 0u, 0u);
+        cmad_p<1>(t + 1, m);      // columns (1,2) (3,4) (5,6) (7,8) += m * p1, p3, p5, p7
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = bea_funnel_r(t[i], t[i + 1], k);
+    } while (!(u[0] & 1u));
+}
+FR_PRIM void inv_bea(Fe& r, const Fe& a) {
     uint32_t u[N], v[N], x1[N], x2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { u[i] = a.l[i]; v[i] = p_limb(i); x1[i] = i == 0; x2[i] = 0; }
-    bea_strip(u, x1);
+    if (!(u[0] & 1u)) bea_strip(u, x1);
     while (true) {
-        // make u > v (both odd, never equal unless both are 1)
-        bool lt = false;
+        // d = u - v; when it borrows the roles swap: (u, x1) <-> (v, x2) and d = v - u
+        uint32_t d[N], lt;
+        sub_cc(d[0], u[0], v[0]);
 #pragma unroll
-        for (int i = N - 1; i >= 0; --i) {
-            if (u[i] != v[i]) { lt = u[i] < v[i]; break; }
-        }
+        for (int i = 1; i < N; ++i) subc_cc(d[i], u[i], v[i]);
+        subc(lt, 0u, 0u);   // 0xffffffff if u < v
         if (lt) {
+            sub_cc(d[0], v[0], u[0]);
+#pragma unroll
+            for (int i = 1; i < N - 1; ++i) subc_cc(d[i], v[i], u[i]);
+            subc(d[N - 1], v[N - 1], u[N - 1]);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                uint32_t t = u[i]; u[i] = v[i]; v[i] = t;
-                t = x1[i]; x1[i] = x2[i]; x2[i] = t;
+                v[i] = u[i];
+                const uint32_t t = x1[i];
+                x1[i] = x2[i];
+                x2[i] = t;
             }
         }
         uint32_t rest = v[0] ^ 1u;
 #pragma unroll
         for (int i = 1; i < N; ++i) rest |= v[i];
-        if (rest == 0) break;   // v == 1: x2 * a == 1
-        long long br = 0;
+        if (rest == 0) break;   // min(u, v) == 1: x2 * a == 1
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            long long d = (long long)u[i] - v[i] + br;
-            u[i] = (uint32_t)d;
-            br = d >> 32;
-        }
-        br = 0;
+        for (int i = 0; i < N; ++i) u[i] = d[i];
+        // x1 = x1 - x2 mod p
+        uint32_t bm;
+        sub_cc(x1[0], x1[0], x2[0]);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            long long d = (long long)x1[i] - x2[i] + br;
-            x1[i] = (uint32_t)d;
-            br = d >> 32;
-        }
-        if (br) {
-            unsigned long long c = 0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                c += (unsigned long long)x1[i] + p_limb(i);
-                x1[i] = (uint32_t)c;
-                c >>= 32;
-            }
-        }
-        bea_strip(u, x1);
+        for (int i = 1; i < N; ++i) subc_cc(x1[i], x1[i], x2[i]);
+        subc(bm, 0u, 0u);
+        add_cc(x1[0], x1[0], FR_P0 & bm);
+        addc_cc(x1[1], x1[1], FR_P1 & bm);
+        addc_cc(x1[2], x1[2], FR_P2 & bm);
+        addc_cc(x1[3], x1[3], FR_P3 & bm);
+        addc_cc(x1[4], x1[4], FR_P4 & bm);
+        addc_cc(x1[5], x1[5], FR_P5 & bm);
+        addc_cc(x1[6], x1[6], FR_P6 & bm);
+        addc(x1[7], x1[7], FR_P7 & bm);
+        bea_strip(u, x1);   // u - v of two odd numbers is even and non-zero
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) r.l[i] = x2[i];

@@ -175,6 +175,23 @@ def test_fr_limb_algorithms_on_host(tmp_path):
         assert L.t_num_bits(arr([z])) == z.bit_length()
 
 
+def test_binary_euclid_inverse_on_host(tmp_path):
+    """fr::inv_bea (the inversion of every curve finaliser) compiled for the host, against pow(a, -1, p)."""
+    so = tmp_path / "fr_host_shim.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "host", "fr_host_shim.cpp")], check=True)
+    L = ctypes.CDLL(str(so))
+    P = ab.P
+    rnd = random.Random(4)
+    arr = lambda v: (ctypes.c_uint32 * 8)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+    cases = [1, 2, 3, P - 1, P - 2, 1 << 32, 3 << 32, 5 << 96, 1 << 200, 1 << 253, (P - 1) // 2, (P + 1) // 2, 0xFFFFFFFF]
+    cases += [rnd.randrange(1, P) for _ in range(3000)]
+    cases += [(rnd.randrange(1, 1 << 60) << rnd.randrange(0, 190)) % P or 1 for _ in range(300)]   # long runs of trailing zeros
+    for a in cases:
+        r = (ctypes.c_uint32 * 8)()
+        L.t_inv_bea(arr(a), r)
+        assert sum(int(r[i]) << (32 * i) for i in range(8)) == pow(a, -1, P), hex(a)
+
+
 def test_plan_heavy_ops_match_oracle():
     b = ab.CircuitBuilder()
     b.hash256("SHA256", [(1, 8), (2, 16), (3, 254)], list(range(10, 42)))
