@@ -205,8 +205,13 @@ FR_PRIM void madc_n_rshift_alu(uint32_t* odd, const uint32_t* a1, uint32_t bi) {
 // One CIOS row for a K-term dot product: acc += sum_k a_k * b_k[i]; then one reduction row.
 // `even` holds columns 0..7, `odd` columns 1..8; the two swap roles every row.
 template <int K, int SPLIT>
-FR_PRIM void dot_row(uint32_t* even, uint32_t* odd, const Fe* const* a, const uint32_t* bi, bool first) {
-    if (first) {
+FR_PRIM void dot_row(uint32_t* even, uint32_t* odd, const Fe* const* a, const uint32_t* bi, bool first, bool has_init = false) {
+    if (first && has_init) {
+        // `even` already holds the initial accumulator (< 2^256): even += a_even*b0 as a chain, its carry joins column 8
+        mul_n(odd, a[0]->l + 1, bi[0]);
+        if (SPLIT >= 1) cmad_n_alu(even, a[0]->l, bi[0]); else cmad_n(even, a[0]->l, bi[0]);
+        addc(odd[N - 1], odd[N - 1], 0);
+    } else if (first) {
         mul_n(odd, a[0]->l + 1, bi[0]);
         mul_n(even, a[0]->l, bi[0]);
     } else {
@@ -227,18 +232,24 @@ FR_PRIM void dot_row(uint32_t* even, uint32_t* odd, const Fe* const* a, const ui
     addc(odd[N - 1], odd[N - 1], 0);
 }
 
-// r = sum_k a_k*b_k * 2^-256 mod p, result in [0, 2p) provided sum_k a_k*b_k < 4.5 p^2.
+// r = (init + sum_k a_k*b_k) * 2^-256 mod p, result in [0, 2p) provided sum_k a_k*b_k < 4.5 p^2; `init`
+// (8 limbs, < 2^256, may be null) is a plan constant in Montgomery form, i.e. the gate's additive constant folded into the
+// reduction: (c*R + sum)/R = c + sum/R, which saves the separate modular addition and its conditional subtraction.
 // `bl(k, i)` returns limb i of b_k: the b operands may live in registers OR be fetched limb by limb
 // from shared memory (the plan-time coefficients), which keeps them out of the register file.
 template <int K, typename BL, int SPLIT = FR_ALU_SPLIT>
-FR_PRIM void mont_dot_fn(Fe& r, const Fe* const* a, BL bl) {
+FR_PRIM void mont_dot_fn(Fe& r, const Fe* const* a, BL bl, const uint32_t* init = nullptr) {
     uint32_t even[N], odd[N];
     uint32_t bi[K];
+    if (init) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) even[i] = init[i];
+    }
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
 #pragma unroll
         for (int k = 0; k < K; ++k) bi[k] = bl(k, i);
-        dot_row<K, SPLIT>(even, odd, a, bi, i == 0);
+        dot_row<K, SPLIT>(even, odd, a, bi, i == 0, init != nullptr);
 #pragma unroll
         for (int k = 0; k < K; ++k) bi[k] = bl(k, i + 1);
         dot_row<K, SPLIT>(odd, even, a, bi, false);

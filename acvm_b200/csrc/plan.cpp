@@ -413,7 +413,9 @@ struct Compiler {
                 put(r.c[2], hf::to_mont(c1));
                 put(r.c[3], hf::to_mont(c2));
             }
-            put(r.c[4], c4);
+            // products present (and not the +-1 add/sub form): the constant is the initial accumulator of the last Montgomery
+            // reduction, so it is stored as cC*R; otherwise it is used as is
+            put(r.c[4], ((flags & GF_Y) && !(flags & GF_ADDSUB)) ? hf::to_mont(c4) : c4);
             if (flags & GF_MUL) reads[nr++] = x;
             if (flags & GF_Y) reads[nr++] = y;
             if (nlin >= 1) reads[nr++] = w1;

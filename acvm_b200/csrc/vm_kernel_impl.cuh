@@ -124,12 +124,12 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
             fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R < 1.76p
             if (nlin == 0) {
                 const Fe* a[1] = {&u};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr}, r->c[4]);
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 const Fe* a[2] = {&u, &w1};
-                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr});
+                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr}, r->c[4]);
             }
         } else if (flags & GF_ADDSUB) {
             // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
@@ -150,28 +150,23 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
             load_w<T>(y, cb, r->w[4]);
             if (nlin == 0) {
                 const Fe* a[1] = {&y};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr});
+                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr}, r->c[4]);
             } else {
                 Fe w1;
                 load_w<T>(w1, cb, r->w[5]);
                 if (nlin == 1) {
                     const Fe* a[2] = {&y, &w1};
-                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr});
+                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr}, r->c[4]);
                 } else {
                     Fe w2;
                     load_w<T>(w2, cb, r->w[6]);
                     const Fe* a[3] = {&y, &w1, &w2};
-                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]});
+                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]}, r->c[4]);
                 }
             }
         }
-        if (!(flags & GF_ADDSUB)) {
-            fr::cond_sub_p(res);
-            Fe cC;
-            lds_fe(cC, r->c[4]);
-            fr::add_raw(res, res, cC);
-            fr::cond_sub_p(res);
-        }
+        // the additive constant rode in the accumulator of the last reduction (c[4] = cC*R): one conditional subtraction
+        if (!(flags & GF_ADDSUB)) fr::cond_sub_p(res);
     } else {
         lds_fe(res, r->c[4]);
     }

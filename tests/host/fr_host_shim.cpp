@@ -18,6 +18,16 @@ void t_mont_dot(int k, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     else mont_dot_raw<4>(R, pa, pb);
     memcpy(r, R.l, 32);
 }
+void t_mont_dot_init(int k, const uint32_t* a, const uint32_t* b, const uint32_t* init, uint32_t* r) {
+    Fe A[4], B[4], R;
+    for (int i = 0; i < k; ++i) { memcpy(A[i].l, a + 8 * i, 32); memcpy(B[i].l, b + 8 * i, 32); }
+    const Fe* pa[4] = {&A[0], &A[1], &A[2], &A[3]};
+    const Fe* pb[4] = {&B[0], &B[1], &B[2], &B[3]};
+    if (k == 1) mont_dot_fn<1>(R, pa, PtrLimbs{pb}, init);
+    else if (k == 2) mont_dot_fn<2>(R, pa, PtrLimbs{pb}, init);
+    else mont_dot_fn<3>(R, pa, PtrLimbs{pb}, init);
+    memcpy(r, R.l, 32);
+}
 void t_mont_mul_split(int split, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fe A, B, R; memcpy(A.l, a, 32); memcpy(B.l, b, 32);
     switch (split) { case 0: mont_mul_s<0>(R, A, B); break; case 1: mont_mul_s<1>(R, A, B); break; case 2: mont_mul_s<2>(R, A, B); break;

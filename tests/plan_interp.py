@@ -354,6 +354,8 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 continue
             if kind in (MK["GATE_ASSIGN"], MK["GATE_CHECK"]):
                 res = c[4]
+                if (flags & GF_Y) and not (flags & 256):
+                    res = c[4] * RINV   # folded into the last Montgomery reduction: stored as cC*R
                 if flags & GF_Y:
                     nlin = (flags >> GF_NLIN_SHIFT) & 3
                     if flags & GF_MUL:

@@ -133,6 +133,17 @@ def test_fr_limb_algorithms_on_host(tmp_path):
         L.t_mont_dot(k, arr(A), arr(B), r)
         got = val(r)
         assert got < 2 * P and got % P == sum(x * y for x, y in zip(A, B)) * Rinv % P
+    for it in range(2000):  # gate constant folded into the reduction as the initial accumulator (any value < 2^256)
+        k = rnd.choice([1, 2, 3])
+        A = [rnd.choice([0, 1, P - 1, rnd.randrange(P)]) for _ in range(k)]
+        B = [rnd.choice([0, 1, P - 1, rnd.randrange(P)]) for _ in range(k)]
+        if k <= 2 and rnd.random() < 0.3:
+            A[0] += (3 * P) // 4   # lazily reduced operand (< 1.76 p)
+        init = rnd.choice([0, 1, P - 1, (1 << 256) - 1, rnd.randrange(P)])
+        r = (ctypes.c_uint32 * 8)()
+        L.t_mont_dot_init(k, arr(A), arr(B), arr([init]), r)
+        got = val(r)
+        assert got < 2 * P and got % P == (init + sum(x * y for x, y in zip(A, B))) * Rinv % P
     for it in range(1500):  # every FMA/ALU pipe split level of the row helpers computes the same product
         x, y = rnd.choice([0, 1, P - 1, rnd.randrange(P)]), rnd.choice([0, 1, P - 1, rnd.randrange(P)])
         for split in range(5):
