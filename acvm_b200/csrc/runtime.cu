@@ -36,7 +36,7 @@ static int set_err(int rc, const std::string& msg) {
 
 struct acvmb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, gather_stream = nullptr;   // VM kernels | D2H copies | output gathers
     cudaDeviceProp prop{};
     uint32_t opt_T = 0;   // 0 = auto
     uint32_t opt_S = 0;   // 0 = auto: 16, or 8 for circuits with curve calls (see circuit_from_struct)
@@ -97,6 +97,8 @@ struct acvmb_batch {
     size_t out_ids_cap = 0;
     size_t stage_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_gather[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr, ev_dl_done = nullptr;   // columns final on the VM stream | last D2H of an async download
+    bool dl_pending = false;
     ~acvmb_batch() {
         if (d_cols) cudaFree(d_cols);
         if (d_fail) cudaFree(d_fail);
@@ -112,6 +114,8 @@ struct acvmb_batch {
         if (d_out_ids) cudaFree(d_out_ids);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        if (ev_dl_done) cudaEventDestroy(ev_dl_done);
         for (int i = 0; i < 2; ++i) {
             if (ev_gather[i]) cudaEventDestroy(ev_gather[i]);
             if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
@@ -153,6 +157,7 @@ extern "C" int acvmb_ctx_create(int device, acvmb_ctx** out) {
                                                 std::to_string(ctx->prop.minor) + "; kernels are built for sm_100a only");
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
     *out = ctx.release();
     return ACVMB_OK;
 }
@@ -164,6 +169,7 @@ extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
     if (ctx->d_pedersen) cudaFree(ctx->d_pedersen);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->gather_stream) cudaStreamDestroy(ctx->gather_stream);
     delete ctx;
 }
 
@@ -393,6 +399,8 @@ extern "C" int acvmb_batch_create(acvmb_circuit* c, uint32_t n_instances, acvmb_
     CUDA_TRY(cudaMalloc(&b->d_in, std::max<size_t>(in_bytes, 16)));
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_dl_done, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&b->ev_gather[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming));
@@ -778,8 +786,27 @@ extern "C" int acvmb_batch_status(acvmb_batch* b, acvmb_status* out_status) {
     return ACVMB_OK;
 }
 
+// Output path: gather kernels (columns -> [inst][witness][32 B BE] staging, double-buffered) on the gather stream, D2H on the
+// copy stream, both ordered by events only.  async: return once everything is enqueued (ev_dl_done marks the last copy), so
+// the caller can run the NEXT sub-batch's VM kernel on the VM stream while this one drains over PCIe.
+static int download_impl(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids, uint8_t* out,
+                         uint8_t* out_present, bool async);
+
+static int wait_download(acvmb_batch* b) {
+    if (b && b->dl_pending) {
+        b->dl_pending = false;
+        CUDA_TRY(cudaEventSynchronize(b->ev_dl_done));
+    }
+    return ACVMB_OK;
+}
+
 extern "C" int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids,
                                        uint8_t* out, uint8_t* out_present) {
+    return download_impl(b, first, n, out_ids, n_out_ids, out, out_present, false);
+}
+
+static int download_impl(acvmb_batch* b, uint32_t first, uint32_t n, const uint32_t* out_ids, uint32_t n_out_ids, uint8_t* out,
+                         uint8_t* out_present, bool async) {
     if (!b || (!out && !out_present) || first + n > b->n_inst) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     acvmb_circuit* c = b->c;
     acvmb_ctx* ctx = c->ctx;
@@ -833,18 +860,21 @@ extern "C" int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first, uint32_t 
     g.mu_assign = b->d_mu;
     g.n_mu = c->plan.n_mu;
     g.static_fail_opcode = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
-    CUDA_TRY(cudaEventRecord(b->ev0, ctx->stream));
+    // everything queued on the VM stream so far (the solve, the id upload above) precedes the first gather
+    CUDA_TRY(cudaEventRecord(b->ev_ready, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->gather_stream, b->ev_ready, 0));
+    CUDA_TRY(cudaEventRecord(b->ev0, ctx->gather_stream));
     uint32_t k = 0;
     for (uint32_t off = 0; off < n; off += chunk, ++k) {
         uint32_t cnt = std::min(chunk, n - off);
         int buf = k & 1;
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, b->ev_copy[buf], 0));  // staging buffer is free again
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->gather_stream, b->ev_copy[buf], 0));  // staging buffer is free again
         g.first_inst = first + off;
         g.n_inst = cnt;
         g.out_be = out ? b->d_stage[buf] : nullptr;
         g.out_present = out_present ? b->d_stage_present[buf] : nullptr;
-        CUDA_TRY(launch_gather_outputs(g, ctx->stream));
-        CUDA_TRY(cudaEventRecord(b->ev_gather[buf], ctx->stream));
+        CUDA_TRY(launch_gather_outputs(g, ctx->gather_stream));
+        CUDA_TRY(cudaEventRecord(b->ev_gather[buf], ctx->gather_stream));
         CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev_gather[buf], 0));
         if (out)
             CUDA_TRY(cudaMemcpyAsync(out + (size_t)off * row, b->d_stage[buf], (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -854,8 +884,13 @@ extern "C" int acvmb_batch_download_ex(acvmb_batch* b, uint32_t first, uint32_t 
         CUDA_TRY(cudaEventRecord(b->ev_copy[buf], ctx->copy_stream));
         c->run.kernel_launches += 1;
     }
-    CUDA_TRY(cudaEventRecord(b->ev1, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventRecord(b->ev1, ctx->gather_stream));
+    if (async) {
+        CUDA_TRY(cudaEventRecord(b->ev_dl_done, ctx->copy_stream));
+        b->dl_pending = true;
+        return ACVMB_OK;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->gather_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, b->ev0, b->ev1);
@@ -901,7 +936,7 @@ static uint32_t resident_instances(acvmb_circuit* c, uint32_t batch, uint32_t T,
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     uint64_t budget = c->ctx->max_resident_bytes ? c->ctx->max_resident_bytes : (uint64_t)(free_b * 0.90);
-    uint64_t fixed = 2 * std::min<uint64_t>(c->ctx->staging_bytes, (uint64_t)batch * n_out * 32) + (64ull << 20);
+    uint64_t fixed = 4 * std::min<uint64_t>(c->ctx->staging_bytes, (uint64_t)batch * n_out * 32) + (64ull << 20);   // two buffers x double staging
     uint64_t per_inst = (uint64_t)c->plan.n_slots * 32 + 8 + c->plan.input_witnesses.size() * 32;
     uint64_t fit = budget > fixed ? (budget - fixed) / per_inst : 0;
     fit = (fit / T) * T;
@@ -925,12 +960,54 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
     memset(&c->run, 0, sizeof(c->run));
     uint32_t T = pick_T(c->ctx, c->plan);
     uint32_t n_out = out_ids ? n_out_ids : c->plan.num_witnesses;
-    uint32_t resident = resident_instances(c, batch, T, (out_witness || out_present) ? n_out : 0);
+    const bool want_out = out_witness || out_present;
+    uint32_t resident = resident_instances(c, batch, T, want_out ? n_out : 0);
     size_t n_in = c->plan.input_witnesses.size();
-    acvmb_batch* b = nullptr;
-    uint32_t cap = 0;
     int rc = ACVMB_OK;
     uint32_t n_sub = 0;
+    if (want_out && batch > resident && resident >= 2 * T) {
+        // The batch does not fit HBM at once and every sub-batch's witness map goes back over PCIe (~55 GB/s), which takes
+        // ~10x longer than solving it.  Two column buffers of half the resident size: while sub-batch k drains (gather + D2H
+        // on their own streams), the VM kernel of sub-batch k+1 runs on the VM stream.
+        uint32_t half = ((resident / 2) / T) * T;
+        acvmb_batch* bufs[2] = {nullptr, nullptr};
+        uint32_t caps[2] = {0, 0};
+        for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += half, ++n_sub) {
+            const uint32_t cnt = std::min(half, batch - off);
+            const int i = n_sub & 1;
+            rc = wait_download(bufs[i]);   // its previous sub-batch has left the device
+            if (rc) break;
+            if (!bufs[i] || caps[i] != cnt) {
+                if (bufs[i]) acvmb_batch_destroy(bufs[i]);
+                bufs[i] = nullptr;
+                rc = acvmb_batch_create(c, cnt, &bufs[i]);
+                if (rc) break;
+                caps[i] = cnt;
+            }
+            acvmb_batch* b = bufs[i];
+            rc = acvmb_batch_upload(b, inputs_be32 ? inputs_be32 + (size_t)off * n_in * 32 : nullptr);
+            if (rc) break;
+            rc = acvmb_batch_run(b, nullptr);
+            if (rc) break;
+            if (out_status) {
+                rc = acvmb_batch_status(b, out_status + off);
+                if (rc) break;
+            }
+            rc = download_impl(b, 0, cnt, out_ids, n_out_ids, out_witness ? out_witness + (size_t)off * n_out * 32 : nullptr,
+                               out_present ? out_present + (size_t)off * n_out : nullptr, /*async=*/true);
+        }
+        for (int i = 0; i < 2; ++i) {
+            int rc2 = wait_download(bufs[i]);
+            if (!rc) rc = rc2;
+        }
+        for (int i = 0; i < 2; ++i)
+            if (bufs[i]) acvmb_batch_destroy(bufs[i]);
+        c->run.resident_instances = half;
+        c->run.n_subbatches = n_sub;
+        return rc;
+    }
+    acvmb_batch* b = nullptr;
+    uint32_t cap = 0;
     for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += resident, ++n_sub) {
         uint32_t cnt = std::min(resident, batch - off);
         if (!b || cnt != cap) {
@@ -948,7 +1025,7 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
             rc = acvmb_batch_status(b, out_status + off);
             if (rc) break;
         }
-        if (out_witness || out_present)
+        if (want_out)
             rc = acvmb_batch_download_ex(b, 0, cnt, out_ids, n_out_ids, out_witness ? out_witness + (size_t)off * n_out * 32 : nullptr,
                                          out_present ? out_present + (size_t)off * n_out : nullptr);
     }
