@@ -301,7 +301,7 @@ def run_ours(args):
     if not args.no_e2e:
         import psutil
         avail = psutil.virtual_memory().available
-        e2e_chunk = int(min(args.batch, max(1, min(args.e2e_chunk_gib * 2**30, avail * 0.5 / world) // (nw * 32))))
+        e2e_chunk = int(min(args.batch, max(1, min(args.e2e_chunk_gib * 2**30, avail * 0.4 / world) // (nw * 32))))
         n_calls = -(-args.batch // e2e_chunk)
         out_bytes = e2e_chunk * nw * 32
         batch_obj.close()
@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-chunk-gib", type=float, default=256.0,
+    ap.add_argument("--e2e-chunk-gib", type=float, default=64.0,
                     help="pinned host buffer per acvmb_solve_batch call; one call for the whole batch lets the library overlap sub-batches")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

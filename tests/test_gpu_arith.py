@@ -215,10 +215,11 @@ def test_device_checksum_matches_host_definition(ctx):
 def test_forced_subbatching_and_ragged_tail(ctx):
     # the sub-batch loop of acvmb_solve_batch (used when the witness columns do not fit in HBM) with a ragged last sub-batch
     data, inputs, _ = ab.synthetic_arith_circuit(256, seed_id=12)
-    # fixed overhead (64 MiB + four staging buffers) + ~40 instances of columns: two half-size column buffers, the VM kernel
-    # of sub-batch k+1 overlapping the gather + D2H of sub-batch k (runtime.cu acvmb_solve_batch_ex)
-    c2 = acvm_b200.Context(0, max_resident_bytes=(64 << 20) + (8 << 20) + 40 * 2400 * 32)
+    # budget = fixed overhead (64 MiB + four staging buffers) + 40 instances of columns: two half-size column buffers, the VM
+    # kernel of sub-batch k+1 overlapping the gather + D2H of sub-batch k (runtime.cu acvmb_solve_batch_ex)
+    c2 = acvm_b200.Context(0)
     circ = acvm_b200.CompiledCircuit(c2, data, inputs)
+    c2.set_option("max_resident_bytes", (64 << 20) + 4 * 103 * circ.num_witnesses * 32 + 40 * (circ.info["n_slots"] * 32 + 8 + len(inputs) * 32))
     batch = 103
     inp = ab.synthetic_inputs(batch, seed_id=12)
     out, st = circ.solve_batch(inp, batch)
