@@ -49,7 +49,13 @@ struct acvmb_ctx {
     uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
     uint32_t* d_pedersen = nullptr;
     bool tables_ready = false;
+    // acvmb_solve_batch keeps the column buffers of its last call (one per context): a caller that streams a large batch
+    // through repeated calls otherwise pays a cudaMalloc + cudaFree of tens of GB per call (measured 20-290 ms)
+    struct acvmb_batch* cached_batch = nullptr;
+    uint64_t cached_bytes = 0;
+    uint32_t opt_cache_batch = 1;
 };
+static void drop_cached_batch(acvmb_ctx* ctx);
 
 struct acvmb_circuit {
     acvmb_ctx* ctx = nullptr;
@@ -165,6 +171,7 @@ extern "C" int acvmb_ctx_create(int device, acvmb_ctx** out) {
 extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    drop_cached_batch(ctx);
     if (ctx->d_fixed_base) cudaFree(ctx->d_fixed_base);
     if (ctx->d_pedersen) cudaFree(ctx->d_pedersen);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -198,6 +205,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "S") ctx->opt_S = (uint32_t)value;
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
     else if (k == "split_curve") ctx->opt_split_curve = (uint32_t)value;
+    else if (k == "cache_batch") { ctx->opt_cache_batch = (uint32_t)value; if (!value) drop_cached_batch(ctx); }
     else if (k == "temp_pool") ctx->opt_temp_pool = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
@@ -299,9 +307,12 @@ extern "C" int acvmb_circuit_from_acir(acvmb_ctx* ctx, const uint8_t* gz, size_t
     return ACVMB_OK;
 }
 
+static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx);
+
 extern "C" void acvmb_circuit_destroy(acvmb_circuit* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
+    if (c->ctx->cached_batch && cached_batch_circuit(c->ctx) == c) drop_cached_batch(c->ctx);
     delete c;
 }
 
@@ -422,6 +433,13 @@ extern "C" void acvmb_batch_destroy(acvmb_batch* b) {
     cudaSetDevice(b->c->ctx->device);
     delete b;
 }
+
+static void drop_cached_batch(acvmb_ctx* ctx) {
+    if (ctx->cached_batch) acvmb_batch_destroy(ctx->cached_batch);
+    ctx->cached_batch = nullptr;
+    ctx->cached_bytes = 0;
+}
+static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx) { return ctx->cached_batch ? ctx->cached_batch->c : nullptr; }
 
 extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
@@ -935,7 +953,7 @@ extern "C" int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out) {
 static uint32_t resident_instances(acvmb_circuit* c, uint32_t batch, uint32_t T, uint32_t n_out) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    uint64_t budget = c->ctx->max_resident_bytes ? c->ctx->max_resident_bytes : (uint64_t)(free_b * 0.90);
+    uint64_t budget = c->ctx->max_resident_bytes ? c->ctx->max_resident_bytes : (uint64_t)((free_b + c->ctx->cached_bytes) * 0.90);
     uint64_t fixed = 4 * std::min<uint64_t>(c->ctx->staging_bytes, (uint64_t)batch * n_out * 32) + (64ull << 20);   // two buffers x double staging
     uint64_t per_inst = (uint64_t)c->plan.n_slots * 32 + 8 + c->plan.input_witnesses.size() * 32;
     uint64_t fit = budget > fixed ? (budget - fixed) / per_inst : 0;
@@ -1008,6 +1026,18 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
     }
     acvmb_batch* b = nullptr;
     uint32_t cap = 0;
+    {
+        acvmb_ctx* ctx = c->ctx;
+        const uint32_t first_cnt = std::min(resident, batch);
+        if (ctx->cached_batch && ctx->cached_batch->c == c && ctx->cached_batch->n_inst == first_cnt && ctx->cached_batch->T == T) {
+            b = ctx->cached_batch;   // same circuit, same size as the previous call: reuse the columns
+            cap = first_cnt;
+            ctx->cached_batch = nullptr;
+            ctx->cached_bytes = 0;
+        } else {
+            drop_cached_batch(ctx);
+        }
+    }
     for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += resident, ++n_sub) {
         uint32_t cnt = std::min(resident, batch - off);
         if (!b || cnt != cap) {
@@ -1029,7 +1059,12 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
             rc = acvmb_batch_download_ex(b, 0, cnt, out_ids, n_out_ids, out_witness ? out_witness + (size_t)off * n_out * 32 : nullptr,
                                          out_present ? out_present + (size_t)off * n_out : nullptr);
     }
-    if (b) acvmb_batch_destroy(b);
+    if (b && rc == ACVMB_OK && c->ctx->opt_cache_batch) {
+        c->ctx->cached_batch = b;
+        c->ctx->cached_bytes = (uint64_t)b->n_tiles * b->T * c->plan.n_slots * 32;
+    } else if (b) {
+        acvmb_batch_destroy(b);
+    }
     c->run.resident_instances = resident;
     c->run.n_subbatches = n_sub;
     return rc;

@@ -213,8 +213,9 @@ int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wid
  * library (fr_mul_per_s[0..4]): the practical Fr-mul ceiling */
 int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step), "chunk_steps", "n_stage", "split", "max_resident_bytes",
- * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns); plan options apply to
- * circuits created afterwards */
+ * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "cache_batch" (0: free
+ * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
+ * identical next call); plan options apply to circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);
 
 #ifdef __cplusplus

@@ -256,3 +256,25 @@ def test_permutation_sort_directive(ctx, n, tup, sort_by):
     assert all(s.status == "Solved" for s in st)
     data, _ = sort_circuit(n, tup, sort_by, preassign_bit=True)
     _check_circuit(ctx, data, inputs, batch, sort_rows(n, tup, batch))
+
+
+def test_solve_batch_reuses_cached_columns(ctx):
+    # repeated calls on one circuit keep the column buffers (runtime.cu cached_batch); another circuit or size drops them
+    data, inputs, _ = ab.synthetic_arith_circuit(200, seed_id=3)
+    data2, inputs2, _ = ab.synthetic_arith_circuit(120, seed_id=4)
+    a = acvm_b200.CompiledCircuit(ctx, data, inputs)
+    b = acvm_b200.CompiledCircuit(ctx, data2, inputs2)
+    oc = acir.decode_circuit(data)
+    for seed, batch in ((1, 9), (2, 9), (3, 17), (4, 17)):
+        inp = ab.synthetic_inputs(batch, seed_id=seed)
+        out, st = a.solve_batch(inp, batch)
+        if seed == 2:
+            b.solve_batch(ab.synthetic_inputs(5, seed_id=9), 5)   # evicts a's buffers
+        rows = witness_rows(out, batch, a.num_witnesses)
+        for i, iw in enumerate(inputs_to_dicts(inp, batch, inputs)):
+            ost, owm, _ = pwg.solve_circuit(oc, iw)
+            assert st[i].status == ost == "Solved" and all(rows[i][w] == v for w, v in owm.items())
+    a.close()       # owner of the cached buffers goes away first
+    out, st = b.solve_batch(ab.synthetic_inputs(5, seed_id=9), 5)
+    assert all(s.status == "Solved" for s in st)
+    b.close()
