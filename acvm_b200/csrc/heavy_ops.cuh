@@ -48,25 +48,43 @@ __device__ __forceinline__ void hv_fail(unsigned long long* fail, uint32_t opcod
 template <int T>
 __device__ __forceinline__ void insert_value_dev(const OpRec* r, bool check, uint32_t slot, const Fe& v, uint4* cb, unsigned long long* fail);
 
-// write digest byte i to output witness i (insert_value semantics when the output is pre-assigned)
+// write digest byte i to output witness i (insert_value semantics when the output is pre-assigned).
+// The output ids live in the payload (global memory): they are fetched eight at a time so that the eight dependent
+// L2 round trips overlap instead of adding up (a rolled one-by-one loop made this the longest part of a hash micro-op).
 template <int T>
 __device__ __forceinline__ void write_digest(const uint8_t* digest, const uint32_t* outs, uint32_t check_mask, uint4* cb,
                                              unsigned long long* fail, uint32_t opcode) {
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
-        Fe v;
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+        uint32_t o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v.l[k] = 0;
-        v.l[0] = digest[i];
-        if ((check_mask >> i) & 1) {
-            Fe old;
-            hv_load<T>(old, cb, outs[i]);
-            if (!fr::eq(old, v)) {  // insert_value replaces the old value before it reports the mismatch
-                hv_fail(fail, opcode, EK_UNSATISFIED_CONSTRAIN, 0);
-                hv_store<T>(cb, outs[i], v);
+        for (int g = 0; g < 8; ++g) o[g] = outs[i0 + g];
+        if (((check_mask >> i0) & 0xFFu) == 0) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint4* p = cb + (size_t)o[g] * (2 * T);
+                p[0] = make_uint4(digest[i0 + g], 0u, 0u, 0u);
+                p[T] = make_uint4(0u, 0u, 0u, 0u);
             }
-        } else {
-            hv_store<T>(cb, outs[i], v);
+            continue;
+        }
+#pragma unroll 1
+        for (int g = 0; g < 8; ++g) {
+            const int i = i0 + g;
+            Fe v;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.l[k] = 0;
+            v.l[0] = digest[i];
+            if ((check_mask >> i) & 1) {
+                Fe old;
+                hv_load<T>(old, cb, o[g]);
+                if (!fr::eq(old, v)) {  // insert_value replaces the old value before it reports the mismatch
+                    hv_fail(fail, opcode, EK_UNSATISFIED_CONSTRAIN, 0);
+                    hv_store<T>(cb, o[g], v);
+                }
+            } else {
+                hv_store<T>(cb, o[g], v);
+            }
         }
     }
 }
@@ -101,6 +119,30 @@ __device__ __forceinline__ void gather_message(const uint4* cb, const uint32_t* 
                 for (uint32_t j = 0; j < nb[g] && take; ++j, --take) push((v.l[j >> 2] >> (8 * (j & 3))) & 0xFF);
             }
         }
+    }
+}
+
+// Fast path of the hash micro-ops (payload flag pl[3]): every input is ONE byte, so message byte j is the low byte of
+// witness ins[2j].  fetch_words packs bytes [base, base + 4*NW) into NW words, byte j at bits 8*(j & 3) (little-endian),
+// zeros past the end of the message.  Sixteen descriptor loads, then sixteen column loads, are in flight together, and
+// every index is a compile-time constant, so the block stays in registers (the byte-at-a-time path indexes its block
+// dynamically, i.e. through local memory, and cost ~67 instructions per message byte).
+template <int T, int NW>
+__device__ __forceinline__ void fetch_words(uint32_t* wds, const uint4* cb, const uint32_t* ins, uint32_t base, uint32_t n_in) {
+#pragma unroll
+    for (int q0 = 0; q0 < NW; q0 += 4) {
+        uint32_t id[16], lo[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            const uint32_t k = base + 4 * q0 + g;
+            id[g] = (4 * q0 + g < 4 * NW && k < n_in) ? ins[2 * k] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+            lo[g] = id[g] != 0xFFFFFFFFu ? (reinterpret_cast<const uint32_t*>(cb + (size_t)id[g] * (2 * T))[0] & 0xFFu) : 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q0 + q < NW) wds[q0 + q] = lo[4 * q] | (lo[4 * q + 1] << 8) | (lo[4 * q + 2] << 16) | (lo[4 * q + 3] << 24);
     }
 }
 
@@ -146,6 +188,44 @@ __device__ __noinline__ void sha256_compress(uint32_t* h, const uint32_t* blk) {
 }
 
 // payload: [n_in][check_mask][var_size witness | NONE][0][ (witness, num_bits) * n_in ][ 32 output witnesses ]
+// SHA-256 of a message whose bytes are one witness each (payload flag pl[3]); see fetch_words
+template <int T>
+__device__ __noinline__ void exec_sha256_bytes(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* pl) {
+    const uint32_t n_in = pl[0], check_mask = pl[1];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t blk[16];
+    uint32_t base = 0;
+#pragma unroll 1
+    for (; n_in - base >= 64; base += 64) {
+        fetch_words<T, 16>(blk, cb, ins, base, n_in);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) blk[i] = __byte_perm(blk[i], 0, 0x0123);
+        sha256_compress(h, blk);
+    }
+    fetch_words<T, 16>(blk, cb, ins, base, n_in);
+    const uint32_t rem = n_in - base;   // 0..63 message bytes in the last block(s)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if ((uint32_t)i == (rem >> 2)) blk[i] |= 0x80u << (8 * (rem & 3));
+        blk[i] = __byte_perm(blk[i], 0, 0x0123);
+    }
+    if (rem >= 56) {
+        sha256_compress(h, blk);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) blk[i] = 0;
+    }
+    const unsigned long long bits = (unsigned long long)n_in * 8;
+    blk[14] = (uint32_t)(bits >> 32);
+    blk[15] = (uint32_t)bits;
+    sha256_compress(h, blk);
+    uint8_t dg[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dg[i] = (uint8_t)(h[i >> 2] >> (24 - 8 * (i & 3)));
+    write_digest<T>(dg, outs, check_mask, cb, fail, r->w[1]);
+}
+
 template <int T>
 __device__ __noinline__ void exec_sha256(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
     const uint32_t* pl = payload + r->w[7];
@@ -222,6 +302,37 @@ __device__ __noinline__ void blake2s_compress(uint32_t* h, const uint32_t* m, un
 #undef B2S_G
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[i + 8];
+}
+
+// Blake2s / HashToField128Security over a message whose bytes are one witness each (payload flag pl[3]); see fetch_words.
+// Whole little-endian blocks; the last one (possibly empty or full) carries the final flag.
+template <int T>
+__device__ __noinline__ void exec_blake2s_bytes(const OpRec* r, bool to_field, uint4* cb, unsigned long long* fail, const uint32_t* pl) {
+    const uint32_t n_in = pl[0], check_mask = pl[1];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    uint32_t h[8] = {0x6A09E667u ^ 0x01010020u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    uint32_t blk[16];
+    uint32_t base = 0;
+#pragma unroll 1
+    for (; n_in - base > 64; base += 64) {
+        fetch_words<T, 16>(blk, cb, ins, base, n_in);
+        blake2s_compress(h, blk, (unsigned long long)base + 64, false);
+    }
+    fetch_words<T, 16>(blk, cb, ins, base, n_in);
+    blake2s_compress(h, blk, n_in, true);
+    if (to_field) {
+        Fe f;   // from_be_bytes_reduce(digest): digest byte 0 is the most significant
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f.l[7 - k] = __byte_perm(h[k], 0, 0x0123);
+        fr::reduce_256(f);
+        insert_value_dev<T>(r, check_mask & 1, outs[0], f, cb, fail);
+    } else {
+        uint8_t dg[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dg[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+        write_digest<T>(dg, outs, check_mask, cb, fail, r->w[1]);
+    }
 }
 
 // to_field: one output = digest reduced mod p (HashToField128Security); else 32 byte outputs (Blake2s)
@@ -304,6 +415,39 @@ __device__ __noinline__ void keccak_f1600(unsigned long long* st) {
     }
 #pragma unroll
     for (int i = 0; i < 25; ++i) st[i] = a[i];
+}
+
+// Keccak-256 of a message whose bytes are one witness each (payload flag pl[3]), no length cut; see fetch_words
+template <int T>
+__device__ __noinline__ void exec_keccak256_bytes(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* pl) {
+    const uint32_t n_in = pl[0], check_mask = pl[1];
+    const uint32_t* ins = pl + 4;
+    const uint32_t* outs = ins + 2 * n_in;
+    unsigned long long st[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) st[i] = 0;
+    uint32_t base = 0, wds[34];
+#pragma unroll 1
+    for (; n_in - base >= 136; base += 136) {
+        fetch_words<T, 34>(wds, cb, ins, base, n_in);
+#pragma unroll
+        for (int i = 0; i < 17; ++i) st[i] ^= ((unsigned long long)wds[2 * i + 1] << 32) | wds[2 * i];
+        keccak_f1600(st);
+    }
+    fetch_words<T, 34>(wds, cb, ins, base, n_in);
+    const uint32_t rem = n_in - base;   // 0..135
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        unsigned long long lane = ((unsigned long long)wds[2 * i + 1] << 32) | wds[2 * i];
+        if ((uint32_t)i == (rem >> 3)) lane ^= 0x01ULL << (8 * (rem & 7));
+        st[i] ^= lane;
+    }
+    st[16] ^= 0x8000000000000000ULL;
+    keccak_f1600(st);
+    uint8_t dg[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dg[i] = (uint8_t)(st[i >> 3] >> (8 * (i & 7)));
+    write_digest<T>(dg, outs, check_mask, cb, fail, r->w[1]);
 }
 
 template <int T>
@@ -1097,17 +1241,17 @@ template <int T>
 __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail,
                                            const uint32_t* payload, uint32_t* mu) {
     switch (kind) {
+        // payload word 3 of a hash op: every message input is one byte -> packed-word variants (fetch_words)
         case MK_SHA256:
-            exec_sha256<T>(r, cb, fail, payload);
+            if (payload[r->w[7] + 3]) exec_sha256_bytes<T>(r, cb, fail, payload + r->w[7]); else exec_sha256<T>(r, cb, fail, payload);
             break;
         case MK_KECCAK256:
-            exec_keccak256<T>(r, cb, fail, payload);
+            if (payload[r->w[7] + 3]) exec_keccak256_bytes<T>(r, cb, fail, payload + r->w[7]); else exec_keccak256<T>(r, cb, fail, payload);
             break;
         case MK_BLAKE2S:
-            exec_blake2s<T>(r, false, cb, fail, payload);
-            break;
         case MK_HASH_TO_FIELD:
-            exec_blake2s<T>(r, true, cb, fail, payload);
+            if (payload[r->w[7] + 3]) exec_blake2s_bytes<T>(r, kind == MK_HASH_TO_FIELD, cb, fail, payload + r->w[7]);
+            else exec_blake2s<T>(r, kind == MK_HASH_TO_FIELD, cb, fail, payload);
             break;
         case MK_FIXED_BASE:
             exec_fixed_base<T>(r, flags, cb, fail);

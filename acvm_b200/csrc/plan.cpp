@@ -1097,7 +1097,12 @@ struct Compiler {
                 plan.payload.push_back(b.n_message_inputs);
                 plan.payload.push_back(known[out] ? 1u : 0u);
                 plan.payload.push_back(NONE);
-                plan.payload.push_back(0);
+                plan.payload.push_back([&] {   // 1: every message input is a single byte (num_bits 1..8) and no length cut: the device takes its packed-word path
+                    if (b.func == BB_Keccak256VariableLength) return 0u;
+                    for (uint32_t k = 0; k < b.n_message_inputs; ++k)
+                        if (b.inputs[k].num_bits == 0 || b.inputs[k].num_bits > 8) return 0u;
+                    return 1u;
+                }());
                 for (uint32_t k = 0; k < b.n_message_inputs; ++k) {
                     plan.payload.push_back(b.inputs[k].witness);
                     plan.payload.push_back(b.inputs[k].num_bits);
@@ -1138,7 +1143,12 @@ struct Compiler {
                 plan.payload.push_back(b.n_message_inputs);
                 plan.payload.push_back(mask);
                 plan.payload.push_back(b.func == BB_Keccak256VariableLength ? b.inputs.back().witness : NONE);
-                plan.payload.push_back(0);
+                plan.payload.push_back([&] {   // 1: every message input is a single byte (num_bits 1..8) and no length cut: the device takes its packed-word path
+                    if (b.func == BB_Keccak256VariableLength) return 0u;
+                    for (uint32_t k = 0; k < b.n_message_inputs; ++k)
+                        if (b.inputs[k].num_bits == 0 || b.inputs[k].num_bits > 8) return 0u;
+                    return 1u;
+                }());
                 for (uint32_t k = 0; k < b.n_message_inputs; ++k) {
                     plan.payload.push_back(b.inputs[k].witness);
                     plan.payload.push_back(b.inputs[k].num_bits);

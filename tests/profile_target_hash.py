@@ -1,0 +1,16 @@
+"""Short single-GPU profiling target (never a bench number): one hash-chain launch of the FULL step-VM variant."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import acvm_b200
+from acvm_b200 import acir_builder as ab
+ctx = acvm_b200.Context(0)
+rng = np.random.default_rng(1)
+data, inputs, nw = ab.hash_chain_circuit(int(sys.argv[1]) if len(sys.argv) > 1 else 256)
+batch = 4096
+arr = np.zeros((batch, len(inputs), 32), dtype=np.uint8)
+arr[:, :, 31] = rng.integers(0, 256, size=(batch, len(inputs)), dtype=np.uint8)
+circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+b = acvm_b200.DeviceBatch(circ, batch)
+b.stage_inputs(0, arr.tobytes())
+print("hash", b.run_staged(0), sum(s.status == "Solved" for s in b.status()))
