@@ -1348,6 +1348,13 @@ extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint
     return ACVMB_OK;
 }
 
+extern "C" int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3) {
+    if (!ctx || !out3) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(run_imad_cc_microbench(out3));
+    return ACVMB_OK;
+}
+
 extern "C" int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s /*[5]*/) {
     if (!ctx) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));

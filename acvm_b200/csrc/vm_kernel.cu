@@ -191,6 +191,38 @@ __global__ void __launch_bounds__(256) imad_bench_kernel(uint32_t* out, uint32_t
 #pragma unroll
         for (int i = 0; i < 8; ++i) s ^= acc[i];
         if (s == 0x12345678ull) out[0] = (uint32_t)s;
+    } else if (VARIANT >= 3) {
+        // 3: wide multiply-add with carry-OUT only, the carry captured by an ALU addc into a side counter (lazy-carry rows)
+        // 4: carry-out only, carry dropped      5: chains of two [carry-out, carry-in+out] with one capture per chain
+        uint32_t lo[8], hi[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { lo[i] = a + i; hi[i] = b + i; c[i] = i; }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (VARIANT == 5) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        fr::mad_lo_cc(lo[i], a + i, b + u, lo[i]);
+                        fr::madc_hi_cc(hi[i], a + i, b + u, hi[i]);
+                        fr::madc_lo_cc(lo[i + 1], a + i, b ^ u, lo[i + 1]);
+                        fr::madc_hi_cc(hi[i + 1], a + i, b ^ u, hi[i + 1]);
+                        fr::addc(c[i], c[i], 0);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        fr::mad_lo_cc(lo[i], a + i, b + u, lo[i]);
+                        fr::madc_hi_cc(hi[i], a + i, b + u, hi[i]);
+                        if (VARIANT == 3) fr::addc(c[i], c[i], 0);
+                    }
+                }
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= lo[i] ^ hi[i] ^ c[i];
+        if (s == 0x12345678u) out[0] = s;
     } else {
         uint32_t e[8], o[8];
 #pragma unroll
@@ -302,6 +334,37 @@ cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, doubl
     if (imad32_per_s) *imad32_per_s = res[0];
     if (imad_wide_per_s) *imad_wide_per_s = res[1];
     if (imad_wide_carry_per_s) *imad_wide_carry_per_s = res[2];
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
+// experiment: rates of the carry-out-only forms (wide IMADs per second), see imad_bench_kernel variants 3..5
+cudaError_t run_imad_cc_microbench(double* out3) {
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 64);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    for (int v = 0; v < 3; ++v) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(t0);
+            if (v == 0) imad_bench_kernel<3><<<blocks, threads>>>(d, 17 + rep, iters);
+            if (v == 1) imad_bench_kernel<4><<<blocks, threads>>>(d, 17 + rep, iters);
+            if (v == 2) imad_bench_kernel<5><<<blocks, threads>>>(d, 17 + rep, iters);
+            cudaEventRecord(t1);
+            e = cudaEventSynchronize(t1);
+            if (e != cudaSuccess) return e;
+            float ms;
+            cudaEventElapsedTime(&ms, t0, t1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out3[v] = (double)iters * 4 * 8 * blocks * threads / (best * 1e-3);
+    }
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     cudaFree(d);

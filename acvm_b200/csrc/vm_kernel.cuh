@@ -64,5 +64,6 @@ cudaError_t imad_microbench(double* imad32_per_s, double* imad_wide_per_s, doubl
 
 // register-resident Montgomery multiplications per second (practical Fr-mul ceiling of this field library)
 cudaError_t frmul_microbench(double* fr_mul_per_s /*[5]*/);
+cudaError_t run_imad_cc_microbench(double* out3);
 
 }  // namespace acvmb

@@ -212,6 +212,8 @@ int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wid
 /* register-resident Montgomery multiplications per second for the 5 FMA/ALU pipe-split levels of the K0 field
  * library (fr_mul_per_s[0..4]): the practical Fr-mul ceiling */
 int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
+/* wide IMADs per second of three carry-OUT-only forms: [0] + addc capture per product, [1] carry dropped, [2] chains of two */
+int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step), "chunk_steps", "n_stage", "split", "max_resident_bytes",
  * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
