@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libacvm_b200.so")
-SOURCES = ["vm_kernel_full.cu", "vm_kernel.cu", "runtime.cu", "acir.cpp", "plan.cpp"]
+SOURCES = ["vm_kernel_full.cu", "vm_kernel_full_b.cu", "vm_kernel.cu", "runtime.cu", "acir.cpp", "plan.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
@@ -45,7 +45,7 @@ def _compile(src, force):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=6) as ex:
         res = list(ex.map(lambda s: _compile(s, force), SOURCES))
     objs = [o for o, _ in res]
     log = "\n".join(l for _, l in res if l)

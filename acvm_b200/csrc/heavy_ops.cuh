@@ -25,7 +25,7 @@ struct CurveTables {
     const uint32_t* fixed_base;   // [32 windows][255][16]  affine (x,y) of (d * 256^w) * G, Montgomery form
     const uint32_t* pedersen;     // see pedersen section
 };
-__constant__ CurveTables g_curve_tables;
+static __constant__ CurveTables g_curve_tables;
 
 template <int T>
 __device__ __forceinline__ void hv_load(Fe& v, const uint4* cb, uint32_t w) {
@@ -149,7 +149,7 @@ __device__ __forceinline__ void fetch_words(uint32_t* wds, const uint4* cb, cons
 // ---------------------------------------------------------------------------------------------
 // SHA-256
 // ---------------------------------------------------------------------------------------------
-__constant__ uint32_t SHA_K[64] = {
+static __constant__ uint32_t SHA_K[64] = {
     0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
     0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
     0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
@@ -267,7 +267,7 @@ __device__ __noinline__ void exec_sha256(const OpRec* r, uint4* cb, unsigned lon
 // ---------------------------------------------------------------------------------------------
 // BLAKE2s-256, unkeyed (RFC 7693) -- Blake2s opcode and HashToField128Security (blackbox_solver/src/lib.rs:52-55,62-65)
 // ---------------------------------------------------------------------------------------------
-__constant__ uint8_t BLAKE2S_SIGMA[10][16] = {
+static __constant__ uint8_t BLAKE2S_SIGMA[10][16] = {
     {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
     {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
     {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
@@ -378,7 +378,7 @@ __device__ __noinline__ void exec_blake2s(const OpRec* r, bool to_field, uint4* 
 // ---------------------------------------------------------------------------------------------
 // Keccak-256 (original Keccak padding 0x01 .. 0x80, rate 136 bytes)
 // ---------------------------------------------------------------------------------------------
-__constant__ unsigned long long KECCAK_RC[24] = {
+static __constant__ unsigned long long KECCAK_RC[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
     0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
     0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,

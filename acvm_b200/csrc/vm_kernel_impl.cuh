@@ -318,8 +318,13 @@ static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
 // tile shapes (T instances x S slots).  The FULL variant (hash / curve / general ops) is instantiated for fewer shapes:
 // it dominates compile time.
 #define ACVMB_CONFIGS_LIGHT(X) X(8, 16) X(4, 16) X(2, 16) X(16, 16) X(16, 8) X(32, 4) X(32, 2) X(32, 1) X(4, 32) X(2, 64) X(32, 8)
-#define ACVMB_CONFIGS_FULL(X) X(8, 16) X(4, 16) X(16, 8) X(32, 4) X(32, 1) X(32, 8)
+// the FULL shapes are compiled in two translation units (vm_kernel_full.cu / vm_kernel_full_b.cu) to halve the build's critical path
+#define ACVMB_CONFIGS_FULL_A(X) X(8, 16) X(4, 16) X(16, 8)
+#define ACVMB_CONFIGS_FULL_B(X) X(32, 4) X(32, 1) X(32, 8)
+#define ACVMB_CONFIGS_FULL(X) ACVMB_CONFIGS_FULL_A(X) ACVMB_CONFIGS_FULL_B(X)
 
 cudaError_t launch_vm_full(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream);   // vm_kernel_full.cu
+cudaError_t launch_vm_full_b(const KernelConfig& cfg, const VmArgs& args, cudaStream_t stream); // vm_kernel_full_b.cu
+cudaError_t set_curve_tables_b(const uint32_t* fixed_base, const uint32_t* pedersen);
 
 }  // namespace acvmb
