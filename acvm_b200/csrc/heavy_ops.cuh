@@ -159,7 +159,7 @@ static __constant__ uint32_t SHA_K[64] = {
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
-__device__ __noinline__ void sha256_compress(uint32_t* h, const uint32_t* blk) {
+static __device__ __noinline__ void sha256_compress(uint32_t* h, const uint32_t* blk) {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = blk[i];
@@ -274,7 +274,7 @@ static __constant__ uint8_t BLAKE2S_SIGMA[10][16] = {
     {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
     {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
 
-__device__ __noinline__ void blake2s_compress(uint32_t* h, const uint32_t* m, unsigned long long t, bool last) {
+static __device__ __noinline__ void blake2s_compress(uint32_t* h, const uint32_t* m, unsigned long long t, bool last) {
     const uint32_t IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
     uint32_t v[16];
 #pragma unroll
@@ -388,7 +388,7 @@ static __constant__ unsigned long long KECCAK_RC[24] = {
 __device__ __forceinline__ unsigned long long rol64(unsigned long long x, int n) { return n ? ((x << n) | (x >> (64 - n))) : x; }
 
 // state index = x + 5*y
-__device__ __noinline__ void keccak_f1600(unsigned long long* st) {
+static __device__ __noinline__ void keccak_f1600(unsigned long long* st) {
     unsigned long long a[25];
 #pragma unroll
     for (int i = 0; i < 25; ++i) a[i] = st[i];
@@ -510,7 +510,7 @@ __device__ __forceinline__ void fe_dbl(Fe& r, const Fe& a) { fr::add_mod(r, a, a
 
 // mixed addition acc += (px, py)  ("madd-2007-bl": 7M + 4S); the plan-level invariants of fixed-base /
 // Pedersen windows exclude acc == +-P except through the explicit checks below.
-__device__ __noinline__ void jac_madd(Jac& acc, const Fe& px, const Fe& py) {
+static __device__ __noinline__ void jac_madd(Jac& acc, const Fe& px, const Fe& py) {
     if (acc.inf) {
         acc.X = px;
         acc.Y = py;
@@ -583,7 +583,7 @@ __device__ __noinline__ void jac_madd(Jac& acc, const Fe& px, const Fe& py) {
 // Montgomery form of 1/a for a Montgomery-form input a != 0: binary extended Euclid on the integer a*R (fr::inv_bea,
 // ~190 uniform iterations) and one product with R^3 to land back in Montgomery form: (aR)^-1 * R^3 / R = a^-1 * R.
 // (Was a Fermat ladder: 253 squarings + 127 products, the single largest cost of every curve micro-op.)
-__device__ __noinline__ void fe_inv(Fe& r, const Fe& a) {
+static __device__ __noinline__ void fe_inv(Fe& r, const Fe& a) {
     Fe w, r3;
     fr::inv_bea(w, a);
     r3.l[0] = 0xb4bf0040u; r3.l[1] = 0x5e94d8e1u; r3.l[2] = 0x1cfbb6b8u; r3.l[3] = 0x2a489cbeu;
@@ -592,7 +592,7 @@ __device__ __noinline__ void fe_inv(Fe& r, const Fe& a) {
 }
 
 // Jacobian (Montgomery) -> affine canonical
-__device__ __noinline__ void jac_to_affine_canonical(Fe& x, Fe& y, const Jac& p) {
+static __device__ __noinline__ void jac_to_affine_canonical(Fe& x, Fe& y, const Jac& p) {
     if (p.inf) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { x.l[k] = 0; y.l[k] = 0; }
@@ -685,7 +685,7 @@ __device__ __noinline__ void exec_fixed_base(const OpRec* r, uint32_t flags, uin
 // ---------------------------------------------------------------------------------------------
 constexpr int PED_WINDOWS = 29, PED_TABLE_SIZE = 512, PED_IV_SIZE = 1024;
 
-__device__ __noinline__ void ped_hash_single(Jac& acc, const Fe& v, int parity) {
+static __device__ __noinline__ void ped_hash_single(Jac& acc, const Fe& v, int parity) {
     uint32_t l[9];
 #pragma unroll
     for (int i = 0; i < 8; ++i) l[i] = v.l[i];
@@ -755,7 +755,7 @@ __device__ __noinline__ void exec_pedersen(const OpRec* r, uint32_t flags, uint4
 // c[0][5];  [1] table: 0 = fixed-base (8-bit windows, digit 0 skipped), 1 = Pedersen (9-bit windows);  [2] first window
 // of the scalar;  [3] number of windows;  [4] table window offset (fixed-base high limb: 16; Pedersen parity 1: 29).
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void jac_dbl(Jac& acc) {   // "dbl-2009-l", a = 0
+static __device__ __noinline__ void jac_dbl(Jac& acc) {   // "dbl-2009-l", a = 0
     if (acc.inf) return;
     if (fr::is_zero(acc.Y)) { acc.inf = true; return; }
     Fe A, B, C, D, E, F, t, X3, Y3, Z3;
@@ -782,7 +782,7 @@ __device__ __noinline__ void jac_dbl(Jac& acc) {   // "dbl-2009-l", a = 0
 }
 
 // a += b, both Jacobian ("add-2007-bl": 11M + 5S), every special case handled
-__device__ __noinline__ void jac_add_full(Jac& a, const Jac& b) {
+static __device__ __noinline__ void jac_add_full(Jac& a, const Jac& b) {
     if (b.inf) return;
     if (a.inf) { a = b; return; }
     Fe z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
@@ -1210,7 +1210,7 @@ __device__ __noinline__ void exec_mem(const OpRec* r, uint32_t kind, uint4* cb, 
 // ECDSA secp256k1 / secp256r1 (signature/ecdsa.rs:12-97): every input is one byte = the low byte of its witness
 // (signature/mod.rs:5-18, to_be_bytes().last()); out := 1 / 0; reference panics -> EK_REFERENCE_PANIC.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ int ecdsa_verify_dev(int curve, const uint8_t* bytes) {
+static __device__ __noinline__ int ecdsa_verify_dev(int curve, const uint8_t* bytes) {
     return ec::ecdsa_verify(curve, bytes + 128, bytes, bytes + 32, bytes + 64);
 }
 template <int T>
