@@ -110,10 +110,16 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
     Fe res;
     if (flags & GF_Y) {
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
+        // Every operand load is issued here, before the code paths part: the slots of a warp may hold different gate forms
+        // (multiplicative / +-1 add-sub / linear), the forms then run one after the other, and with the loads inside each
+        // form their L2 latencies added up (measured: the cheap "noir-like" mix was slower per step than all-dense).
+        Fe x, y, w1, w2;
+        if (flags & GF_MUL) load_w<T>(x, cb, r->w[3]);
+        load_w<T>(y, cb, r->w[4]);
+        if (nlin >= 1) load_w<T>(w1, cb, r->w[5]);
+        if (nlin >= 2) load_w<T>(w2, cb, r->w[6]);
         if (flags & GF_MUL) {
-            Fe x, y, u, t;
-            load_w<T>(x, cb, r->w[3]);
-            load_w<T>(y, cb, r->w[4]);
+            Fe u, t;
             // lazy reduction: x+alpha, y+beta < 2p stay unreduced (4p^2/R + p < 1.76p), and so does u
             // ((1.76 + 1) p^2 / R + p < 1.52p for the second product): one conditional subtraction per gate instead of three
             lds_fe(t, r->c[1]);
@@ -126,43 +132,29 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
                 const Fe* a[1] = {&u};
                 fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr}, r->c[4]);
             } else {
-                Fe w1;
-                load_w<T>(w1, cb, r->w[5]);
                 const Fe* a[2] = {&u, &w1};
                 fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr}, r->c[4]);
             }
         } else if (flags & GF_ADDSUB) {
             // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
-            Fe y, t;
-            load_w<T>(y, cb, r->w[4]);
             lds_fe(res, r->c[4]);
             if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
             if (nlin >= 1) {
-                load_w<T>(t, cb, r->w[5]);
-                if (flags & GF_NEG_W1) fr::sub_mod(res, res, t); else fr::add_mod(res, res, t);
+                if (flags & GF_NEG_W1) fr::sub_mod(res, res, w1); else fr::add_mod(res, res, w1);
             }
             if (nlin >= 2) {
-                load_w<T>(t, cb, r->w[6]);
-                if (flags & GF_NEG_W2) fr::sub_mod(res, res, t); else fr::add_mod(res, res, t);
+                if (flags & GF_NEG_W2) fr::sub_mod(res, res, w2); else fr::add_mod(res, res, w2);
             }
         } else {
-            Fe y;
-            load_w<T>(y, cb, r->w[4]);
             if (nlin == 0) {
                 const Fe* a[1] = {&y};
                 fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr}, r->c[4]);
+            } else if (nlin == 1) {
+                const Fe* a[2] = {&y, &w1};
+                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr}, r->c[4]);
             } else {
-                Fe w1;
-                load_w<T>(w1, cb, r->w[5]);
-                if (nlin == 1) {
-                    const Fe* a[2] = {&y, &w1};
-                    fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr}, r->c[4]);
-                } else {
-                    Fe w2;
-                    load_w<T>(w2, cb, r->w[6]);
-                    const Fe* a[3] = {&y, &w1, &w2};
-                    fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]}, r->c[4]);
-                }
+                const Fe* a[3] = {&y, &w1, &w2};
+                fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]}, r->c[4]);
             }
         }
         // the additive constant rode in the accumulator of the last reduction (c[4] = cC*R): one conditional subtraction
