@@ -118,24 +118,7 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
         load_w<T>(y, cb, r->w[4]);
         if (nlin >= 1) load_w<T>(w1, cb, r->w[5]);
         if (nlin >= 2) load_w<T>(w2, cb, r->w[6]);
-        if (flags & GF_MUL) {
-            Fe u, t;
-            // lazy reduction: x+alpha, y+beta < 2p stay unreduced (4p^2/R + p < 1.76p), and so does u
-            // ((1.76 + 1) p^2 / R + p < 1.52p for the second product): one conditional subtraction per gate instead of three
-            lds_fe(t, r->c[1]);
-            fr::add_raw(x, x, t);
-            lds_fe(t, r->c[2]);
-            fr::add_raw(y, y, t);
-            const Fe* a1[1] = {&x};
-            fr::mont_dot_fn<1, RegLimbs, SPLIT>(u, a1, RegLimbs{y});   // (x+alpha)(y+beta)/R < 1.76p
-            if (nlin == 0) {
-                const Fe* a[1] = {&u};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], nullptr, nullptr}, r->c[4]);
-            } else {
-                const Fe* a[2] = {&u, &w1};
-                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[0], r->c[3], nullptr}, r->c[4]);
-            }
-        } else if (flags & GF_ADDSUB) {
+        if (flags & GF_ADDSUB) {
             // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
             lds_fe(res, r->c[4]);
             if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
@@ -146,19 +129,41 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
                 if (flags & GF_NEG_W2) fr::sub_mod(res, res, w2); else fr::add_mod(res, res, w2);
             }
         } else {
-            if (nlin == 0) {
-                const Fe* a[1] = {&y};
-                fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], nullptr, nullptr}, r->c[4]);
-            } else if (nlin == 1) {
-                const Fe* a[2] = {&y, &w1};
-                fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], nullptr}, r->c[4]);
-            } else {
-                const Fe* a[3] = {&y, &w1, &w2};
-                fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, SmemLimbs3{r->c[1], r->c[2], r->c[3]}, r->c[4]);
+            // Multiplicative and linear forms share ONE reduction of warp-uniform width: the lanes of this warp that are here
+            // agree on K = the widest dot product among them, narrower lanes pad with zero operands.  (Each form used to
+            // run its own width, so a warp holding several forms executed them one after the other.)
+            const unsigned lanes = __activemask();
+            const bool mul = (flags & GF_MUL) != 0;
+            if (mul) {
+                // lazy reduction: x+alpha, y+beta < 2p stay unreduced (4p^2/R + p < 1.76p), and so does u
+                // ((1.76 + 1) p^2 / R + p < 1.52p for the second product): one conditional subtraction per gate instead of three
+                Fe t;
+                lds_fe(t, r->c[1]);
+                fr::add_raw(x, x, t);
+                lds_fe(t, r->c[2]);
+                fr::add_raw(y, y, t);
+                const Fe* a1[1] = {&x};
+                fr::mont_dot_fn<1, RegLimbs, SPLIT>(t, a1, RegLimbs{y});   // u = (x+alpha)(y+beta)/R < 1.76p
+                y = t;
             }
+            __syncwarp(lanes);
+            if (nlin < 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w1.l[i] = 0;
+            }
+            if (nlin < 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w2.l[i] = 0;
+            }
+            const uint32_t K = __reduce_max_sync(lanes, 1u + nlin);
+            // constants: multiplicative (u, w1) . (c0, c3); linear (y, w1, w2) . (c1, c2, c3); c4 = cC*R rides in the accumulator
+            const SmemLimbs3 bl{mul ? r->c[0] : r->c[1], mul ? r->c[3] : r->c[2], r->c[3]};
+            const Fe* a[3] = {&y, &w1, &w2};
+            if (K == 1) fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
+            else if (K == 2) fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
+            else fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
+            fr::cond_sub_p(res);
         }
-        // the additive constant rode in the accumulator of the last reduction (c[4] = cC*R): one conditional subtraction
-        if (!(flags & GF_ADDSUB)) fr::cond_sub_p(res);
     } else {
         lds_fe(res, r->c[4]);
     }
