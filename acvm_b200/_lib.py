@@ -25,7 +25,7 @@ class PlanInfo(C.Structure):
         "n_opcodes", "n_micro_ops", "n_steps", "n_slots_filled", "n_gate_assign", "n_gate_check", "n_logic", "n_range",
         "n_hash", "n_curve", "ref_fr_mul", "ref_fr_inv", "dev_imad", "alg_bytes", "n_temps")] + [(n, C.c_uint32) for n in (
         "num_witnesses", "n_slots", "S", "needs_full_kernel", "static_fail_present", "static_fail_opcode",
-        "static_fail_kind", "static_fail_aux")]
+        "static_fail_kind", "static_fail_aux", "n_segments", "n_host_segments", "n_brillig", "n_brillig_device")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -68,6 +68,7 @@ def load():
         "acvmb_vm_new": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p, C.c_char_p, C.c_uint32, C.POINTER(vp)]),
         "acvmb_vm_destroy": (None, [vp]),
         "acvmb_vm_solve": (C.c_int, [vp, C.POINTER(Status)]),
+        "acvmb_vm_solve_opcode": (C.c_int, [vp, C.POINTER(Status)]),
         "acvmb_vm_status": (C.c_int, [vp, C.POINTER(Status)]),
         "acvmb_vm_instruction_pointer": (C.c_int, [vp, u32p]),
         "acvmb_vm_num_witnesses": (C.c_int, [vp, u32p]),
@@ -85,6 +86,8 @@ def load():
         "acvmb_ecdsa_secp256r1_verify": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, vp, C.POINTER(Status)]),
         "acvmb_plan_compile_host": (C.c_int, [C.c_char_p, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.POINTER(PlanInfo), vp,
                                               C.c_size_t, C.POINTER(C.c_size_t)]),
+        "acvmb_plan_compile_host_ex": (C.c_int, [C.c_char_p, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 C.POINTER(PlanInfo), vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "acvmb_imad_cc_microbench": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "acvmb_pedersen_generator_host": (C.c_int, [C.c_uint32, C.c_char_p]),
         "acvmb_permutation_route_host": (C.c_int, [u32p, C.c_uint32, vp, C.c_uint32, u32p]),

@@ -384,7 +384,9 @@ FR_PRIM void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_s<FR_ALU_SPLIT
 // x1 := x1 / 2^k mod p through one Montgomery-style correction x1 + ((-x1 / p) mod 2^k) * p, exact for k <= 32).
 // ~190 iterations of ~110 instructions instead of the ~380 Montgomery products of a Fermat ladder; lanes only differ
 // in their trip count.  Plain C++ (no carry asm) so the host test build runs the same code.
-// a: 0 < a < p, any representation (the value is inverted as an integer mod p); r = a^-1 mod p, canonical.
+// a: any representation (the value is inverted as an integer mod p); r = a^-1 mod p, canonical.  a == 0 (mod p) gives 0,
+// like FieldElement::inverse (acir_field/src/generic_ark.rs:242-245) -- and, more to the point, terminates: lanes that
+// already failed and the padding lanes of a last tile run every micro-op on arbitrary column contents.
 // ---------------------------------------------------------------------------------------------
 FR_PRIM uint32_t bea_funnel_r(uint32_t lo, uint32_t hi, uint32_t k) {   // (hi:lo) >> k, 0 <= k <= 32
 #if defined(__CUDA_ARCH__)
@@ -423,6 +425,16 @@ FR_PRIM void inv_bea(Fe& r, const Fe& a) {
     uint32_t u[N], v[N], x1[N], x2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { u[i] = a.l[i]; v[i] = p_limb(i); x1[i] = i == 0; x2[i] = 0; }
+    {
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) any |= u[i];
+        if (any == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) r.l[i] = 0;
+            return;
+        }
+    }
     if (!(u[0] & 1u)) bea_strip(u, x1);
     while (true) {
         // d = u - v; when it borrows the roles swap: (u, x1) <-> (v, x2) and d = v - u
@@ -448,8 +460,14 @@ FR_PRIM void inv_bea(Fe& r, const Fe& a) {
 #pragma unroll
         for (int i = 1; i < N; ++i) rest |= v[i];
         if (rest == 0) break;   // min(u, v) == 1: x2 * a == 1
+        uint32_t dz = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) u[i] = d[i];
+        for (int i = 0; i < N; ++i) { u[i] = d[i]; dz |= d[i]; }
+        if (dz == 0) {          // u == v != 1: gcd(a, p) = p, i.e. a == 0 (mod p) -> 0
+#pragma unroll
+            for (int i = 0; i < N; ++i) x2[i] = 0;
+            break;
+        }
         // x1 = x1 - x2 mod p
         uint32_t bm;
         sub_cc(x1[0], x1[0], x2[0]);

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 #include <thread>
 
@@ -259,6 +260,27 @@ struct Compiler {
         temp_next += 3;
         return t;
     }
+
+    // Dedicated (non-recycled) slots for values that must outlive the round-robin pool: the expression values a host
+    // segment reads (Brillig inputs / predicate, PermutationSort tuples) stay live until that segment, the H1 points of a
+    // Pedersen call until the chaining round that consumes them.  The round-robin pool never checks liveness, so anything
+    // that is not consumed by the very next micro-ops of its own lowering lives here, after the pool, next to the memory
+    // blocks.  Released slots are reused first-in-first-out, and only once `min_queue` others are waiting: immediate reuse
+    // would chain independent curve calls through a false write-after-read dependency on the slot.
+    std::deque<uint32_t> free1_, free3_;
+    uint32_t new_pinned(uint32_t n, size_t min_queue) {
+        auto& q = n == 1 ? free1_ : free3_;
+        if (q.size() > min_queue) {
+            uint32_t s = q.front();
+            q.pop_front();
+            return s;
+        }
+        uint32_t s = extra_slots_base + extra_slots;
+        extra_slots += n;
+        sched.grow_slots(s + n);
+        return s;
+    }
+    void release_pinned(uint32_t s, uint32_t n) { (n == 1 ? free1_ : free3_).push_back(s); }
 
     static void put(uint32_t dst[8], const U256& v) { hf::to_limbs32(v, dst); }
 
@@ -553,17 +575,25 @@ struct Compiler {
 
     // get_value(expr) (pwg/mod.rs:321-332) for an expression whose witnesses are all statically known: returns the slot
     // that holds the value (the witness itself for `1*w`, else a temporary).  false => static MissingAssignment recorded.
-    bool expr_to_slot(uint32_t idx, const Expression& e, uint32_t& slot) {
+    // `pinned`: the value is read by a host segment (or much later): give it a dedicated slot and list it for release.
+    bool expr_to_slot(uint32_t idx, const Expression& e, uint32_t& slot, std::vector<uint32_t>* pinned = nullptr) {
         std::vector<Prod> prods;
         std::vector<Lin> lins;
-        uint32_t missing = NONE;
+        // get_value = evaluate + to_const, else MissingAssignment(any_witness_from_expression) (pwg/mod.rs:321-332,362-372):
+        // the first entry of the evaluated linear_combinations (unknown linear terms, in order), else w1 of the first
+        // surviving mul term.  A mul term with exactly one known operand turns into a linear entry only when
+        // q_M * w_known != 0 -- per instance -- so it is refused here rather than decided statically.
+        uint32_t missing_lin = NONE, missing_mul = NONE;
         for (auto& t : e.mul_terms) {
             if (known[t.a] == W_MAYBE || known[t.b] == W_MAYBE)
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": expression over a conditionally assigned witness is not supported here yet");
             if (known[t.a] && known[t.b]) {
                 if (!t.c.is_zero()) prods.push_back({t.c, t.a, t.b});
-            } else if (!t.c.is_zero() && missing == NONE) {
-                missing = known[t.a] ? t.b : t.a;
+            } else if (!t.c.is_zero()) {
+                if (known[t.a] || known[t.b])
+                    throw std::runtime_error("opcode " + std::to_string(idx) + ": directive / memory / Brillig input expression with a half-known "
+                                             "multiplication term (value-dependent MissingAssignment) is not supported");
+                if (missing_mul == NONE) missing_mul = t.a;
             }
         }
         for (auto& t : e.linear_combinations) {
@@ -571,10 +601,11 @@ struct Compiler {
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": expression over a conditionally assigned witness is not supported here yet");
             if (known[t.w]) {
                 if (!t.c.is_zero()) lins.push_back({t.c, t.w});
-            } else if (!t.c.is_zero() && missing == NONE) {
-                missing = t.w;
+            } else if (!t.c.is_zero() && missing_lin == NONE) {
+                missing_lin = t.w;
             }
         }
+        const uint32_t missing = missing_lin != NONE ? missing_lin : missing_mul;
         if (missing != NONE) {
             fail_static(idx, EK_MISSING_ASSIGNMENT, missing, "missing assignment for witness index " + std::to_string(missing));
             return false;
@@ -583,7 +614,12 @@ struct Compiler {
             slot = lins[0].w;
             return true;
         }
-        slot = new_temp();
+        if (pinned) {
+            slot = new_pinned(1, 0);
+            pinned->push_back(slot);
+        } else {
+            slot = new_temp();
+        }
         ++plan.stats.n_temps;
         lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, slot, idx, false);
         return true;
@@ -681,7 +717,7 @@ struct Compiler {
         // Directive::PermutationSort (directives/mod.rs:88-121): tuples are evaluated into slots on the device, the sort and
         // the switch routing run on the host between two device segments (sort_host.hpp), like Brillig.
         const uint32_t n = (uint32_t)d.sort_inputs.size();
-        std::vector<uint32_t> slots;
+        std::vector<uint32_t> slots, pinned;
         for (auto& element : d.sort_inputs) {
             if (element.size() != d.tuple) {
                 fail_static(idx, EK_REFERENCE_PANIC, 0, "PermutationSort element does not have `tuple` entries");
@@ -689,7 +725,7 @@ struct Compiler {
             }
             for (auto& e : element) {
                 uint32_t s;
-                if (!expr_to_slot(idx, e, s)) return false;
+                if (!expr_to_slot(idx, e, s, &pinned)) return false;
                 slots.push_back(s);
             }
         }
@@ -718,6 +754,7 @@ struct Compiler {
         uint32_t off = (uint32_t)plan.host_desc.size();
         plan.host_desc.insert(plan.host_desc.end(), desc.begin(), desc.end());
         plan.segments.push_back(Segment{2, idx, off, 0});
+        for (uint32_t s : pinned) release_pinned(s, 1);
         for (uint32_t w : outs)
             if (!known[w]) mark_assigned(w, idx);
         ++plan.stats.n_directive;
@@ -839,6 +876,121 @@ struct Compiler {
         seg_start = end;
     }
 
+    // ---- Brillig on the device: plan-time symbolic execution of straight-line field bytecode ------------------------
+    // A VM register / memory cell is a constant or a slot.  Supported: BinaryFieldOp Add/Sub/Mul, Const, Mov, Stop (and
+    // running off the end of the bytecode, which the VM also treats as Finished, brillig_vm/src/lib.rs:140-151); no
+    // predicate, no control flow, no memory opcodes; array inputs / outputs through constant pointers (brillig.rs:46-76,
+    // 97-113).  Everything else keeps the host VM.  emit == false is a dry run that only decides feasibility.
+    struct Sym {
+        bool is_const = true;
+        U256 c;
+        uint32_t slot = NONE;
+    };
+    bool brillig_symbolic(uint32_t idx, const Brillig& br, bool emit, std::vector<uint32_t>& pinned) {
+        if (br.bytecode.empty() || br.predicate.present) return false;
+        std::vector<Sym> regs, mem;
+        auto get = [&](uint64_t r) { return r < regs.size() ? regs[r] : Sym{}; };
+        auto set = [&](uint64_t r, const Sym& v) {
+            if (regs.size() <= r) regs.resize(r + 1);
+            regs[r] = v;
+        };
+        auto input = [&](const Expression& e, Sym& out) {
+            U256 cv;
+            if (expr_is_const(e, cv)) {
+                out = Sym{true, cv, NONE};
+                return true;
+            }
+            out.is_const = false;
+            out.slot = NONE;
+            if (!emit) {   // feasibility only: every witness of the expression must be statically known
+                for (auto& t : e.mul_terms)
+                    if (!t.c.is_zero() && (known[t.a] != W_KNOWN || known[t.b] != W_KNOWN)) return false;
+                for (auto& t : e.linear_combinations)
+                    if (!t.c.is_zero() && known[t.w] != W_KNOWN) return false;
+                return true;
+            }
+            return expr_to_slot(idx, e, out.slot, &pinned);
+        };
+        for (auto& in : br.inputs) {
+            if (!in.is_array) {
+                Sym v;
+                if (!input(in.exprs[0], v)) return false;
+                regs.push_back(v);
+            } else {
+                regs.push_back(Sym{true, hf::from_u64(mem.size()), NONE});
+                for (auto& e : in.exprs) {
+                    Sym v;
+                    if (!input(e, v)) return false;
+                    mem.push_back(v);
+                }
+            }
+        }
+        const U256 one = hf::from_u64(1);
+        for (size_t pc = 0; pc < br.bytecode.size(); ++pc) {
+            const BrilligOp& o = br.bytecode[pc];
+            if (o.r0 >= (1u << 16) || o.r1 >= (1u << 16) || o.r2 >= (1u << 16)) return false;
+            if (o.tag == 14) break;                                    // Stop
+            if (o.tag == 6) { set(o.r0, Sym{true, o.value, NONE}); continue; }   // Const
+            if (o.tag == 9) { set(o.r0, get(o.r1)); continue; }                  // Mov
+            if (o.tag != 0 || o.bop > 2) return false;                 // only BinaryFieldOp Add / Sub / Mul
+            Sym a = get(o.r1), b = get(o.r2), r;
+            if (a.is_const && b.is_const) {
+                r.c = o.bop == 0 ? hf::add(a.c, b.c) : o.bop == 1 ? hf::sub(a.c, b.c) : hf::mul(a.c, b.c);
+            } else {
+                r.is_const = false;
+                if (emit) {
+                    r.slot = new_pinned(1, 0);
+                    pinned.push_back(r.slot);
+                    std::vector<Prod> prods;
+                    std::vector<Lin> lins;
+                    U256 cst;
+                    if (o.bop == 2) {
+                        if (!a.is_const && !b.is_const) prods.push_back({one, a.slot, b.slot});
+                        else if (a.is_const) { if (!a.c.is_zero()) lins.push_back({a.c, b.slot}); }
+                        else if (!b.c.is_zero()) lins.push_back({b.c, a.slot});
+                    } else {
+                        const U256 sb = o.bop == 0 ? one : hf::neg(one);
+                        if (a.is_const) cst = a.c; else lins.push_back({one, a.slot});
+                        if (b.is_const) cst = hf::add(cst, o.bop == 0 ? b.c : hf::neg(b.c));
+                        else if (!a.is_const && a.slot == b.slot) {   // x + x / x - x: one linear term
+                            lins.clear();
+                            if (o.bop == 0) lins.push_back({hf::from_u64(2), a.slot});
+                        } else lins.push_back({sb, b.slot});
+                    }
+                    ++plan.stats.n_temps;
+                    lower_sum(std::move(prods), std::move(lins), cst, /*assign=*/true, r.slot, idx, false);
+                }
+            }
+            set(o.r0, r);
+        }
+        // outputs (brillig.rs:97-113): register i, or memory behind the pointer in register i; insert_value semantics
+        std::vector<std::pair<uint32_t, Sym>> outs;
+        for (size_t i = 0; i < br.outputs.size(); ++i) {
+            Sym v = get(i);
+            if (!br.outputs[i].is_array) {
+                outs.emplace_back(br.outputs[i].witnesses[0], v);
+                continue;
+            }
+            if (!v.is_const || v.c.l[1] || v.c.l[2] || v.c.l[3]) return false;
+            for (size_t k = 0; k < br.outputs[i].witnesses.size(); ++k) {
+                uint64_t p = v.c.l[0] + k;
+                if (p >= mem.size()) return false;   // the reference panics on the index: leave it to the host VM's report
+                outs.emplace_back(br.outputs[i].witnesses[k], mem[p]);
+            }
+        }
+        for (auto& ov : outs)
+            if (known[ov.first] == W_MAYBE) return false;
+        if (!emit) return true;
+        for (auto& ov : outs) {
+            const uint32_t w = ov.first;
+            const bool chk = known[w] != 0;
+            if (ov.second.is_const) lower_sum({}, {}, ov.second.c, /*assign=*/true, w, idx, chk);
+            else lower_sum({}, {Lin{one, ov.second.slot}}, U256{}, /*assign=*/true, w, idx, chk);
+            if (!chk) mark_assigned(w, idx);
+        }
+        return true;
+    }
+
     // Opcode::Brillig (acvm/src/pwg/brillig.rs:20-131): predicate and input expressions are evaluated on the device into
     // slots; the VM itself runs on the host between two device segments.
     bool brillig(uint32_t idx, const Brillig& br) {
@@ -847,7 +999,15 @@ struct Compiler {
                 throw std::runtime_error("opcode " + std::to_string(idx) + ": Brillig BlackBox op " + std::to_string(o.bb_tag) +
                                          " is not supported by the host VM yet");
         uint32_t sp = NONE;
-        if (br.predicate.present && !expr_to_slot(idx, br.predicate, sp)) return false;
+        std::vector<uint32_t> pinned;
+        if (opt.device_brillig && brillig_symbolic(idx, br, /*emit=*/false, pinned)) {
+            if (!brillig_symbolic(idx, br, /*emit=*/true, pinned)) throw std::runtime_error("plan: device Brillig lowering diverged from its dry run");
+            for (uint32_t s : pinned) release_pinned(s, 1);
+            ++plan.stats.n_brillig;
+            ++plan.stats.n_brillig_device;
+            return true;
+        }
+        if (br.predicate.present && !expr_to_slot(idx, br.predicate, sp, &pinned)) return false;
         std::vector<uint32_t> desc;
         desc.push_back(sp);
         desc.push_back((uint32_t)br.inputs.size());
@@ -856,7 +1016,7 @@ struct Compiler {
             desc.push_back((uint32_t)in.exprs.size());
             for (auto& e : in.exprs) {
                 uint32_t s;
-                if (!expr_to_slot(idx, e, s)) {
+                if (!expr_to_slot(idx, e, s, &pinned)) {
                     // get_value() failure on an input is reported as ExpressionHasTooManyUnknowns (brillig.rs:49-55)
                     plan.static_fail.kind = EK_TOO_MANY_UNKNOWNS;
                     plan.static_fail.aux = 0;
@@ -883,6 +1043,7 @@ struct Compiler {
         uint32_t off = (uint32_t)plan.host_desc.size();
         plan.host_desc.insert(plan.host_desc.end(), desc.begin(), desc.end());
         plan.segments.push_back(Segment{1, idx, off, 0});
+        for (uint32_t s : pinned) release_pinned(s, 1);
         for (uint32_t w : outs)
             if (!known[w]) mark_assigned(w, idx);
         ++plan.stats.n_brillig;
@@ -980,13 +1141,16 @@ struct Compiler {
         }
     }
     // pairwise tree of Jacobian additions until at most `keep` points remain
-    void curve_reduce(uint32_t idx, std::vector<uint32_t>& points, size_t keep) {
+    // `final_dst` (with keep == 1): the slot triple that receives the one remaining point
+    void curve_reduce(uint32_t idx, std::vector<uint32_t>& points, size_t keep, uint32_t final_dst = NONE) {
+        if (final_dst != NONE && (keep != 1 || points.size() < 2)) throw std::runtime_error("plan: curve_reduce final_dst misuse");
         while (points.size() > keep) {
             std::vector<uint32_t> next;
             size_t n_pairs = std::min(points.size() / 2, points.size() - keep);
             for (size_t i = 0; i < n_pairs; ++i) {
                 OpRec r{};
-                uint32_t a = points[2 * i], b = points[2 * i + 1], out = new_temp3();
+                uint32_t a = points[2 * i], b = points[2 * i + 1];
+                uint32_t out = (final_dst != NONE && points.size() == 2) ? final_dst : new_temp3();
                 r.w[0] = MK_JAC_ADD;
                 r.w[1] = idx;
                 r.w[2] = out;
@@ -1216,6 +1380,10 @@ struct Compiler {
                 return true;
             }
             case BB_Pedersen: {
+                if (!opt.allow_unpinned_pedersen)
+                    throw std::runtime_error("opcode " + std::to_string(idx) + ": BlackBoxFuncCall::Pedersen is not supported: barretenberg's "
+                                             "generator tables are not reproducible here, results would differ from the reference "
+                                             "(opt in with the context option pedersen_unpinned=1 to run the structurally identical kernel)");
                 uint32_t ox = b.outputs[0], oy = b.outputs[1];
                 uint32_t flags = GF_HEAVY;
                 if (split_curve_ops() && !b.inputs.empty()) {
@@ -1230,8 +1398,8 @@ struct Compiler {
                         std::vector<uint32_t> pts;
                         if (k < n_in) curve_parts(idx, 0, b.inputs[k].witness, 0, 1, 29, 4, 29, pts);   // num_bits is ignored (pedersen.rs:18-20)
                         else curve_parts(idx, 2, NONE, n_in, 1, 29, 4, 29, pts);                          // the length block: an immediate scalar
-                        curve_reduce(idx, pts, 1);
-                        h1[k] = pts[0];
+                        h1[k] = new_pinned(3, 1024);   // consumed n_in + 1 - k chaining rounds later: not a pool slot
+                        curve_reduce(idx, pts, 1, h1[k]);
                     }
                     uint32_t chain = NONE;   // slot holding r_k (canonical x of the previous round)
                     for (uint32_t k = 0; k <= n_in; ++k) {
@@ -1246,6 +1414,7 @@ struct Compiler {
                         } else {
                             curve_final(idx, pts, ox, oy, flags, false, NONE, NONE);
                         }
+                        release_pinned(h1[k], 3);   // read for the last time by this round's finaliser
                     }
                     if (!known[ox]) mark_assigned(ox, idx);
                     if (!known[oy]) mark_assigned(oy, idx);
@@ -1535,7 +1704,7 @@ struct Cursor {
         return v;
     }
 };
-constexpr uint64_t kPlanMagic = 0x3130304e414c5042ULL;  // "BPLAN001"
+constexpr uint64_t kPlanMagic = 0x3230304e414c5042ULL;  // "BPLAN002"
 }  // namespace
 
 std::vector<uint8_t> serialize_plan(const Plan& p) {

@@ -99,6 +99,7 @@ struct PlanStats {
     uint64_t n_temps = 0;
     uint64_t n_gate_general = 0;   // value-dependent gates resolved per lane
     uint64_t n_directive = 0, n_memory = 0, n_brillig = 0;
+    uint64_t n_brillig_device = 0;   // Brillig opcodes lowered to device gates (no host segment)
 };
 
 // The opcode list is cut into segments: device segments are step ranges of the record stream; a host segment is one
@@ -139,6 +140,15 @@ struct PlanOptions {
     uint32_t chunk_steps = 2;
     uint32_t temp_pool = 2048;
     bool split_curve = true;   // lower FixedBaseScalarMul / Pedersen into parallel partial-sum micro-ops when S >= 8
+    // BlackBoxFuncCall::Pedersen is REFUSED unless this is set: barretenberg's generator tables cannot be reproduced from
+    // the reference tree (both reference KATs fail), so the kernel computes the plookup-structured
+    // commitment over this project's own generators -- benchmarks and structure tests opt in, a drop-in caller must not
+    // receive a different hash behind the reference's opcode tag.
+    bool allow_unpinned_pedersen = false;
+    // Lower Brillig opcodes whose bytecode is straight-line field arithmetic (Const / Mov / BinaryFieldOp Add, Sub, Mul /
+    // Stop -- the stdlib's `bytecode: vec![Stop]` constant loads, stdlib/src/blackbox_fallbacks/uint.rs:51-63,85) to device
+    // gates at plan time instead of a host segment each.
+    bool device_brillig = true;
 };
 
 // Throws std::runtime_error for opcodes outside the device scope.

@@ -42,6 +42,8 @@ struct acvmb_ctx {
     uint32_t opt_S = 0;   // 0 = auto: 16, or 8 for circuits with curve calls (see circuit_from_struct)
     uint32_t opt_chunk_steps = 2;
     uint32_t opt_split_curve = 1, opt_temp_pool = 0;
+    uint32_t opt_device_brillig = 1;
+    uint32_t opt_pedersen_unpinned = 0;   // 1: accept Pedersen opcodes / acvmb_pedersen although parity with barretenberg is unpinned
     int opt_split = -1;
     uint32_t opt_n_stage = 4;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
@@ -141,6 +143,12 @@ struct acvmb_vm {
     std::vector<uint8_t> present;     // dense [num_witnesses] after solve
     std::vector<uint32_t> assign;
     bool solved_once = false;
+    // ACVM::solve_opcode (mod.rs:243-303) steps one opcode at a time.  The device executes a re-ordered schedule of the whole
+    // circuit, so the mirror solves once and then walks `ip` over the already-solved state: a witness is visible once the
+    // opcode that assigns it is behind ip, the recorded outcome is reported when ip reaches its opcode.
+    acvmb_status final_status{ACVMB_IN_PROGRESS, 0, 0, 0};
+    uint32_t ip = 0;
+    std::vector<uint32_t> mu;         // instance 0 of the per-lane "assigned by opcode" table (value-dependent witnesses)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -207,6 +215,8 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "split_curve") ctx->opt_split_curve = (uint32_t)value;
     else if (k == "cache_batch") { ctx->opt_cache_batch = (uint32_t)value; if (!value) drop_cached_batch(ctx); }
     else if (k == "temp_pool") ctx->opt_temp_pool = (uint32_t)value;
+    else if (k == "pedersen_unpinned") ctx->opt_pedersen_unpinned = value ? 1u : 0u;
+    else if (k == "device_brillig") ctx->opt_device_brillig = value ? 1u : 0u;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
@@ -274,6 +284,8 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     opt.chunk_steps = ctx->opt_chunk_steps;
     opt.split_curve = ctx->opt_split_curve != 0;
     if (ctx->opt_temp_pool) opt.temp_pool = ctx->opt_temp_pool;
+    opt.allow_unpinned_pedersen = ctx->opt_pedersen_unpinned != 0;
+    opt.device_brillig = ctx->opt_device_brillig != 0;
     std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
     try {
         c->plan = compile_plan(circ, inputs, opt);
@@ -343,6 +355,10 @@ extern "C" int acvmb_circuit_info(const acvmb_circuit* c, acvmb_plan_info* o) {
     o->static_fail_opcode = p.static_fail.opcode;
     o->static_fail_kind = p.static_fail.kind;
     o->static_fail_aux = p.static_fail.aux;
+    o->n_segments = (uint32_t)p.segments.size();
+    for (auto& sg : p.segments) o->n_host_segments += sg.kind != 0;
+    o->n_brillig = (uint32_t)p.stats.n_brillig;
+    o->n_brillig_device = (uint32_t)p.stats.n_brillig_device;
     return ACVMB_OK;
 }
 
@@ -987,6 +1003,8 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
         // The batch does not fit HBM at once and every sub-batch's witness map goes back over PCIe (~55 GB/s), which takes
         // ~10x longer than solving it.  Two column buffers of half the resident size: while sub-batch k drains (gather + D2H
         // on their own streams), the VM kernel of sub-batch k+1 runs on the VM stream.
+        // resident_instances() budgeted the cached column buffers of an earlier call as free memory: release them first
+        drop_cached_batch(c->ctx);
         uint32_t half = ((resident / 2) / T) * T;
         acvmb_batch* bufs[2] = {nullptr, nullptr};
         uint32_t caps[2] = {0, 0};
@@ -1100,24 +1118,64 @@ extern "C" void acvmb_vm_destroy(acvmb_vm* vm) {
     delete vm;
 }
 
+static int vm_ensure_solved(acvmb_vm* vm) {
+    if (vm->solved_once) return ACVMB_OK;
+    vm->witness.assign((size_t)vm->c->plan.num_witnesses * 32, 0);
+    vm->present.assign((size_t)vm->c->plan.num_witnesses, 0);
+    acvmb_batch* b = nullptr;
+    int rc = acvmb_batch_create(vm->c, 1, &b);
+    if (rc) return rc;
+    rc = acvmb_batch_upload(b, vm->inputs.data());
+    if (!rc) rc = acvmb_batch_run(b, nullptr);
+    if (!rc) rc = acvmb_batch_status(b, &vm->final_status);
+    if (!rc) rc = acvmb_batch_download_ex(b, 0, 1, nullptr, 0, vm->witness.data(), vm->present.data());
+    vm->mu.assign(vm->c->plan.n_mu, 0xFFFFFFFFu);
+    if (!rc && vm->c->plan.n_mu) {   // lane 0 of tile 0: stride T words
+        std::vector<uint32_t> all((size_t)vm->c->plan.n_mu * b->T);
+        cudaError_t e = cudaMemcpy(all.data(), b->d_mu, all.size() * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_err(ACVMB_ERR_CUDA, cudaGetErrorString(e));
+        else for (uint32_t m = 0; m < vm->c->plan.n_mu; ++m) vm->mu[m] = all[(size_t)m * b->T];
+    }
+    vm->fc_pending = b->fc_pending && vm->final_status.code == ACVMB_REQUIRES_FOREIGN_CALL;
+    vm->fc_function = b->fc_function;
+    vm->fc_inputs = b->fc_inputs;
+    acvmb_batch_destroy(b);
+    if (rc) return rc;
+    vm->solved_once = true;
+    return ACVMB_OK;
+}
+// opcodes [0, vm_limit) execute successfully; the recorded outcome belongs to opcode vm_limit
+static uint32_t vm_limit(const acvmb_vm* vm) {
+    return vm->final_status.code == ACVMB_SOLVED ? vm->c->plan.n_opcodes : vm->final_status.opcode_index;
+}
+
 extern "C" int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out) {
     if (!vm) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
-    if (!vm->solved_once) {
-        vm->witness.assign((size_t)vm->c->plan.num_witnesses * 32, 0);
-        vm->present.assign((size_t)vm->c->plan.num_witnesses, 0);
-        acvmb_batch* b = nullptr;
-        int rc = acvmb_batch_create(vm->c, 1, &b);
+    if (vm->c->plan.n_opcodes) {   // ACVM::new is already Solved without opcodes (mod.rs:147)
+        int rc = vm_ensure_solved(vm);
         if (rc) return rc;
-        rc = acvmb_batch_upload(b, vm->inputs.data());
-        if (!rc) rc = acvmb_batch_run(b, nullptr);
-        if (!rc) rc = acvmb_batch_status(b, &vm->status);
-        if (!rc) rc = acvmb_batch_download_ex(b, 0, 1, nullptr, 0, vm->witness.data(), vm->present.data());
-        vm->fc_pending = b->fc_pending && vm->status.code == ACVMB_REQUIRES_FOREIGN_CALL;
-        vm->fc_function = b->fc_function;
-        vm->fc_inputs = b->fc_inputs;
-        acvmb_batch_destroy(b);
-        if (rc) return rc;
-        vm->solved_once = true;
+        vm->status = vm->final_status;
+        vm->ip = vm_limit(vm);
+    }
+    if (out) *out = vm->status;
+    return ACVMB_OK;
+}
+
+// ACVM::solve_opcode (acvm/src/pwg/mod.rs:243-303): execute the opcode at the instruction pointer.  Solved: the reference
+// indexes past the end of `opcodes` and panics -> ACVMB_ERR_STATE.  Failure / an unresolved foreign call: the same opcode is
+// attempted again with the same outcome.
+extern "C" int acvmb_vm_solve_opcode(acvmb_vm* vm, acvmb_status* out) {
+    if (!vm) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (vm->status.code == ACVMB_SOLVED) return set_err(ACVMB_ERR_STATE, "no opcode left to solve (the reference panics on the index)");
+    int rc = vm_ensure_solved(vm);
+    if (rc) return rc;
+    const uint32_t limit = vm_limit(vm), n_op = vm->c->plan.n_opcodes;
+    if (vm->ip < limit) {
+        ++vm->ip;
+        if (vm->ip == n_op) vm->status = vm->final_status;   // Solved (limit == n_opcodes only then)
+        else vm->status = acvmb_status{ACVMB_IN_PROGRESS, ACVMB_E_NONE, vm->ip, 0};
+    } else {
+        vm->status = vm->final_status;
     }
     if (out) *out = vm->status;
     return ACVMB_OK;
@@ -1131,7 +1189,7 @@ extern "C" int acvmb_vm_status(const acvmb_vm* vm, acvmb_status* out) {
 
 extern "C" int acvmb_vm_instruction_pointer(const acvmb_vm* vm, uint32_t* out) {
     if (!vm || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
-    *out = vm->solved_once ? vm->status.opcode_index : 0;
+    *out = vm->ip;
     return ACVMB_OK;
 }
 
@@ -1142,12 +1200,16 @@ extern "C" int acvmb_vm_num_witnesses(const acvmb_vm* vm, uint32_t* out) {
 }
 
 static bool vm_present(const acvmb_vm* vm, uint32_t w) {
-    if (vm->solved_once && !vm->present.empty()) return vm->present[w] != 0;
     uint32_t ao = vm->assign[w];
-    if (ao == 0xFFFFFFFEu) return true;
+    if (ao == 0xFFFFFFFEu) return true;                       // initial witness
     if (!vm->solved_once || ao == 0xFFFFFFFFu) return false;
-    uint32_t limit = vm->status.code == ACVMB_SOLVED ? 0xFFFFFFFFu : vm->status.opcode_index;
-    return ao < limit;
+    if (vm->ip >= vm_limit(vm)) return vm->present[w] != 0;   // every opcode that runs has run: the device's own answer
+    if (ao == 0xFFFFFFFDu) {                                  // value-dependent: this instance's "assigned by opcode" word
+        uint32_t m = vm->c->plan.mu_index_of[w];
+        ao = m < vm->mu.size() ? vm->mu[m] : 0xFFFFFFFFu;
+        if (ao == 0xFFFFFFFFu) return false;
+    }
+    return ao < vm->ip;
 }
 
 extern "C" int acvmb_vm_witness(const acvmb_vm* vm, uint32_t w, uint8_t out[32], int* present) {
@@ -1224,6 +1286,9 @@ extern "C" int acvmb_fixed_base_scalar_mul(acvmb_ctx* ctx, const uint8_t* low, c
 extern "C" int acvmb_pedersen(acvmb_ctx* ctx, const uint8_t* inputs, uint32_t n_inputs, uint32_t batch, uint32_t domain_separator,
                               uint8_t* out_xy, acvmb_status* st) {
     if (!ctx || (!inputs && n_inputs) || !out_xy) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    if (!ctx->opt_pedersen_unpinned)
+        return set_err(ACVMB_ERR_UNSUPPORTED, "acvmb_pedersen: parity with barretenberg's generator tables is unpinned (both reference KATs "
+                                              "fail); set the context option pedersen_unpinned=1 to run the structurally identical kernel");
     Opcode op;
     op.kind = OP_BlackBox;
     op.bb.func = BB_Pedersen;
@@ -1319,8 +1384,9 @@ extern "C" int acvmb_imad_microbench(acvmb_ctx* ctx, double* a, double* b, doubl
 // host-only entry point (no device needed): decode + compile, return info and the plan blob.
 // Used by the CPU test-suite to check the decoder and the plan compiler without a GPU.
 // ---------------------------------------------------------------------------------------------
-extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
-                                       acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed) {
+extern "C" int acvmb_plan_compile_host_ex(const uint8_t* gz, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
+                                          uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap,
+                                          size_t* needed) {
     if (!gz || (n_inputs && !input_witnesses)) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     Circuit circ;
     try {
@@ -1331,6 +1397,9 @@ extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint
     acvmb_circuit tmp;
     PlanOptions opt;
     opt.S = S ? S : 16;
+    if (temp_pool) opt.temp_pool = temp_pool;
+    opt.allow_unpinned_pedersen = (flags & 1u) != 0;
+    opt.device_brillig = (flags & 2u) == 0;
     try {
         tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);
     } catch (const std::exception& e) {
@@ -1346,6 +1415,10 @@ extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint
         }
     }
     return ACVMB_OK;
+}
+extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
+                                       acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed) {
+    return acvmb_plan_compile_host_ex(gz, len, input_witnesses, n_inputs, S, 0, 0, info, blob, cap, needed);
 }
 
 extern "C" int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3) {
@@ -1477,6 +1550,7 @@ extern "C" int acvmb_vm_resolve_foreign_call(acvmb_vm* vm, uint32_t n_outputs, c
     op.brillig.foreign_call_results.push_back(std::move(res));
     vm->fc_pending = false;
     vm->solved_once = false;
+    vm->ip = vm->status.opcode_index;   // the Brillig opcode is attempted again (mod.rs:214-228)
     vm->status = acvmb_status{ACVMB_IN_PROGRESS, 0, vm->status.opcode_index, 0};
     return ACVMB_OK;
 }

@@ -85,6 +85,10 @@ typedef struct {
     uint64_t n_temps;
     uint32_t num_witnesses, n_slots, S, needs_full_kernel;
     uint32_t static_fail_present, static_fail_opcode, static_fail_kind, static_fail_aux;
+    uint32_t n_segments;        /* device + host segments of the plan */
+    uint32_t n_host_segments;   /* host segments: Brillig opcodes that need the host VM, PermutationSort directives */
+    uint32_t n_brillig;         /* Brillig opcodes in the circuit */
+    uint32_t n_brillig_device;  /* ... of which lowered to device gates at plan time (straight-line field bytecode) */
 } acvmb_plan_info;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -151,6 +155,11 @@ int acvmb_vm_new(acvmb_ctx* ctx, const uint8_t* gz_bincode, size_t len, const ui
                  const uint8_t* witness_be32, uint32_t n_initial, acvmb_vm** out);
 void acvmb_vm_destroy(acvmb_vm* vm);
 int acvmb_vm_solve(acvmb_vm* vm, acvmb_status* out);                         /* ACVM::solve */
+/* ACVM::solve_opcode (acvm/src/pwg/mod.rs:243-303): one opcode per call.  The device runs a re-ordered schedule of the whole
+ * circuit, so the first call solves everything and each call then advances the instruction pointer over the solved state:
+ * status, instruction_pointer and the witnesses visible through acvmb_vm_witness are those the reference has after the same
+ * number of solve_opcode calls.  ACVMB_ERR_STATE once Solved (the reference indexes past `opcodes` and panics). */
+int acvmb_vm_solve_opcode(acvmb_vm* vm, acvmb_status* out);
 int acvmb_vm_status(const acvmb_vm* vm, acvmb_status* out);                  /* ACVM::get_status */
 int acvmb_vm_instruction_pointer(const acvmb_vm* vm, uint32_t* out);         /* ACVM::instruction_pointer */
 int acvmb_vm_num_witnesses(const acvmb_vm* vm, uint32_t* out);
@@ -194,6 +203,10 @@ int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg, cons
 /* ---- host-only: decode + compile without a device (CPU tests of the decoder / plan compiler) ---- */
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
+/* same with plan options: temp_pool (0 = default), flags bit 0 = accept Pedersen (parity unpinned, see "pedersen_unpinned"),
+ * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates) */
+int acvmb_plan_compile_host_ex(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
+                               uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
 int acvmb_pedersen_generator_host(uint32_t index, uint8_t out_xy_be32[64]);
 
@@ -215,7 +228,9 @@ int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);
 /* wide IMADs per second of three carry-OUT-only forms: [0] + addc capture per product, [1] carry dropped, [2] chains of two */
 int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step), "chunk_steps", "n_stage", "split", "max_resident_bytes",
- * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "cache_batch" (0: free
+ * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "pedersen_unpinned" (1: accept
+ * BlackBoxFuncCall::Pedersen / acvmb_pedersen although the values are NOT barretenberg's -- refused by default),
+ * "device_brillig" (0: every Brillig opcode runs on the host VM), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
  * identical next call); plan options apply to circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);

@@ -27,6 +27,16 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="session")
+def pctx():
+    """Context that opted in to the Pedersen kernel (parity with barretenberg unpinned: refused by default)."""
+    import acvm_b200
+    c = acvm_b200.Context(0)
+    c.set_option("pedersen_unpinned", 1)
+    yield c
+    c.close()
+
+
 def inputs_to_dicts(inp: bytes, batch: int, input_witnesses):
     n = len(input_witnesses)
     return [{w: int.from_bytes(inp[(i * n + k) * 32:(i * n + k + 1) * 32], "big") for k, w in enumerate(input_witnesses)}

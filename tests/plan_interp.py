@@ -24,12 +24,12 @@ class PlanBlob:
         o = 0
         magic, = struct.unpack_from("<Q", blob, o)
         o += 8
-        assert magic == 0x3130304E414C5042, "bad magic"
+        assert magic == 0x3230304E414C5042, "bad magic"
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
          self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
         o += 48
-        self.stats = struct.unpack_from("<19Q", blob, o)
-        o += 152
+        self.stats = struct.unpack_from("<20Q", blob, o)   # PlanStats (plan.hpp), a POD of 20 u64
+        o += 160
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):

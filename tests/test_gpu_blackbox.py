@@ -152,7 +152,20 @@ def test_mixed_circuit_config4_style(ctx):
     _check_circuit(ctx, data, list(range(1, 9)), batch, inp)
 
 
-def test_pedersen_vs_oracle(ctx):
+def test_pedersen_refused_by_default(ctx, golden):
+    """Both reference KATs fail (barretenberg's generators are not reproducible here), so a default context must refuse the
+    opcode and the trait call loudly instead of returning another function's hash behind the reference's tag."""
+    fx = golden["acvm_js_shared"]["pedersen"]
+    with pytest.raises(acvm_b200.AcvmError) as e:
+        acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
+    assert e.value.rc == -5 and "pedersen_unpinned" in str(e.value)
+    with pytest.raises(acvm_b200.AcvmError) as e:
+        ctx.pedersen([[0, 1]], 0)
+    assert e.value.rc == -5
+
+
+def test_pedersen_vs_oracle(pctx):
+    ctx = pctx
     from oracle import pedersen
     rnd = random.Random(8)
     cases = [[0, 1], [1, 0], [F.P - 1, F.P - 2], [rnd.randrange(F.P), rnd.randrange(F.P)], [(1 << 9) - 1, 1 << 252]]
@@ -167,19 +180,21 @@ def test_pedersen_vs_oracle(ctx):
         assert pts == [pedersen.commit_native(c, iv) for c in cases]
 
 
-def test_pedersen_golden_circuit_runs(ctx, golden):
-    # acvm_js/test/shared/pedersen.ts: the circuit bytes decode and solve; the VALUES are those of this project's
-    # documented generator derivation (parity with barretenberg's tables is unpinned, see oracle/pedersen.py)
-    from oracle import pedersen
+@pytest.mark.xfail(strict=True, reason="Pedersen parity unpinned: barretenberg v0.5.0's generator derivation could not be "
+                                       "reproduced (tools/pedersen_generator_search*.py); the opcode is opt-in only")
+def test_pedersen_golden_circuit_matches_reference(pctx, golden):
+    # acvm_js/test/shared/pedersen.ts: expectedWitnessMap {2: x, 3: y} of Pedersen([w1 = 1], domain 0) -- the reference's value
     fx = golden["acvm_js_shared"]["pedersen"]
-    vm = acvm_b200.ACVM(ctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
+    want = next(k for k in golden["kats"]["pedersen"] if k["inputs"] == [1])
+    vm = acvm_b200.ACVM(pctx, bytes(fx["bytecode"]), {int(k): int(v, 16) for k, v in fx["initialWitnessMap"].items()})
     assert vm.solve().status == "Solved"
     wm = vm.finalize()
-    assert (wm[2], wm[3]) == pedersen.commit_native([1], 0)
     assert grumpkin.on_curve((wm[2], wm[3]))
+    assert (wm[2], wm[3]) == (int(want["x"], 16), int(want["y"], 16))
 
 
-def test_pedersen_chain_circuit(ctx):
+def test_pedersen_chain_circuit(pctx):
+    ctx = pctx
     # BASELINE config 2 shape, tiny: chained Pedersen{[prev.x, fresh_i]}
     b = ab.CircuitBuilder()
     prev = 1
@@ -252,6 +267,7 @@ def test_curve_ops_every_tile_shape_and_lowering(T, S, split):
     ctx = acvm_b200.Context(0)
     try:
         ctx.set_option("T", T); ctx.set_option("S", S); ctx.set_option("split_curve", split)
+        ctx.set_option("pedersen_unpinned", 1)
         b = ab.CircuitBuilder()
         b.pedersen([(1, 254), (2, 254)], 0, (10, 11))
         b.pedersen([(10, 254), (3, 254)], 7, (12, 13))

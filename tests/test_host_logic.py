@@ -34,8 +34,8 @@ def test_no_gpu_means_loud_failure():
     assert e.value.rc == -2 and "no CPU fallback" in str(e.value)
 
 
-def _interp_vs_oracle(data, inputs, inp, batch, S=16):
-    info, blob = acvm_b200.compile_plan_host(data, inputs, S)
+def _interp_vs_oracle(data, inputs, inp, batch, S=16, **plan_options):
+    info, blob = acvm_b200.compile_plan_host(data, inputs, S, **plan_options)
     plan = plan_interp.PlanBlob(blob)
     oc = acir.decode_circuit(data)
     n = len(inputs)
@@ -605,7 +605,10 @@ def test_curve_ops_monolithic_and_split_plans_vs_oracle(S):
     b.arithmetic([(1, 20, 21)], [(1, 16), (ab.P - 1, 24)], 0)
     b.fixed_base_scalar_mul((1, 254), (19, 128), (22, 23))   # low limb >= 2^128 in the random rows: BlackBoxFunctionFailed
     data = b.to_bytes()
-    info = _interp_vs_oracle(data, [1, 2, 3], ab.synthetic_inputs(3, n_inputs=3, seed_id=9), 3, S=S)
+    with pytest.raises(acvm_b200.AcvmError) as e:      # Pedersen is opt-in: parity with barretenberg's tables is unpinned
+        acvm_b200.compile_plan_host(data, [1, 2, 3], S)
+    assert e.value.rc == -5 and "pedersen_unpinned" in str(e.value)
+    info = _interp_vs_oracle(data, [1, 2, 3], ab.synthetic_inputs(3, n_inputs=3, seed_id=9), 3, S=S, pedersen_unpinned=True)
     assert info["n_curve"] == 6 and (info["n_micro_ops"] > 100) == (S >= 8)
     b = ab.CircuitBuilder()
     b.fixed_base_scalar_mul((1, 128), (2, 128), (4, 3))      # y is pre-assigned: insert_value compares
@@ -613,3 +616,60 @@ def test_curve_ops_monolithic_and_split_plans_vs_oracle(S):
     g5 = grumpkin.fixed_base_scalar_mul(5, 0)
     rows = [[0, 0, 0], [5, 0, g5[1]], [1 << 128, 0, 7]]
     _interp_vs_oracle(b.to_bytes(), [1, 2, 3], b"".join(int(v).to_bytes(32, "big") for r in rows for v in r), 3, S=S)
+
+
+def test_values_that_outlive_the_temporary_pool():
+    """Round-1 advisor finding: the round-robin temporaries wrapped over values that were still live (Brillig inputs wait for
+    their host segment, the H1 points of a Pedersen call for their chaining round).  Such values now get dedicated slots."""
+    # 2100 expression inputs (> the 2048-slot pool) to a host-VM Brillig op; outputs = the first three inputs
+    b = ab.CircuitBuilder()
+    b.brillig([("Array", [([], [(1, 1)], i + 1) for i in range(2100)])], [("Array", [10, 11, 12])], [dict(op="Stop")])
+    data = b.to_bytes()
+    for dev in (False, True):
+        info, blob = acvm_b200.compile_plan_host(data, [1], 16, device_brillig=dev)
+        assert info["n_host_segments"] == (0 if dev else 1)
+        st, wm = plan_interp.run_plan(plan_interp.PlanBlob(blob), {1: 5}, circuit=acir.decode_circuit(data))
+        assert st[0] == "Solved" and (wm[10], wm[11], wm[12]) == (6, 7, 8)
+    # Pedersen with enough inputs for the H1 partial sums to wrap a small pool several times
+    b = ab.CircuitBuilder()
+    b.pedersen([(1 + (k % 3), 254) for k in range(24)], 2, (10, 11))
+    info = _interp_vs_oracle(b.to_bytes(), [1, 2, 3], ab.synthetic_inputs(1, n_inputs=3, seed_id=12), 1, S=8, temp_pool=96,
+                             pedersen_unpinned=True)
+    assert info["n_micro_ops"] > 24 * 15
+
+
+def test_straight_line_brillig_is_lowered_to_device_gates():
+    """stdlib emits `bytecode: vec![Stop]` constant loads and one-instruction field ops by the thousand
+    (stdlib/src/blackbox_fallbacks/uint.rs:51-63,85, hash_to_field.rs:107): no host segment for those."""
+    b = ab.CircuitBuilder()
+    b.brillig([("Single", ([], [], 1 << 32))], [("Simple", 10)], [dict(op="Stop")])                   # load_constant
+    b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", 11)],
+              [dict(op="BinaryFieldOp", destination=0, bop=0, lhs=0, rhs=1)])                         # runs off the end: Finished
+    b.brillig([("Single", ab.wexpr(1)), ("Single", ([(3, 1, 2)], [(1, 10)], 7)), ("Array", [ab.wexpr(3), ab.wexpr(11)])],
+              [("Simple", 12), ("Array", [13, 14]), ("Simple", 15), ("Simple", 16)], [
+        dict(op="BinaryFieldOp", destination=3, bop=2, lhs=0, rhs=1),       # r3 = r0 * r1
+        dict(op="Const", destination=4, value=9),
+        dict(op="BinaryFieldOp", destination=0, bop=1, lhs=3, rhs=4),       # r0 = r3 - 9
+        dict(op="Mov", destination=1, source=2),                            # r1 = pointer to the input array (0)
+        dict(op="BinaryFieldOp", destination=2, bop=1, lhs=0, rhs=0),       # r2 = 0
+        dict(op="Stop"),
+        dict(op="Trap"),
+    ])
+    b.arithmetic([], [(1, 12), (1, 13), (ab.P - 1, 17)], 0)
+    # an output that is already assigned is compared (insert_value): w11 again, equal by construction; then a mismatch
+    b.brillig([("Single", ab.wexpr(11))], [("Simple", 11)], [dict(op="Stop")])
+    b.brillig([("Single", ab.wexpr(3))], [("Simple", 1)], [dict(op="Stop")])                          # fails unless w3 == w1
+    data = b.to_bytes()
+    rows = [(5, 6, 9), (0, 0, 0), (7, 8, 7), (ab.P - 1, 2, 3)]
+    inp = b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+    info = _interp_vs_oracle(data, [1, 2, 3], inp, len(rows))
+    assert info["n_brillig"] == 5 and info["n_brillig_device"] == 5 and info["n_host_segments"] == 0
+    info = _interp_vs_oracle(data, [1, 2, 3], inp, len(rows), device_brillig=False)
+    assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 5
+    # not straight-line field code (integer op, predicate): stays on the host VM
+    b = ab.CircuitBuilder()
+    b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", 10)],
+              [dict(op="BinaryIntOp", destination=0, bop=0, bit_size=127, lhs=0, rhs=1)])
+    b.brillig([("Single", ab.wexpr(1))], [("Simple", 11)], [dict(op="Stop")], predicate=ab.wexpr(2))
+    info = _interp_vs_oracle(b.to_bytes(), [1, 2], inp[:64] + inp[96:160], 2)
+    assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 2

@@ -151,16 +151,19 @@ def test_cpp_restatement_matches_python_oracle():
     assert list(res[0]) == [2, 4, 1, 0] and res[1, 0] == 0
 
 
-def test_pedersen_kats_unpinned(golden):
-    """Records the parity status honestly: the reference's two Pedersen KATs are on the curve, and the oracle's
-    structure-restatement (own generator derivation) does NOT reproduce them -- parity is unpinned for this row."""
+def test_pedersen_kats_are_curve_points(golden):
+    for k in golden["kats"]["pedersen"]:
+        assert grumpkin.on_curve((int(k["x"], 16), int(k["y"], 16)))
+
+
+@pytest.mark.xfail(strict=True, reason="Pedersen parity unpinned: the oracle restates the STRUCTURE over its own generators; "
+                                       "barretenberg's derivation could not be reproduced (tools/pedersen_generator_search*.py)")
+def test_pedersen_kats(golden):
+    """The reference's two Pedersen KATs (wasm/pedersen.rs:38-54, acvm_js/test/shared/pedersen.ts:8-16).  Strict xfail: the day
+    the oracle reproduces them this test XPASSes, fails the suite, and the opt-in gate (pedersen_unpinned) can be removed."""
     from oracle import pedersen
     for k in golden["kats"]["pedersen"]:
-        ref_pt = (int(k["x"], 16), int(k["y"], 16))
-        assert grumpkin.on_curve(ref_pt)
-        ours = pedersen.commit_native(k["inputs"], k["hash_index"])
-        assert grumpkin.on_curve(ours)
-        assert ours != ref_pt  # if this ever fails, parity has become pinned: update DESIGN.md
+        assert pedersen.commit_native(k["inputs"], k["hash_index"]) == (int(k["x"], 16), int(k["y"], 16))
 
 
 def test_pedersen_structure():
