@@ -25,7 +25,8 @@ class PlanInfo(C.Structure):
         "n_opcodes", "n_micro_ops", "n_steps", "n_slots_filled", "n_gate_assign", "n_gate_check", "n_logic", "n_range",
         "n_hash", "n_curve", "ref_fr_mul", "ref_fr_inv", "dev_imad", "alg_bytes", "n_temps")] + [(n, C.c_uint32) for n in (
         "num_witnesses", "n_slots", "S", "needs_full_kernel", "static_fail_present", "static_fail_opcode",
-        "static_fail_kind", "static_fail_aux", "n_segments", "n_host_segments", "n_brillig", "n_brillig_device")]
+        "static_fail_kind", "static_fail_aux", "n_segments", "n_host_segments", "n_brillig", "n_brillig_device")] + [("n_gate_one_reduction", C.c_uint64),
+                                                                                  ("scaled_columns", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

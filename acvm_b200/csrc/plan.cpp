@@ -220,6 +220,9 @@ class Scheduler {
     uint32_t floor_ = 0;
 };
 
+// thrown when a value-dependent gate meets a scaled column: compile_plan() starts over with canonical columns
+struct NeedsCanonicalColumns {};
+
 struct Compiler {
     const Circuit& c;
     PlanOptions opt;
@@ -250,6 +253,7 @@ struct Compiler {
     uint32_t new_temp() {
         uint32_t t = temp_base + (temp_next % opt.temp_pool);
         ++temp_next;
+        set_canonical(t);   // whatever scale its previous value had
         return t;
     }
 
@@ -258,6 +262,7 @@ struct Compiler {
         if ((temp_next % opt.temp_pool) + 3 > opt.temp_pool) temp_next += opt.temp_pool - (temp_next % opt.temp_pool);
         uint32_t t = temp_base + (temp_next % opt.temp_pool);
         temp_next += 3;
+        for (uint32_t i = 0; i < 3; ++i) set_canonical(t + i);
         return t;
     }
 
@@ -273,6 +278,7 @@ struct Compiler {
         if (q.size() > min_queue) {
             uint32_t s = q.front();
             q.pop_front();
+            for (uint32_t i = 0; i < n; ++i) set_canonical(s + i);
             return s;
         }
         uint32_t s = extra_slots_base + extra_slots;
@@ -297,38 +303,85 @@ struct Compiler {
         plan.assign_opcode[w] = opcode;
     }
 
+    // ---- scaled columns ----------------------------------------------------------------------------------------------
+    // A column does not have to hold the canonical value w: it holds s_w = lambda_w * w for a plan-time constant lambda_w
+    // per slot -- Montgomery form (lambda = R for every value) generalised to one radix per column.  A gate
+    //     out = M*(x+alpha)*(y+beta) + sum L_i*w_i + G
+    // then needs ONE Montgomery reduction instead of two: with X' = s_x + alpha*lambda_x, Y' = s_y + beta*lambda_y,
+    //     s_out = ( X'*Y' + sum s_i*(C_i*R) + (lambda_out*G)*R ) / R,   lambda_out = lambda_x*lambda_y / (M*R),
+    //     C_i = lambda_out * L_i / lambda_i,
+    // i.e. the multiplication by the gate's own coefficient M is absorbed into the scale of the output column, and a linear
+    // term whose C_i is +-1 is a plain modular addition.  lambda and mu = 1/lambda are tracked with multiplications only
+    // (the inverses needed are of circuit constants, which the record/replay batch inversion serves).  Canonical bytes are
+    // produced where they are needed: the output gather multiplies by mu_w (Plan::unscale), and every column that a
+    // non-arithmetic micro-op reads directly (blackbox inputs, memory blocks, host segments) is forced to lambda = 1.
+    std::vector<U256> lam_, mu_;   // per slot; absent / never set = 1 (canonical)
+    std::vector<uint8_t> need_canon;   // per witness: read directly by a non-gate micro-op
+    bool scaled = false;
+    const U256& lam_of(uint32_t s) const { return s < lam_.size() ? lam_[s] : hf::consts().one; }
+    const U256& mu_of(uint32_t s) const { return s < mu_.size() ? mu_[s] : hf::consts().one; }
+    void set_scale(uint32_t s, const U256& l, const U256& m) {
+        if (!scaled) return;
+        if (s >= lam_.size()) {
+            if (l == hf::consts().one) return;
+            lam_.resize((size_t)s + 1, hf::consts().one);
+            mu_.resize((size_t)s + 1, hf::consts().one);
+        }
+        lam_[s] = l;
+        mu_[s] = m;
+    }
+    void set_canonical(uint32_t s) { set_scale(s, hf::consts().one, hf::consts().one); }
+    bool is_canonical(uint32_t s) const { return lam_of(s) == hf::consts().one; }
+
     // Lower  sum(products) + sum(linears) + constant  into chained micro-gates.
     // assign: write the value to `out`; otherwise CHECK it is zero.
     // out_check: `out` is already assigned -> compare instead of store (insert_value semantics).
-    // `k` scales the whole sum (k = -1/coeff of the unknown for ASSIGN gates).  Terms arrive UNSCALED so that the values
-    // handed to inv() never depend on another inverse (required by the record/replay batching of inversions).
+    // `k` scales the whole sum (k = -1/coeff of the unknown for ASSIGN gates; `kinv` = 1/k = -coeff comes for free).  Terms
+    // arrive UNSCALED so that the values handed to inv() never depend on another inverse (required by the record/replay
+    // batching of inversions).  canonical_out: the value is read by something other than a gate -> lambda_out = 1.
     void lower_sum(std::vector<Prod> prods, std::vector<Lin> lins, const U256& constant, bool assign, uint32_t out,
-                   uint32_t opcode, bool out_check, const U256* k = nullptr) {
+                   uint32_t opcode, bool out_check, const U256* k = nullptr, const U256* kinv = nullptr, bool canonical_out = false) {
         uint32_t acc = NONE;
-        const U256 one = hf::from_u64(1);
+        const U256 one = hf::from_u64(1), pm1 = hf::neg(one);
+        const U256 R = hf::consts().R, invR = hf::from_mont(one);
         auto sc = [&](const U256& v) { return k ? hf::mul(v, *k) : v; };
+        struct Term {   // linear operand: true coefficient L (k applied), slot, and what is needed to invert L
+            U256 L, Linv;
+            uint32_t w;
+        };
         bool first_gate = true;
         while (first_gate || !prods.empty() || !lins.empty()) {
             first_gate = false;
             OpRec r{};
             uint32_t flags = 0;
-            uint32_t x = NONE, y = NONE, w1 = NONE, w2 = NONE;
-            U256 cM, cY, c1, c2;
-            uint32_t reads[4];
-            size_t nr = 0;
-            uint64_t imad = 0;
-            U256 alpha, beta, gamma_part;
-            bool y_is_acc = false, w1_is_acc = false, w2_is_acc = false;
+            uint32_t x = NONE, y = NONE;
+            bool mul = false;
+            U256 M, Minv, alpha, beta, gamma_part;
+            std::vector<Term> terms;
+            auto push_acc = [&] {
+                terms.push_back(Term{one, one, acc});   // partial sums held in temporaries are already scaled by k
+                acc = NONE;
+            };
+            // the inverse of a linear coefficient is only ever used to choose lambda_out of a gate without a product
+            auto push_lin = [&](const Lin& l, bool want_inv) {
+                Term t{sc(l.c), U256{}, l.w};
+                if (want_inv) {
+                    if (l.c == one) t.Linv = one;
+                    else if (l.c == pm1) t.Linv = pm1;
+                    else t.Linv = inv(l.c);
+                    if (kinv) t.Linv = hf::mul(t.Linv, *kinv);
+                }
+                terms.push_back(t);
+            };
             if (!prods.empty()) {
-                // cM*x*y + cX*x + cY*y  ==  cM*(x + cY/cM)*(y + cX/cM) - cX*cY/cM : two Montgomery products
-                // instead of three; the x/y linear terms ride along as plan-time constants.
+                // cM*x*y + cX*x + cY*y  ==  cM*(x + cY/cM)*(y + cX/cM) - cX*cY/cM : the x/y linear terms ride along as
+                // plan-time constants
                 Prod p = prods.back();
                 prods.pop_back();
-                flags |= GF_MUL | GF_Y;
+                mul = true;
                 x = p.a;
                 y = p.b;
-                cM = p.c;
-                U256 cX;
+                U256 cX, cY;
                 for (size_t i = 0; i < lins.size(); ++i)
                     if (lins[i].w == y) {
                         cY = lins[i].c;
@@ -342,68 +395,132 @@ struct Compiler {
                             lins.erase(lins.begin() + i);
                             break;
                         }
-                if (!cX.is_zero() || !cY.is_zero()) {
-                    U256 invM = inv(cM);
+                const bool fold = !cX.is_zero() || !cY.is_zero();
+                U256 invM;
+                if (fold || scaled) invM = inv(p.c);
+                if (fold) {
                     alpha = hf::mul(cY, invM);
                     beta = hf::mul(cX, invM);
                     gamma_part = hf::neg(hf::mul(hf::mul(cX, cY), invM));
                 }
-                imad += 136;
-            } else if (acc != NONE) {
-                flags |= GF_Y;
-                y = acc;
-                cY = one;
-                y_is_acc = true;
-                acc = NONE;
-            } else if (!lins.empty()) {
-                flags |= GF_Y;
-                y = lins.back().w;
-                cY = lins.back().c;
-                lins.pop_back();
-            }
-            const uint32_t max_lin = (flags & GF_MUL) ? 1u : 2u;
-            uint32_t nlin = 0;
-            auto push_lin = [&](const U256& cc, uint32_t w) {
-                if (nlin == 0) {
-                    c1 = cc;
-                    w1 = w;
-                } else {
-                    c2 = cc;
-                    w2 = w;
+                M = sc(p.c);
+                Minv = kinv ? hf::mul(invM, *kinv) : invM;
+                if (acc != NONE) push_acc();
+                else if (!lins.empty()) {
+                    push_lin(lins.back(), false);
+                    lins.pop_back();
                 }
-                ++nlin;
-            };
-            if (acc != NONE && nlin < max_lin) {
-                (nlin == 0 ? w1_is_acc : w2_is_acc) = true;
-                push_lin(one, acc);
-                acc = NONE;
+            } else {
+                if (acc != NONE) push_acc();
+                while (terms.size() < 3 && !lins.empty()) {
+                    push_lin(lins.back(), scaled);
+                    lins.pop_back();
+                }
             }
-            while (nlin < max_lin && !lins.empty() && acc == NONE) {
-                push_lin(lins.back().c, lins.back().w);
-                lins.pop_back();
-            }
-            bool final_gate = prods.empty() && lins.empty() && acc == NONE;
-            flags |= nlin << GF_NLIN_SHIFT;
-            uint32_t kind;
-            uint32_t dst = NONE;
-            // apply the scale: partial sums held in temporaries are already scaled, everything else is not
-            cM = sc(cM);
-            if (!y_is_acc) cY = sc(cY);
-            if (!w1_is_acc) c1 = sc(c1);
-            if (!w2_is_acc) c2 = sc(c2);
-            U256 c4 = sc(gamma_part);
+            const bool final_gate = prods.empty() && lins.empty() && acc == NONE;
+            U256 G = sc(gamma_part);
+            uint32_t kind, dst = NONE;
             if (final_gate) {
                 kind = assign ? MK_GATE_ASSIGN : MK_GATE_CHECK;
                 if (assign) {
                     dst = out;
                     if (out_check) flags |= GF_OUT_CHECK;
                 }
-                c4 = hf::add(c4, sc(constant));
+                G = hf::add(G, sc(constant));
             } else {
                 kind = MK_GATE_ASSIGN;
                 dst = new_temp();
                 ++plan.stats.n_temps;
             }
+            // ---- scale of the output column ----
+            bool forced = !scaled;
+            U256 lo = one, mo = one;   // lambda_out, mu_out
+            if (scaled && final_gate && assign) {
+                if (out_check) {
+                    forced = true;
+                    lo = lam_of(out);
+                    mo = mu_of(out);
+                } else if (canonical_out || (out < need_canon.size() && need_canon[out])) {
+                    forced = true;
+                }
+            }
+            if (!forced) {
+                if (mul) {   // absorb M: the product enters the reduction with coefficient 1
+                    lo = hf::mul(hf::mul(hf::mul(lam_of(x), lam_of(y)), Minv), invR);
+                    mo = hf::mul(hf::mul(hf::mul(mu_of(x), mu_of(y)), M), R);
+                } else if (!terms.empty()) {
+                    // lambda_out = lambda_i / L_i turns term i into a plain addition; keep the candidate that turns the most
+                    // terms into additions (uniformly scaled operands with +-1 coefficients all become additions)
+                    int best = -1;
+                    for (size_t c = 0; c < terms.size(); ++c) {
+                        U256 cl = hf::mul(lam_of(terms[c].w), terms[c].Linv);
+                        int n_add = 0;
+                        for (auto& t : terms) {
+                            U256 C = hf::mul(hf::mul(cl, t.L), mu_of(t.w));
+                            n_add += (C == one || C == pm1);
+                        }
+                        if (n_add > best) {
+                            best = n_add;
+                            lo = cl;
+                            mo = hf::mul(mu_of(terms[c].w), terms[c].L);
+                        }
+                    }
+                }
+            }
+            // ---- stored-value coefficients ----
+            bool one_red = false;
+            U256 coefM;
+            if (mul) {
+                coefM = hf::mul(hf::mul(lo, M), hf::mul(mu_of(x), mu_of(y)));
+                one_red = scaled && coefM == invR;
+                alpha = hf::mul(alpha, lam_of(x));
+                beta = hf::mul(beta, lam_of(y));
+            }
+            struct Operand {
+                U256 C;
+                uint32_t w;
+                bool add, neg;
+            };
+            std::vector<Operand> ops;
+            for (auto& t : terms) {
+                Operand o{hf::mul(hf::mul(lo, t.L), mu_of(t.w)), t.w, false, false};
+                if (o.C == one) o.add = true;
+                else if (o.C == pm1) o.add = o.neg = true;
+                if (!o.C.is_zero()) ops.push_back(o);   // (a zero coefficient can only come from a dummy inverse of the record pass)
+                else ops.push_back(Operand{one, t.w, true, false});
+            }
+            std::stable_sort(ops.begin(), ops.end(), [](const Operand& a, const Operand& b) { return !a.add && b.add; });
+            uint32_t nprod = 0;
+            for (auto& o : ops) nprod += !o.add;
+            const uint32_t K = (mul ? 1u : 0u) + nprod;
+            U256 Gs = hf::mul(lo, G);
+            uint32_t w1 = NONE, w2 = NONE;
+            if (mul) {
+                flags |= GF_MUL | GF_Y;
+                if (one_red) flags |= GF_ONE_RED;
+                if (!ops.empty()) w1 = ops[0].w;
+                flags |= (uint32_t)ops.size() << GF_NLIN_SHIFT;
+                if (!ops.empty() && ops[0].neg) flags |= GF_NEG_W1;
+                if (!one_red) put(r.c[0], hf::to_mont2(coefM));
+                put(r.c[1], alpha);
+                put(r.c[2], beta);
+                if (!ops.empty() && !ops[0].add) put(r.c[3], hf::to_mont(ops[0].C));
+            } else if (!ops.empty()) {
+                flags |= GF_Y;
+                y = ops[0].w;
+                if (ops.size() > 1) w1 = ops[1].w;
+                if (ops.size() > 2) w2 = ops[2].w;
+                flags |= (uint32_t)(ops.size() - 1) << GF_NLIN_SHIFT;
+                const uint32_t negbit[3] = {GF_NEG_Y, GF_NEG_W1, GF_NEG_W2};
+                for (size_t i = 0; i < ops.size(); ++i) {
+                    if (ops[i].neg) flags |= negbit[i];
+                    if (!ops[i].add) put(r.c[1 + i], hf::to_mont(ops[i].C));
+                }
+                if (nprod == 0) flags |= GF_ADDSUB;
+            }
+            flags |= nprod << GF_NPROD_SHIFT;
+            // with a reduction the constant is its initial accumulator (stored as const*R); otherwise it is used as is
+            put(r.c[4], K ? hf::to_mont(Gs) : Gs);
             r.w[0] = kind | (flags << 8);
             r.w[1] = opcode;
             r.w[2] = dst;
@@ -412,41 +529,19 @@ struct Compiler {
             r.w[5] = w1;
             r.w[6] = w2;
             r.w[7] = 0;
-            if (!(flags & GF_MUL) && (flags & GF_Y)) {
-                // all coefficients +-1 (the common case in compiled Noir): additions only
-                const U256 pm1 = hf::neg(one);
-                auto pm = [&](const U256& v) { return v == one || v == pm1; };
-                if (pm(cY) && (nlin < 1 || pm(c1)) && (nlin < 2 || pm(c2))) {
-                    flags |= GF_ADDSUB;
-                    if (cY == pm1) flags |= GF_NEG_Y;
-                    if (nlin >= 1 && c1 == pm1) flags |= GF_NEG_W1;
-                    if (nlin >= 2 && c2 == pm1) flags |= GF_NEG_W2;
-                    imad = 0;
-                    r.w[0] = kind | (flags << 8);
-                }
-            }
-            if (flags & GF_MUL) {
-                put(r.c[0], hf::to_mont2(cM));
-                put(r.c[1], alpha);
-                put(r.c[2], beta);
-                put(r.c[3], hf::to_mont(c1));
+            uint32_t reads[5];
+            size_t nr = 0;
+            if (mul) {
+                reads[nr++] = x;
+                reads[nr++] = y;
+                if (w1 != NONE) reads[nr++] = w1;
             } else {
-                put(r.c[1], hf::to_mont(cY));
-                put(r.c[2], hf::to_mont(c1));
-                put(r.c[3], hf::to_mont(c2));
+                if (y != NONE) reads[nr++] = y;
+                if (w1 != NONE) reads[nr++] = w1;
+                if (w2 != NONE) reads[nr++] = w2;
             }
-            // products present (and not the +-1 add/sub form): the constant is the initial accumulator of the last Montgomery
-            // reduction, so it is stored as cC*R; otherwise it is used as is
-            put(r.c[4], ((flags & GF_Y) && !(flags & GF_ADDSUB)) ? hf::to_mont(c4) : c4);
-            if (flags & GF_MUL) reads[nr++] = x;
-            if (flags & GF_Y) reads[nr++] = y;
-            if (nlin >= 1) reads[nr++] = w1;
-            if (nlin >= 2) reads[nr++] = w2;
-            uint32_t K = ((flags & GF_Y) ? 1 : 0) + nlin;
-            if (K && !(flags & GF_ADDSUB)) imad += 64 * K + 72;
-            plan.stats.dev_imad += imad;
-            // distinct operand reads
-            {
+            plan.stats.dev_imad += ((mul && !one_red) ? 136u : 0u) + (K ? 64u * K + 72u : 0u);
+            {   // distinct operand reads
                 uint32_t tmp[4];
                 size_t nd = 0;
                 for (size_t i = 0; i < nr; ++i) {
@@ -459,19 +554,15 @@ struct Compiler {
             uint32_t writes[1];
             size_t nw = 0;
             if (dst != NONE) {
-                if (flags & GF_OUT_CHECK) {
-                    // compared, and REPLACED on mismatch (insert_value): order it like a write
-                    reads[nr++] = dst;
-                    writes[nw++] = dst;
-                    plan.stats.alg_bytes += 32;
-                } else {
-                    writes[nw++] = dst;
-                    plan.stats.alg_bytes += 32;
-                }
+                if (flags & GF_OUT_CHECK) reads[nr++] = dst;   // compared, and REPLACED on mismatch (insert_value): ordered like a write
+                writes[nw++] = dst;
+                plan.stats.alg_bytes += 32;
+                set_scale(dst, lo, mo);
             }
             sched.place(r, reads, nr, writes, nw);
             ++plan.stats.n_micro;
             if (kind == MK_GATE_ASSIGN) ++plan.stats.n_gate_assign; else ++plan.stats.n_gate_check;
+            if (mul && one_red) ++plan.stats.n_gate_one_reduction;
             if (!final_gate) acc = dst;
         }
     }
@@ -494,6 +585,12 @@ struct Compiler {
     // payload: n_mul, n_lin, qc[8], then per mul term {cR[8], cR2[8], w1, mu1, w2, mu2}, per lin term {cR[8], c[8], w, mu}
     // (mu = NONE for a statically known witness).
     void general_gate(uint32_t idx, const Expression& e) {
+        if (scaled) {   // exec_general evaluates the reference's decision procedure on canonical values
+            for (auto& t : e.mul_terms)
+                if (!is_canonical(t.a) || !is_canonical(t.b)) throw NeedsCanonicalColumns{};
+            for (auto& t : e.linear_combinations)
+                if (!is_canonical(t.w)) throw NeedsCanonicalColumns{};
+        }
         OpRec r{};
         std::vector<uint32_t> rd, wr;
         uint32_t off = (uint32_t)plan.payload.size();
@@ -610,7 +707,7 @@ struct Compiler {
             fail_static(idx, EK_MISSING_ASSIGNMENT, missing, "missing assignment for witness index " + std::to_string(missing));
             return false;
         }
-        if (prods.empty() && lins.size() == 1 && e.q_c.is_zero() && lins[0].c == hf::from_u64(1)) {
+        if (prods.empty() && lins.size() == 1 && e.q_c.is_zero() && lins[0].c == hf::from_u64(1) && is_canonical(lins[0].w)) {
             slot = lins[0].w;
             return true;
         }
@@ -621,7 +718,8 @@ struct Compiler {
             slot = new_temp();
         }
         ++plan.stats.n_temps;
-        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, slot, idx, false);
+        // the consumer is not a gate (directive, memory op, host segment): canonical value
+        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, slot, idx, false, nullptr, nullptr, /*canonical_out=*/true);
         return true;
     }
 
@@ -1105,11 +1203,11 @@ struct Compiler {
             return true;
         }
         // exactly one unknown (coeff != 0): w := -(sum)/coeff ; fold k = -1/coeff into every term
-        U256 k = hf::neg(inv(unknown[0].c));
+        U256 k = hf::neg(inv(unknown[0].c)), kinv = hf::neg(unknown[0].c);
         plan.stats.ref_fr_mul += 1;
         plan.stats.ref_fr_inv += 1;
         uint32_t w = unknown[0].w;
-        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, w, idx, false, &k);
+        lower_sum(std::move(prods), std::move(lins), e.q_c, /*assign=*/true, w, idx, false, &k, &kinv);
         mark_assigned(w, idx);
         return true;
     }
@@ -1515,9 +1613,46 @@ struct Compiler {
         plan.input_witnesses = inputs;
         plan.assign_opcode.assign(known.size(), ASSIGN_NEVER);
         plan.mu_index_of.assign(known.size(), NONE);
-        for (uint32_t w : inputs) {
+        scaled = opt.scaled_columns;
+        if (scaled) {
+            // columns that something other than an arithmetic gate reads (or compares) directly stay canonical
+            need_canon.assign(known.size(), 0);
+            auto canon = [&](uint32_t w) { need_canon[w] = 1; };
+            for (auto& op : c.opcodes) {
+                switch (op.kind) {
+                    case OP_BlackBox:
+                        for (auto& in : op.bb.inputs) canon(in.witness);
+                        for (uint32_t w : op.bb.outputs) canon(w);
+                        break;
+                    case OP_Directive:
+                        canon(op.dir.q);
+                        canon(op.dir.r);
+                        for (uint32_t w : op.dir.out) canon(w);
+                        break;
+                    case OP_MemoryInit:
+                        for (uint32_t w : op.init) canon(w);
+                        break;
+                    case OP_MemoryOp:   // a read lands in the witness of `value` (memory_op.rs:89-101)
+                        for (auto& t : op.mem.value.linear_combinations) canon(t.w);
+                        break;
+                    case OP_Brillig:
+                        for (auto& out : op.brillig.outputs)
+                            for (uint32_t w : out.witnesses) canon(w);
+                        break;
+                    default:
+                        break;
+                }
+            }
+        }
+        plan.input_scaled.assign(inputs.size(), 0);
+        for (size_t i = 0; i < inputs.size(); ++i) {
+            const uint32_t w = inputs[i];
             known[w] = 1;
             plan.assign_opcode[w] = ASSIGN_INPUT;
+            if (scaled && !need_canon[w]) {   // Montgomery form: products of inputs with unit coefficients stay uniformly scaled
+                set_scale(w, hf::consts().R, hf::from_mont(hf::consts().one));
+                plan.input_scaled[i] = 1;
+            }
         }
         for (uint32_t i = 0; i < c.opcodes.size(); ++i) {
             const Opcode& op = c.opcodes[i];
@@ -1550,6 +1685,16 @@ struct Compiler {
         close_device_segment();
         sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
         plan.n_slots = temp_base + opt.temp_pool + extra_slots;
+        if (scaled) {
+            bool any = false;
+            for (uint32_t w = 0; w < plan.num_witnesses && !any; ++w) any = !is_canonical(w);
+            if (any) {
+                plan.unscale.resize((size_t)plan.num_witnesses * 8);
+                for (uint32_t w = 0; w < plan.num_witnesses; ++w) put(&plan.unscale[(size_t)w * 8], hf::to_mont(mu_of(w)));
+            } else {
+                std::fill(plan.input_scaled.begin(), plan.input_scaled.end(), 0u);
+            }
+        }
         plan.stats.n_opcodes = c.opcodes.size();
         plan.stats.n_steps = sched.n_steps();
         plan.stats.n_slots_filled = sched.n_ops();
@@ -1637,18 +1782,7 @@ static std::vector<U256> batch_inverse(const std::vector<U256>& v) {
     return out;
 }
 
-Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt_in) {
-    PlanOptions opt = opt_in;
-    if (opt.S == 0 || opt.S > 64) throw std::runtime_error("plan: S must be in 1..64");
-    uint32_t nw = witness_span(c, input_witnesses);
-    // Jacobian points of the split curve micro-ops travel through temporaries (3 slots each, ~270 per Pedersen): a larger
-    // round-robin pool keeps slot reuse (a false WAR dependency) from serialising independent curve operations
-    if (opt.split_curve && opt.S >= 8)
-        for (auto& op : c.opcodes)
-            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul)) {
-                opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 32768);
-                break;
-            }
+static Plan compile_plan_once(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt, uint32_t nw) {
     if (c.opcodes.size() < 2048) {   // small circuits: direct inversions
         Compiler comp(c, opt, nw);
         comp.run(input_witnesses);
@@ -1666,6 +1800,28 @@ Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses
     comp.run(input_witnesses);
     if (comp.inv_pos != inverses.size()) throw std::runtime_error("plan: inversion replay out of sync");
     return std::move(comp.plan);
+}
+
+Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses, const PlanOptions& opt_in) {
+    PlanOptions opt = opt_in;
+    if (opt.S == 0 || opt.S > 64) throw std::runtime_error("plan: S must be in 1..64");
+    uint32_t nw = witness_span(c, input_witnesses);
+    // Jacobian points of the split curve micro-ops travel through temporaries (3 slots each, ~270 per Pedersen): a larger
+    // round-robin pool keeps slot reuse (a false WAR dependency) from serialising independent curve operations
+    if (opt.split_curve && opt.S >= 8)
+        for (auto& op : c.opcodes)
+            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul)) {
+                opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 32768);
+                break;
+            }
+    try {
+        return compile_plan_once(c, input_witnesses, opt, nw);
+    } catch (const NeedsCanonicalColumns&) {
+        // a value-dependent gate (arithmetic.rs:217-221) reads a column that an earlier gate left scaled: such circuits keep
+        // every column canonical
+        opt.scaled_columns = false;
+        return compile_plan_once(c, input_witnesses, opt, nw);
+    }
 }
 
 // ---- (de)serialisation: one flat blob for the multi-GPU broadcast -----------------------------
@@ -1704,7 +1860,7 @@ struct Cursor {
         return v;
     }
 };
-constexpr uint64_t kPlanMagic = 0x3230304e414c5042ULL;  // "BPLAN002"
+constexpr uint64_t kPlanMagic = 0x3330304e414c5042ULL;  // "BPLAN003"
 }  // namespace
 
 std::vector<uint8_t> serialize_plan(const Plan& p) {
@@ -1725,6 +1881,8 @@ std::vector<uint8_t> serialize_plan(const Plan& p) {
     put_pod<PlanStats>(b, p.stats);
     while (b.size() % 16) b.push_back(0);
     put_vec(b, p.input_witnesses);
+    put_vec(b, p.input_scaled);
+    put_vec(b, p.unscale);
     put_vec(b, p.assign_opcode);
     put_vec(b, p.mu_index_of);
     put_vec(b, p.payload);
@@ -1754,6 +1912,8 @@ Plan deserialize_plan(const uint8_t* data, size_t len) {
     p.stats = c.pod<PlanStats>();
     while (c.o % 16) ++c.o;
     p.input_witnesses = c.vec<uint32_t>();
+    p.input_scaled = c.vec<uint32_t>();
+    p.unscale = c.vec<uint32_t>();
     p.assign_opcode = c.vec<uint32_t>();
     p.mu_index_of = c.vec<uint32_t>();
     p.payload = c.vec<uint32_t>();

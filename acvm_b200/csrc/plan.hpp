@@ -23,7 +23,10 @@ struct OpRec {
     uint32_t w[8];      // [0]=kind|flags<<8  [1]=acir opcode index  [2]=out slot  [3]=x  [4]=y  [5]=w1  [6]=w2  [7]=aux
     // gate constants (8 x u32 little-endian limbs each), layout by flag:
     //   GF_MUL   : c0 = cM*R^2, c1 = alpha, c2 = beta, c3 = c1*R (w1), c4 = gamma     out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma
+    //   GF_MUL|GF_ONE_RED : no c0                                                     out = (x+alpha)*(y+beta)/R + c1*w1 + gamma
     //   otherwise: c1 = cY*R (y), c2 = c1*R (w1), c3 = c2*R (w2), c4 = cC            out = cY*y + c1*w1 + c2*w2 + cC
+    // all in terms of STORED column values (plan.cpp "scaled columns"); linear operands beyond GF_NPROD are +- additions;
+    // c4 is stored as const*R when the gate has a reduction (it is its initial accumulator), as is otherwise
     uint32_t c[5][8];
 };
 static_assert(sizeof(OpRec) == 192, "OpRec layout");
@@ -66,6 +69,9 @@ enum : uint32_t {
     GF_OUT2_CHECK = 1u << 7, // second output (point y coordinate) already holds a value
     GF_ADDSUB = 1u << 8,     // linear gate whose coefficients are all +-1: out = +-y +-w1 +-w2 + cC, no multiplication
     GF_NEG_Y = 1u << 9, GF_NEG_W1 = 1u << 10, GF_NEG_W2 = 1u << 11,
+    GF_ONE_RED = 1u << 12,   // GF_MUL gate whose product (x+c1)*(y+c2) enters the SAME reduction as the linear products (scaled columns)
+    GF_NPROD_SHIFT = 13,     // bits 13..14: how many of the linear operands (y, w1, w2 in this order; w1 for GF_MUL) are products
+                             // with a plan constant; the others are plain +- additions (signs in GF_NEG_*)
 };
 
 // error kinds mirrored from OpcodeResolutionError (acvm/src/pwg/mod.rs:100-114) + reference panics
@@ -100,6 +106,7 @@ struct PlanStats {
     uint64_t n_gate_general = 0;   // value-dependent gates resolved per lane
     uint64_t n_directive = 0, n_memory = 0, n_brillig = 0;
     uint64_t n_brillig_device = 0;   // Brillig opcodes lowered to device gates (no host segment)
+    uint64_t n_gate_one_reduction = 0;   // multiplicative gates that need ONE Montgomery reduction (scaled columns)
 };
 
 // The opcode list is cut into segments: device segments are step ranges of the record stream; a host segment is one
@@ -120,6 +127,10 @@ struct Plan {
     uint32_t chunk_steps = 2;          // steps per TMA stage
     bool needs_full_kernel = false;
     std::vector<uint32_t> input_witnesses;  // order of the per-instance input columns
+    std::vector<uint32_t> input_scaled;     // per input: 1 = the column holds value*R (Montgomery), the scatter converts
+    // scaled columns (plan.cpp): per witness, 8 limbs of mu_w * R -- the output gather multiplies the stored value by it
+    // (Montgomery product) to get the canonical value.  Empty: every column is canonical.
+    std::vector<uint32_t> unscale;
     std::vector<OpRec> stream;         // n_steps_padded * S records
     uint32_t n_steps = 0;              // padded to a multiple of chunk_steps
     std::vector<uint32_t> payload;     // variable-length operand lists (hash inputs ...)
@@ -149,6 +160,9 @@ struct PlanOptions {
     // Stop -- the stdlib's `bytecode: vec![Stop]` constant loads, stdlib/src/blackbox_fallbacks/uint.rs:51-63,85) to device
     // gates at plan time instead of a host segment each.
     bool device_brillig = true;
+    // Columns written and read only by arithmetic gates hold lambda_w * value for a per-column plan constant lambda_w
+    // (plan.cpp "scaled columns"): one Montgomery reduction per multiplicative gate instead of two.
+    bool scaled_columns = true;
 };
 
 // Throws std::runtime_error for opcodes outside the device scope.

@@ -43,6 +43,7 @@ struct acvmb_ctx {
     uint32_t opt_chunk_steps = 2;
     uint32_t opt_split_curve = 1, opt_temp_pool = 0;
     uint32_t opt_device_brillig = 1;
+    uint32_t opt_scaled_columns = 1;
     uint32_t opt_pedersen_unpinned = 0;   // 1: accept Pedersen opcodes / acvmb_pedersen although parity with barretenberg is unpinned
     int opt_split = -1;
     uint32_t opt_n_stage = 4;
@@ -69,6 +70,7 @@ struct acvmb_circuit {
     uint32_t* d_assign = nullptr;
     uint32_t* d_input_slots = nullptr;
     uint32_t* d_mu_index_of = nullptr;
+    uint32_t* d_unscale = nullptr;   // scaled columns: (1/lambda_w)*R per witness, for the output gather
     acvmb_run_info run{};
     ~acvmb_circuit() {
         if (d_stream) cudaFree(d_stream);
@@ -76,6 +78,7 @@ struct acvmb_circuit {
         if (d_assign) cudaFree(d_assign);
         if (d_input_slots) cudaFree(d_input_slots);
         if (d_mu_index_of) cudaFree(d_mu_index_of);
+        if (d_unscale) cudaFree(d_unscale);
     }
 };
 
@@ -217,6 +220,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "temp_pool") ctx->opt_temp_pool = (uint32_t)value;
     else if (k == "pedersen_unpinned") ctx->opt_pedersen_unpinned = value ? 1u : 0u;
     else if (k == "device_brillig") ctx->opt_device_brillig = value ? 1u : 0u;
+    else if (k == "scaled_columns") ctx->opt_scaled_columns = value ? 1u : 0u;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
@@ -254,8 +258,16 @@ static int upload_plan(acvmb_circuit* c) {
     CUDA_TRY(cudaMalloc(&c->d_assign, std::max<size_t>(p.assign_opcode.size() * 4, 16)));
     CUDA_TRY(cudaMemcpy(c->d_assign, p.assign_opcode.data(), p.assign_opcode.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&c->d_input_slots, std::max<size_t>(p.input_witnesses.size() * 4, 16)));
-    if (!p.input_witnesses.empty())
-        CUDA_TRY(cudaMemcpy(c->d_input_slots, p.input_witnesses.data(), p.input_witnesses.size() * 4, cudaMemcpyHostToDevice));
+    if (!p.input_witnesses.empty()) {
+        std::vector<uint32_t> slots(p.input_witnesses);   // bit 31: the scatter stores value * R (scaled column)
+        for (size_t i = 0; i < slots.size() && i < p.input_scaled.size(); ++i)
+            if (p.input_scaled[i]) slots[i] |= 0x80000000u;
+        CUDA_TRY(cudaMemcpy(c->d_input_slots, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!p.unscale.empty()) {
+        CUDA_TRY(cudaMalloc(&c->d_unscale, p.unscale.size() * 4));
+        CUDA_TRY(cudaMemcpy(c->d_unscale, p.unscale.data(), p.unscale.size() * 4, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&c->d_mu_index_of, std::max<size_t>(p.mu_index_of.size() * 4, 16)));
     if (!p.mu_index_of.empty())
         CUDA_TRY(cudaMemcpy(c->d_mu_index_of, p.mu_index_of.data(), p.mu_index_of.size() * 4, cudaMemcpyHostToDevice));
@@ -286,6 +298,7 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     if (ctx->opt_temp_pool) opt.temp_pool = ctx->opt_temp_pool;
     opt.allow_unpinned_pedersen = ctx->opt_pedersen_unpinned != 0;
     opt.device_brillig = ctx->opt_device_brillig != 0;
+    opt.scaled_columns = ctx->opt_scaled_columns != 0;
     std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
     try {
         c->plan = compile_plan(circ, inputs, opt);
@@ -359,6 +372,8 @@ extern "C" int acvmb_circuit_info(const acvmb_circuit* c, acvmb_plan_info* o) {
     for (auto& sg : p.segments) o->n_host_segments += sg.kind != 0;
     o->n_brillig = (uint32_t)p.stats.n_brillig;
     o->n_brillig_device = (uint32_t)p.stats.n_brillig_device;
+    o->n_gate_one_reduction = p.stats.n_gate_one_reduction;
+    o->scaled_columns = p.unscale.empty() ? 0u : 1u;
     return ACVMB_OK;
 }
 
@@ -894,6 +909,7 @@ static int download_impl(acvmb_batch* b, uint32_t first, uint32_t n, const uint3
     g.mu_assign = b->d_mu;
     g.n_mu = c->plan.n_mu;
     g.static_fail_opcode = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
+    g.unscale = c->d_unscale;
     // everything queued on the VM stream so far (the solve, the id upload above) precedes the first gather
     CUDA_TRY(cudaEventRecord(b->ev_ready, ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->gather_stream, b->ev_ready, 0));
@@ -954,6 +970,7 @@ extern "C" int acvmb_batch_checksum(acvmb_batch* b, uint64_t* out) {
     g.mu_assign = b->d_mu;
     g.n_mu = c->plan.n_mu;
     g.static_fail_opcode = c->plan.static_fail.present ? c->plan.static_fail.opcode : 0xFFFFFFFFu;
+    g.unscale = c->d_unscale;
     unsigned long long* d_out = nullptr;
     CUDA_TRY(cudaMalloc(&d_out, (size_t)b->n_inst * 8));
     cudaError_t e = launch_checksum(g, d_out, c->ctx->stream);
@@ -1400,6 +1417,7 @@ extern "C" int acvmb_plan_compile_host_ex(const uint8_t* gz, size_t len, const u
     if (temp_pool) opt.temp_pool = temp_pool;
     opt.allow_unpinned_pedersen = (flags & 1u) != 0;
     opt.device_brillig = (flags & 2u) == 0;
+    opt.scaled_columns = (flags & 4u) == 0;
     try {
         tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);
     } catch (const std::exception& e) {

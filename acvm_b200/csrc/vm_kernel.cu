@@ -49,8 +49,16 @@ __global__ void scatter_inputs_kernel(const uint8_t* __restrict__ in_be, const u
 #pragma unroll
     for (int m = 0; m < 8; ++m) v.l[7 - m] = __byte_perm(src[m], 0, 0x0123);
     fr::reduce_256(v);
+    uint32_t slot = input_slots[k];
+    if (slot & 0x80000000u) {   // scaled column (plan.cpp): the plan wants this input in Montgomery form, value * R
+        slot &= 0x7FFFFFFFu;
+        Fe r2;
+        r2.l[0] = 0xae216da7u; r2.l[1] = 0x1bb8e645u; r2.l[2] = 0xe35c59e3u; r2.l[3] = 0x53fe3ab1u;
+        r2.l[4] = 0x53bb8085u; r2.l[5] = 0x8c49833du; r2.l[6] = 0x7f4e44a5u; r2.l[7] = 0x0216d0b1u;
+        fr::mont_mul(v, v, r2);
+    }
     uint32_t tile = inst / T, lane = inst % T;
-    uint4* p = cols + ((size_t)tile * n_slots + input_slots[k]) * (2 * T) + lane;
+    uint4* p = cols + ((size_t)tile * n_slots + slot) * (2 * T) + lane;
     p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
@@ -67,6 +75,19 @@ cudaError_t launch_scatter_inputs(const uint8_t* in_be, const uint32_t* input_sl
 // output gather: columns -> [inst][n_out][32 B big-endian]; a witness that the instance never
 // assigned (it failed earlier, or nothing assigns it) is written as zeros.
 // ---------------------------------------------------------------------------------------------
+// scaled columns (plan.cpp): the column holds lambda_w * value; unscale[w] = (1/lambda_w) * R, so one Montgomery product
+// gives the canonical value
+__device__ __forceinline__ void unscale_value(const uint32_t* unscale, uint32_t w, uint4& lo, uint4& hi) {
+    const uint4* u = reinterpret_cast<const uint4*>(unscale + (size_t)w * 8);
+    const uint4 ul = u[0], uh = u[1];
+    Fe s, m;
+    s.l[0] = lo.x; s.l[1] = lo.y; s.l[2] = lo.z; s.l[3] = lo.w; s.l[4] = hi.x; s.l[5] = hi.y; s.l[6] = hi.z; s.l[7] = hi.w;
+    m.l[0] = ul.x; m.l[1] = ul.y; m.l[2] = ul.z; m.l[3] = ul.w; m.l[4] = uh.x; m.l[5] = uh.y; m.l[6] = uh.z; m.l[7] = uh.w;
+    fr::mont_mul(s, s, m);
+    lo = make_uint4(s.l[0], s.l[1], s.l[2], s.l[3]);
+    hi = make_uint4(s.l[4], s.l[5], s.l[6], s.l[7]);
+}
+
 __global__ void gather_outputs_kernel(const GatherArgs g) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)g.n_inst * g.n_out) return;
@@ -90,6 +111,7 @@ __global__ void gather_outputs_kernel(const GatherArgs g) {
         const uint4* p = g.cols + ((size_t)tile * g.n_slots + w) * (2 * g.T) + lane;
         lo = p[0];
         hi = p[g.T];
+        if (g.unscale && !g.raw) unscale_value(g.unscale, w, lo, hi);
     }
     uint4* dst = reinterpret_cast<uint4*>(g.out_be + gid * 32);
     dst[0] = make_uint4(__byte_perm(hi.w, 0, 0x0123), __byte_perm(hi.z, 0, 0x0123), __byte_perm(hi.y, 0, 0x0123), __byte_perm(hi.x, 0, 0x0123));
@@ -124,7 +146,9 @@ __global__ void checksum_kernel(const GatherArgs g, unsigned long long* out) {
         if (ao == 0xFFFFFFFDu) ao = g.mu_assign[((size_t)tile * g.n_mu + g.mu_index_of[w]) * g.T + lane];
         if (!((ao == 0xFFFFFFFEu) || (ao != 0xFFFFFFFFu && ao < fail_op))) continue;
         const uint4* p = g.cols + ((size_t)tile * g.n_slots + w) * (2 * g.T) + lane;
-        acc += mix_witness(w, p[0], p[g.T]);
+        uint4 lo = p[0], hi = p[g.T];
+        if (g.unscale) unscale_value(g.unscale, w, lo, hi);
+        acc += mix_witness(w, lo, hi);
     }
     __shared__ unsigned long long red[256];
     red[threadIdx.x] = acc;

@@ -53,6 +53,7 @@ struct GatherArgs {
     uint8_t* out_be;               // [n_inst][n_out][32] or NULL
     uint8_t* out_present;          // [n_inst][n_out] or NULL
     int raw;                       // 1 = witness_ids are raw column slots (temporaries allowed), no presence logic
+    const uint32_t* unscale;       // scaled columns: per witness 8 limbs of (1/lambda_w)*R, or NULL when every column is canonical
 };
 cudaError_t launch_gather_outputs(const GatherArgs& g, cudaStream_t stream);
 // out[inst] = sum over the witnesses instance `inst` holds of mix(index, value)  (g.n_out = num_witnesses, g.n_inst instances from 0)

@@ -102,67 +102,93 @@ struct RegLimbs {
     __device__ __forceinline__ uint32_t operator()(int, int i) const { return b.l[i]; }
 };
 
-// GF_MUL : out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma   -- two Montgomery reductions: u = (x+alpha)(y+beta)/R,
-//          then <u, w1> . <cM*R^2, c1*R> / R in ONE interleaved reduction (fr::mont_dot_fn).
-// linear : out = cY*y + c1*w1 + c2*w2 + cC               -- one reduction for up to three products.
+// b-limb source of the gate's dot product: plan constants fetched limb by limb from shared memory, except that the first
+// operand of a one-reduction multiplicative gate is the lane's own (y + beta)
+struct GateLimbs {
+    const uint32_t* c0;
+    const uint32_t* c1;
+    const uint32_t* c2;
+    const Fe& yreg;
+    bool k0_reg;
+    __device__ __forceinline__ uint32_t operator()(int k, int i) const {
+        if (k == 0) return k0_reg ? yreg.l[i] : c0[i];
+        return k == 1 ? c1[i] : c2[i];
+    }
+};
+
+// Arithmetic gate on STORED column values (plan.cpp "scaled columns"; canonical columns are the special case lambda = 1):
+//   GF_MUL|GF_ONE_RED : out = ( (x+c1)*(y+c2) + w1*c3 + c4 ) / R                        one reduction, width 1..2
+//   GF_MUL            : u = (x+c1)*(y+c2)/R ; out = ( u*c0 + w1*c3 + c4 ) / R            two reductions
+//   otherwise         : out = ( y*c1 + w1*c2 + w2*c3 + c4 ) / R                          one reduction, width 0..3
+// where only the first GF_NPROD linear operands are products; the rest are added or subtracted after the reduction, and a
+// gate without any product is c4 +- operands with no multiplication at all.
 template <int T, int SPLIT>
 __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
     Fe res;
     if (flags & GF_Y) {
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
-        // Every operand load is issued here, before the code paths part: the slots of a warp may hold different gate forms
-        // (multiplicative / +-1 add-sub / linear), the forms then run one after the other, and with the loads inside each
-        // form their L2 latencies added up (measured: the cheap "noir-like" mix was slower per step than all-dense).
+        const uint32_t nprod = (flags >> GF_NPROD_SHIFT) & 3;
+        const bool mul = (flags & GF_MUL) != 0;
+        // Every operand load is issued here, before the code paths part: the slots of a warp may hold different gate forms,
+        // the forms then run one after the other, and with the loads inside each form their L2 latencies added up.
         Fe x, y, w1, w2;
-        if (flags & GF_MUL) load_w<T>(x, cb, r->w[3]);
+        if (mul) load_w<T>(x, cb, r->w[3]);
         load_w<T>(y, cb, r->w[4]);
         if (nlin >= 1) load_w<T>(w1, cb, r->w[5]);
         if (nlin >= 2) load_w<T>(w2, cb, r->w[6]);
-        if (flags & GF_ADDSUB) {
-            // coefficients are all +-1: out = +-y +-w1 +-w2 + cC with modular additions only
+        const uint32_t K = (mul ? 1u : 0u) + nprod;   // width of this lane's dot product
+        if (K == 0) {
             lds_fe(res, r->c[4]);
-            if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
-            if (nlin >= 1) {
-                if (flags & GF_NEG_W1) fr::sub_mod(res, res, w1); else fr::add_mod(res, res, w1);
-            }
-            if (nlin >= 2) {
-                if (flags & GF_NEG_W2) fr::sub_mod(res, res, w2); else fr::add_mod(res, res, w2);
-            }
         } else {
-            // Multiplicative and linear forms share ONE reduction of warp-uniform width: the lanes of this warp that are here
-            // agree on K = the widest dot product among them, narrower lanes pad with zero operands.  (Each form used to
-            // run its own width, so a warp holding several forms executed them one after the other.)
+            // Every form shares ONE reduction of warp-uniform width: the lanes of this warp that are here agree on the widest
+            // dot product among them, narrower lanes pad with zero operands.
             const unsigned lanes = __activemask();
-            const bool mul = (flags & GF_MUL) != 0;
+            const bool one_red = (flags & GF_ONE_RED) != 0;
+            Fe a1, a2;   // product operands 1 and 2 (zero when this lane has none)
             if (mul) {
-                // lazy reduction: x+alpha, y+beta < 2p stay unreduced (4p^2/R + p < 1.76p), and so does u
-                // ((1.76 + 1) p^2 / R + p < 1.52p for the second product): one conditional subtraction per gate instead of three
+                // lazy reduction: x+c1, y+c2 < 2p stay unreduced ((4p^2 + p^2)/R + p < 1.95p: one conditional subtraction)
                 Fe t;
                 lds_fe(t, r->c[1]);
                 fr::add_raw(x, x, t);
                 lds_fe(t, r->c[2]);
                 fr::add_raw(y, y, t);
-                const Fe* a1[1] = {&x};
-                fr::mont_dot_fn<1, RegLimbs, SPLIT>(t, a1, RegLimbs{y});   // u = (x+alpha)(y+beta)/R < 1.76p
-                y = t;
+                if (!one_red) {
+                    const Fe* p1[1] = {&x};
+                    fr::mont_dot_fn<1, RegLimbs, SPLIT>(t, p1, RegLimbs{y});   // u = (x+c1)(y+c2)/R < 1.76p
+                    x = t;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a1.l[i] = nprod >= 1 ? w1.l[i] : 0u; a2.l[i] = 0u; }
+            } else {
+                x = y;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a1.l[i] = nprod >= 2 ? w1.l[i] : 0u; a2.l[i] = nprod >= 3 ? w2.l[i] : 0u; }
             }
             __syncwarp(lanes);
-            if (nlin < 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w1.l[i] = 0;
-            }
-            if (nlin < 2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w2.l[i] = 0;
-            }
-            const uint32_t K = __reduce_max_sync(lanes, 1u + nlin);
-            // constants: multiplicative (u, w1) . (c0, c3); linear (y, w1, w2) . (c1, c2, c3); c4 = cC*R rides in the accumulator
-            const SmemLimbs3 bl{mul ? r->c[0] : r->c[1], mul ? r->c[3] : r->c[2], r->c[3]};
-            const Fe* a[3] = {&y, &w1, &w2};
-            if (K == 1) fr::mont_dot_fn<1, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
-            else if (K == 2) fr::mont_dot_fn<2, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
-            else fr::mont_dot_fn<3, SmemLimbs3, SPLIT>(res, a, bl, r->c[4]);
+            const uint32_t Kmax = __reduce_max_sync(lanes, K);
+            // operand k pairs with: multiplicative (x', w1) . (y' or c0, c3); linear (y, w1, w2) . (c1, c2, c3)
+            const GateLimbs bl{mul ? r->c[0] : r->c[1], mul ? r->c[3] : r->c[2], r->c[3], y, mul && one_red};
+            const Fe* a[3] = {&x, &a1, &a2};
+            if (Kmax == 1) fr::mont_dot_fn<1, GateLimbs, SPLIT>(res, a, bl, r->c[4]);
+            else if (Kmax == 2) fr::mont_dot_fn<2, GateLimbs, SPLIT>(res, a, bl, r->c[4]);
+            else fr::mont_dot_fn<3, GateLimbs, SPLIT>(res, a, bl, r->c[4]);
             fr::cond_sub_p(res);
+        }
+        // linear operands that are plain additions: index >= nprod in (y, w1, w2), resp. (w1) for a multiplicative gate
+        if (mul) {
+            if (nlin >= 1 && nprod == 0) {
+                if (flags & GF_NEG_W1) fr::sub_mod(res, res, w1); else fr::add_mod(res, res, w1);
+            }
+        } else {
+            if (nprod == 0) {
+                if (flags & GF_NEG_Y) fr::sub_mod(res, res, y); else fr::add_mod(res, res, y);
+            }
+            if (nlin >= 1 && nprod <= 1) {
+                if (flags & GF_NEG_W1) fr::sub_mod(res, res, w1); else fr::add_mod(res, res, w1);
+            }
+            if (nlin >= 2 && nprod <= 2) {
+                if (flags & GF_NEG_W2) fr::sub_mod(res, res, w2); else fr::add_mod(res, res, w2);
+            }
         }
     } else {
         lds_fe(res, r->c[4]);

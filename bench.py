@@ -227,6 +227,8 @@ def run_ours(args):
         ctx.set_option("S", args.S)
     if args.T:
         ctx.set_option("T", args.T)
+    if os.environ.get("ACVMB_SCALED") is not None:   # A/B hook: 0 = canonical columns (two reductions per multiplicative gate)
+        ctx.set_option("scaled_columns", int(os.environ["ACVMB_SCALED"]))
 
     # ---- circuit: compiled on rank 0, broadcast once (the only collective on this path) ----
     data, inputs = (None, list(range(ab.N_INPUTS)))

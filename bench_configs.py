@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="context option key=value (e.g. split_curve=0, temp_pool=65536)")
     args = ap.parse_args()
     ctx = acvm_b200.Context(0)
+    ctx.set_option("pedersen_unpinned", 1)   # configs 2 and 4 measure the Pedersen kernel (structure-identical, parity unpinned)
     if args.S:
         ctx.set_option("S", args.S)
     for kv in args.opt:

@@ -89,6 +89,9 @@ typedef struct {
     uint32_t n_host_segments;   /* host segments: Brillig opcodes that need the host VM, PermutationSort directives */
     uint32_t n_brillig;         /* Brillig opcodes in the circuit */
     uint32_t n_brillig_device;  /* ... of which lowered to device gates at plan time (straight-line field bytecode) */
+    uint64_t n_gate_one_reduction; /* multiplicative gates that run ONE Montgomery reduction (scaled columns) */
+    uint32_t scaled_columns;    /* 1: some columns hold lambda_w * value; canonical values are produced by the output gather */
+    uint32_t reserved;
 } acvmb_plan_info;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -204,7 +207,7 @@ int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg, cons
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 /* same with plan options: temp_pool (0 = default), flags bit 0 = accept Pedersen (parity unpinned, see "pedersen_unpinned"),
- * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates) */
+ * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only */
 int acvmb_plan_compile_host_ex(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                                uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
@@ -230,7 +233,8 @@ int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
 /* tuning knobs: "T" (instances per CTA), "S" (slots per step), "chunk_steps", "n_stage", "split", "max_resident_bytes",
  * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "pedersen_unpinned" (1: accept
  * BlackBoxFuncCall::Pedersen / acvmb_pedersen although the values are NOT barretenberg's -- refused by default),
- * "device_brillig" (0: every Brillig opcode runs on the host VM), "cache_batch" (0: free
+ * "device_brillig" (0: every Brillig opcode runs on the host VM), "scaled_columns" (0: every witness column holds the
+ * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
  * identical next call); plan options apply to circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);

@@ -14,7 +14,7 @@ from . import acir as oacir
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libref_solver.so")
 ERR_NAMES = {0: None, 1: "OpcodeNotSolvable.MissingAssignment", 2: "OpcodeNotSolvable.ExpressionHasTooManyUnknowns",
-             4: "UnsatisfiedConstrain", 8: "ReferencePanic"}
+             4: "UnsatisfiedConstrain", 6: "BlackBoxFunctionFailed", 8: "ReferencePanic"}
 
 
 def build(force=False):
@@ -37,6 +37,22 @@ def lib():
     return _lib
 
 
+_ped_ready = False
+
+
+def _ensure_pedersen_tables():
+    """Hand the oracle's generators (oracle/pedersen.py; parity with barretenberg UNPINNED) to the C++ side, once."""
+    global _ped_ready
+    if _ped_ready:
+        return
+    from . import grumpkin, pedersen
+    g = pedersen.generators()
+    pts = [g[par][i] for par in range(2) for i in range(pedersen.NUM_WINDOWS)] + [grumpkin.G]
+    arr = np.array([_limbs(c) for pt in pts for c in pt], dtype=np.uint64)
+    lib().ref_set_pedersen_generators(arr.ctypes.data_as(C.c_void_p))
+    _ped_ready = True
+
+
 def _limbs(v):
     return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
 
@@ -57,6 +73,19 @@ def pack_circuit(circuit: oacir.Circuit) -> np.ndarray:
             words += [1 if bb["name"] == "AND" else 2, bb["lhs"][0], bb["rhs"][0], bb["lhs"][1], bb["output"]]
         elif op.kind == "BlackBoxFuncCall" and op.body["name"] == "RANGE":
             words += [3, op.body["input"][0], op.body["input"][1]]
+        elif op.kind == "BlackBoxFuncCall" and op.body["name"] in ("SHA256", "Keccak256"):
+            bb = op.body
+            words += [4 if bb["name"] == "SHA256" else 5, len(bb["inputs"])]
+            for (w, nb) in bb["inputs"]:
+                words += [w, nb]
+            words += list(bb["outputs"])
+        elif op.kind == "BlackBoxFuncCall" and op.body["name"] == "FixedBaseScalarMul":
+            bb = op.body
+            words += [6, bb["low"][0], bb["high"][0], bb["outputs"][0], bb["outputs"][1]]
+        elif op.kind == "BlackBoxFuncCall" and op.body["name"] == "Pedersen":
+            bb = op.body
+            _ensure_pedersen_tables()
+            words += [7, len(bb["inputs"])] + [w for (w, _) in bb["inputs"]] + [bb["domain_separator"], bb["outputs"][0], bb["outputs"][1]]
         else:
             raise NotImplementedError(f"ref_solver.cpp does not restate {op.kind}/{op.body.get('name') if isinstance(op.body, dict) else ''}")
     return np.array(words, dtype=np.uint64)

@@ -8,6 +8,7 @@ import struct
 
 P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 RINV = pow(1 << 256, -1, P)
+R_MONT = (1 << 256) % P
 NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
@@ -24,12 +25,12 @@ class PlanBlob:
         o = 0
         magic, = struct.unpack_from("<Q", blob, o)
         o += 8
-        assert magic == 0x3230304E414C5042, "bad magic"
+        assert magic == 0x3330304E414C5042, "bad magic"
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
          self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
         o += 48
-        self.stats = struct.unpack_from("<20Q", blob, o)   # PlanStats (plan.hpp), a POD of 20 u64
-        o += 160
+        self.stats = struct.unpack_from("<21Q", blob, o)   # PlanStats (plan.hpp), a POD of 21 u64
+        o += 168
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):
@@ -43,6 +44,12 @@ class PlanBlob:
 
         n, d = vec("I", 4)
         self.input_witnesses = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("I", 4)
+        self.input_scaled = list(struct.unpack(f"<{n}I", d))
+        n, d = vec("I", 4)
+        limbs = struct.unpack(f"<{n}I", d)
+        # scaled columns: per witness (1/lambda_w)*R; canonical value = stored * that / R
+        self.unscale = [sum(limbs[8 * w + j] << (32 * j) for j in range(8)) for w in range(n // 8)]
         n, d = vec("I", 4)
         self.assign_opcode = list(struct.unpack(f"<{n}I", d))
         n, d = vec("I", 4)
@@ -238,8 +245,10 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
         def __missing__(self, k):
             return 0
     cols = Cols()
-    for w in plan.input_witnesses:
+    for k_, w in enumerate(plan.input_witnesses):
         cols[w] = inputs[w] % P
+        if plan.input_scaled and plan.input_scaled[k_]:
+            cols[w] = cols[w] * R_MONT % P   # the scatter stores value * R for this input
     mu = {}      # mu index -> opcode that assigned it (this lane)
     fail = None  # (opcode, kind, aux)
 
@@ -353,28 +362,28 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
             if kind == MK["NOP"]:
                 continue
             if kind in (MK["GATE_ASSIGN"], MK["GATE_CHECK"]):
-                res = c[4]
-                if (flags & GF_Y) and not (flags & 256):
-                    res = c[4] * RINV   # folded into the last Montgomery reduction: stored as cC*R
+                # gate semantics on STORED values (plan.hpp OpRec, vm_kernel_impl.cuh exec_gate)
+                nlin = (flags >> GF_NLIN_SHIFT) & 3
+                nprod = (flags >> 13) & 3
+                is_mul = bool(flags & GF_MUL)
+                K = (1 if is_mul else 0) + nprod if (flags & GF_Y) else 0
+                res = c[4] * RINV if K else c[4]   # with a reduction the constant is its initial accumulator, stored as const*R
                 if flags & GF_Y:
-                    nlin = (flags >> GF_NLIN_SHIFT) & 3
-                    if flags & GF_MUL:
+                    if is_mul:
                         assert nlin <= 1
-                        res += c[0] * RINV * RINV * (cols[x] + c[1]) * (cols[y] + c[2])
-                        if nlin >= 1:
-                            res += c[3] * RINV * cols[w1]
-                    elif flags & 256:   # GF_ADDSUB: coefficients +-1, signs in flag bits 9..11
-                        res += -cols[y] if flags & 512 else cols[y]
-                        if nlin >= 1:
-                            res += -cols[w1] if flags & 1024 else cols[w1]
-                        if nlin >= 2:
-                            res += -cols[w2] if flags & 2048 else cols[w2]
+                        prod = (cols[x] + c[1]) * (cols[y] + c[2])
+                        if flags & 4096:   # GF_ONE_RED
+                            res += prod * RINV
+                        else:
+                            res += c[0] * RINV * RINV * prod
+                        operands = [(w1, c[3], flags & 1024)][:nlin]
                     else:
-                        res += c[1] * RINV * cols[y]
-                        if nlin >= 1:
-                            res += c[2] * RINV * cols[w1]
-                        if nlin >= 2:
-                            res += c[3] * RINV * cols[w2]
+                        operands = [(y, c[1], flags & 512), (w1, c[2], flags & 1024), (w2, c[3], flags & 2048)][:nlin + 1]
+                    for i_, (slot_, coef_, neg_) in enumerate(operands):
+                        if i_ < nprod:
+                            res += coef_ * RINV * cols[slot_]
+                        else:
+                            res += -cols[slot_] if neg_ else cols[slot_]
                 res %= P
                 if kind == MK["GATE_ASSIGN"]:
                     if flags & GF_OUT_CHECK:
@@ -523,5 +532,5 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
         if ao == 0xFFFFFFFD:
             ao = mu.get(plan.mu_index_of[w], 0xFFFFFFFF)
         if ao == 0xFFFFFFFE or (ao != 0xFFFFFFFF and ao < fop):
-            wm[w] = cols[w]
+            wm[w] = cols[w] * plan.unscale[w] * RINV % P if plan.unscale else cols[w]   # what the output gather does
     return status, wm

@@ -5,6 +5,7 @@ import numpy as np
 import acvm_b200
 from acvm_b200 import acir_builder as ab
 ctx = acvm_b200.Context(0)
+ctx.set_option("pedersen_unpinned", 1)   # structure/cost measurement only: values are not barretenberg's
 rng = np.random.default_rng(1)
 for name, (data, inputs, nw), byte_valued in (("hash", ab.hash_chain_circuit(256), True), ("pedersen", ab.pedersen_chain_circuit(16), False)):
     batch = 4096

@@ -39,6 +39,38 @@ def test_synthetic_1k(ctx, batch, mode, coeffs):
     _check(ctx, data, inputs, batch, ab.synthetic_inputs(batch))
 
 
+@pytest.mark.parametrize("scaled", [0, 1])
+@pytest.mark.parametrize("mode,coeffs", [("local", "dense"), ("local", "noir-like")])
+def test_scaled_and_canonical_columns_agree(scaled, mode, coeffs):
+    """Columns written and read only by gates hold lambda_w * value (one Montgomery reduction per multiplicative gate); with
+    the option off every column is canonical (two reductions).  Both must return the oracle's canonical witness map, and the
+    device checksum (which un-scales on the device) must be the same number."""
+    c = acvm_b200.Context(0)
+    try:
+        c.set_option("scaled_columns", scaled)
+        data, inputs, _ = ab.synthetic_arith_circuit(2000, mode=mode, coeffs=coeffs, seed_id=5)
+        circ = acvm_b200.CompiledCircuit(c, data, inputs)
+        assert circ.info["scaled_columns"] == scaled
+        assert (circ.info["n_gate_one_reduction"] > 0) == bool(scaled)
+        circ.close()
+        batch = 19
+        inp = ab.synthetic_inputs(batch, seed_id=5)
+        _check(c, data, inputs, batch, inp)
+        circ = acvm_b200.CompiledCircuit(c, data, inputs)
+        b = acvm_b200.DeviceBatch(circ, batch)
+        b.stage_inputs(0, inp)
+        b.run_staged(0)
+        sums = b.checksums()
+        b.close()
+        circ.close()
+    finally:
+        c.close()
+    assert _CHECKSUMS.setdefault((mode, coeffs), sums) == sums
+
+
+_CHECKSUMS = {}
+
+
 def test_addition_golden(ctx, golden):
     fx = golden["acvm_js_shared"]["addition"]
     data = bytes(fx["bytecode"])
