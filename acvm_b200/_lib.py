@@ -26,7 +26,8 @@ class PlanInfo(C.Structure):
         "n_hash", "n_curve", "ref_fr_mul", "ref_fr_inv", "dev_imad", "alg_bytes", "n_temps")] + [(n, C.c_uint32) for n in (
         "num_witnesses", "n_slots", "S", "needs_full_kernel", "static_fail_present", "static_fail_opcode",
         "static_fail_kind", "static_fail_aux", "n_segments", "n_host_segments", "n_brillig", "n_brillig_device")] + [("n_gate_one_reduction", C.c_uint64),
-                                                                                  ("scaled_columns", C.c_uint32), ("reserved", C.c_uint32)]
+                                                                                  ("scaled_columns", C.c_uint32), ("ring_slots", C.c_uint32),
+                                                                                  ("n_operand_reads", C.c_uint64), ("n_ring_reads", C.c_uint64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -41,6 +42,9 @@ def load():
     vp, u8p, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
     sig = {
         "acvmb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "acvmb_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "acvmb_ctx_n_devices": (C.c_int, [vp]),
+        "acvmb_ctx_broadcast_backend": (C.c_char_p, [vp]),
         "acvmb_ctx_destroy": (None, [vp]),
         "acvmb_last_error": (C.c_char_p, []),
         "acvmb_device_name": (C.c_int, [vp, C.c_char_p, C.c_size_t]),

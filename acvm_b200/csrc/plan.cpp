@@ -53,7 +53,12 @@ class Scheduler {
         flush();
         floor_ = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
         n_steps_ = floor_;
+        seg_starts_.push_back(floor_);   // a new kernel launch: the shared-memory ring starts empty
         return floor_;
+    }
+
+    static bool ring_kind(uint32_t kind) {
+        return kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK || kind == MK_AND || kind == MK_XOR || kind == MK_RANGE;
     }
 
     // Curve micro-ops are 10..1000x slower than an arithmetic gate and a step costs as much as its slowest slot, so a
@@ -150,6 +155,11 @@ class Scheduler {
         if (++fill_[s] == S_) next_[s] = s + 1;
         steps_.push_back(s);
         ops_.push_back(rec);
+        if (!ring_kind(rec.w[0] & 0xFF)) {   // its writes bypass the ring: emit() must forget ring copies of those slots
+            other_writes_at_.push_back((uint32_t)ops_.size() - 1);
+            other_writes_off_.push_back((uint32_t)other_writes_.size());
+            other_writes_.insert(other_writes_.end(), writes, writes + nw);
+        }
         for (size_t i = 0; i < nw; ++i) ready_[writes[i]] = s + 1;
         for (size_t i = 0; i < nr; ++i) war_[reads[i]] = std::max(war_[reads[i]], s + 1);
         n_steps_ = std::max(n_steps_, s + 1);
@@ -157,6 +167,101 @@ class Scheduler {
 
     uint32_t n_steps() { flush(); return n_steps_; }
     size_t n_ops() { flush(); return ops_.size(); }
+
+    // Shared-memory ring of recent values (vm_kernel_impl.cuh): the k-th value written by a gate / logic micro-op of a segment
+    // lives in ring entry k % W until the (k+W)-th one replaces it.  A read in step s may use the ring copy iff the value is
+    // still there when step s ENDS (writes of step s land without a barrier).  Operand fields of such reads are rewritten to
+    // RING_FLAG | entry; outputs get their entry in w[7] (gates) / w[5] (AND, XOR).
+    void assign_ring(uint32_t W, uint64_t& n_reads, uint64_t& n_ring_reads) {
+        flush();
+        n_reads = n_ring_reads = 0;
+        if (W == 0) return;
+        const size_t n_ops = ops_.size();
+        std::vector<uint32_t> order(n_ops);
+        for (size_t i = 0; i < n_ops; ++i) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return steps_[a] < steps_[b]; });
+        std::vector<uint64_t> seq_of(ready_.size(), ~0ull);   // slot -> sequence number of its ring copy
+        std::vector<uint32_t> ow_index(n_ops, 0xFFFFFFFFu);
+        for (size_t k = 0; k < other_writes_at_.size(); ++k) ow_index[other_writes_at_[k]] = (uint32_t)k;
+        std::vector<uint32_t> seg(seg_starts_);
+        std::sort(seg.begin(), seg.end());
+        size_t seg_pos = 0;
+        uint64_t next_seq = 0;
+        std::vector<uint32_t> touched;
+        size_t i = 0;
+        while (i < n_ops) {
+            const uint32_t step = steps_[order[i]];
+            size_t j = i;
+            while (j < n_ops && steps_[order[j]] == step) ++j;
+            while (seg_pos < seg.size() && seg[seg_pos] <= step) {   // new launch: forget everything
+                for (uint32_t s : touched) seq_of[s] = ~0ull;
+                touched.clear();
+                ++seg_pos;
+            }
+            uint64_t n_writes = 0;
+            for (size_t k = i; k < j; ++k) {
+                const OpRec& r = ops_[order[k]];
+                const uint32_t kind = r.w[0] & 0xFF;
+                if ((kind == MK_GATE_ASSIGN || kind == MK_AND || kind == MK_XOR) && r.w[2] != 0xFFFFFFFFu) ++n_writes;
+            }
+            // more writes in one step than the ring holds: only the last W get an entry (two writes of one step must never
+            // target the same entry -- nothing orders them)
+            uint64_t skip = n_writes > W ? n_writes - W : 0;
+            const uint64_t seq_end = next_seq + (n_writes - skip);
+            auto rd = [&](uint32_t& field) {
+                ++n_reads;
+                const uint64_t q = field < seq_of.size() ? seq_of[field] : ~0ull;
+                if (q != ~0ull && q + W >= seq_end) {
+                    field = RING_FLAG | (uint32_t)(q % W);
+                    ++n_ring_reads;
+                }
+            };
+            for (size_t k = i; k < j; ++k) {
+                OpRec& r = ops_[order[k]];
+                const uint32_t kind = r.w[0] & 0xFF, flags = r.w[0] >> 8;
+                if (kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK) {
+                    if (flags & GF_Y) {
+                        const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
+                        if (flags & GF_MUL) rd(r.w[3]);
+                        rd(r.w[4]);
+                        if (nlin >= 1) rd(r.w[5]);
+                        if (nlin >= 2) rd(r.w[6]);
+                    }
+                } else if (kind == MK_AND || kind == MK_XOR) {
+                    rd(r.w[3]);
+                    rd(r.w[4]);
+                } else if (kind == MK_RANGE) {
+                    rd(r.w[3]);
+                }
+            }
+            for (size_t k = i; k < j; ++k) {
+                OpRec& r = ops_[order[k]];
+                const uint32_t kind = r.w[0] & 0xFF;
+                if (kind == MK_GATE_ASSIGN || kind == MK_AND || kind == MK_XOR) {
+                    uint32_t& ring_field = kind == MK_GATE_ASSIGN ? r.w[7] : r.w[5];
+                    ring_field = RING_NONE;
+                    if (r.w[2] != 0xFFFFFFFFu && skip > 0) {
+                        --skip;
+                        if (r.w[2] < seq_of.size()) seq_of[r.w[2]] = ~0ull;
+                    } else if (r.w[2] != 0xFFFFFFFFu) {
+                        const uint64_t q = next_seq++;
+                        ring_field = (uint32_t)(q % W);
+                        if (seq_of[r.w[2]] == ~0ull) touched.push_back(r.w[2]);
+                        seq_of[r.w[2]] = q;
+                    }
+                } else if (kind == MK_GATE_CHECK) {
+                    r.w[7] = RING_NONE;
+                } else if (ow_index[order[k]] != 0xFFFFFFFFu) {
+                    const uint32_t o = ow_index[order[k]];
+                    const uint32_t lo = other_writes_off_[o];
+                    const uint32_t hi = o + 1 < other_writes_off_.size() ? other_writes_off_[o + 1] : (uint32_t)other_writes_.size();
+                    for (uint32_t t = lo; t < hi; ++t)
+                        if (other_writes_[t] < seq_of.size()) seq_of[other_writes_[t]] = ~0ull;
+                }
+            }
+            i = j;
+        }
+    }
 
     // emit the dense [n_steps_padded][S] record array
     void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps) {
@@ -216,6 +321,8 @@ class Scheduler {
     std::vector<uint32_t> fill_, next_;
     std::vector<uint32_t> steps_;
     std::vector<OpRec> ops_;
+    std::vector<uint32_t> other_writes_at_, other_writes_off_, other_writes_;   // write sets of the ops that bypass the ring
+    std::vector<uint32_t> seg_starts_;
     uint32_t n_steps_ = 0;
     uint32_t floor_ = 0;
 };
@@ -1683,6 +1790,8 @@ struct Compiler {
             if (!ok) break;
         }
         close_device_segment();
+        plan.ring_slots = opt.ring_slots;
+        sched.assign_ring(opt.ring_slots, plan.stats.n_operand_reads, plan.stats.n_ring_reads);
         sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
         plan.n_slots = temp_base + opt.temp_pool + extra_slots;
         if (scaled) {
@@ -1860,7 +1969,7 @@ struct Cursor {
         return v;
     }
 };
-constexpr uint64_t kPlanMagic = 0x3330304e414c5042ULL;  // "BPLAN003"
+constexpr uint64_t kPlanMagic = 0x3430304e414c5042ULL;  // "BPLAN004"
 }  // namespace
 
 std::vector<uint8_t> serialize_plan(const Plan& p) {
@@ -1878,6 +1987,8 @@ std::vector<uint8_t> serialize_plan(const Plan& p) {
     put_pod<uint32_t>(b, p.static_fail.kind);
     put_pod<uint32_t>(b, p.static_fail.aux);
     put_pod<uint32_t>(b, p.n_mu);
+    put_pod<uint32_t>(b, p.ring_slots);
+    put_pod<uint32_t>(b, 0u);
     put_pod<PlanStats>(b, p.stats);
     while (b.size() % 16) b.push_back(0);
     put_vec(b, p.input_witnesses);
@@ -1909,6 +2020,8 @@ Plan deserialize_plan(const uint8_t* data, size_t len) {
     p.static_fail.kind = c.pod<uint32_t>();
     p.static_fail.aux = c.pod<uint32_t>();
     p.n_mu = c.pod<uint32_t>();
+    p.ring_slots = c.pod<uint32_t>();
+    (void)c.pod<uint32_t>();
     p.stats = c.pod<PlanStats>();
     while (c.o % 16) ++c.o;
     p.input_witnesses = c.vec<uint32_t>();

@@ -21,6 +21,9 @@ namespace acvmb {
 // ---- device record (192 B, 16 B aligned) ------------------------------------------------------
 struct OpRec {
     uint32_t w[8];      // [0]=kind|flags<<8  [1]=acir opcode index  [2]=out slot  [3]=x  [4]=y  [5]=w1  [6]=w2  [7]=aux
+                        // gate / logic / range micro-ops: an operand field with bit 31 set is an index into the shared-memory ring of
+                        // recent values instead of a column; the output of a gate also goes to ring entry w[7], that of AND / XOR to
+                        // ring entry w[5] (RING_NONE = not kept)
     // gate constants (8 x u32 little-endian limbs each), layout by flag:
     //   GF_MUL   : c0 = cM*R^2, c1 = alpha, c2 = beta, c3 = c1*R (w1), c4 = gamma     out = cM*(x+alpha)*(y+beta) + c1*w1 + gamma
     //   GF_MUL|GF_ONE_RED : no c0                                                     out = (x+alpha)*(y+beta)/R + c1*w1 + gamma
@@ -87,6 +90,8 @@ enum ErrKind : uint32_t {
     EK_REFERENCE_PANIC = 8,           // the reference would panic!() here (malformed circuit / API misuse)
 };
 
+constexpr uint32_t RING_FLAG = 0x80000000u, RING_NONE = 0xFFFFFFFFu;
+
 enum StatusCode : uint32_t { ST_SOLVED = 0, ST_IN_PROGRESS = 1, ST_FAILURE = 2, ST_REQUIRES_FOREIGN_CALL = 3 };
 
 struct StaticFail {
@@ -107,6 +112,7 @@ struct PlanStats {
     uint64_t n_directive = 0, n_memory = 0, n_brillig = 0;
     uint64_t n_brillig_device = 0;   // Brillig opcodes lowered to device gates (no host segment)
     uint64_t n_gate_one_reduction = 0;   // multiplicative gates that need ONE Montgomery reduction (scaled columns)
+    uint64_t n_operand_reads = 0, n_ring_reads = 0;   // operand loads of gate / logic / range micro-ops, and how many come from the ring
 };
 
 // The opcode list is cut into segments: device segments are step ranges of the record stream; a host segment is one
@@ -125,6 +131,7 @@ struct Plan {
     uint32_t n_slots = 0;              // witnesses + temporaries
     uint32_t n_opcodes = 0;
     uint32_t chunk_steps = 2;          // steps per TMA stage
+    uint32_t ring_slots = 0;           // entries of the shared-memory ring of recent values the stream was compiled for (0 = none)
     bool needs_full_kernel = false;
     std::vector<uint32_t> input_witnesses;  // order of the per-instance input columns
     std::vector<uint32_t> input_scaled;     // per input: 1 = the column holds value*R (Montgomery), the scatter converts
@@ -163,6 +170,10 @@ struct PlanOptions {
     // Columns written and read only by arithmetic gates hold lambda_w * value for a per-column plan constant lambda_w
     // (plan.cpp "scaled columns"): one Montgomery reduction per multiplicative gate instead of two.
     bool scaled_columns = true;
+    // Recent-value ring in shared memory (vm_kernel_impl.cuh): the last `ring_slots` values written by gate / logic micro-ops
+    // of a tile are kept on chip, and an operand whose producer is that recent is read from there instead of from L2
+    // (operand fields get bit 31 set and carry the ring index).  0 disables.
+    uint32_t ring_slots = 0;
 };
 
 // Throws std::runtime_error for opcodes outside the device scope.

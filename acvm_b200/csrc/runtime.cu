@@ -2,6 +2,7 @@
 // batch, sub-batching, I/O staging.  Mirrors the ownership model of the reference's ACVM struct
 // (acvm/src/pwg/mod.rs:129-181): the circuit owns the opcodes/plan, a batch owns the witness columns.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -44,6 +45,9 @@ struct acvmb_ctx {
     uint32_t opt_split_curve = 1, opt_temp_pool = 0;
     uint32_t opt_device_brillig = 1;
     uint32_t opt_scaled_columns = 1;
+    // shared memory per CTA for the ring of recent values; 0 = no ring, the default: measured on B200 at full size the ring
+    // is within 1 % of the plain kernel (operand loads hit L2 and four resident CTAs per SM hide that latency already)
+    uint32_t opt_ring_bytes = 0;
     uint32_t opt_pedersen_unpinned = 0;   // 1: accept Pedersen opcodes / acvmb_pedersen although parity with barretenberg is unpinned
     int opt_split = -1;
     uint32_t opt_n_stage = 4;
@@ -55,10 +59,17 @@ struct acvmb_ctx {
     // acvmb_solve_batch keeps the column buffers of its last call (one per context): a caller that streams a large batch
     // through repeated calls otherwise pays a cudaMalloc + cudaFree of tens of GB per call (measured 20-290 ms)
     struct acvmb_batch* cached_batch = nullptr;
+    struct acvmb_batch* pipe_batch[2] = {nullptr, nullptr};   // the two column buffers of the pipelined (solve | drain) path
     uint64_t cached_bytes = 0;
     uint32_t opt_cache_batch = 1;
+    // multi-device context (acvmb_ctx_create_multi): this context is bound to devices[0], `peers` are the contexts of
+    // devices[1..]; circuits created on it are replicated to every peer, acvmb_solve_batch shards the batch.
+    std::vector<acvmb_ctx*> peers;
+    void* nccl_comms = nullptr;      // ncclComm_t[1 + peers.size()], created with the first circuit
+    const char* bcast_backend = "none";
 };
 static void drop_cached_batch(acvmb_ctx* ctx);
+static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx);
 
 struct acvmb_circuit {
     acvmb_ctx* ctx = nullptr;
@@ -71,6 +82,8 @@ struct acvmb_circuit {
     uint32_t* d_input_slots = nullptr;
     uint32_t* d_mu_index_of = nullptr;
     uint32_t* d_unscale = nullptr;   // scaled columns: (1/lambda_w)*R per witness, for the output gather
+    std::vector<acvmb_circuit*> shards;   // multi-device context: the replicas on the peer devices (owned)
+    size_t stream_bytes = 0;
     acvmb_run_info run{};
     ~acvmb_circuit() {
         if (d_stream) cudaFree(d_stream);
@@ -81,6 +94,7 @@ struct acvmb_circuit {
         if (d_unscale) cudaFree(d_unscale);
     }
 };
+static void destroy_shards(acvmb_circuit* c);
 
 struct acvmb_batch {
     acvmb_circuit* c = nullptr;
@@ -179,8 +193,13 @@ extern "C" int acvmb_ctx_create(int device, acvmb_ctx** out) {
     return ACVMB_OK;
 }
 
+static void destroy_nccl(acvmb_ctx* ctx);
+
 extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
     if (!ctx) return;
+    destroy_nccl(ctx);
+    for (acvmb_ctx* p : ctx->peers) acvmb_ctx_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     drop_cached_batch(ctx);
     if (ctx->d_fixed_base) cudaFree(ctx->d_fixed_base);
@@ -199,7 +218,7 @@ extern "C" int acvmb_device_name(acvmb_ctx* ctx, char* buf, size_t len) {
 
 extern "C" void* acvmb_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {   // pinned for every device of a multi-device context
         cudaGetLastError();
         return nullptr;
     }
@@ -211,6 +230,10 @@ extern "C" void acvmb_host_free(void* p) {
 
 extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value) {
     if (!ctx || !key) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    for (acvmb_ctx* p : ctx->peers) {
+        int rc = acvmb_ctx_set_option(p, key, value);
+        if (rc) return rc;
+    }
     std::string k(key);
     if (k == "T") ctx->opt_T = (uint32_t)value;
     else if (k == "S") ctx->opt_S = (uint32_t)value;
@@ -221,6 +244,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "pedersen_unpinned") ctx->opt_pedersen_unpinned = value ? 1u : 0u;
     else if (k == "device_brillig") ctx->opt_device_brillig = value ? 1u : 0u;
     else if (k == "scaled_columns") ctx->opt_scaled_columns = value ? 1u : 0u;
+    else if (k == "ring_bytes") ctx->opt_ring_bytes = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
     else if (k == "max_resident_bytes") ctx->max_resident_bytes = value;
@@ -243,6 +267,27 @@ static int ensure_curve_tables(acvmb_ctx* ctx) {
     return ACVMB_OK;
 }
 
+// device buffers of a plan: {field, bytes}
+struct PlanBuf {
+    void** dev;
+    size_t bytes;
+    const void* host;
+};
+static std::vector<PlanBuf> plan_buffers(acvmb_circuit* c, std::vector<uint32_t>& slots_scratch) {
+    const Plan& p = c->plan;
+    slots_scratch = p.input_witnesses;   // bit 31: the scatter stores value * R (scaled column)
+    for (size_t i = 0; i < slots_scratch.size() && i < p.input_scaled.size(); ++i)
+        if (p.input_scaled[i]) slots_scratch[i] |= 0x80000000u;
+    std::vector<PlanBuf> b;
+    b.push_back({(void**)&c->d_stream, c->stream_bytes, p.stream.data()});
+    b.push_back({(void**)&c->d_payload, p.payload.size() * 4, p.payload.data()});
+    b.push_back({(void**)&c->d_assign, p.assign_opcode.size() * 4, p.assign_opcode.data()});
+    b.push_back({(void**)&c->d_input_slots, slots_scratch.size() * 4, slots_scratch.data()});
+    b.push_back({(void**)&c->d_mu_index_of, p.mu_index_of.size() * 4, p.mu_index_of.data()});
+    if (!p.unscale.empty()) b.push_back({(void**)&c->d_unscale, p.unscale.size() * 4, p.unscale.data()});
+    return b;
+}
+
 static int upload_plan(acvmb_circuit* c) {
     const Plan& p = c->plan;
     CUDA_TRY(cudaSetDevice(c->ctx->device));
@@ -250,27 +295,160 @@ static int upload_plan(acvmb_circuit* c) {
         int rc = ensure_curve_tables(c->ctx);
         if (rc) return rc;
     }
-    size_t sb = p.stream.size() * sizeof(OpRec);
-    CUDA_TRY(cudaMalloc(&c->d_stream, std::max<size_t>(sb, 16)));
-    CUDA_TRY(cudaMemcpy(c->d_stream, p.stream.data(), sb, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&c->d_payload, std::max<size_t>(p.payload.size() * 4, 16)));
-    if (!p.payload.empty()) CUDA_TRY(cudaMemcpy(c->d_payload, p.payload.data(), p.payload.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&c->d_assign, std::max<size_t>(p.assign_opcode.size() * 4, 16)));
-    CUDA_TRY(cudaMemcpy(c->d_assign, p.assign_opcode.data(), p.assign_opcode.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&c->d_input_slots, std::max<size_t>(p.input_witnesses.size() * 4, 16)));
-    if (!p.input_witnesses.empty()) {
-        std::vector<uint32_t> slots(p.input_witnesses);   // bit 31: the scatter stores value * R (scaled column)
-        for (size_t i = 0; i < slots.size() && i < p.input_scaled.size(); ++i)
-            if (p.input_scaled[i]) slots[i] |= 0x80000000u;
-        CUDA_TRY(cudaMemcpy(c->d_input_slots, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+    c->stream_bytes = p.stream.size() * sizeof(OpRec);
+    std::vector<uint32_t> slots;
+    for (PlanBuf& b : plan_buffers(c, slots)) {
+        CUDA_TRY(cudaMalloc(b.dev, std::max<size_t>(b.bytes, 16)));
+        if (b.bytes) CUDA_TRY(cudaMemcpy(*b.dev, b.host, b.bytes, cudaMemcpyHostToDevice));
     }
-    if (!p.unscale.empty()) {
-        CUDA_TRY(cudaMalloc(&c->d_unscale, p.unscale.size() * 4));
-        CUDA_TRY(cudaMemcpy(c->d_unscale, p.unscale.data(), p.unscale.size() * 4, cudaMemcpyHostToDevice));
+    return ACVMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-device context (SURVEY 8b `acvmb_create(devices, n)`, 8e): the batch shards contiguously over the devices, the
+// compiled plan reaches them through ONE broadcast from devices[0] -- NCCL (ncclBroadcast over NVLink) when libnccl.so.2
+// can be loaded, peer copies otherwise -- and nothing moves between devices during a solve.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) {
+            a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
+            a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+            a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+            a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+            a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+            a.ok = a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Broadcast;
+        }
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+static void destroy_nccl(acvmb_ctx* ctx) {
+    if (!ctx->nccl_comms) return;
+    void** comms = (void**)ctx->nccl_comms;
+    for (size_t i = 0; i < 1 + ctx->peers.size(); ++i)
+        if (comms[i]) nccl_api().CommDestroy(comms[i]);
+    delete[] comms;
+    ctx->nccl_comms = nullptr;
+}
+
+extern "C" int acvmb_ctx_create_multi(const int* devices, int n, acvmb_ctx** out) {
+    if (!devices || n < 1 || !out) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return set_err(ACVMB_ERR_INVALID_ARG, "a device is listed twice");
+    acvmb_ctx* root = nullptr;
+    int rc = acvmb_ctx_create(devices[0], &root);
+    if (rc) return rc;
+    for (int i = 1; i < n; ++i) {
+        acvmb_ctx* p = nullptr;
+        rc = acvmb_ctx_create(devices[i], &p);
+        if (rc) {
+            acvmb_ctx_destroy(root);
+            return rc;
+        }
+        root->peers.push_back(p);
     }
-    CUDA_TRY(cudaMalloc(&c->d_mu_index_of, std::max<size_t>(p.mu_index_of.size() * 4, 16)));
-    if (!p.mu_index_of.empty())
-        CUDA_TRY(cudaMemcpy(c->d_mu_index_of, p.mu_index_of.data(), p.mu_index_of.size() * 4, cudaMemcpyHostToDevice));
+    *out = root;
+    return ACVMB_OK;
+}
+
+extern "C" int acvmb_ctx_n_devices(const acvmb_ctx* ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
+extern "C" const char* acvmb_ctx_broadcast_backend(const acvmb_ctx* ctx) { return ctx ? ctx->bcast_backend : "none"; }
+
+static void destroy_shards(acvmb_circuit* c) {
+    for (acvmb_circuit* sh : c->shards) {
+        cudaSetDevice(sh->ctx->device);
+        if (cached_batch_circuit(sh->ctx) == sh) drop_cached_batch(sh->ctx);
+        delete sh;
+    }
+    c->shards.clear();
+}
+
+// replicate the uploaded plan of `c` (on devices[0]) to every peer device: the one collective of the path
+static int replicate_to_peers(acvmb_circuit* c) {
+    acvmb_ctx* root = c->ctx;
+    if (root->peers.empty()) return ACVMB_OK;
+    const size_t n = 1 + root->peers.size();
+    std::vector<acvmb_circuit*> all = {c};
+    for (acvmb_ctx* p : root->peers) {
+        auto sh = std::make_unique<acvmb_circuit>();
+        sh->ctx = p;
+        sh->plan = c->plan;
+        sh->plan.stream.clear();           // host copy of the record stream stays with the root (serialisation)
+        sh->plan.stream.shrink_to_fit();
+        sh->stream_bytes = c->stream_bytes;
+        sh->circuit = c->circuit;
+        sh->has_circuit = c->has_circuit;
+        c->shards.push_back(sh.release());
+        all.push_back(c->shards.back());
+    }
+    std::vector<std::vector<uint32_t>> scratch(n);
+    std::vector<std::vector<PlanBuf>> bufs(n);
+    for (size_t i = 0; i < n; ++i) {
+        bufs[i] = plan_buffers(all[i], scratch[i]);
+        if (i == 0) continue;
+        CUDA_TRY(cudaSetDevice(all[i]->ctx->device));
+        if (c->plan.needs_full_kernel) {
+            int rc = ensure_curve_tables(all[i]->ctx);
+            if (rc) return rc;
+        }
+        for (PlanBuf& b : bufs[i]) CUDA_TRY(cudaMalloc(b.dev, std::max<size_t>(b.bytes, 16)));
+    }
+    NcclApi& api = nccl_api();
+    bool use_nccl = api.ok;
+    if (use_nccl && !root->nccl_comms) {
+        std::vector<int> devs;
+        for (acvmb_circuit* x : all) devs.push_back(x->ctx->device);
+        void** comms = new void*[n]();
+        if (api.CommInitAll(comms, (int)n, devs.data()) != 0) {
+            delete[] comms;
+            use_nccl = false;
+        } else {
+            root->nccl_comms = comms;
+        }
+    }
+    if (use_nccl) {
+        void** comms = (void**)root->nccl_comms;
+        for (size_t k = 0; k < bufs[0].size(); ++k) {
+            if (!bufs[0][k].bytes) continue;
+            int e = api.GroupStart();
+            for (size_t i = 0; i < n && e == 0; ++i) {
+                cudaSetDevice(all[i]->ctx->device);
+                e = api.Broadcast(*bufs[0][k].dev, *bufs[i][k].dev, bufs[0][k].bytes, /*ncclUint8*/ 1, 0, comms[i], all[i]->ctx->stream);
+            }
+            if (e == 0) e = api.GroupEnd(); else api.GroupEnd();
+            if (e != 0) return set_err(ACVMB_ERR_CUDA, "ncclBroadcast of the plan failed (nccl error " + std::to_string(e) + ")");
+        }
+        root->bcast_backend = "nccl";
+    } else {
+        CUDA_TRY(cudaSetDevice(root->device));
+        for (size_t i = 1; i < n; ++i)
+            for (size_t k = 0; k < bufs[0].size(); ++k)
+                if (bufs[0][k].bytes)
+                    CUDA_TRY(cudaMemcpyPeerAsync(*bufs[i][k].dev, all[i]->ctx->device, *bufs[0][k].dev, root->device, bufs[0][k].bytes, root->stream));
+        root->bcast_backend = "peer-copy";
+    }
+    for (size_t i = 0; i < n; ++i) {
+        CUDA_TRY(cudaSetDevice(all[i]->ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(all[i]->ctx->stream));
+    }
+    CUDA_TRY(cudaSetDevice(root->device));
     return ACVMB_OK;
 }
 
@@ -299,9 +477,23 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     opt.allow_unpinned_pedersen = ctx->opt_pedersen_unpinned != 0;
     opt.device_brillig = ctx->opt_device_brillig != 0;
     opt.scaled_columns = ctx->opt_scaled_columns != 0;
+    {
+        // the ring is [entries][T lanes][32 B]: size it for the tile width pick_T() will choose for this circuit
+        bool curve = false;
+        for (auto& op : circ.opcodes)
+            curve |= op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul ||
+                                                op.bb.func == BB_EcdsaSecp256k1 || op.bb.func == BB_EcdsaSecp256r1);
+        uint32_t T_guess = ctx->opt_T ? ctx->opt_T : (curve ? 32u : std::max(1u, 128u / opt.S));
+        if (T_guess > 32) T_guess = 32;
+        opt.ring_slots = std::min<uint32_t>(1024u, ctx->opt_ring_bytes / (T_guess * 32u));
+    }
     std::vector<uint32_t> inputs(input_witnesses, input_witnesses + n_inputs);
     try {
         c->plan = compile_plan(circ, inputs, opt);
+        if (c->plan.needs_full_kernel && c->plan.ring_slots) {   // the ring variant exists for the arithmetic / logic kernel only
+            opt.ring_slots = 0;
+            c->plan = compile_plan(circ, inputs, opt);
+        }
     } catch (const std::exception& e) {
         return set_err(ACVMB_ERR_UNSUPPORTED, e.what());
     }
@@ -329,7 +521,12 @@ extern "C" int acvmb_circuit_from_acir(acvmb_ctx* ctx, const uint8_t* gz, size_t
         (*out)->circuit = std::move(circ);
         (*out)->has_circuit = true;
     }
-    return ACVMB_OK;
+    rc = replicate_to_peers(*out);
+    if (rc) {
+        acvmb_circuit_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
 }
 
 static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx);
@@ -337,7 +534,9 @@ static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx);
 extern "C" void acvmb_circuit_destroy(acvmb_circuit* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
-    if (c->ctx->cached_batch && cached_batch_circuit(c->ctx) == c) drop_cached_batch(c->ctx);
+    destroy_shards(c);
+    cudaSetDevice(c->ctx->device);
+    if (cached_batch_circuit(c->ctx) == c) drop_cached_batch(c->ctx);
     delete c;
 }
 
@@ -374,6 +573,9 @@ extern "C" int acvmb_circuit_info(const acvmb_circuit* c, acvmb_plan_info* o) {
     o->n_brillig_device = (uint32_t)p.stats.n_brillig_device;
     o->n_gate_one_reduction = p.stats.n_gate_one_reduction;
     o->scaled_columns = p.unscale.empty() ? 0u : 1u;
+    o->ring_slots = p.ring_slots;
+    o->n_operand_reads = p.stats.n_operand_reads;
+    o->n_ring_reads = p.stats.n_ring_reads;
     return ACVMB_OK;
 }
 
@@ -408,6 +610,8 @@ extern "C" int acvmb_circuit_deserialize(acvmb_ctx* ctx, const uint8_t* blob, si
         return set_err(ACVMB_ERR_DECODE, e.what());
     }
     int rc = upload_plan(c.get());
+    if (rc) return rc;
+    rc = replicate_to_peers(c.get());
     if (rc) return rc;
     *out = c.release();
     return ACVMB_OK;
@@ -468,9 +672,16 @@ extern "C" void acvmb_batch_destroy(acvmb_batch* b) {
 static void drop_cached_batch(acvmb_ctx* ctx) {
     if (ctx->cached_batch) acvmb_batch_destroy(ctx->cached_batch);
     ctx->cached_batch = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pipe_batch[i]) acvmb_batch_destroy(ctx->pipe_batch[i]);
+        ctx->pipe_batch[i] = nullptr;
+    }
     ctx->cached_bytes = 0;
 }
-static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx) { return ctx->cached_batch ? ctx->cached_batch->c : nullptr; }
+static acvmb_circuit* cached_batch_circuit(acvmb_ctx* ctx) {
+    if (ctx->cached_batch) return ctx->cached_batch->c;
+    return ctx->pipe_batch[0] ? ctx->pipe_batch[0]->c : nullptr;
+}
 
 extern "C" int acvmb_batch_upload(acvmb_batch* b, const uint8_t* inputs_be32) {
     if (!b) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
@@ -515,6 +726,7 @@ extern "C" int acvmb_batch_run(acvmb_batch* b, float* kernel_ms) {
     a.n_tiles = b->n_tiles;
     a.mu_assign = b->d_mu;
     a.n_mu = c->plan.n_mu;
+    a.ring_slots = c->plan.ring_slots;
     KernelConfig cfg{(int)b->T, (int)c->plan.S, c->plan.needs_full_kernel, c->ctx->opt_split};
     float total = 0;
     for (const Segment& sg : c->plan.segments) {
@@ -1003,10 +1215,57 @@ extern "C" int acvmb_solve_batch(acvmb_circuit* c, uint32_t batch, const uint8_t
     return acvmb_solve_batch_ex(c, batch, inputs_be32, out_ids, n_out_ids, out_witness, nullptr, out_status);
 }
 
+static int solve_batch_single(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                              uint32_t n_out_ids, uint8_t* out_witness, uint8_t* out_present, acvmb_status* out_status);
+
 extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
                                     uint32_t n_out_ids, uint8_t* out_witness, uint8_t* out_present, acvmb_status* out_status) {
     if (!c) return set_err(ACVMB_ERR_INVALID_ARG, "circuit is NULL");
     if (batch == 0) return ACVMB_OK;
+    if (c->shards.empty()) return solve_batch_single(c, batch, inputs_be32, out_ids, n_out_ids, out_witness, out_present, out_status);
+    // multi-device context: contiguous instance ranges, one host thread per device, no traffic between devices
+    std::vector<acvmb_circuit*> all = {c};
+    all.insert(all.end(), c->shards.begin(), c->shards.end());
+    const uint32_t n_dev = (uint32_t)all.size();
+    const uint32_t T = pick_T(c->ctx, c->plan);
+    uint32_t per = (batch + n_dev - 1) / n_dev;
+    per = ((per + T - 1) / T) * T;   // whole tiles per device
+    const size_t n_in = c->plan.input_witnesses.size();
+    const uint32_t n_out = out_ids ? n_out_ids : c->plan.num_witnesses;
+    std::vector<int> rcs(n_dev, ACVMB_OK);
+    std::vector<std::string> errs(n_dev);
+    auto work = [&](uint32_t d) {
+        const uint32_t lo = std::min<uint64_t>((uint64_t)d * per, batch), hi = std::min<uint64_t>((uint64_t)(d + 1) * per, batch);
+        memset(&all[d]->run, 0, sizeof(all[d]->run));
+        if (hi == lo) return;
+        rcs[d] = solve_batch_single(all[d], hi - lo, inputs_be32 ? inputs_be32 + (size_t)lo * n_in * 32 : nullptr, out_ids, n_out_ids,
+                                    out_witness ? out_witness + (size_t)lo * n_out * 32 : nullptr,
+                                    out_present ? out_present + (size_t)lo * n_out : nullptr, out_status ? out_status + lo : nullptr);
+        if (rcs[d]) errs[d] = g_last_error;
+    };
+    std::vector<std::thread> th;
+    for (uint32_t d = 1; d < n_dev; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto& t : th) t.join();
+    cudaSetDevice(c->ctx->device);
+    acvmb_run_info agg = c->run;
+    for (uint32_t d = 1; d < n_dev; ++d) {   // run record: device times are the max over devices, launches the sum
+        const acvmb_run_info& r = all[d]->run;
+        agg.kernel_ms = std::max(agg.kernel_ms, r.kernel_ms);
+        agg.scatter_ms = std::max(agg.scatter_ms, r.scatter_ms);
+        agg.gather_ms = std::max(agg.gather_ms, r.gather_ms);
+        agg.kernel_launches += r.kernel_launches;
+        agg.n_tiles += r.n_tiles;
+        agg.n_subbatches = std::max(agg.n_subbatches, r.n_subbatches);
+    }
+    c->run = agg;
+    for (uint32_t d = 0; d < n_dev; ++d)
+        if (rcs[d]) return set_err(rcs[d], "device " + std::to_string(all[d]->ctx->device) + ": " + errs[d]);
+    return ACVMB_OK;
+}
+
+static int solve_batch_single(acvmb_circuit* c, uint32_t batch, const uint8_t* inputs_be32, const uint32_t* out_ids,
+                              uint32_t n_out_ids, uint8_t* out_witness, uint8_t* out_present, acvmb_status* out_status) {
     CUDA_TRY(cudaSetDevice(c->ctx->device));
     memset(&c->run, 0, sizeof(c->run));
     uint32_t T = pick_T(c->ctx, c->plan);
@@ -1016,28 +1275,30 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
     size_t n_in = c->plan.input_witnesses.size();
     int rc = ACVMB_OK;
     uint32_t n_sub = 0;
-    if (want_out && batch > resident && resident >= 2 * T) {
-        // The batch does not fit HBM at once and every sub-batch's witness map goes back over PCIe (~55 GB/s), which takes
-        // ~10x longer than solving it.  Two column buffers of half the resident size: while sub-batch k drains (gather + D2H
-        // on their own streams), the VM kernel of sub-batch k+1 runs on the VM stream.
-        // resident_instances() budgeted the cached column buffers of an earlier call as free memory: release them first
-        drop_cached_batch(c->ctx);
-        uint32_t half = ((resident / 2) / T) * T;
-        acvmb_batch* bufs[2] = {nullptr, nullptr};
-        uint32_t caps[2] = {0, 0};
-        for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += half, ++n_sub) {
-            const uint32_t cnt = std::min(half, batch - off);
+    const uint64_t out_bytes = (uint64_t)batch * n_out * (out_witness ? 32 : 1);
+    if (want_out && resident >= 2 * T && batch >= 2 * T && (batch > resident || out_bytes >= (256ull << 20))) {
+        // Every witness map goes back over PCIe (~55 GB/s), which takes ~10x longer than solving it.  Two column buffers:
+        // while piece k drains (gather + D2H on their own streams), the VM kernel of piece k+1 runs on the VM stream.  A batch
+        // that does not fit HBM is cut into halves of the resident size, one that does into four pieces.
+        acvmb_ctx* ctx = c->ctx;
+        uint32_t piece = batch > resident ? ((resident / 2) / T) * T : (((batch + 3) / 4 + T - 1) / T) * T;
+        if (piece < T) piece = T;
+        acvmb_batch** bufs = ctx->pipe_batch;
+        const bool reuse = bufs[0] && bufs[1] && bufs[0]->c == c && bufs[0]->T == T && bufs[0]->capacity == piece && bufs[1]->capacity == piece;
+        if (!reuse) drop_cached_batch(ctx);   // (resident_instances() budgeted every cached column buffer as free memory)
+        else if (ctx->cached_batch) { acvmb_batch_destroy(ctx->cached_batch); ctx->cached_batch = nullptr; }
+        for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += piece, ++n_sub) {
+            const uint32_t cnt = std::min(piece, batch - off);
             const int i = n_sub & 1;
-            rc = wait_download(bufs[i]);   // its previous sub-batch has left the device
+            rc = wait_download(bufs[i]);   // its previous piece has left the device
             if (rc) break;
-            if (!bufs[i] || caps[i] != cnt) {
-                if (bufs[i]) acvmb_batch_destroy(bufs[i]);
-                bufs[i] = nullptr;
-                rc = acvmb_batch_create(c, cnt, &bufs[i]);
+            if (!bufs[i]) {
+                rc = acvmb_batch_create(c, piece, &bufs[i]);
                 if (rc) break;
-                caps[i] = cnt;
             }
             acvmb_batch* b = bufs[i];
+            rc = acvmb_batch_resize(b, cnt);
+            if (rc) break;
             rc = acvmb_batch_upload(b, inputs_be32 ? inputs_be32 + (size_t)off * n_in * 32 : nullptr);
             if (rc) break;
             rc = acvmb_batch_run(b, nullptr);
@@ -1053,9 +1314,9 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
             int rc2 = wait_download(bufs[i]);
             if (!rc) rc = rc2;
         }
-        for (int i = 0; i < 2; ++i)
-            if (bufs[i]) acvmb_batch_destroy(bufs[i]);
-        c->run.resident_instances = half;
+        if (rc != ACVMB_OK || !ctx->opt_cache_batch) drop_cached_batch(ctx);
+        else ctx->cached_bytes = 2ull * ((uint64_t)(piece + T - 1) / T) * T * c->plan.n_slots * 32;
+        c->run.resident_instances = piece;
         c->run.n_subbatches = n_sub;
         return rc;
     }
@@ -1071,6 +1332,10 @@ extern "C" int acvmb_solve_batch_ex(acvmb_circuit* c, uint32_t batch, const uint
             ctx->cached_bytes = 0;
         } else {
             drop_cached_batch(ctx);
+        }
+        for (int i = 0; i < 2; ++i) {   // the pipelined path's buffers are not used here
+            if (ctx->pipe_batch[i]) acvmb_batch_destroy(ctx->pipe_batch[i]);
+            ctx->pipe_batch[i] = nullptr;
         }
     }
     for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += resident, ++n_sub) {
@@ -1418,6 +1683,7 @@ extern "C" int acvmb_plan_compile_host_ex(const uint8_t* gz, size_t len, const u
     opt.allow_unpinned_pedersen = (flags & 1u) != 0;
     opt.device_brillig = (flags & 2u) == 0;
     opt.scaled_columns = (flags & 4u) == 0;
+    if (const uint32_t rs = (flags >> 8) & 0xFFFFu) opt.ring_slots = rs == 0xFFFFu ? 0u : rs;
     try {
         tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);
     } catch (const std::exception& e) {

@@ -22,6 +22,7 @@ struct VmArgs {
     uint32_t n_tiles;
     uint32_t* mu_assign;          // [tile][n_mu][T]: opcode index that assigned a value-dependent witness, ~0 = unassigned
     uint32_t n_mu;
+    uint32_t ring_slots;          // entries of the shared-memory ring of recent values the stream was compiled for (0 = none)
 };
 
 struct KernelConfig {

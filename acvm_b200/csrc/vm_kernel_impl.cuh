@@ -78,6 +78,25 @@ __device__ __forceinline__ void store_w(uint4* cb, uint32_t w, const Fe& v) {
     p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
+// Operand of a gate / logic / range micro-op: a column, or (bit 31 of the field) an entry of the tile's shared-memory ring of
+// recent values -- same [plane][lane] layout as a column, ~30 cycles away instead of an L2 round trip.  One generic load
+// serves both, so slots of a warp that differ in where their operand lives do not diverge.
+template <int T, bool RING>
+__device__ __forceinline__ void load_op(Fe& v, const uint4* cb, const uint4* ring, uint32_t w) {
+    const uint4* p = cb + (size_t)w * (2 * T);
+    if constexpr (RING) p = (w & RING_FLAG) ? ring + (size_t)(w & ~RING_FLAG) * (2 * T) : p;
+    uint4 lo = p[0], hi = p[T];
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+}
+template <int T, bool RING>
+__device__ __forceinline__ void store_ring(uint4* ring, uint32_t entry, const Fe& v) {
+    if constexpr (!RING) return;
+    if (ring == nullptr || entry == RING_NONE) return;
+    uint4* p = ring + (size_t)entry * (2 * T);
+    p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[T] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
 __device__ __forceinline__ void lds_fe(Fe& v, const uint32_t* c) {
     const uint4* p = reinterpret_cast<const uint4*>(c);
     uint4 lo = p[0], hi = p[1];
@@ -122,9 +141,32 @@ struct GateLimbs {
 //   otherwise         : out = ( y*c1 + w1*c2 + w2*c3 + c4 ) / R                          one reduction, width 0..3
 // where only the first GF_NPROD linear operands are products; the rest are added or subtracted after the reduction, and a
 // gate without any product is c4 +- operands with no multiplication at all.
-template <int T, int SPLIT>
-__device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
+template <int T, int SPLIT, bool RING>
+__device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, uint4* ring,
+                                          unsigned long long* fail) {
     Fe res;
+    // The dominant form -- one product, one reduction, nothing else: out = ((x+c1)*(y+c2) + c4)/R -- runs straight through,
+    // without the width agreement and operand bookkeeping of the general path below (395 -> ~250 instructions per gate).
+    constexpr uint32_t FORM_MASK = GF_MUL | GF_Y | (3u << GF_NLIN_SHIFT) | GF_OUT_CHECK | GF_ONE_RED | (3u << GF_NPROD_SHIFT);
+    if ((flags & FORM_MASK) == (GF_MUL | GF_Y | GF_ONE_RED)) {
+        Fe x, y, t;
+        load_op<T, RING>(x, cb, ring, r->w[3]);
+        load_op<T, RING>(y, cb, ring, r->w[4]);
+        lds_fe(t, r->c[1]);
+        fr::add_raw(x, x, t);
+        lds_fe(t, r->c[2]);
+        fr::add_raw(y, y, t);
+        const Fe* a1[1] = {&x};
+        fr::mont_dot_fn<1, RegLimbs, SPLIT>(res, a1, RegLimbs{y}, r->c[4]);
+        fr::cond_sub_p(res);
+        if (kind == MK_GATE_ASSIGN) {
+            store_w<T>(cb, r->w[2], res);
+            store_ring<T, RING>(ring, r->w[7], res);
+        } else if (!fr::is_zero(res)) {
+            record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
+        }
+        return;
+    }
     if (flags & GF_Y) {
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
         const uint32_t nprod = (flags >> GF_NPROD_SHIFT) & 3;
@@ -132,10 +174,10 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
         // Every operand load is issued here, before the code paths part: the slots of a warp may hold different gate forms,
         // the forms then run one after the other, and with the loads inside each form their L2 latencies added up.
         Fe x, y, w1, w2;
-        if (mul) load_w<T>(x, cb, r->w[3]);
-        load_w<T>(y, cb, r->w[4]);
-        if (nlin >= 1) load_w<T>(w1, cb, r->w[5]);
-        if (nlin >= 2) load_w<T>(w2, cb, r->w[6]);
+        if (mul) load_op<T, RING>(x, cb, ring, r->w[3]);
+        load_op<T, RING>(y, cb, ring, r->w[4]);
+        if (nlin >= 1) load_op<T, RING>(w1, cb, ring, r->w[5]);
+        if (nlin >= 2) load_op<T, RING>(w2, cb, ring, r->w[6]);
         const uint32_t K = (mul ? 1u : 0u) + nprod;   // width of this lane's dot product
         if (K == 0) {
             lds_fe(res, r->c[4]);
@@ -204,17 +246,19 @@ __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_
         } else {
             store_w<T>(cb, r->w[2], res);
         }
+        store_ring<T, RING>(ring, r->w[7], res);
     } else {
         if (!fr::is_zero(res)) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
     }
 }
 
 // AND / XOR on the low `nb` bits of the canonical values (acir_field/src/generic_ark.rs:322-354,446-473)
-template <int T>
-__device__ __forceinline__ void exec_logic(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, unsigned long long* fail) {
+template <int T, bool RING>
+__device__ __forceinline__ void exec_logic(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, uint4* ring,
+                                           unsigned long long* fail) {
     Fe x, y, res;
-    load_w<T>(x, cb, r->w[3]);
-    load_w<T>(y, cb, r->w[4]);
+    load_op<T, RING>(x, cb, ring, r->w[3]);
+    load_op<T, RING>(y, cb, ring, r->w[4]);
     const uint32_t nb = r->w[7];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -236,12 +280,13 @@ __device__ __forceinline__ void exec_logic(const OpRec* r, uint32_t kind, uint32
     } else {
         store_w<T>(cb, r->w[2], res);
     }
+    store_ring<T, RING>(ring, r->w[5], res);
 }
 
-template <int T>
-__device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned long long* fail) {
+template <int T, bool RING>
+__device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, const uint4* ring, unsigned long long* fail) {
     Fe x;
-    load_w<T>(x, cb, r->w[3]);
+    load_op<T, RING>(x, cb, ring, r->w[3]);
     if (fr::num_bits(x) > r->w[7]) record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
 }
 
@@ -250,18 +295,23 @@ __device__ __forceinline__ void exec_range(const OpRec* r, uint4* cb, unsigned l
 // latencies) and keeping the whole sub-batch in ONE wave matters more than spill-free heavy ops: cap at 7 CTAs/SM.
 // CAP selects the register-capped build; the launcher uses it only when the uncapped one could not hold the sub-batch in a
 // single wave (it costs ~30 % on Keccak, whose state then spills).
-template <int T, int S, bool FULL, int SPLIT, bool CAP = false>
+template <int T, int S, bool FULL, int SPLIT, bool CAP = false, bool RING = false>
 __global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : (FULL ? 512 / (T * S) : 1)) : ((FULL && T * S <= 512) ? 512 / (T * S) : 1)) vm_kernel(const VmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t chunk_bytes = a.chunk_steps * S * (uint32_t)sizeof(OpRec);
     const uint32_t NSTAGE = a.n_stage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGE * chunk_bytes);
+    // ring of recent values: [entry][plane][lane] uint4, after the staging ring and its barriers (16 B aligned)
+    uint4* ring = (RING && a.ring_slots)
+                      ? reinterpret_cast<uint4*>(smem + (((size_t)NSTAGE * chunk_bytes + NSTAGE * sizeof(uint64_t) + 15) & ~(size_t)15))
+                      : nullptr;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t slot = tid / T;
     const uint32_t lane = tid % T;
     const uint32_t tile = blockIdx.x;
     uint4* cb = a.cols + (size_t)tile * a.n_slots * (2 * T) + lane;
+    uint4* ring_lane = ring ? ring + lane : nullptr;
     unsigned long long* fail = a.fail + (size_t)tile * T + lane;
     uint32_t* mu = a.mu_assign + (size_t)tile * a.n_mu * T + lane;
 
@@ -289,25 +339,16 @@ __global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : 
             const OpRec* r = recs + s * S + slot;
             const uint32_t hdr = r->w[0];
             const uint32_t kind = hdr & 0xFF, flags = hdr >> 8;
-            switch (kind) {
-                case MK_NOP:
-                    break;
-                case MK_GATE_ASSIGN:
-                case MK_GATE_CHECK:
-                    exec_gate<T, SPLIT>(r, kind, flags, cb, fail);
-                    break;
-                case MK_AND:
-                case MK_XOR:
-                    exec_logic<T>(r, kind, flags, cb, fail);
-                    break;
-                case MK_RANGE:
-                    exec_range<T>(r, cb, fail);
-                    break;
-                default:
+            if (kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK) {
+                exec_gate<T, SPLIT, RING>(r, kind, flags, cb, ring_lane, fail);
+            } else if (kind == MK_AND || kind == MK_XOR) {
+                exec_logic<T, RING>(r, kind, flags, cb, ring_lane, fail);
+            } else if (kind == MK_RANGE) {
+                exec_range<T, RING>(r, cb, ring_lane, fail);
+            } else if (kind != MK_NOP) {
 #ifdef ACVMB_HEAVY_OPS_TU
-                    if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload, mu);
+                if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload, mu);
 #endif
-                    break;
             }
             __syncthreads();
         }
@@ -323,7 +364,15 @@ template <int T, int S, bool FULL, int SPLIT = FR_ALU_SPLIT>
 static cudaError_t launch_one(const VmArgs& args, cudaStream_t stream) {
     if (args.n_stage < 1 || args.n_stage > MAX_NSTAGE) return cudaErrorInvalidValue;
     size_t smem = (size_t)args.n_stage * args.chunk_steps * S * sizeof(OpRec) + args.n_stage * sizeof(uint64_t);
+    if (args.ring_slots) {
+        if (FULL) return cudaErrorInvalidValue;   // the ring variant is built for the arithmetic / logic kernel only
+        smem = ((smem + 15) & ~(size_t)15) + (size_t)args.ring_slots * T * 32;
+    }
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     auto k = vm_kernel<T, S, FULL, SPLIT, false>;
+    if constexpr (!FULL) {
+        if (args.ring_slots) k = vm_kernel<T, S, FULL, SPLIT, false, true>;
+    }
     if constexpr (FULL && T * S <= 128) {
         // uncapped FULL build: ~128 registers -> 65536 / (128 * threads) CTAs per SM
         int sms = 148;

@@ -55,12 +55,24 @@ def _u32_array(xs):
 class Context:
     """One CUDA device.  Fails loudly when there is no sm_100 GPU (no CPU fallback)."""
 
-    def __init__(self, device: int = 0, **options):
+    def __init__(self, device=0, **options):
+        """device: one CUDA device index, or a list of indices for a multi-device context (acvmb_ctx_create_multi): circuits are
+        replicated to every device with one broadcast and solve_batch shards the batch over them."""
         self._h = C.c_void_p()
         self._children = weakref.WeakSet()   # circuits / VMs created on this context: closed before the context itself
-        _check(lib().acvmb_ctx_create(device, C.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            _check(lib().acvmb_ctx_create_multi(devs, len(device), C.byref(self._h)))
+        else:
+            _check(lib().acvmb_ctx_create(device, C.byref(self._h)))
         for k, v in options.items():
             self.set_option(k, v)
+
+    def n_devices(self):
+        return lib().acvmb_ctx_n_devices(self._h)
+
+    def broadcast_backend(self):
+        return lib().acvmb_ctx_broadcast_backend(self._h).decode()
 
     def set_option(self, key, value):
         _check(lib().acvmb_ctx_set_option(self._h, key.encode(), int(value)))
@@ -407,12 +419,15 @@ def decompress_witness_map(data: bytes) -> Dict[int, int]:
 
 
 def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int = 16, temp_pool: int = 0,
-                      pedersen_unpinned: bool = False, device_brillig: bool = True, scaled_columns: bool = True):
+                      pedersen_unpinned: bool = False, device_brillig: bool = True, scaled_columns: bool = True,
+                      ring_slots: int = None):
     """Decode + compile on the host only (no device): returns (info dict, plan blob)."""
     info = _lib.PlanInfo()
     need = C.c_size_t()
     ids = _u32_array(list(input_witnesses))
     flags = (1 if pedersen_unpinned else 0) | (0 if device_brillig else 2) | (0 if scaled_columns else 4)
+    if ring_slots is not None:   # entries of the shared-memory ring of recent values (0 = none)
+        flags |= (0xFFFF if ring_slots == 0 else ring_slots) << 8
     _check(lib().acvmb_plan_compile_host_ex(acir_bytes, len(acir_bytes), ids, len(input_witnesses), S, temp_pool, flags,
                                             C.byref(info), None, 0, C.byref(need)))
     buf = (C.c_uint8 * need.value)()

@@ -178,6 +178,137 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 2-4 at their stated sizes, reported in the `secondary` object of the JSON line.
+# One timed pass each (they take 0.2-35 s per pass; the kernels are latency bound at these batch sizes), after a one-tile
+# warm-up launch of the same kernel that absorbs module load and the lookup-table upload.
+# ---------------------------------------------------------------------------------------------------------------------
+PEDERSEN_ALG_FR_MUL = 57 * 3 * 11 + 3 * 380     # 57(k+1) mixed additions x 11 Fr-mul + (k+1) Fermat inversions, k = 2
+
+
+def _byte_inputs(batch, n_inputs, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, n_inputs, 32), dtype=np.uint8)
+    out[:, :, 31] = rng.integers(0, 256, size=(batch, n_inputs), dtype=np.uint8)
+    return out.tobytes()
+
+
+def _field_inputs(batch, n_inputs, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 256, size=(batch, n_inputs, 32), dtype=np.uint8)
+    out[:, :, 0] &= 0x1F   # < 2^253 < p
+    return out.tobytes()
+
+
+def secondary_circuit(which, scale):
+    """(data, inputs, n_witnesses, units per instance, description, batch per GPU) of a BASELINE config at 1/scale size."""
+    from acvm_b200 import acir_builder as ab
+    if which == "config2":
+        n = (1 << 16) // scale
+        data, inputs, nw = ab.pedersen_chain_circuit(n)
+        return data, inputs, nw, n, f"configs[2]: {n} chained Pedersen{{[prev.x, fresh_i], domain 0}} calls on Grumpkin, batch 4096", 4096
+    if which == "config3":
+        n = (1 << 14) // scale
+        data, inputs, nw = ab.hash_chain_circuit(n)
+        return data, inputs, nw, n, f"configs[3]: {n} chained hash calls alternating SHA256 / Keccak256 over 64 byte-witnesses, batch 4096", 4096
+    n = (1 << 20) // scale
+    data, inputs, nw, counts = ab.mixed_circuit(n)
+    return data, inputs, nw, 1, (f"configs[4]: {n} mixed opcodes (93% dense arithmetic, 4% RANGE/AND/XOR(32), 2% SHA256/Keccak256(64 B), "
+                                 f"1% Pedersen(2)/FixedBaseScalarMul), batch 8192 per GPU; counts {counts}"), 8192
+
+
+def run_secondary(ctx, which, scale, hbm_peak, imad_peak, first_instance=0, cpu_threads=0):
+    import acvm_b200
+    from acvm_b200 import acir_builder as ab
+    t0 = time.time()
+    data, inputs, nw, units, desc, batch = secondary_circuit(which, scale)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+    t_plan = time.time() - t0
+    info = circ.info
+    if which == "config3":
+        make_inputs = lambda n, first: _byte_inputs(n, len(inputs), 3 + first)
+    elif which == "config2":
+        make_inputs = lambda n, first: _field_inputs(n, len(inputs), 2 + first)
+    else:
+        make_inputs = lambda n, first: ab.synthetic_inputs(n, seed_id=4, first_instance=first)
+    import torch
+    free_b, _ = torch.cuda.mem_get_info()
+    per_inst = info["n_slots"] * 32 + 8 + len(inputs) * 32
+    T = 32 if info["n_curve"] else max(1, 128 // info["S"])
+    fit = max(T, (int(free_b * 0.88) // per_inst) // T * T)
+    sizes, left = [], batch
+    while left > 0:
+        take = min(left, fit)
+        sizes.append(take)
+        left -= take
+    b = acvm_b200.DeviceBatch(circ, max(sizes))
+    off = 0
+    for k, sz in enumerate(sizes):
+        b.resize(sz)
+        b.stage_inputs(k, make_inputs(sz, first_instance + off))
+        off += sz
+    b.resize(min(T, sizes[0]))          # warm-up: one tile through the same kernel
+    b.stage_inputs(len(sizes), make_inputs(min(T, sizes[0]), first_instance))
+    b.run_staged(len(sizes))
+    tot = vm = 0.0
+    solved = 0
+    for k, sz in enumerate(sizes):
+        b.resize(sz)
+        t, v = b.run_staged(k)
+        tot += t
+        vm += v
+        solved += sum(1 for s_ in b.status() if s_.status == "Solved")
+    b.close()
+    assert solved == batch, f"{which}: {batch - solved} instances did not solve"
+    sec = tot * 1e-3
+    line = {"workload": desc, "batch_per_gpu": batch, "sub_batches": sizes, "ms_per_step": tot, "steps": 1, "warmup": "one tile",
+            "witnesses_per_s": batch / sec, "n_micro_ops": info["n_micro_ops"], "n_steps": info["n_steps"], "S": info["S"], "T": T,
+            "plan_compile_s": round(t_plan, 1), "circuit_gen_s": round(t_gen, 1)}
+    vm_launch_s = vm * 1e-3 / len(sizes)
+    inst_per_launch = batch / len(sizes)
+    if which == "config2":
+        line.update(metric="pedersen_hashes_per_s", value=units * batch / sec, unit="hashes/s",
+                    parity="UNPINNED vs barretenberg (opt-in kernel, structure-identical; DESIGN.md section 6)")
+        alg = PEDERSEN_ALG_FR_MUL * 136 * units * inst_per_launch / vm_launch_s
+        line["roofline"] = {"bound": "imad", "achieved": alg / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": alg / imad_peak,
+                            "traffic": None, "algorithmic": f"{PEDERSEN_ALG_FR_MUL} Fr-mul x 136 IMAD per Pedersen(2) call (SURVEY 8d)",
+                            "kernel": "vm_kernel<32,8,FULL>"}
+    elif which == "config3":
+        line.update(metric="hashes_per_s", value=units * batch / sec, unit="hashes/s")
+        alg = 3072.0 * units * inst_per_launch / vm_launch_s / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": alg, "peak": hbm_peak, "unit": "GB/s", "frac": alg / hbm_peak, "traffic": None,
+                            "algorithmic": "3 KiB per hash call-instance: 64 x 32 B in + 32 x 32 B out (SURVEY 8d)", "kernel": "vm_kernel<8,16,FULL>"}
+    else:
+        line.update(metric="witnesses_per_s", value=batch / sec, unit="witnesses/s")
+        alg = info["alg_bytes"] * inst_per_launch / vm_launch_s / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": alg, "peak": hbm_peak, "unit": "GB/s", "frac": alg / hbm_peak, "traffic": None,
+                            "algorithmic": f"{info['alg_bytes']} B per instance (plan.stats.alg_bytes: 32 B per operand read / witness written)",
+                            "kernel": "vm_kernel<32,8,FULL>"}
+    if cpu_threads:
+        # CPU comparator: the C++ reference-algorithm restatement on a bounded sample (one instance per host thread)
+        from oracle import acir as oacir, cref
+        cref.build()
+        cpu_scale = {"config2": 64, "config3": 1, "config4": 8}[which]
+        cdata, cinputs, cnw, cunits, _, _ = secondary_circuit(which, scale * cpu_scale) if cpu_scale > 1 else (data, inputs, nw, units, None, None)
+        oc = oacir.decode_circuit(cdata)
+        packed = cref.pack_circuit(oc)
+        cinp = make_inputs(cpu_threads, 0)
+        t0 = time.perf_counter()
+        res, _, _ = cref.solve_batch(oc, cinputs, cinp, cpu_threads, cnw, threads=cpu_threads, packed=packed)
+        dt = time.perf_counter() - t0
+        assert (res[:, 0] == 0).all()
+        per_s = cpu_threads * (cunits if which != "config4" else 1.0 / cpu_scale) / dt
+        line["cpu_baseline"] = {"value": per_s, "unit": line["unit"], "cores": cpu_threads, "kind": "port",
+                                "sample": f"{cpu_threads} instances (one per host thread) of the same circuit at 1/{cpu_scale} length "
+                                          f"({dt:.1f}s; oracle/ref_solver.cpp); rate scaled by length for config 4"}
+    circ.close()
+    return line
+
+
 def workload_config(args, extra):
     cfg = {"workload": f"configs[1]: {args.gates} arithmetic-only width-3 PLONK gates (BN254 Fr), batch {args.batch} per GPU, "
                        f"operands={args.mode}, coefficients={args.coeffs}, every 16th opcode an all-known check",
@@ -227,8 +358,9 @@ def run_ours(args):
         ctx.set_option("S", args.S)
     if args.T:
         ctx.set_option("T", args.T)
-    if os.environ.get("ACVMB_SCALED") is not None:   # A/B hook: 0 = canonical columns (two reductions per multiplicative gate)
-        ctx.set_option("scaled_columns", int(os.environ["ACVMB_SCALED"]))
+    for kv in filter(None, os.environ.get("ACVMB_OPTS", "").split(",")):   # A/B hook: context options, e.g. scaled_columns=0,ring_bytes=0
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     # ---- circuit: compiled on rank 0, broadcast once (the only collective on this path) ----
     data, inputs = (None, list(range(ab.N_INPUTS)))
@@ -421,6 +553,19 @@ def run_ours(args):
         line["cpu_baseline_optimized"] = {"value": n_o / dt_o, "unit": UNIT, "cores": threads, "kind": "port",
                                           "sample": f"{n_o} full solves, dense witness vector + plan-time inverses + 4x64 Montgomery "
                                                     f"({dt_o:.1f}s incl. the one-time plan; oracle/ref_solver.cpp ref_solve_batch_optimized)"}
+    # ---- BASELINE configs 2-4 at their stated sizes (rank 0 at N = 1) ----
+    if world == 1 and args.secondary != "none":
+        scale = 1 if args.secondary == "full" else 64
+        ctx.set_option("pedersen_unpinned", 1)   # configs 2 and 4 contain Pedersen calls: measured on the opt-in kernel, stated in the line
+        line["secondary"] = {}
+        threads = 0 if args.no_cpu_baseline else (os.cpu_count() or 1)
+        for which in ("config3", "config2", "config4"):
+            t0 = time.time()
+            try:
+                line["secondary"][which] = run_secondary(ctx, which, scale, hbm_peak, imad["imad_wide_per_s"], cpu_threads=threads)
+            except Exception as e:   # a secondary measurement must never take the headline line down
+                line["secondary"][which] = {"error": f"{type(e).__name__}: {e}"}
+            log(f"[bench] secondary {which}: {time.time() - t0:.1f}s {line['secondary'][which].get('value')}")
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -461,6 +606,8 @@ def main():
     ap.add_argument("--S", type=int, default=0)
     ap.add_argument("--T", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--secondary", default="full", choices=["full", "quick", "none"],
+                    help="BASELINE configs 2-4 in the `secondary` object: full = stated sizes, quick = 1/64 length, none = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk-gib", type=float, default=64.0,

@@ -6,7 +6,7 @@
  * only; the caller owns every buffer; nothing unwinds across the boundary (all functions return
  * 0 on success or a negative acvmb_rc, with a message available from acvmb_last_error()).
  *
- * A context is bound to one CUDA device and is single-threaded, like the reference's
+ * A context is bound to one CUDA device (or to several, acvmb_ctx_create_multi) and is single-threaded, like the reference's
  * `Barretenberg` (RefCell<Store>, barretenberg_blackbox_solver/src/wasm/mod.rs:59-63).
  * There is NO CPU fallback: creating a context without a usable sm_100 device fails.
  *
@@ -91,11 +91,20 @@ typedef struct {
     uint32_t n_brillig_device;  /* ... of which lowered to device gates at plan time (straight-line field bytecode) */
     uint64_t n_gate_one_reduction; /* multiplicative gates that run ONE Montgomery reduction (scaled columns) */
     uint32_t scaled_columns;    /* 1: some columns hold lambda_w * value; canonical values are produced by the output gather */
-    uint32_t reserved;
+    uint32_t ring_slots;        /* entries of the shared-memory ring of recent values the stream was compiled for */
+    uint64_t n_operand_reads;   /* operand loads of gate / logic / range micro-ops per instance ... */
+    uint64_t n_ring_reads;      /* ... of which served from the shared-memory ring */
 } acvmb_plan_info;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int acvmb_ctx_create(int device, acvmb_ctx** out);
+/* Multi-device context (one node): circuits created on it are compiled once and replicated to every device with ONE broadcast
+ * (ncclBroadcast when libnccl.so.2 can be loaded, peer copies otherwise); acvmb_solve_batch / _ex shard the batch contiguously
+ * over the devices (one host thread each) and fill the caller's buffers; nothing moves between devices during a solve.  The
+ * device-resident acvmb_batch_* calls and the single-instance acvmb_vm_* mirror use devices[0]. */
+int acvmb_ctx_create_multi(const int* devices, int n, acvmb_ctx** out);
+int acvmb_ctx_n_devices(const acvmb_ctx* ctx);
+const char* acvmb_ctx_broadcast_backend(const acvmb_ctx* ctx);   /* "nccl" | "peer-copy" | "none" (nothing replicated yet) */
 /* destroy every circuit / batch / vm created on a context BEFORE the context itself (they keep a pointer to it) */
 void acvmb_ctx_destroy(acvmb_ctx* ctx);
 const char* acvmb_last_error(void);           /* thread-local message of the last failing call */
@@ -207,7 +216,8 @@ int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg, cons
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 /* same with plan options: temp_pool (0 = default), flags bit 0 = accept Pedersen (parity unpinned, see "pedersen_unpinned"),
- * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only */
+ * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only, bits 8..23 = entries of the shared-memory
+ * ring of recent values (0 = default, 0xFFFF = none) */
 int acvmb_plan_compile_host_ex(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                                uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 
@@ -234,7 +244,8 @@ int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
  * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "pedersen_unpinned" (1: accept
  * BlackBoxFuncCall::Pedersen / acvmb_pedersen although the values are NOT barretenberg's -- refused by default),
  * "device_brillig" (0: every Brillig opcode runs on the host VM), "scaled_columns" (0: every witness column holds the
- * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "cache_batch" (0: free
+ * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "ring_bytes" (shared memory per CTA
+ * for the ring of recent values that serves operand reads on chip; 0: every operand comes from L2 / HBM), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
  * identical next call); plan options apply to circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);

@@ -25,12 +25,12 @@ class PlanBlob:
         o = 0
         magic, = struct.unpack_from("<Q", blob, o)
         o += 8
-        assert magic == 0x3330304E414C5042, "bad magic"
+        assert magic == 0x3430304E414C5042, "bad magic"
         (self.S, self.num_witnesses, self.n_slots, self.n_opcodes, self.chunk_steps, self.needs_full, self.n_steps,
-         self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu) = struct.unpack_from("<12I", blob, o)
-        o += 48
-        self.stats = struct.unpack_from("<21Q", blob, o)   # PlanStats (plan.hpp), a POD of 21 u64
-        o += 168
+         self.sf_present, self.sf_opcode, self.sf_kind, self.sf_aux, self.n_mu, self.ring_slots, _pad) = struct.unpack_from("<14I", blob, o)
+        o += 56
+        self.stats = struct.unpack_from("<23Q", blob, o)   # PlanStats (plan.hpp), a POD of 23 u64
+        o += 184
         o = (o + 15) // 16 * 16
 
         def vec(fmt, size):
@@ -346,6 +346,21 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 step_plan.append(("host" if kind_ == 1 else "sort", a_, b_))
     else:
         step_plan = [("step", s_) for s_ in range(plan.n_steps)]
+    # shared-memory ring of recent values: entry -> value; empty at every kernel launch (= device segment)
+    ring = {}
+    seg_first = {a_ for (kind_, a_, b_, _c) in plan.segments if kind_ == 0} if plan.segments else {0}
+
+    class Operands:
+        """cols[...] for the gate / logic / range micro-ops: a field with bit 31 set reads the ring (vm_kernel_impl.cuh load_op)"""
+        def __init__(self):
+            self.ring_reads = set()
+
+        def __getitem__(self, field):
+            if field & 0x80000000:
+                self.ring_reads.add(field & 0x7FFFFFFF)
+                return ring[field & 0x7FFFFFFF]   # KeyError = the plan points at an entry nothing wrote
+            return cols[field]
+
     for item in step_plan:
         if item[0] == "host":
             host_segment(item[1], item[2])
@@ -354,7 +369,12 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
             sort_segment(item[1], item[2])
             continue
         step = item[1]
+        if step in seg_first:
+            ring = {}
         writes = []
+        ring_writes = []
+        real_cols, cols = cols, cols   # (names kept: the gate code below reads operands through `ops`)
+        ops = Operands()
         for s in range(plan.S):
             hdr, c = plan.record(step * plan.S + s)
             kind, flags = hdr[0] & 0xFF, hdr[0] >> 8
@@ -371,7 +391,7 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 if flags & GF_Y:
                     if is_mul:
                         assert nlin <= 1
-                        prod = (cols[x] + c[1]) * (cols[y] + c[2])
+                        prod = (ops[x] + c[1]) * (ops[y] + c[2])
                         if flags & 4096:   # GF_ONE_RED
                             res += prod * RINV
                         else:
@@ -381,9 +401,9 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                         operands = [(y, c[1], flags & 512), (w1, c[2], flags & 1024), (w2, c[3], flags & 2048)][:nlin + 1]
                     for i_, (slot_, coef_, neg_) in enumerate(operands):
                         if i_ < nprod:
-                            res += coef_ * RINV * cols[slot_]
+                            res += coef_ * RINV * ops[slot_]
                         else:
-                            res += -cols[slot_] if neg_ else cols[slot_]
+                            res += -ops[slot_] if neg_ else ops[slot_]
                 res %= P
                 if kind == MK["GATE_ASSIGN"]:
                     if flags & GF_OUT_CHECK:
@@ -392,11 +412,13 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                             writes.append((out, res))
                     else:
                         writes.append((out, res))
+                    if plan.ring_slots and aux != NONE:
+                        ring_writes.append((aux, res))
                 elif res != 0:
                     record_fail(opcode, EK_UNSAT)
             elif kind in (MK["AND"], MK["XOR"]):
                 m = (1 << aux) - 1 if aux < 256 else (1 << 256) - 1
-                a, b = cols[x] & m, cols[y] & m
+                a, b = ops[x] & m, ops[y] & m
                 res = ((a & b) if kind == MK["AND"] else (a ^ b)) % P
                 if flags & GF_OUT_CHECK:
                     if cols[out] != res:
@@ -404,8 +426,10 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                         writes.append((out, res))
                 else:
                     writes.append((out, res))
+                if plan.ring_slots and w1 != NONE:
+                    ring_writes.append((w1, res))
             elif kind == MK["RANGE"]:
-                if cols[x].bit_length() > aux:
+                if ops[x].bit_length() > aux:
                     record_fail(opcode, EK_UNSAT)
             elif kind == MK["GATE_GENERAL"]:
                 pl = plan.payload
@@ -516,6 +540,11 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 raise NotImplementedError(f"plan_interp: micro-op kind {kind}")
         for (slot, v) in writes:
             cols[slot] = v
+        # ring entries are written during the step with no barrier against its reads: no entry may be both
+        assert not (ops.ring_reads & {e for e, _ in ring_writes}), f"step {step}: ring entry read and rewritten in the same step"
+        assert len({e for e, _ in ring_writes}) == len(ring_writes) and all(e < plan.ring_slots for e, _ in ring_writes)
+        for (e, v) in ring_writes:
+            ring[e] = v
     fop = fail[0] if fail else 0xFFFFFFFF
     if plan.sf_present and plan.sf_opcode <= fop:
         status = ("Failure", plan.sf_kind, plan.sf_opcode, plan.sf_aux)

@@ -7,6 +7,9 @@ gates = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4736
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ctx = acvm_b200.Context(0)
+for kv in filter(None, os.environ.get("ACVMB_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 data, inputs, _ = ab.synthetic_arith_circuit(gates)
 circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
 b = acvm_b200.DeviceBatch(circ, batch)

@@ -71,6 +71,28 @@ def test_scaled_and_canonical_columns_agree(scaled, mode, coeffs):
 _CHECKSUMS = {}
 
 
+def test_ring_of_recent_values_kernel_variant():
+    """Opt-in shared-memory ring (context option ring_bytes): operands produced by recent gate / logic micro-ops are read from
+    shared memory.  Same results as the default kernel, bit-exact vs the oracle."""
+    c = acvm_b200.Context(0)
+    try:
+        c.set_option("ring_bytes", 24576)
+        data, inputs, _ = ab.synthetic_arith_circuit(3000, mode="local", coeffs="dense", seed_id=6)
+        circ = acvm_b200.CompiledCircuit(c, data, inputs)
+        assert circ.info["ring_slots"] == 96 and circ.info["n_ring_reads"] > 0.8 * circ.info["n_operand_reads"]
+        circ.close()
+        _check(c, data, inputs, 41, ab.synthetic_inputs(41, seed_id=6))
+        b = ab.CircuitBuilder()
+        b.logic("AND", (1, 64), (2, 64), 10)
+        b.logic("XOR", (10, 64), (1, 64), 11)
+        b.range((11, 64))
+        b.arithmetic([(3, 10, 11)], [(1, 1), (ab.P - 1, 12)], 7)
+        b.arithmetic([], [(1, 12), (1, 11), (ab.P - 1, 13)], 0)
+        _check(c, b.to_bytes(), [1, 2], 9, ab.synthetic_inputs(9, n_inputs=2, seed_id=6))
+    finally:
+        c.close()
+
+
 def test_addition_golden(ctx, golden):
     fx = golden["acvm_js_shared"]["addition"]
     data = bytes(fx["bytecode"])

@@ -673,3 +673,24 @@ def test_straight_line_brillig_is_lowered_to_device_gates():
     b.brillig([("Single", ab.wexpr(1))], [("Simple", 11)], [dict(op="Stop")], predicate=ab.wexpr(2))
     info = _interp_vs_oracle(b.to_bytes(), [1, 2], inp[:64] + inp[96:160], 2)
     assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 2
+
+
+@pytest.mark.parametrize("W", [4, 24, 96])
+def test_ring_of_recent_values_plan_vs_oracle(W):
+    """Opt-in shared-memory ring (plan.cpp assign_ring): operand fields flagged to read ring entries must name the entry that
+    holds the value when the step runs -- the interpreter models the ring, asserts that no entry is read and rewritten in one
+    step, and the witness map must still equal the oracle's."""
+    data, inputs, _ = ab.synthetic_arith_circuit(900, mode="local", coeffs="noir-like", seed_id=3)
+    # (a step of S slots may write S values: with W <= S nothing written in one step survives the next one)
+    info = _interp_vs_oracle(data, inputs, ab.synthetic_inputs(2, seed_id=3), 2, 2 if W == 4 else 16, ring_slots=W)
+    assert info["ring_slots"] == W and 0 < info["n_ring_reads"] <= info["n_operand_reads"]
+    b = ab.CircuitBuilder()
+    b.logic("AND", (1, 64), (2, 64), 10)
+    b.logic("XOR", (10, 64), (1, 64), 11)
+    b.range((11, 64))
+    b.arithmetic([(3, 10, 11)], [(1, 1), (ab.P - 1, 12)], 7)
+    b.arithmetic([], [(1, 12), (1, 11), (ab.P - 1, 13)], 0)
+    b.logic("AND", (13, 254), (12, 254), 14)
+    b.arithmetic([(1, 14, 14)], [(ab.P - 1, 12)], 0)      # check, fails for random inputs
+    info = _interp_vs_oracle(b.to_bytes(), [1, 2], ab.synthetic_inputs(3, n_inputs=2, seed_id=6), 3, 2, ring_slots=W)
+    assert info["n_ring_reads"] > 0
