@@ -385,7 +385,20 @@ static __constant__ unsigned long long KECCAK_RC[24] = {
     0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
 
-__device__ __forceinline__ unsigned long long rol64(unsigned long long x, int n) { return n ? ((x << n) | (x >> (64 - n))) : x; }
+// 64-bit rotate as two 32-bit funnel shifts (the generic shift/or form costs six instructions on the 32-bit datapath); n is a
+// compile-time constant wherever this is called from an unrolled loop
+__device__ __forceinline__ unsigned long long rol64(unsigned long long x, int n) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (n >= 32) {
+        const uint32_t t = lo;
+        lo = hi;
+        hi = t;
+        n -= 32;
+    }
+    if (n == 0) return ((unsigned long long)hi << 32) | lo;
+    const uint32_t rh = __funnelshift_l(lo, hi, n), rl = __funnelshift_l(hi, lo, n);
+    return ((unsigned long long)rh << 32) | rl;
+}
 
 // state index = x + 5*y
 static __device__ __noinline__ void keccak_f1600(unsigned long long* st) {

@@ -145,28 +145,6 @@ template <int T, int SPLIT, bool RING>
 __device__ __forceinline__ void exec_gate(const OpRec* r, uint32_t kind, uint32_t flags, uint4* cb, uint4* ring,
                                           unsigned long long* fail) {
     Fe res;
-    // The dominant form -- one product, one reduction, nothing else: out = ((x+c1)*(y+c2) + c4)/R -- runs straight through,
-    // without the width agreement and operand bookkeeping of the general path below (395 -> ~250 instructions per gate).
-    constexpr uint32_t FORM_MASK = GF_MUL | GF_Y | (3u << GF_NLIN_SHIFT) | GF_OUT_CHECK | GF_ONE_RED | (3u << GF_NPROD_SHIFT);
-    if ((flags & FORM_MASK) == (GF_MUL | GF_Y | GF_ONE_RED)) {
-        Fe x, y, t;
-        load_op<T, RING>(x, cb, ring, r->w[3]);
-        load_op<T, RING>(y, cb, ring, r->w[4]);
-        lds_fe(t, r->c[1]);
-        fr::add_raw(x, x, t);
-        lds_fe(t, r->c[2]);
-        fr::add_raw(y, y, t);
-        const Fe* a1[1] = {&x};
-        fr::mont_dot_fn<1, RegLimbs, SPLIT>(res, a1, RegLimbs{y}, r->c[4]);
-        fr::cond_sub_p(res);
-        if (kind == MK_GATE_ASSIGN) {
-            store_w<T>(cb, r->w[2], res);
-            store_ring<T, RING>(ring, r->w[7], res);
-        } else if (!fr::is_zero(res)) {
-            record_fail(fail, r->w[1], EK_UNSATISFIED_CONSTRAIN, 0);
-        }
-        return;
-    }
     if (flags & GF_Y) {
         const uint32_t nlin = (flags >> GF_NLIN_SHIFT) & 3;
         const uint32_t nprod = (flags >> GF_NPROD_SHIFT) & 3;
@@ -339,16 +317,25 @@ __global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : 
             const OpRec* r = recs + s * S + slot;
             const uint32_t hdr = r->w[0];
             const uint32_t kind = hdr & 0xFF, flags = hdr >> 8;
-            if (kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK) {
-                exec_gate<T, SPLIT, RING>(r, kind, flags, cb, ring_lane, fail);
-            } else if (kind == MK_AND || kind == MK_XOR) {
-                exec_logic<T, RING>(r, kind, flags, cb, ring_lane, fail);
-            } else if (kind == MK_RANGE) {
-                exec_range<T, RING>(r, cb, ring_lane, fail);
-            } else if (kind != MK_NOP) {
+            switch (kind) {
+                case MK_NOP:
+                    break;
+                case MK_GATE_ASSIGN:
+                case MK_GATE_CHECK:
+                    exec_gate<T, SPLIT, RING>(r, kind, flags, cb, ring_lane, fail);
+                    break;
+                case MK_AND:
+                case MK_XOR:
+                    exec_logic<T, RING>(r, kind, flags, cb, ring_lane, fail);
+                    break;
+                case MK_RANGE:
+                    exec_range<T, RING>(r, cb, ring_lane, fail);
+                    break;
+                default:
 #ifdef ACVMB_HEAVY_OPS_TU
-                if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload, mu);
+                    if constexpr (FULL) exec_heavy<T>(r, kind, flags, cb, fail, a.payload, mu);
 #endif
+                    break;
             }
             __syncthreads();
         }

@@ -31,10 +31,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+T_START = time.time()
 METRIC = "witnesses_per_s_2^20_gate_bn254_acir"
-# DRAM bytes per gate-instance of vm_kernel from the committed `ncu --set full` capture (profiles/r1_vm_kernel_ncu_full_v2.txt:
-# dram read 1.70 GB + write 9.26 GB for 4736 instances x 65599 micro-gates): writes are the 32 B result, operand reads hit L2.
-NCU_DRAM_BYTES_PER_GATE_INSTANCE = (1.701491e9 + 9.262512e9) / (4736 * 65599)
+# DRAM bytes per gate-instance of vm_kernel from the committed `ncu --set full` capture of the round-2 kernel AT FULL SIZE
+# (profiles/r2_vm_kernel_ncu_full_v6.txt: dram read 28.97 GB + write 149.09 GB for one launch of 4736 instances x 1 049 616
+# micro-gates): the write is the 32 B result, operand reads hit L2 in "local" mode.
+NCU_DRAM_BYTES_PER_GATE_INSTANCE = (28.973338e9 + 149.086287e9) / (4736 * 1049616)
 UNIT = "witnesses/s"
 
 
@@ -309,6 +311,35 @@ def run_secondary(ctx, which, scale, hbm_peak, imad_peak, first_instance=0, cpu_
     return line
 
 
+def multi_device_c_abi_line(n_dev):
+    """N > 1: the same sharded solve through ONE multi-device context of the C ABI (acvmb_ctx_create_multi) -- one process, one
+    host thread per GPU inside the library, the plan broadcast once (NCCL or peer copies) -- on a 2^16-gate circuit with 8192
+    instances per GPU, only the last 32 witnesses of every instance brought back.  Rank 0 runs it after the other ranks are done."""
+    import acvm_b200
+    from acvm_b200 import acir_builder as ab
+    data, inputs, _ = ab.synthetic_arith_circuit(1 << 16, seed_id=1)
+    ctx = acvm_b200.Context(list(range(n_dev)))
+    try:
+        t0 = time.time()
+        circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
+        t_circ = time.time() - t0
+        batch = 8192 * n_dev
+        inp = ab.synthetic_inputs(256, seed_id=1) * (batch // 256)
+        tail = list(range(circ.num_witnesses - 32, circ.num_witnesses))
+        out, st = circ.solve_batch(inp, batch, out_ids=tail)          # warm-up (allocations, module load on every device)
+        t0 = time.perf_counter()
+        out, st = circ.solve_batch(inp, batch, out_ids=tail)
+        dt = time.perf_counter() - t0
+        assert all(s_.status == "Solved" for s_ in st)
+        assert out[:32 * 32] == out[256 * 32 * 32:257 * 32 * 32]      # instance 256 repeats instance 0: same witnesses, other shard
+        ri = circ.run_info()
+        return {"devices": ctx.n_devices(), "broadcast": ctx.broadcast_backend(), "gates": 1 << 16, "batch": batch,
+                "witnesses_per_s": batch / dt, "wall_ms": 1e3 * dt, "max_device_kernel_ms": ri["kernel_ms"],
+                "kernel_launches": ri["kernel_launches"], "circuit_create_and_broadcast_s": round(t_circ, 2)}
+    finally:
+        ctx.close()
+
+
 def workload_config(args, extra):
     cfg = {"workload": f"configs[1]: {args.gates} arithmetic-only width-3 PLONK gates (BN254 Fr), batch {args.batch} per GPU, "
                        f"operands={args.mode}, coefficients={args.coeffs}, every 16th opcode an all-known check",
@@ -482,16 +513,30 @@ def run_ours(args):
         assert all(st_arr[i].code == 0 for i in range(ins[-1][0]))
         lib.acvmb_host_free(C.c_void_p(host_out))
         os.sched_setaffinity(0, saved_affinity)
+        ri = circ.run_info()
         e2e = {"wall_s_per_step": e2e_wall, "h2d": args.batch * len(inputs) * 32, "d2h": args.batch * (nw * 32 + 16),
-               "calls_per_step": n_calls, "instances_per_call": e2e_chunk}
+               "calls_per_step": n_calls, "instances_per_call": e2e_chunk, "pieces_per_call": ri["n_subbatches"]}
 
+    hbm_peak, peak_src = measured_peaks()
+    imad = ctx.imad_microbench()
+    # ---- BASELINE configs[4] as stated: 65536 instances of the 2^20-op mixed circuit sharded 8192 per GPU over 8 GPUs ----
+    sec4 = None
+    if world == 8 and args.secondary != "none":
+        if e2e is None:
+            batch_obj.close()
+        ctx.set_option("pedersen_unpinned", 1)
+        try:
+            sec4 = run_secondary(ctx, "config4", 1 if args.secondary == "full" else 64, hbm_peak, imad["imad_wide_per_s"],
+                                 first_instance=rank * 8192)
+        except Exception as e_:
+            sec4 = {"error": f"{type(e_).__name__}: {e_}", "ms_per_step": 0.0}
     # ---- reduce over ranks (max time) ----
-    vals = [dev_ms, vm_ms, wall, e2e["wall_s_per_step"] if e2e else 0.0]
+    vals = [dev_ms, vm_ms, wall, e2e["wall_s_per_step"] if e2e else 0.0, sec4["ms_per_step"] if sec4 else 0.0]
     if dist is not None:
         t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = t.tolist()
-    dev_ms, vm_ms, wall, e2e_wall = vals
+    dev_ms, vm_ms, wall, e2e_wall, sec4_ms = vals
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -500,13 +545,37 @@ def run_ours(args):
     total_inst = args.batch * world
     ms_per_step = dev_ms / args.steps
     value = total_inst / (ms_per_step * 1e-3)
-    hbm_peak, peak_src = measured_peaks()
     vm_launch_ms = vm_ms / (args.steps * len(sizes))          # average step-VM kernel launch
     inst_per_launch = sum(sizes) / len(sizes)
     alg_bytes_launch = info["alg_bytes"] * inst_per_launch
     achieved_gbs = alg_bytes_launch / (vm_launch_ms * 1e-3) / 1e9
-    imad = ctx.imad_microbench()
     imad_achieved = info["dev_imad"] * inst_per_launch / (vm_launch_ms * 1e-3)
+    launch_s = vm_launch_ms * 1e-3
+    hbm_frac = achieved_gbs / hbm_peak
+    imad_frac = imad_achieved / imad["imad_wide_per_s"]
+    traffic = NCU_DRAM_BYTES_PER_GATE_INSTANCE * info["n_micro_ops"] * inst_per_launch
+    hbm_obj = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "traffic": traffic,
+               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+               "algorithmic": "96 B per gate-instance: two 32 B operands + the 32 B result (SURVEY 8d; plan.stats.alg_bytes is the exact sum)"}
+    imad_obj = {"bound": "imad", "achieved": imad_achieved / 1e12, "peak": imad["imad_wide_per_s"] / 1e12, "unit": "T IMAD/s",
+                "frac": imad_frac, "traffic": traffic,
+                "peak_source": "measured in this run: independent mad.wide.u32 chains on all SMs (profiles/IMAD_PEAKS.json holds the "
+                               "committed copy)",
+                "peak_imad32_per_s": imad["imad32_per_s"], "peak_wide_carry_per_s": imad["imad_wide_carry_per_s"],
+                "frac_of_carry_peak": imad_achieved / imad["imad_wide_carry_per_s"],
+                "imad_per_instance": info["dev_imad"], "executed": "32x32 multiply-accumulates the kernel executes (plan.stats.dev_imad)"}
+    # the roofline that binds is the one the kernel sits closer to; the other one is reported beside it
+    roof, other = (hbm_obj, imad_obj) if hbm_frac >= imad_frac else (imad_obj, hbm_obj)
+    roof = dict(roof)
+    roof.update({"kernel": "vm_kernel", "kernel_ms_per_launch": vm_launch_ms,
+                 "traffic_source": "ncu --set full capture of this kernel at full size (profiles/r2_vm_kernel_ncu_full_v6.txt), "
+                                   "35.8 B of DRAM traffic per gate-instance, scaled by gate-instances per launch",
+                 "other": other,
+                 "fr_mul": {"reference_fr_mul_per_instance": info["ref_fr_mul"], "reference_fr_inv_per_instance": info["ref_fr_inv"],
+                            "algorithmic_fr_mul_per_s": info["ref_fr_mul"] * inst_per_launch / launch_s,
+                            "device_montgomery_reductions_per_instance": info["n_gate_one_reduction"],
+                            "note": "the reference performs 5 Fr-mul + 1 inversion per gate; scaled columns leave ONE Montgomery "
+                                    "reduction (136 IMAD) per gate on the device"}})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -514,29 +583,27 @@ def run_ours(args):
         "config": workload_config(args, {"sub_batches": sizes, "T": T, "S": info["S"], "n_steps": info["n_steps"],
                                          "slot_fill": info["n_slots_filled"] / max(1, info["n_steps"] * info["S"]),
                                          "resident_warps_per_sm": [round(-(-sz // T) * (T * info["S"] // 32) / 148, 2) for sz in sizes],
-                                         "d2h_overlapped_with_solve": False}),
+                                         "scaled_columns": bool(info["scaled_columns"]),
+                                         "d2h_overlapped_with_solve": bool(e2e and e2e.get("pieces_per_call", 1) > 1)}),
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {
-            "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-            "traffic": NCU_DRAM_BYTES_PER_GATE_INSTANCE * info["n_micro_ops"] * inst_per_launch,
-            "traffic_source": "ncu --set full capture of the same kernel on a 2^16-gate circuit (profiles/r1_vm_kernel_ncu_full_v2.txt), "
-                              "scaled by gate-instances per launch",
-            "peak_source": peak_src, "kernel": "vm_kernel", "kernel_ms_per_launch": vm_launch_ms,
-            "algorithmic_bytes_per_launch": alg_bytes_launch,
-            "note": "dense-coefficient gates are integer-multiply bound, not HBM bound: see imad",
-            "imad": {"achieved_per_s": imad_achieved, "peak_per_s": imad["imad_wide_per_s"], "frac": imad_achieved / imad["imad_wide_per_s"],
-                     "peak_source": "measured in this run: independent mad.wide.u32 chains on all SMs",
-                     "peak_imad32_per_s": imad["imad32_per_s"], "peak_wide_carry_per_s": imad["imad_wide_carry_per_s"],
-                     "imad_per_instance": info["dev_imad"]},
-            "fr_mul": {"reference_fr_mul_per_instance": info["ref_fr_mul"], "reference_fr_inv_per_instance": info["ref_fr_inv"],
-                       "algorithmic_fr_mul_per_s": info["ref_fr_mul"] * inst_per_launch / (vm_launch_ms * 1e-3)},
-        },
+        "roofline": roof,
     }
+    try:   # committed copy of the measured integer-multiply peaks (SURVEY 8d asks for them next to MEASURED_PEAKS.json)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "IMAD_PEAKS.json"), "w") as f:
+            json.dump({"imad32_per_s": imad["imad32_per_s"], "imad_wide_per_s": imad["imad_wide_per_s"],
+                       "imad_wide_carry_per_s": imad["imad_wide_carry_per_s"], "fr_mul_per_s": imad["fr_mul_per_s"],
+                       "sm_clock_mhz": imad["sm_clock_mhz"], "how": "acvmb_imad_microbench / acvmb_frmul_microbench (vm_kernel.cu): "
+                       "independent chains on 148 SMs x 8 CTAs x 256 threads, best of 3 after a warm-up"}, f, indent=1)
+    except OSError:
+        pass
     if e2e:
         line["e2e"] = {"value": total_inst / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "calls_per_step": e2e["calls_per_step"], "instances_per_call": e2e["instances_per_call"],
+                       "pieces_per_call": e2e["pieces_per_call"],
+                       "pipeline": "every call is cut into pieces: the VM kernel of piece k+1 runs while piece k drains (gather + D2H)",
                        "output": "full dense witness map of every instance (ACVM::finalize), pinned host buffer"}
     # ---- cpu baseline beside it (rank 0, N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:
@@ -553,14 +620,35 @@ def run_ours(args):
         line["cpu_baseline_optimized"] = {"value": n_o / dt_o, "unit": UNIT, "cores": threads, "kind": "port",
                                           "sample": f"{n_o} full solves, dense witness vector + plan-time inverses + 4x64 Montgomery "
                                                     f"({dt_o:.1f}s incl. the one-time plan; oracle/ref_solver.cpp ref_solve_batch_optimized)"}
+    if sec4 is not None and "error" not in sec4:
+        sec4.update(n_gpus=world, batch_total=8192 * world, ms_per_step=sec4_ms, value=8192 * world / (sec4_ms * 1e-3),
+                    witnesses_per_s=8192 * world / (sec4_ms * 1e-3), note="max over ranks of the per-GPU time; roofline object is rank 0's")
+    if sec4 is not None:
+        line["secondary"] = {"config4": sec4}
+    if world > 1:
+        try:
+            batch_obj.close() if args.no_e2e else None
+            circ.close()
+            ctx.close()
+            if dist is not None:
+                dist.destroy_process_group()
+                dist = None
+            time.sleep(2.0)   # the other ranks are exiting: let their device memory go
+            line["multi_gpu_c_abi"] = multi_device_c_abi_line(world)
+        except Exception as e:
+            line["multi_gpu_c_abi"] = {"error": f"{type(e).__name__}: {e}"}
     # ---- BASELINE configs 2-4 at their stated sizes (rank 0 at N = 1) ----
     if world == 1 and args.secondary != "none":
         scale = 1 if args.secondary == "full" else 64
         ctx.set_option("pedersen_unpinned", 1)   # configs 2 and 4 contain Pedersen calls: measured on the opt-in kernel, stated in the line
         line["secondary"] = {}
         threads = 0 if args.no_cpu_baseline else (os.cpu_count() or 1)
-        for which in ("config3", "config2", "config4"):
+        batch_obj.close()
+        for which in ("config3", "config4", "config2"):
             t0 = time.time()
+            if time.time() - T_START > args.time_budget_s:   # the headline line must come out: skip what no longer fits
+                line["secondary"][which] = {"skipped": f"time budget of {args.time_budget_s} s used up before this configuration"}
+                continue
             try:
                 line["secondary"][which] = run_secondary(ctx, which, scale, hbm_peak, imad["imad_wide_per_s"], cpu_threads=threads)
             except Exception as e:   # a secondary measurement must never take the headline line down
@@ -606,6 +694,8 @@ def main():
     ap.add_argument("--S", type=int, default=0)
     ap.add_argument("--T", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--time-budget-s", type=float, default=420.0,
+                    help="no further secondary configuration is started once the run is this old")
     ap.add_argument("--secondary", default="full", choices=["full", "quick", "none"],
                     help="BASELINE configs 2-4 in the `secondary` object: full = stated sizes, quick = 1/64 length, none = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
