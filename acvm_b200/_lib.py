@@ -93,6 +93,7 @@ def load():
                                               C.c_size_t, C.POINTER(C.c_size_t)]),
         "acvmb_plan_compile_host_ex": (C.c_int, [C.c_char_p, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                  C.POINTER(PlanInfo), vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "acvmb_d2h_microbench": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_double)]),
         "acvmb_imad_cc_microbench": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "acvmb_pedersen_generator_host": (C.c_int, [C.c_uint32, C.c_char_p]),
         "acvmb_permutation_route_host": (C.c_int, [u32p, C.c_uint32, vp, C.c_uint32, u32p]),

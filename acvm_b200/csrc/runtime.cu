@@ -1705,6 +1705,31 @@ extern "C" int acvmb_plan_compile_host(const uint8_t* gz, size_t len, const uint
     return acvmb_plan_compile_host_ex(gz, len, input_witnesses, n_inputs, S, 0, 0, info, blob, cap, needed);
 }
 
+// measurement helper: bare device->host rate of this context's device into the caller's (pinned) buffer -- the ceiling of
+// every end-to-end number that returns witness maps
+extern "C" int acvmb_d2h_microbench(acvmb_ctx* ctx, void* host, size_t bytes, uint32_t reps, double* gb_per_s) {
+    if (!ctx || !host || !bytes || !reps || !gb_per_s) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t e = cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);   // warm-up
+    if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->copy_stream);
+    for (uint32_t i = 0; i < reps && e == cudaSuccess; ++i) e = cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    CUDA_TRY(e);
+    *gb_per_s = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    return ACVMB_OK;
+}
+
 extern "C" int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3) {
     if (!ctx || !out3) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));

@@ -503,6 +503,11 @@ def run_ours(args):
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_step()  # warm-up (also faults in the pinned pages)
+        # bare D2H rate of THIS box into the same pinned buffer, all ranks copying at once: the ceiling of the number below
+        barrier()
+        gbps = C.c_double()
+        rc = lib.acvmb_d2h_microbench(ctx._h, C.c_void_p(host_out), min(out_bytes, 4 << 30), 4, C.byref(gbps))
+        d2h_ceiling = gbps.value if rc == 0 else None
         barrier()
         w0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -515,7 +520,8 @@ def run_ours(args):
         os.sched_setaffinity(0, saved_affinity)
         ri = circ.run_info()
         e2e = {"wall_s_per_step": e2e_wall, "h2d": args.batch * len(inputs) * 32, "d2h": args.batch * (nw * 32 + 16),
-               "calls_per_step": n_calls, "instances_per_call": e2e_chunk, "pieces_per_call": ri["n_subbatches"]}
+               "calls_per_step": n_calls, "instances_per_call": e2e_chunk, "pieces_per_call": ri["n_subbatches"],
+               "d2h_ceiling": d2h_ceiling}
 
     hbm_peak, peak_src = measured_peaks()
     imad = ctx.imad_microbench()
@@ -531,12 +537,14 @@ def run_ours(args):
         except Exception as e_:
             sec4 = {"error": f"{type(e_).__name__}: {e_}", "ms_per_step": 0.0}
     # ---- reduce over ranks (max time) ----
-    vals = [dev_ms, vm_ms, wall, e2e["wall_s_per_step"] if e2e else 0.0, sec4["ms_per_step"] if sec4 else 0.0]
+    vals = [dev_ms, vm_ms, wall, e2e["wall_s_per_step"] if e2e else 0.0, sec4["ms_per_step"] if sec4 else 0.0,
+            -(e2e["d2h_ceiling"] or 0.0) if e2e else 0.0]
     if dist is not None:
         t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = t.tolist()
-    dev_ms, vm_ms, wall, e2e_wall, sec4_ms = vals
+    dev_ms, vm_ms, wall, e2e_wall, sec4_ms, neg_ceiling = vals
+    d2h_ceiling_min = -neg_ceiling   # the slowest rank's bare rate (all ranks copied concurrently)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -603,6 +611,11 @@ def run_ours(args):
         line["e2e"] = {"value": total_inst / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "calls_per_step": e2e["calls_per_step"], "instances_per_call": e2e["instances_per_call"],
                        "pieces_per_call": e2e["pieces_per_call"],
+                       "d2h_ceiling_GBps_per_gpu": d2h_ceiling_min,
+                       "d2h_achieved_GBps_per_gpu": e2e["d2h"] / e2e_wall / 1e9,
+                       "frac_of_d2h_ceiling": (e2e["d2h"] / e2e_wall / 1e9) / d2h_ceiling_min if d2h_ceiling_min else None,
+                       "d2h_ceiling_how": "cudaMemcpyAsync of 4 GiB x 4 from HBM into the same pinned buffer, every rank at the same "
+                                          "time (acvmb_d2h_microbench); the slowest rank is reported",
                        "pipeline": "every call is cut into pieces: the VM kernel of piece k+1 runs while piece k drains (gather + D2H)",
                        "output": "full dense witness map of every instance (ACVM::finalize), pinned host buffer"}
     # ---- cpu baseline beside it (rank 0, N=1 only) ----

@@ -235,6 +235,9 @@ int acvmb_brillig_run_host(const uint8_t* gz_bincode, size_t len, uint32_t opcod
 /* ---- measurement helpers ---- */
 int acvmb_imad_microbench(acvmb_ctx* ctx, double* imad32_per_s, double* imad_wide_per_s, double* imad_wide_carry_per_s,
                           double* sm_clock_mhz);
+/* bare device->host copy rate (GB/s) of the context's device into `host` (pinned memory from acvmb_host_alloc): the ceiling of
+ * every end-to-end number that returns witness maps */
+int acvmb_d2h_microbench(acvmb_ctx* ctx, void* host, size_t bytes, uint32_t reps, double* gb_per_s);
 /* register-resident Montgomery multiplications per second for the 5 FMA/ALU pipe-split levels of the K0 field
  * library (fr_mul_per_s[0..4]): the practical Fr-mul ceiling */
 int acvmb_frmul_microbench(acvmb_ctx* ctx, double* fr_mul_per_s);

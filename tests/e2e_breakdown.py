@@ -8,6 +8,9 @@ from acvm_b200 import acir_builder as ab
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2184
 gates = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 ctx = acvm_b200.Context(0)
+for kv in filter(None, os.environ.get("ACVMB_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 data, inputs, nw = ab.synthetic_arith_circuit(gates, mode="local", coeffs="dense")
 t = time.time(); circ = acvm_b200.CompiledCircuit(ctx, data, inputs); print("compile", round(time.time() - t, 2))
 lib = acvm_b200.lib()
