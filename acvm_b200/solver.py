@@ -316,6 +316,12 @@ class ACVM:
         _check(lib().acvmb_vm_solve(self._h, C.byref(st)))
         return _status(st)
 
+    def solve_opcode(self) -> InstanceStatus:
+        """ACVM::solve_opcode (acvm/src/pwg/mod.rs:243-303): one opcode per call."""
+        st = _lib.Status()
+        _check(lib().acvmb_vm_solve_opcode(self._h, C.byref(st)))
+        return _status(st)
+
     def get_status(self) -> InstanceStatus:
         st = _lib.Status()
         _check(lib().acvmb_vm_status(self._h, C.byref(st)))

@@ -21,7 +21,7 @@
 #pragma once
 #include <stdint.h>
 
-#include "fr.cuh"
+#include "../../acvm_b200/csrc/fr.cuh"
 
 namespace fr29 {
 

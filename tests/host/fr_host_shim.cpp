@@ -42,7 +42,7 @@ uint32_t t_num_bits(const uint32_t* a) { Fe A; memcpy(A.l, a, 32); return num_bi
 }
 
 // ---- 9 x 29-bit carry-free representation (fr29.cuh) ----
-#include "../../acvm_b200/csrc/fr29.cuh"
+#include "fr29.cuh"   // rejected experiment (measured slower), kept as a tested reference for a future 29-bit-limb column format
 extern "C" {
 void t_dot9(int k, const uint32_t* a8, const uint32_t* b8, uint32_t* r8) {
     fr::Fe A[4], B[4];

@@ -134,3 +134,69 @@ def test_gpu_memory_operations(ctx):
     vm = acvm_b200.ACVM(ctx, _memory_operations(), {1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 4})
     assert vm.solve().status == "Solved"
     assert vm.finalize()[8] == 6
+
+
+def _lockstep(ctx, data, initial, probe):
+    """acvmb_vm_solve_opcode against the oracle's ACVM::solve_opcode, call by call: status, instruction pointer and the
+    witnesses visible through witness_map() must agree after every step."""
+    from oracle import acir as oacir
+    vm = acvm_b200.ACVM(ctx, data, initial)
+    ovm = pwg.ACVM(pwg.OracleBackend(), oacir.decode_circuit(data).opcodes, dict(initial))
+    steps = 0
+    while ovm.status == "InProgress":
+        ost = ovm.solve_opcode()
+        st = vm.solve_opcode()
+        steps += 1
+        assert st.status == ost, (steps, st, ost)
+        assert vm.instruction_pointer() == ovm.instruction_pointer
+        wm = vm.witness_map()
+        for w in probe:
+            assert wm.get(w) == ovm.witness_map.get(w), (steps, w)
+        if ost == "Failure":
+            assert st.error == ovm.error.kind
+    return vm, ovm, steps
+
+
+@pytest.mark.gpu
+def test_gpu_solve_opcode_steps_like_the_reference(ctx):
+    # five arithmetic opcodes + a logic op; the check at opcode 4 fails unless w1 == 2
+    b = ab.CircuitBuilder()
+    b.arithmetic([(1, 1, 2)], [(ab.P - 1, 3)], 0)        # w3 = w1*w2
+    b.arithmetic([], [(1, 3), (ab.P - 1, 4)], 5)         # w4 = w3 + 5
+    b.logic("XOR", (1, 64), (2, 64), 5)
+    b.arithmetic([(1, 4, 5)], [(ab.P - 1, 6)], 0)        # w6 = w4*w5
+    b.arithmetic([], [(1, 1)], ab.P - 2)                 # check w1 == 2
+    b.arithmetic([(1, 6, 6)], [(ab.P - 1, 7)], 0)        # w7 = w6^2
+    data = b.to_bytes()
+    vm, ovm, steps = _lockstep(ctx, data, {1: 2, 2: 9}, range(1, 8))
+    assert steps == 6 and vm.get_status().status == "Solved" and vm.finalize() == ovm.finalize()
+    with pytest.raises(acvm_b200.AcvmError) as e:        # one more step indexes past the opcodes: the reference panics
+        vm.solve_opcode()
+    assert e.value.rc == -7
+    vm, ovm, steps = _lockstep(ctx, data, {1: 3, 2: 9}, range(1, 8))
+    assert steps == 5 and vm.instruction_pointer() == 4
+    st = vm.solve_opcode()                               # failure is terminal: the same opcode fails again
+    assert (st.status, st.error, st.opcode_index) == ("Failure", "UnsatisfiedConstrain", 4)
+    # solve() after a few single steps finishes the job
+    vm = acvm_b200.ACVM(ctx, data, {1: 2, 2: 9})
+    assert vm.solve_opcode().status == "InProgress" and vm.instruction_pointer() == 1
+    assert 4 not in vm.witness_map() and vm.witness_map()[3] == 18
+    assert vm.solve().status == "Solved" and vm.instruction_pointer() == 6
+
+
+@pytest.mark.gpu
+def test_gpu_solve_opcode_stops_at_a_foreign_call(ctx):
+    data = _oracle_dependent_execution()
+    vm = acvm_b200.ACVM(ctx, data, {1: 2, 2: 2})
+    assert vm.solve_opcode().status == "InProgress" and vm.instruction_pointer() == 1
+    st = vm.solve_opcode()
+    assert st.status == "RequiresForeignCall" and vm.instruction_pointer() == 1
+    assert vm.solve_opcode().status == "RequiresForeignCall"      # unresolved: the Brillig opcode waits again
+    fn, inputs = vm.get_pending_foreign_call()
+    vm.resolve_pending_foreign_call([F.inverse(inputs[0][0])])
+    assert vm.instruction_pointer() == 1
+    st = vm.solve_opcode()
+    assert st.status == "RequiresForeignCall" and vm.instruction_pointer() == 1   # second foreign call of the same opcode
+    fn, inputs = vm.get_pending_foreign_call()
+    vm.resolve_pending_foreign_call([F.inverse(inputs[0][0])])
+    assert vm.solve().status == "Solved"
