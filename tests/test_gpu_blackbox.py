@@ -88,6 +88,32 @@ def test_hash_output_preassigned_is_checked(ctx):
     assert st[0].status == "Solved" and (st[1].status, st[1].error) == ("Failure", "UnsatisfiedConstrain")
 
 
+def test_failed_multi_output_opcode_witness_map_deviation_is_pinned(ctx):
+    """DESIGN.md section 6, known deviation: when insert_value fails at output i of a multi-output opcode, the reference's map
+    (of that FAILED instance) holds outputs 0..i of the opcode and nothing after; here the status is identical, the
+    pre-assigned witness holds the replacing value like in the reference, but every witness the failing opcode itself
+    assigns is reported absent."""
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 2), (ab.P - 1, 13)], 0)                 # w13 := w2  -> output 3 of the hash is pre-assigned
+    b.hash256("SHA256", [(1, 8)], list(range(10, 42)))
+    data = b.to_bytes()
+    good = hashlib.sha256(b"\x05").digest()
+    inp = (5).to_bytes(32, "big") + good[3].to_bytes(32, "big") + (5).to_bytes(32, "big") + ((good[3] + 1) % 256).to_bytes(32, "big")
+    circ = acvm_b200.CompiledCircuit(ctx, data, [1, 2])
+    out, st, pres = circ.solve_batch(inp, 2, want_present=True)
+    nw = circ.num_witnesses
+    val = lambda i, w: int.from_bytes(out[(i * nw + w) * 32:(i * nw + w + 1) * 32], "big")
+    assert st[0].status == "Solved" and [val(0, 10 + k) for k in range(32)] == list(good)
+    assert (st[1].status, st[1].error, st[1].opcode_index) == ("Failure", "UnsatisfiedConstrain", 1)
+    oc = acir.decode_circuit(data)
+    ost, owm, oerr = pwg.solve_circuit(oc, {1: 5, 2: (good[3] + 1) % 256})
+    assert ost == "Failure" and oerr.opcode_location == 1
+    assert sorted(owm) == [1, 2, 10, 11, 12, 13] and owm[13] == good[3]          # the reference: outputs 0..3, w13 replaced
+    present = {w for w in range(nw) if pres[1 * nw + w]}
+    assert present == {1, 2, 13} and val(1, 13) == good[3]                       # here: w10..w12 absent (the deviation)
+    circ.close()
+
+
 def test_fixed_base_kats(ctx, golden):  # barretenberg_blackbox_solver/src/wasm/scalar_mul.rs:72-97
     ks = golden["kats"]["fixed_base"]
     pts, st = ctx.fixed_base_scalar_mul([k["low"] for k in ks], [k["high"] for k in ks])
