@@ -53,9 +53,7 @@ struct acvmb_ctx {
     uint32_t opt_n_stage = 4;
     uint64_t max_resident_bytes = 0;  // 0 = auto (fraction of free memory)
     uint64_t staging_bytes = 512ull << 20;
-    uint32_t* d_fixed_base = nullptr;   // Grumpkin fixed-base table (built lazily for plans with curve ops)
-    uint32_t* d_pedersen = nullptr;
-    bool tables_ready = false;
+    bool tables_ready = false;          // the per-device lookup tables (ensure_curve_tables) exist
     // acvmb_solve_batch keeps the column buffers of its last call (one per context): a caller that streams a large batch
     // through repeated calls otherwise pays a cudaMalloc + cudaFree of tens of GB per call (measured 20-290 ms)
     struct acvmb_batch* cached_batch = nullptr;
@@ -202,8 +200,6 @@ extern "C" void acvmb_ctx_destroy(acvmb_ctx* ctx) {
     ctx->peers.clear();
     cudaSetDevice(ctx->device);
     drop_cached_batch(ctx);
-    if (ctx->d_fixed_base) cudaFree(ctx->d_fixed_base);
-    if (ctx->d_pedersen) cudaFree(ctx->d_pedersen);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->gather_stream) cudaStreamDestroy(ctx->gather_stream);
@@ -254,15 +250,33 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
 }
 
 // ---------------------------------------------------------------------------------------------
+// The kernels find the lookup tables through a __constant__ pointer pair, which is per DEVICE (not per context), and the
+// tables are the same data for every context: they are built and uploaded once per device for the life of the process and
+// shared by all contexts of that device (a table owned by one context would dangle in the symbol once that context is gone).
+#include <mutex>
+static std::mutex g_tables_mutex;
+static struct {
+    uint32_t* fixed_base = nullptr;
+    uint32_t* pedersen = nullptr;
+    bool ready = false;
+} g_tables[64];
+
 static int ensure_curve_tables(acvmb_ctx* ctx) {
     if (ctx->tables_ready) return ACVMB_OK;
-    std::vector<uint32_t> fb = gk::build_fixed_base_table();
-    CUDA_TRY(cudaMalloc(&ctx->d_fixed_base, fb.size() * 4));
-    CUDA_TRY(cudaMemcpy(ctx->d_fixed_base, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice));
-    std::vector<uint32_t> pt = gk::build_pedersen_tables();
-    CUDA_TRY(cudaMalloc(&ctx->d_pedersen, pt.size() * 4));
-    CUDA_TRY(cudaMemcpy(ctx->d_pedersen, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(set_curve_tables(ctx->d_fixed_base, ctx->d_pedersen));
+    const int d = ctx->device;
+    if (d < 0 || d >= 64) return set_err(ACVMB_ERR_INVALID_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lk(g_tables_mutex);
+    CUDA_TRY(cudaSetDevice(d));
+    if (!g_tables[d].ready) {
+        std::vector<uint32_t> fb = gk::build_fixed_base_table();
+        CUDA_TRY(cudaMalloc(&g_tables[d].fixed_base, fb.size() * 4));
+        CUDA_TRY(cudaMemcpy(g_tables[d].fixed_base, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<uint32_t> pt = gk::build_pedersen_tables();
+        CUDA_TRY(cudaMalloc(&g_tables[d].pedersen, pt.size() * 4));
+        CUDA_TRY(cudaMemcpy(g_tables[d].pedersen, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(set_curve_tables(g_tables[d].fixed_base, g_tables[d].pedersen));
+        g_tables[d].ready = true;
+    }
     ctx->tables_ready = true;
     return ACVMB_OK;
 }

@@ -114,6 +114,27 @@ def test_failed_multi_output_opcode_witness_map_deviation_is_pinned(ctx):
     circ.close()
 
 
+def test_lookup_tables_outlive_the_context_that_built_them(golden):
+    """The curve lookup tables hang off a per-device __constant__ symbol: they are shared by every context of the device and
+    must stay valid when the context that first built them is destroyed (round 2: a context's own tables used to dangle in
+    the symbol after acvmb_ctx_destroy -> illegal memory access in a later, unrelated context)."""
+    import torch
+    ks = golden["kats"]["fixed_base"]
+    want = [(int(k["x"], 16), int(k["y"], 16)) for k in ks]
+    a = acvm_b200.Context(0)
+    b = acvm_b200.Context(0)
+    try:
+        assert b.fixed_base_scalar_mul([k["low"] for k in ks], [k["high"] for k in ks])[0] == want
+        b.close()
+        filler = torch.empty(8 << 30, dtype=torch.uint8, device="cuda:0")   # reuse whatever b freed
+        filler.fill_(0xA5)
+        del filler
+        torch.cuda.empty_cache()
+        assert a.fixed_base_scalar_mul([k["low"] for k in ks], [k["high"] for k in ks])[0] == want
+    finally:
+        a.close()
+
+
 def test_fixed_base_kats(ctx, golden):  # barretenberg_blackbox_solver/src/wasm/scalar_mul.rs:72-97
     ks = golden["kats"]["fixed_base"]
     pts, st = ctx.fixed_base_scalar_mul([k["low"] for k in ks], [k["high"] for k in ks])
