@@ -274,11 +274,23 @@ class Scheduler {
             uint32_t s = steps_[i];
             stream[(size_t)s * S_ + cursor[s]++] = ops_[i];
         }
-        // slots of one step are independent: order them by (kind, flags) so that the slots sharing a warp run the same
-        // code path (a warp covers 32/T consecutive slots); NOPs (kind 0) go last
+        // slots of one step are independent: order them so that the slots sharing a warp (32/T consecutive slots) run the same
+        // code path -- by kind, then, for gates, by the width of their dot product (the lanes of a warp agree on the widest
+        // one among them and the narrower lanes pad, vm_kernel_impl.cuh exec_gate), then by form; NOPs (kind 0) go last
+        auto key = [](const OpRec& r) -> uint64_t {
+            const uint32_t kind = r.w[0] & 0xFF, flags = r.w[0] >> 8;
+            uint64_t k = kind == MK_GATE_CHECK ? MK_GATE_ASSIGN : kind;   // checks and assignments share the gate code
+            uint32_t width = 0, two_red = 0;
+            if (kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK) {
+                const uint32_t mul = (flags & GF_MUL) ? 1u : 0u;
+                width = (flags & GF_Y) ? mul + ((flags >> GF_NPROD_SHIFT) & 3) : 0;
+                two_red = (mul && !(flags & GF_ONE_RED)) ? 1u : 0u;
+            }
+            return (k << 40) | ((uint64_t)width << 36) | ((uint64_t)two_red << 35) | (r.w[0] >> 8);
+        };
         for (uint32_t s = 0; s < n_steps_padded; ++s) {
             OpRec* first = &stream[(size_t)s * S_];
-            std::stable_sort(first, first + cursor[s], [](const OpRec& x, const OpRec& y) { return x.w[0] < y.w[0]; });
+            std::stable_sort(first, first + cursor[s], [&](const OpRec& x, const OpRec& y) { return key(x) < key(y); });
         }
     }
 
