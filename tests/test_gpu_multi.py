@@ -69,3 +69,29 @@ def test_multi_device_context_reports_per_instance_failures_in_place():
                 assert (st[i].status, st[i].error, st[i].opcode_index) == ("Failure", "UnsatisfiedConstrain", 1)
     finally:
         ctx.close()
+
+
+def test_multi_device_context_runs_host_segments_on_every_shard():
+    """A circuit with host segments (Brillig on the host VM between device segments) and directives: every shard of a
+    multi-device context carries its own copy of the circuit for the host VM; results must equal the single-device ones."""
+    import test_host_logic as thl
+    devs = _devices()
+    mctx = acvm_b200.Context(devs)
+    sctx = acvm_b200.Context(devs[0])
+    try:
+        data = thl._brillig_circuit()
+        rows, one = thl._brillig_inputs()
+        reps = 40                                   # 240 instances: several tiles per device
+        inp = one * reps
+        batch = len(rows) * reps
+        mc = acvm_b200.CompiledCircuit(mctx, data, [1, 2, 3])
+        sc = acvm_b200.CompiledCircuit(sctx, data, [1, 2, 3])
+        assert mc.info["n_host_segments"] >= 1
+        m_out, m_st, m_pr = mc.solve_batch(inp, batch, want_present=True)
+        s_out, s_st, s_pr = sc.solve_batch(inp, batch, want_present=True)
+        assert [(s.status, s.error, s.opcode_index, s.aux) for s in m_st] == [(s.status, s.error, s.opcode_index, s.aux) for s in s_st]
+        assert m_pr == s_pr and m_out == s_out
+        assert len({s.status for s in m_st}) > 1     # the input rows mix solved and failing instances
+    finally:
+        mctx.close()
+        sctx.close()
