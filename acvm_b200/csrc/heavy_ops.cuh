@@ -1174,6 +1174,159 @@ __device__ __noinline__ void exec_quotient(const OpRec* r, uint32_t flags, uint4
     insert_value_dev<T>(r, flags & GF_OUT2_CHECK, r->w[6], rem, cb, fail);
 }
 
+// BinaryIntOp of a Brillig opcode that the plan lowered to the device (plan.cpp brillig_symbolic), on canonical values:
+// evaluate_binary_bigint_op (brillig_vm/src/arithmetic.rs:23-81) for 1 <= bit_size <= 128, every op but SignedDiv.  Operands
+// are whole field values (the reference reduces mod 2^bit_size only where it says so); results are < 2^128 < p.
+template <int T>
+__device__ __noinline__ void exec_int_op(const OpRec* r, uint32_t flags, uint4* cb, unsigned long long* fail) {
+    Fe a, b, res;
+    hv_load<T>(a, cb, r->w[3]);
+    hv_load<T>(b, cb, r->w[4]);
+    const uint32_t op = r->w[7] & 0xFF, bs = r->w[7] >> 8;
+    auto mask = [&](Fe& v) {   // v mod 2^bs
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (bs <= 32u * k) v.l[k] = 0;
+            else if (bs < 32u * (k + 1)) v.l[k] &= (1u << (bs - 32u * k)) - 1u;
+        }
+    };
+    auto geq = [&](const Fe& x, const Fe& y) {   // x >= y
+        uint32_t t, borrow;
+        fr::sub_cc(t, x.l[0], y.l[0]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) fr::subc_cc(t, x.l[k], y.l[k]);
+        fr::subc(borrow, 0, 0);
+        return borrow == 0;
+    };
+    bool panic = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) res.l[k] = 0;
+    switch (op) {
+        case 0:   // Add: (a + b) % 2^bs  (a, b < p: no carry out of 256 bits)
+            fr::add_raw(res, a, b);
+            mask(res);
+            break;
+        case 1: {   // Sub: (2^bs + a - b) % 2^bs ; BigUint underflow panics
+            Fe t;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t.l[k] = ((uint32_t)k == (bs >> 5)) ? (1u << (bs & 31)) : 0u;
+            fr::add_raw(t, t, a);   // bs <= 128 and a < 2^254: fits
+            if (!geq(t, b)) panic = true;
+            fr::sub_cc(res.l[0], t.l[0], b.l[0]);
+#pragma unroll
+            for (int k = 1; k < 7; ++k) fr::subc_cc(res.l[k], t.l[k], b.l[k]);
+            fr::subc(res.l[7], t.l[7], b.l[7]);
+            mask(res);
+            break;
+        }
+        case 2: {   // Mul: low bs <= 128 bits of a * b
+            uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t carry = 0;
+#pragma unroll
+                for (int j = 0; i + j < 4; ++j) {
+                    const unsigned long long t = (unsigned long long)a.l[j] * b.l[i] + acc[i + j] + carry;
+                    acc[i + j] = (uint32_t)t;
+                    carry = (uint32_t)(t >> 32);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) res.l[k] = acc[k];
+            mask(res);
+            break;
+        }
+        case 4: {   // UnsignedDiv: (a % 2^bs) / (b % 2^bs) ; division by zero panics
+            mask(a);
+            mask(b);
+            if (fr::is_zero(b)) {
+                panic = true;
+                break;
+            }
+            Fe rem;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rem.l[k] = 0;
+            const int top = (int)fr::num_bits(a) - 1;
+#pragma unroll 1
+            for (int i = top; i >= 0; --i) {
+#pragma unroll
+                for (int k = 7; k > 0; --k) rem.l[k] = __funnelshift_l(rem.l[k - 1], rem.l[k], 1);
+                uint32_t limb = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k == (i >> 5)) limb = a.l[k];
+                rem.l[0] = (rem.l[0] << 1) | ((limb >> (i & 31)) & 1);
+                if (geq(rem, b)) {
+                    fr::sub_cc(rem.l[0], rem.l[0], b.l[0]);
+#pragma unroll
+                    for (int k = 1; k < 7; ++k) fr::subc_cc(rem.l[k], rem.l[k], b.l[k]);
+                    fr::subc(rem.l[7], rem.l[7], b.l[7]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k == (i >> 5)) res.l[k] |= 1u << (i & 31);
+                }
+            }
+            break;
+        }
+        case 5:   // Equals / LessThan / LessThanEquals on the values mod 2^bs
+        case 6:
+        case 7: {
+            mask(a);
+            mask(b);
+            const bool ge = geq(a, b), le = geq(b, a);
+            res.l[0] = (op == 5) ? (ge && le) : (op == 6 ? !ge : le);
+            break;
+        }
+        case 8:
+        case 9:
+        case 10:
+#pragma unroll
+            for (int k = 0; k < 8; ++k) res.l[k] = op == 8 ? (a.l[k] & b.l[k]) : (op == 9 ? (a.l[k] | b.l[k]) : (a.l[k] ^ b.l[k]));
+            mask(res);
+            break;
+        case 11:
+        case 12: {   // Shl / Shr: the shift amount must fit u128; (a << s) % 2^bs resp. (a >> s) % 2^bs
+            if (b.l[4] | b.l[5] | b.l[6] | b.l[7]) {
+                panic = true;
+                break;
+            }
+            const uint32_t s = (b.l[1] | b.l[2] | b.l[3] || b.l[0] >= 256u) ? 256u : b.l[0];
+            if (s < 256u) {
+                const uint32_t ws = s >> 5, bsft = s & 31;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t lo = 0, hi = 0;   // limbs that land in position k
+                    if (op == 11) {           // left: res[k] = a[k-ws] << bsft | a[k-ws-1] >> (32-bsft)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if ((uint32_t)j + ws == (uint32_t)k) hi = a.l[j];
+                            if ((uint32_t)j + ws + 1 == (uint32_t)k) lo = a.l[j];
+                        }
+                        res.l[k] = bsft ? ((hi << bsft) | (lo >> (32 - bsft))) : hi;
+                    } else {                  // right: res[k] = a[k+ws] >> bsft | a[k+ws+1] << (32-bsft)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if ((uint32_t)k + ws == (uint32_t)j) lo = a.l[j];
+                            if ((uint32_t)k + ws + 1 == (uint32_t)j) hi = a.l[j];
+                        }
+                        res.l[k] = bsft ? ((lo >> bsft) | (hi << (32 - bsft))) : lo;
+                    }
+                }
+            }
+            mask(res);
+            break;
+        }
+        default:
+            panic = true;
+            break;
+    }
+    if (panic) {
+        hv_fail(fail, r->w[1], EK_REFERENCE_PANIC, 0);
+        return;
+    }
+    insert_value_dev<T>(r, flags & GF_OUT_CHECK, r->w[2], res, cb, fail);
+}
+
 // index.try_to_u64().unwrap() as u32  (memory_op.rs:70-72): > 64 bits panics in the reference
 __device__ __forceinline__ bool mem_index(const Fe& idx, uint32_t& out) {
     out = idx.l[0];
@@ -1301,6 +1454,9 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_QUOTIENT:
             exec_quotient<T>(r, flags, cb, fail);
+            break;
+        case MK_INT_OP:
+            exec_int_op<T>(r, flags, cb, fail);
             break;
         case MK_MEM_READ:
         case MK_MEM_WRITE:

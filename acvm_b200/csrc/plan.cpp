@@ -3,6 +3,7 @@
 //   solvable / check / too-many-unknowns classification    acvm/src/pwg/arithmetic.rs:27-127,176-209
 //   blackbox input pre-check + output insert_value          acvm/src/pwg/blackbox/mod.rs:32-62, pwg/mod.rs:338-357
 #include "plan.hpp"
+#include "brillig_host.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -75,7 +76,10 @@ class Scheduler {
                kind == MK_JAC_FINAL;
     }
 
+    bool dry = false;   // the inversion-recording pass of compile_plan(): its schedule is thrown away, do not build one
+
     void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
+        if (dry) return;
         const bool costly = is_costly(rec.w[0] & 0xFF);
         if (!buffering_ && !costly) {
             place_now(rec, reads, nr, writes, nw);
@@ -1105,6 +1109,9 @@ struct Compiler {
     };
     bool brillig_symbolic(uint32_t idx, const Brillig& br, bool emit, std::vector<uint32_t>& pinned) {
         if (br.bytecode.empty() || br.predicate.present) return false;
+        // integer ops read canonical values: with any of them in the bytecode every intermediate value is kept canonical
+        bool has_int = false;
+        for (auto& o : br.bytecode) has_int |= o.tag == 1;
         std::vector<Sym> regs, mem;
         auto get = [&](uint64_t r) { return r < regs.size() ? regs[r] : Sym{}; };
         auto set = [&](uint64_t r, const Sym& v) {
@@ -1149,7 +1156,46 @@ struct Compiler {
             if (o.tag == 14) break;                                    // Stop
             if (o.tag == 6) { set(o.r0, Sym{true, o.value, NONE}); continue; }   // Const
             if (o.tag == 9) { set(o.r0, get(o.r1)); continue; }                  // Mov
-            if (o.tag != 0 || o.bop > 2) return false;                 // only BinaryFieldOp Add / Sub / Mul
+            if (o.tag == 1) {   // BinaryIntOp (brillig_vm/src/arithmetic.rs:23-81): every op but SignedDiv, 1 <= bit_size <= 128
+                if (o.bop == 3 || o.bop > 12 || o.bit_size < 1 || o.bit_size > 128) return false;
+                Sym a = get(o.r1), b = get(o.r2), r;
+                if (a.is_const && b.is_const) {
+                    try {
+                        r.c = hf::reduce(bvm::bigint_op(o.bop, a.c, b.c, o.bit_size));
+                    } catch (const bvm::PanicEx&) {
+                        return false;   // the reference panics for every instance: the host VM reports it
+                    }
+                } else {
+                    r.is_const = false;
+                    if (emit) {
+                        auto slot_of = [&](const Sym& v) {   // a constant operand gets a (canonical) column of its own
+                            if (!v.is_const) return v.slot;
+                            uint32_t t = new_pinned(1, 0);
+                            pinned.push_back(t);
+                            ++plan.stats.n_temps;
+                            lower_sum({}, {}, v.c, /*assign=*/true, t, idx, false, nullptr, nullptr, /*canonical_out=*/true);
+                            return t;
+                        };
+                        const uint32_t sa = slot_of(a), sb = slot_of(b);
+                        r.slot = new_pinned(1, 0);
+                        pinned.push_back(r.slot);
+                        OpRec rec{};
+                        rec.w[0] = MK_INT_OP;
+                        rec.w[1] = idx;
+                        rec.w[2] = r.slot;
+                        rec.w[3] = sa;
+                        rec.w[4] = sb;
+                        rec.w[5] = rec.w[6] = NONE;
+                        rec.w[7] = o.bop | (o.bit_size << 8);
+                        std::vector<uint32_t> rd = {sa, sb}, wr = {r.slot};
+                        place_heavy(rec, rd, wr);
+                        plan.stats.alg_bytes += 96;
+                    }
+                }
+                set(o.r0, r);
+                continue;
+            }
+            if (o.tag != 0 || o.bop > 2) return false;                 // BinaryFieldOp: Add / Sub / Mul only
             Sym a = get(o.r1), b = get(o.r2), r;
             if (a.is_const && b.is_const) {
                 r.c = o.bop == 0 ? hf::add(a.c, b.c) : o.bop == 1 ? hf::sub(a.c, b.c) : hf::mul(a.c, b.c);
@@ -1175,7 +1221,8 @@ struct Compiler {
                         } else lins.push_back({sb, b.slot});
                     }
                     ++plan.stats.n_temps;
-                    lower_sum(std::move(prods), std::move(lins), cst, /*assign=*/true, r.slot, idx, false);
+                    lower_sum(std::move(prods), std::move(lins), cst, /*assign=*/true, r.slot, idx, false, nullptr, nullptr,
+                              /*canonical_out=*/has_int);
                 }
             }
             set(o.r0, r);
@@ -1913,6 +1960,7 @@ static Plan compile_plan_once(const Circuit& c, const std::vector<uint32_t>& inp
     {
         Compiler dry(c, opt, nw);
         dry.inv_record = &requests;
+        dry.sched.dry = true;
         dry.run(input_witnesses);
     }
     std::vector<U256> inverses = batch_inverse(requests);

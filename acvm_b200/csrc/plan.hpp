@@ -59,6 +59,8 @@ enum MicroKind : uint32_t {
     MK_JAC_ADD = 22,      // out (3 slots from w[2]) := point at w[3] + point at w[4]   (Jacobian, Montgomery form, Z = 0 is infinity)
     MK_JAC_FINAL = 23,    // (x, y) at w[2], w[5] := affine(point at w[3] [+ point at w[4]]); c[0][0]: validate fixed-base scalar w[6], w[7]
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
+    MK_INT_OP = 24,       // out := BinaryIntOp(x, y) of a lowered Brillig opcode; w[7] = op | bit_size << 8, 1 <= bit_size <= 128
+                          // (brillig_vm/src/arithmetic.rs:23-81; a condition on which the reference panics => EK_REFERENCE_PANIC)
 };
 
 // flags (w[0] >> 8)

@@ -13,7 +13,7 @@ NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
           GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17,
-          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20, CURVE_PART=21, JAC_ADD=22, JAC_FINAL=23)
+          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20, CURVE_PART=21, JAC_ADD=22, JAC_FINAL=23, INT_OP=24)
 EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
@@ -525,6 +525,16 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                             record_fail(opcode, EK_OOB, mi)
                         else:
                             writes.append((base + mi, cols[y]))
+            elif kind == MK["INT_OP"]:   # a lowered Brillig BinaryIntOp (heavy_ops.cuh exec_int_op)
+                from oracle import brillig_vm as obv, pwg as opwg
+                try:
+                    res = obv.bigint_op(aux & 0xFF, cols[x], cols[y], aux >> 8) % P
+                except opwg.ReferencePanic:
+                    record_fail(opcode, EK_PANIC)
+                else:
+                    if (flags & GF_OUT_CHECK) and cols[out] != res:
+                        record_fail(opcode, EK_UNSAT)
+                    writes.append((out, res))
             elif kind == MK["REQUIRE"]:
                 pl = plan.payload
                 for i in range(pl[aux]):

@@ -329,3 +329,22 @@ def test_curve_ops_every_tile_shape_and_lowering(T, S, split):
         assert all(s.error == "BlackBoxFunctionFailed" and s.opcode_index == 7 for s in st)
     finally:
         ctx.close()
+
+
+def test_integer_brillig_ops_on_the_device(ctx):
+    """Brillig BinaryIntOp bytecode lowered to MK_INT_OP micro-ops (heavy_ops.cuh exec_int_op): every op but SignedDiv, several
+    bit sizes, operands that exceed the bit size, underflow / division by zero (reference panics) -- vs the oracle's VM."""
+    import test_host_logic as thl
+    data, nw = thl._int_brillig_circuit()
+    rows, inp = thl._int_brillig_inputs()
+    circ = acvm_b200.CompiledCircuit(ctx, data, [1, 2, 3, 4])
+    assert circ.info["n_brillig_device"] == 16 and circ.info["n_host_segments"] == 0
+    circ.close()
+    st = _check_circuit(ctx, data, [1, 2, 3, 4], len(rows), inp)
+    assert {s.status for s in st} == {"Solved", "Failure"}          # (3, 5, ..): 2^1 + 3 - 5 underflows at bit size 1
+    # random operands, many instances
+    rnd = random.Random(5)
+    many = [(rnd.randrange(1 << rnd.choice((8, 64, 127, 128, 200, 254)) ), rnd.randrange(1, 1 << rnd.choice((3, 8, 64, 127, 130))),
+             rnd.randrange(1 << 64), rnd.randrange(1 << 32)) for _ in range(96)]
+    inp2 = b"".join((v % F.P).to_bytes(32, "big") for r in many for v in r)
+    _check_circuit(ctx, data, [1, 2, 3, 4], len(many), inp2)

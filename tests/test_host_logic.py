@@ -666,10 +666,10 @@ def test_straight_line_brillig_is_lowered_to_device_gates():
     assert info["n_brillig"] == 5 and info["n_brillig_device"] == 5 and info["n_host_segments"] == 0
     info = _interp_vs_oracle(data, [1, 2, 3], inp, len(rows), device_brillig=False)
     assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 5
-    # not straight-line field code (integer op, predicate): stays on the host VM
+    # not straight-line code (a jump, a predicate): stays on the host VM
     b = ab.CircuitBuilder()
     b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", 10)],
-              [dict(op="BinaryIntOp", destination=0, bop=0, bit_size=127, lhs=0, rhs=1)])
+              [dict(op="Jump", location=1), dict(op="BinaryFieldOp", destination=0, bop=0, lhs=0, rhs=1)])
     b.brillig([("Single", ab.wexpr(1))], [("Simple", 11)], [dict(op="Stop")], predicate=ab.wexpr(2))
     info = _interp_vs_oracle(b.to_bytes(), [1, 2], inp[:64] + inp[96:160], 2)
     assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 2
@@ -694,3 +694,50 @@ def test_ring_of_recent_values_plan_vs_oracle(W):
     b.arithmetic([(1, 14, 14)], [(ab.P - 1, 12)], 0)      # check, fails for random inputs
     info = _interp_vs_oracle(b.to_bytes(), [1, 2], ab.synthetic_inputs(3, n_inputs=2, seed_id=6), 3, 2, ring_slots=W)
     assert info["n_ring_reads"] > 0
+
+
+def _int_brillig_circuit():
+    """stdlib uint fallbacks (stdlib/src/blackbox_fallbacks/uint.rs:220-330, 510-600): one-instruction BinaryIntOp Brillig
+    opcodes with bit_size 127 feeding arithmetic constraints -- plus every other integer op the device lowering covers."""
+    b = ab.CircuitBuilder()
+    nxt = 10
+    ops = [(0, 127), (1, 127), (2, 127), (4, 64), (5, 32), (6, 32), (7, 32), (8, 100), (9, 100), (10, 100), (11, 64), (12, 64),
+           (0, 8), (2, 128), (1, 1)]
+    for bop, bits in ops:
+        b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", nxt)],
+                  [dict(op="BinaryIntOp", destination=0, bop=bop, bit_size=bits, lhs=0, rhs=1)])
+        nxt += 1
+    # uint.rs sub: (a + 2^width) - b with a constant in register 2, then a field op on the result
+    b.brillig([("Single", ab.wexpr(3)), ("Single", ab.wexpr(4)), ("Single", ([], [], 1 << 32))], [("Simple", nxt), ("Simple", nxt + 1)], [
+        dict(op="BinaryIntOp", destination=0, bop=0, bit_size=127, lhs=0, rhs=2),
+        dict(op="BinaryIntOp", destination=0, bop=1, bit_size=127, lhs=0, rhs=1),
+        dict(op="BinaryFieldOp", destination=1, bop=2, lhs=0, rhs=0),
+        dict(op="Const", destination=3, value=5),
+        dict(op="BinaryIntOp", destination=1, bop=12, bit_size=64, lhs=1, rhs=3),     # (r0^2) >> 5, mod 2^64
+    ])
+    b.arithmetic([], [(1, nxt), (1, nxt + 1), (ab.P - 1, nxt + 2)], 0)
+    return b.to_bytes(), nxt + 3
+
+
+def _int_brillig_inputs():
+    rows = [(5, 3, 9, 4), (3, 5, 4, 9), (ab.P - 1, 2, (1 << 70) + 5, 77), (1 << 127, (1 << 127) - 1, 0, 0), (12345678901234567890, 0, 1, 1),
+            (7, 300, 1 << 40, 1 << 33), ((1 << 200) + 17, (1 << 130) + 3, 5, 6)]
+    return rows, b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+
+
+def test_integer_brillig_ops_are_lowered_to_the_device():
+    data, _ = _int_brillig_circuit()
+    rows, inp = _int_brillig_inputs()
+    info = _interp_vs_oracle(data, [1, 2, 3, 4], inp, len(rows))
+    assert info["n_brillig"] == 16 and info["n_brillig_device"] == 16 and info["n_host_segments"] == 0
+    assert info["needs_full_kernel"] == 1
+    info = _interp_vs_oracle(data, [1, 2, 3, 4], inp, len(rows), device_brillig=False)
+    assert info["n_host_segments"] == 16
+    # SignedDiv and bit sizes above 128 stay on the host VM
+    b = ab.CircuitBuilder()
+    b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", 10)],
+              [dict(op="BinaryIntOp", destination=0, bop=3, bit_size=8, lhs=0, rhs=1)])
+    b.brillig([("Single", ab.wexpr(1)), ("Single", ab.wexpr(2))], [("Simple", 11)],
+              [dict(op="BinaryIntOp", destination=0, bop=0, bit_size=200, lhs=0, rhs=1)])
+    info = _interp_vs_oracle(b.to_bytes(), [1, 2], inp[:64] + inp[128:192], 2)
+    assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 2
