@@ -17,6 +17,8 @@ def _check(ctx, data, input_witnesses, batch, inp, expect_all_solved=True):
     assign = circ.assign_opcodes()
     nw = circ.num_witnesses
     for i, iw in enumerate(inputs_to_dicts(inp, batch, input_witnesses)):
+        if batch > 64 and i >= 32 and i % 8 and i < batch - 8:   # large batches: the pure-Python oracle checks a sample
+            continue
         ost, owm, oerr = pwg.solve_circuit(oc, iw)
         assert st[i].status == ost, (i, st[i], oerr)
         if ost == "Failure":
