@@ -1352,6 +1352,13 @@ static int solve_batch_single(acvmb_circuit* c, uint32_t batch, const uint8_t* i
             ctx->pipe_batch[i] = nullptr;
         }
     }
+    // equal sub-batches: a launch of the step-VM kernel is latency bound (its time hardly depends on the instance count), so
+    // [r, r, r, small remainder] costs a whole extra pass; ceil(batch / n) per pass does not
+    if (batch > resident) {
+        const uint32_t n_pass = (batch + resident - 1) / resident;
+        const uint32_t even = (((batch + n_pass - 1) / n_pass + T - 1) / T) * T;
+        if (even <= resident) resident = even;
+    }
     for (uint32_t off = 0; off < batch && rc == ACVMB_OK; off += resident, ++n_sub) {
         uint32_t cnt = std::min(resident, batch - off);
         if (!b || cnt != cap) {
