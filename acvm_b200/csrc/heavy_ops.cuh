@@ -335,6 +335,129 @@ __device__ __noinline__ void exec_blake2s_bytes(const OpRec* r, bool to_field, u
     }
 }
 
+static __device__ __noinline__ void keccak_f1600(unsigned long long* st);
+
+// ---------------------------------------------------------------------------------------------
+// Packed hash pipeline (plan.cpp hash_packed): the message arrives as columns of 32 packed bytes (byte i of a chunk at limb
+// i >> 2, bits 8 * (i & 3)), the digest leaves as one such column.  Only exec_hash_core sits on the dependency chain of a
+// hash chain: two 128-bit loads per 32 message bytes instead of a descriptor load + a column load per byte, one column
+// store instead of 64; gathering the message bytes and scattering the digest bytes run on other slot threads.
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __noinline__ void exec_hash_pack(const OpRec* r, uint4* cb, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t n = pl[0];
+    uint32_t id[32], lo[32];
+#pragma unroll
+    for (int g = 0; g < 32; ++g) id[g] = (uint32_t)g < n ? pl[1 + g] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int g = 0; g < 32; ++g)
+        lo[g] = id[g] != 0xFFFFFFFFu ? (reinterpret_cast<const uint32_t*>(cb + (size_t)id[g] * (2 * T))[0] & 0xFFu) : 0u;
+    Fe v;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v.l[q] = lo[4 * q] | (lo[4 * q + 1] << 8) | (lo[4 * q + 2] << 16) | (lo[4 * q + 3] << 24);
+    hv_store<T>(cb, r->w[2], v);
+}
+
+// words [8c, 8c + 8) of the message = column chunk[c]
+template <int T, int NCHUNK>
+__device__ __forceinline__ void load_chunks(uint32_t* wds, const uint4* cb, const uint32_t* chunk, uint32_t first, uint32_t n_chunks) {
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        Fe v;
+        if (first + c < n_chunks) {
+            hv_load<T>(v, cb, chunk[first + c]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.l[k] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wds[8 * c + k] = v.l[k];
+    }
+}
+
+template <int T>
+__device__ __noinline__ void exec_hash_core(const OpRec* r, uint4* cb, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    const uint32_t func = pl[0], n_in = pl[1], n_chunks = pl[2];
+    const uint32_t* chunk = pl + 3;
+    Fe dg;
+    if (func == 0) {   // SHA-256: 64-byte blocks = two chunks
+        uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+        uint32_t blk[16];
+        uint32_t base = 0;
+#pragma unroll 1
+        for (; n_in - base >= 64; base += 64) {
+            load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) blk[i] = __byte_perm(blk[i], 0, 0x0123);
+            sha256_compress(h, blk);
+        }
+        load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
+        const uint32_t rem = n_in - base;   // 0..63 message bytes in the last block(s); bytes past the message are zero
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((uint32_t)i == (rem >> 2)) blk[i] |= 0x80u << (8 * (rem & 3));
+            blk[i] = __byte_perm(blk[i], 0, 0x0123);
+        }
+        if (rem >= 56) {
+            sha256_compress(h, blk);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) blk[i] = 0;
+        }
+        const unsigned long long bits = (unsigned long long)n_in * 8;
+        blk[14] = (uint32_t)(bits >> 32);
+        blk[15] = (uint32_t)bits;
+        sha256_compress(h, blk);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dg.l[k] = __byte_perm(h[k], 0, 0x0123);   // digest byte 4k at the low end of limb k
+    } else if (func == 1) {   // Keccak-256, one block (n_in <= 135): 34 words from five chunks
+        unsigned long long st[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) st[i] = 0;
+        uint32_t wds[40];
+        load_chunks<T, 5>(wds, cb, chunk, 0, n_chunks);
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            unsigned long long lane = ((unsigned long long)wds[2 * i + 1] << 32) | wds[2 * i];
+            if ((uint32_t)i == (n_in >> 3)) lane ^= 0x01ULL << (8 * (n_in & 7));
+            st[i] ^= lane;
+        }
+        st[16] ^= 0x8000000000000000ULL;
+        keccak_f1600(st);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dg.l[2 * k] = (uint32_t)st[k];
+            dg.l[2 * k + 1] = (uint32_t)(st[k] >> 32);
+        }
+    } else {   // Blake2s: 64-byte little-endian blocks, the last one (possibly full) carries the final flag
+        uint32_t h[8] = {0x6A09E667u ^ 0x01010020u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+        uint32_t blk[16];
+        uint32_t base = 0;
+#pragma unroll 1
+        for (; n_in - base > 64; base += 64) {
+            load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
+            blake2s_compress(h, blk, (unsigned long long)base + 64, false);
+        }
+        load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
+        blake2s_compress(h, blk, n_in, true);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dg.l[k] = h[k];
+    }
+    hv_store<T>(cb, r->w[2], dg);
+}
+
+template <int T>
+__device__ __noinline__ void exec_hash_unpack(const OpRec* r, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
+    const uint32_t* pl = payload + r->w[7];
+    Fe v;
+    hv_load<T>(v, cb, r->w[3]);
+    uint8_t dg[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dg[i] = (uint8_t)(v.l[i >> 2] >> (8 * (i & 3)));
+    write_digest<T>(dg, pl + 1, pl[0], cb, fail, r->w[1]);
+}
+
 // to_field: one output = digest reduced mod p (HashToField128Security); else 32 byte outputs (Blake2s)
 template <int T>
 __device__ __noinline__ void exec_blake2s(const OpRec* r, bool to_field, uint4* cb, unsigned long long* fail, const uint32_t* payload) {
@@ -1457,6 +1580,15 @@ __device__ __forceinline__ void exec_heavy(const OpRec* r, uint32_t kind, uint32
             break;
         case MK_INT_OP:
             exec_int_op<T>(r, flags, cb, fail);
+            break;
+        case MK_HASH_PACK:
+            exec_hash_pack<T>(r, cb, payload);
+            break;
+        case MK_HASH_CORE:
+            exec_hash_core<T>(r, cb, payload);
+            break;
+        case MK_HASH_UNPACK:
+            exec_hash_unpack<T>(r, cb, fail, payload);
             break;
         case MK_MEM_READ:
         case MK_MEM_WRITE:

@@ -1453,6 +1453,107 @@ struct Compiler {
         place_heavy(r, rd, wr);
     }
 
+    // ---- packed hash pipeline ------------------------------------------------------------------------------------------
+    // digest column of an earlier packed hash call, keyed by its first output witness
+    struct DigestCol {
+        uint32_t slot;
+        std::vector<uint32_t> outs;
+    };
+    std::vector<std::pair<uint32_t, DigestCol>> digest_cols_;   // (first output, column), searched from the back (recent first)
+
+    // returns false when the call does not qualify (the caller then emits the one-micro-op form)
+    bool hash_packed(uint32_t idx, const BlackBoxCall& b) {
+        if (!opt.packed_hashes) return false;
+        const uint32_t func = b.func == BB_SHA256 ? 0u : b.func == BB_Keccak256 ? 1u : b.func == BB_Blake2s ? 2u : 3u;
+        if (func > 2) return false;
+        const uint32_t n = b.n_message_inputs;
+        if (n == 0 || n > 4096) return false;
+        if (func == 1 && n > 135) return false;            // one Keccak block: the core indexes its words statically
+        for (uint32_t k = 0; k < n; ++k)
+            if (b.inputs[k].num_bits == 0 || b.inputs[k].num_bits > 8) return false;
+        for (uint32_t i = 0; i < 32; ++i)                   // 32 distinct outputs, none of them an input of this call
+            for (uint32_t j = 0; j < i; ++j)
+                if (b.outputs[i] == b.outputs[j]) return false;
+        const uint32_t n_chunks = (n + 31) / 32;
+        std::vector<uint32_t> chunks, packs;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t cnt = std::min(32u, n - 32 * c);
+            uint32_t slot = NONE;
+            if (cnt == 32) {   // exactly the digest of an earlier call, in order: take its packed column
+                for (size_t d = digest_cols_.size(); d-- > 0 && slot == NONE;) {
+                    if (digest_cols_[d].first != b.inputs[32 * c].witness) continue;
+                    bool same = true;
+                    for (uint32_t k = 0; k < 32 && same; ++k) same = digest_cols_[d].second.outs[k] == b.inputs[32 * c + k].witness;
+                    if (same) slot = digest_cols_[d].second.slot;
+                }
+            }
+            if (slot == NONE) {
+                slot = new_pinned(1, 64);
+                packs.push_back(slot);
+                OpRec r{};
+                const uint32_t off = (uint32_t)plan.payload.size();
+                plan.payload.push_back(cnt);
+                std::vector<uint32_t> rd, wr = {slot};
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    plan.payload.push_back(b.inputs[32 * c + k].witness);
+                    rd.push_back(b.inputs[32 * c + k].witness);
+                }
+                r.w[0] = MK_HASH_PACK;
+                r.w[1] = idx;
+                r.w[2] = slot;
+                r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+                r.w[7] = off;
+                place_heavy(r, rd, wr);
+            }
+            chunks.push_back(slot);
+        }
+        const uint32_t dslot = new_pinned(1, 1u << 30);   // lives as long as a later call may take it as its message: never reused
+        {
+            OpRec r{};
+            const uint32_t off = (uint32_t)plan.payload.size();
+            plan.payload.push_back(func);
+            plan.payload.push_back(n);
+            plan.payload.push_back(n_chunks);
+            plan.payload.insert(plan.payload.end(), chunks.begin(), chunks.end());
+            std::vector<uint32_t> rd(chunks), wr = {dslot};
+            r.w[0] = MK_HASH_CORE;
+            r.w[1] = idx;
+            r.w[2] = dslot;
+            r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
+            r.w[7] = off;
+            place_heavy(r, rd, wr);
+        }
+        for (uint32_t s_ : packs) release_pinned(s_, 1);
+        {
+            OpRec r{};
+            const uint32_t off = (uint32_t)plan.payload.size();
+            uint32_t mask = 0;
+            for (uint32_t i = 0; i < 32; ++i)
+                if (known[b.outputs[i]]) mask |= 1u << i;
+            plan.payload.push_back(mask);
+            std::vector<uint32_t> rd = {dslot}, wr;
+            for (uint32_t i = 0; i < 32; ++i) {
+                plan.payload.push_back(b.outputs[i]);
+                if (mask & (1u << i)) rd.push_back(b.outputs[i]);
+                wr.push_back(b.outputs[i]);
+            }
+            r.w[0] = MK_HASH_UNPACK;
+            r.w[1] = idx;
+            r.w[2] = NONE;
+            r.w[3] = dslot;
+            r.w[4] = r.w[5] = r.w[6] = NONE;
+            r.w[7] = off;
+            place_heavy(r, rd, wr);
+        }
+        digest_cols_.push_back({b.outputs[0], DigestCol{dslot, std::vector<uint32_t>(b.outputs.begin(), b.outputs.begin() + 32)}});
+        if (digest_cols_.size() > 4096) digest_cols_.erase(digest_cols_.begin(), digest_cols_.begin() + 2048);   // recent calls only
+        for (uint32_t i = 0; i < 32; ++i)
+            if (!known[b.outputs[i]]) mark_assigned(b.outputs[i], idx);
+        plan.stats.alg_bytes += 32ull * (n + 32);
+        ++plan.stats.n_hash;
+        return true;
+    }
+
     bool blackbox(uint32_t idx, const BlackBoxCall& b) {
         for (uint32_t w : b.outputs)
             if (known[w] == W_MAYBE && b.func != BB_RecursiveAggregation)
@@ -1563,6 +1664,7 @@ struct Compiler {
                         fail_static(idx, EK_REFERENCE_PANIC, 0, "hash input wider than 256 bits");
                         return false;
                     }
+                if (b.func != BB_Keccak256VariableLength && hash_packed(idx, b)) return true;
                 std::vector<uint32_t> rd, wr;
                 uint32_t off = (uint32_t)plan.payload.size();
                 uint32_t mask = 0;

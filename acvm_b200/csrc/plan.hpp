@@ -59,6 +59,11 @@ enum MicroKind : uint32_t {
     MK_JAC_ADD = 22,      // out (3 slots from w[2]) := point at w[3] + point at w[4]   (Jacobian, Montgomery form, Z = 0 is infinity)
     MK_JAC_FINAL = 23,    // (x, y) at w[2], w[5] := affine(point at w[3] [+ point at w[4]]); c[0][0]: validate fixed-base scalar w[6], w[7]
     MK_REQUIRE = 12,      // payload[aux..]: n, (witness, mu_index)*n : first one not assigned in this lane => MissingAssignment
+    // Hash calls over byte-valued inputs, split so that only the compression is on the dependency chain (plan.cpp hash_packed):
+    MK_HASH_PACK = 25,    // out column := up to 32 message bytes packed (byte i at bit 8i); payload[aux..]: n, witness * n
+    MK_HASH_CORE = 26,    // out column := digest (32 bytes packed); payload[aux..]: func (0 SHA256, 1 Keccak256, 2 Blake2s), n_bytes,
+                          // n_chunks, chunk column * n_chunks (32 message bytes each: a MK_HASH_PACK column or an earlier digest column)
+    MK_HASH_UNPACK = 27,  // x = digest column; payload[aux..]: check_mask, 32 output witnesses (insert_value each byte)
     MK_INT_OP = 24,       // out := BinaryIntOp(x, y) of a lowered Brillig opcode; w[7] = op | bit_size << 8, 1 <= bit_size <= 128
                           // (brillig_vm/src/arithmetic.rs:23-81; a condition on which the reference panics => EK_REFERENCE_PANIC)
 };
@@ -172,6 +177,10 @@ struct PlanOptions {
     // Columns written and read only by arithmetic gates hold lambda_w * value for a per-column plan constant lambda_w
     // (plan.cpp "scaled columns"): one Montgomery reduction per multiplicative gate instead of two.
     bool scaled_columns = true;
+    // SHA256 / Keccak256 / Blake2s calls over byte inputs become pack / core / unpack micro-ops (MK_HASH_*): the gather of the
+    // message and the scatter of the digest run on other slot threads, a digest that is the message of a later call is
+    // handed over as one packed column.
+    bool packed_hashes = true;
     // Recent-value ring in shared memory (vm_kernel_impl.cuh): the last `ring_slots` values written by gate / logic micro-ops
     // of a tile are kept on chip, and an operand whose producer is that recent is read from there instead of from L2
     // (operand fields get bit 31 set and carry the ring index).  0 disables.

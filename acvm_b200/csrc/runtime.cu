@@ -45,6 +45,7 @@ struct acvmb_ctx {
     uint32_t opt_split_curve = 1, opt_temp_pool = 0;
     uint32_t opt_device_brillig = 1;
     uint32_t opt_scaled_columns = 1;
+    uint32_t opt_packed_hashes = 1;
     // shared memory per CTA for the ring of recent values; 0 = no ring, the default: measured on B200 at full size the ring
     // is within 1 % of the plain kernel (operand loads hit L2 and four resident CTAs per SM hide that latency already)
     uint32_t opt_ring_bytes = 0;
@@ -240,6 +241,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "pedersen_unpinned") ctx->opt_pedersen_unpinned = value ? 1u : 0u;
     else if (k == "device_brillig") ctx->opt_device_brillig = value ? 1u : 0u;
     else if (k == "scaled_columns") ctx->opt_scaled_columns = value ? 1u : 0u;
+    else if (k == "packed_hashes") ctx->opt_packed_hashes = value ? 1u : 0u;
     else if (k == "ring_bytes") ctx->opt_ring_bytes = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
@@ -491,6 +493,7 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     opt.allow_unpinned_pedersen = ctx->opt_pedersen_unpinned != 0;
     opt.device_brillig = ctx->opt_device_brillig != 0;
     opt.scaled_columns = ctx->opt_scaled_columns != 0;
+    opt.packed_hashes = ctx->opt_packed_hashes != 0;
     {
         // the ring is [entries][T lanes][32 B]: size it for the tile width pick_T() will choose for this circuit
         bool curve = false;
@@ -1704,6 +1707,7 @@ extern "C" int acvmb_plan_compile_host_ex(const uint8_t* gz, size_t len, const u
     opt.allow_unpinned_pedersen = (flags & 1u) != 0;
     opt.device_brillig = (flags & 2u) == 0;
     opt.scaled_columns = (flags & 4u) == 0;
+    opt.packed_hashes = (flags & 8u) == 0;
     if (const uint32_t rs = (flags >> 8) & 0xFFFFu) opt.ring_slots = rs == 0xFFFFu ? 0u : rs;
     try {
         tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);

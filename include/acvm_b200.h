@@ -216,7 +216,8 @@ int acvmb_ecdsa_secp256r1_verify(acvmb_ctx* ctx, const uint8_t* hashed_msg, cons
 int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 /* same with plan options: temp_pool (0 = default), flags bit 0 = accept Pedersen (parity unpinned, see "pedersen_unpinned"),
- * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only, bits 8..23 = entries of the shared-memory
+ * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only, bit 3 = one micro-op per
+ * hash call (no pack / core / unpack split), bits 8..23 = entries of the shared-memory
  * ring of recent values (0 = default, 0xFFFF = none) */
 int acvmb_plan_compile_host_ex(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                                uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
@@ -247,7 +248,8 @@ int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
  * "staging_bytes", "split_curve" (0: one micro-op per curve call), "temp_pool" (temporary columns), "pedersen_unpinned" (1: accept
  * BlackBoxFuncCall::Pedersen / acvmb_pedersen although the values are NOT barretenberg's -- refused by default),
  * "device_brillig" (0: every Brillig opcode runs on the host VM), "scaled_columns" (0: every witness column holds the
- * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "ring_bytes" (shared memory per CTA
+ * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "packed_hashes" (0: a hash call is ONE micro-op that gathers its
+ * message byte by byte and scatters its digest itself), "ring_bytes" (shared memory per CTA
  * for the ring of recent values that serves operand reads on chip; 0: every operand comes from L2 / HBM), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
  * identical next call); plan options apply to circuits created afterwards */

@@ -13,7 +13,8 @@ NONE = 0xFFFFFFFF
 
 MK = dict(NOP=0, GATE_ASSIGN=1, GATE_CHECK=2, AND=3, XOR=4, RANGE=5, SHA256=6, KECCAK256=7, FIXED_BASE=8, PEDERSEN=9,
           GATE_GENERAL=10, COPY_CHECK=11, REQUIRE=12, COPY=13, TO_LE_RADIX=14, QUOTIENT=15, MEM_READ=16, MEM_WRITE=17,
-          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20, CURVE_PART=21, JAC_ADD=22, JAC_FINAL=23, INT_OP=24)
+          BLAKE2S=18, HASH_TO_FIELD=19, ECDSA=20, CURVE_PART=21, JAC_ADD=22, JAC_FINAL=23, INT_OP=24,
+          HASH_PACK=25, HASH_CORE=26, HASH_UNPACK=27)
 EK_OOB = 5
 EK_PANIC = 8
 GF_MUL, GF_Y, GF_NLIN_SHIFT, GF_W1_IS_X, GF_OUT_CHECK = 1, 2, 2, 16, 32
@@ -525,6 +526,26 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                             record_fail(opcode, EK_OOB, mi)
                         else:
                             writes.append((base + mi, cols[y]))
+            elif kind == MK["HASH_PACK"]:   # packed hash pipeline (heavy_ops.cuh exec_hash_pack / _core / _unpack)
+                pl = plan.payload
+                n_ = pl[aux]
+                writes.append((out, sum((cols[pl[aux + 1 + k_]] & 0xFF) << (8 * k_) for k_ in range(n_))))
+            elif kind == MK["HASH_CORE"]:
+                from oracle import hashes as ohashes
+                pl = plan.payload
+                func_, n_, nch_ = pl[aux:aux + 3]
+                msg = b"".join(cols[pl[aux + 3 + c_]].to_bytes(32, "little") for c_ in range(nch_))[:n_]
+                dg_ = (ohashes.sha256, ohashes.keccak256, ohashes.blake2s)[func_](msg)
+                writes.append((out, int.from_bytes(dg_, "little")))
+            elif kind == MK["HASH_UNPACK"]:
+                pl = plan.payload
+                mask_ = pl[aux]
+                dg_ = cols[x].to_bytes(32, "little")
+                for i_ in range(32):
+                    w_ = pl[aux + 1 + i_]
+                    if (mask_ >> i_) & 1 and cols[w_] != dg_[i_]:
+                        record_fail(opcode, EK_UNSAT)
+                    writes.append((w_, dg_[i_]))
             elif kind == MK["INT_OP"]:   # a lowered Brillig BinaryIntOp (heavy_ops.cuh exec_int_op)
                 from oracle import brillig_vm as obv, pwg as opwg
                 try:

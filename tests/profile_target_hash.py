@@ -5,6 +5,9 @@ import numpy as np
 import acvm_b200
 from acvm_b200 import acir_builder as ab
 ctx = acvm_b200.Context(0)
+for kv in filter(None, os.environ.get("ACVMB_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 rng = np.random.default_rng(1)
 data, inputs, nw = ab.hash_chain_circuit(int(sys.argv[1]) if len(sys.argv) > 1 else 256)
 batch = 4096
@@ -13,4 +16,5 @@ arr[:, :, 31] = rng.integers(0, 256, size=(batch, len(inputs)), dtype=np.uint8)
 circ = acvm_b200.CompiledCircuit(ctx, data, inputs)
 b = acvm_b200.DeviceBatch(circ, batch)
 b.stage_inputs(0, arr.tobytes())
-print("hash", b.run_staged(0), sum(s.status == "Solved" for s in b.status()))
+b.run_staged(0)
+print("hash", b.run_staged(0), sum(s.status == "Solved" for s in b.status()), circ.info["n_steps"], circ.info["n_micro_ops"])

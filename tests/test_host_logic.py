@@ -1,6 +1,7 @@
 """CPU tests of the product's host side: library loads and exports the header's symbols, the C++ decoder
 and plan compiler agree with the oracle (through the test-only plan interpreter), field limb algorithms."""
 import ctypes
+import hashlib
 import os
 import random
 import re
@@ -741,3 +742,39 @@ def test_integer_brillig_ops_are_lowered_to_the_device():
               [dict(op="BinaryIntOp", destination=0, bop=0, bit_size=200, lhs=0, rhs=1)])
     info = _interp_vs_oracle(b.to_bytes(), [1, 2], inp[:64] + inp[128:192], 2)
     assert info["n_brillig_device"] == 0 and info["n_host_segments"] == 2
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_packed_hash_pipeline_plan_vs_oracle(packed):
+    """SHA256 / Keccak256 / Blake2s over byte inputs are lowered to pack / core / unpack micro-ops (plan.cpp hash_packed): block
+    edges, partial chunks, a digest handed to the next call as one packed column (the config-3 chain), a pre-assigned
+    output that does not match, and the same circuits with the one-micro-op form."""
+    data, inputs, nw = ab.hash_chain_circuit(6)
+    rng = random.Random(3)
+    inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(2 * len(inputs)))
+    info = _interp_vs_oracle(data, inputs, inp, 2, 16, packed_hashes=packed)
+    assert info["n_hash"] == 6 and (info["n_micro_ops"] > 6) == packed
+    if packed:   # 6 cores + 6 unpacks + packs: two for the first call (nothing to hand over), one (the fresh half) afterwards
+        assert info["n_micro_ops"] == 6 + 6 + 2 + 5
+    for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 200)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
+                          ("Blake2s", (1, 32, 63, 64, 65, 128, 129))):
+        b = ab.CircuitBuilder()
+        nxt = 300
+        for n in lengths:
+            b.hash256(name, [(1 + (k * 7 + n) % 200, 8 if k % 3 else 5) for k in range(n)], list(range(nxt, nxt + 32)))
+            nxt += 32
+        b.hash256(name, [(w, 8) for w in range(300, 332)] + [(3, 8)], list(range(nxt, nxt + 32)))   # digest of call 0 + one byte
+        ins = list(range(1, 201))
+        inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(ins)))
+        _interp_vs_oracle(b.to_bytes(), ins, inp, 1, 16, packed_hashes=packed)
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 2), (ab.P - 1, 13)], 0)                 # w13 := w2: output 3 of the hash is pre-assigned
+    b.hash256("SHA256", [(1, 8)], list(range(10, 42)))
+    good = hashlib.sha256(b"\x05").digest()
+    data = b.to_bytes()
+    _interp_vs_oracle(data, [1, 2], (5).to_bytes(32, "big") + good[3].to_bytes(32, "big"), 1, 16, packed_hashes=packed)
+    # the mismatching instance: same status as the oracle; its witness map is the documented deviation (DESIGN.md section 6)
+    info, blob = acvm_b200.compile_plan_host(data, [1, 2], 16, packed_hashes=packed)
+    st, wm = plan_interp.run_plan(plan_interp.PlanBlob(blob), {1: 5, 2: (good[3] + 1) % 256}, circuit=acir.decode_circuit(data))
+    assert st[0] == "Failure" and acvm_b200.solver.ERR_NAMES[st[1]] == "UnsatisfiedConstrain" and st[2] == 1
+    assert wm == {1: 5, 2: (good[3] + 1) % 256, 13: good[3]}
