@@ -268,7 +268,7 @@ class Scheduler {
     }
 
     // emit the dense [n_steps_padded][S] record array
-    void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps) {
+    void emit(std::vector<OpRec>& stream, uint32_t& n_steps_padded, uint32_t chunk_steps, uint32_t slots_per_warp = 1) {
         flush();
         n_steps_padded = ((n_steps_ + chunk_steps - 1) / chunk_steps) * chunk_steps;
         if (n_steps_padded == 0) n_steps_padded = chunk_steps;
@@ -292,9 +292,48 @@ class Scheduler {
             }
             return (k << 40) | ((uint64_t)width << 36) | ((uint64_t)two_red << 35) | (r.w[0] >> 8);
         };
+        // Tiles narrower than a warp (slots_per_warp = 32 / T > 1): the heavy micro-ops of a step (hash, curve, general ops --
+        // thousands of instructions each) go to DIFFERENT warps, one per warp before any warp gets a second one, so that a hash
+        // core and the pack / unpack micro-ops beside it are not serialised by divergence inside one warp; the light ops keep
+        // their sorted order in the slots that remain, warps without a heavy op first.
+        const uint32_t spw = slots_per_warp > 1 && S_ % slots_per_warp == 0 ? slots_per_warp : 1;
+        const uint32_t n_warps = S_ / spw;
+        auto heavy = [](const OpRec& r) {
+            const uint32_t kind = r.w[0] & 0xFF;
+            return !(kind == MK_NOP || kind == MK_GATE_ASSIGN || kind == MK_GATE_CHECK || kind == MK_AND || kind == MK_XOR || kind == MK_RANGE);
+        };
+        std::vector<OpRec> tmp(S_);
+        std::vector<uint8_t> taken(S_);
         for (uint32_t s = 0; s < n_steps_padded; ++s) {
             OpRec* first = &stream[(size_t)s * S_];
             std::stable_sort(first, first + cursor[s], [&](const OpRec& x, const OpRec& y) { return key(x) < key(y); });
+            if (spw == 1 || n_warps < 2) continue;
+            uint32_t n_heavy = 0;
+            for (uint32_t j = 0; j < cursor[s]; ++j) n_heavy += heavy(first[j]) ? 1u : 0u;
+            if (n_heavy == 0) continue;
+            std::fill(tmp.begin(), tmp.end(), OpRec{});
+            std::fill(taken.begin(), taken.end(), 0);
+            uint32_t h = 0;
+            for (uint32_t j = 0; j < cursor[s]; ++j)
+                if (heavy(first[j])) {
+                    const uint32_t pos = (h % n_warps) * spw + h / n_warps;
+                    tmp[pos] = first[j];
+                    taken[pos] = 1;
+                    ++h;
+                }
+            // light ops: free slots of the warps that hold no heavy op first, then the rest, ascending
+            std::vector<uint32_t> free_pos;
+            for (int pass = 0; pass < 2; ++pass)
+                for (uint32_t w = 0; w < n_warps; ++w) {
+                    const bool has_heavy = w < std::min(n_heavy, n_warps);
+                    if (has_heavy != (pass == 1)) continue;
+                    for (uint32_t k = 0; k < spw; ++k)
+                        if (!taken[w * spw + k]) free_pos.push_back(w * spw + k);
+                }
+            uint32_t f = 0;
+            for (uint32_t j = 0; j < cursor[s]; ++j)
+                if (!heavy(first[j])) tmp[free_pos[f++]] = first[j];
+            std::copy(tmp.begin(), tmp.end(), first);
         }
     }
 
@@ -1510,17 +1549,29 @@ struct Compiler {
         const uint32_t dslot = new_pinned(1, 1u << 30);   // lives as long as a later call may take it as its message: never reused
         {
             OpRec r{};
-            const uint32_t off = (uint32_t)plan.payload.size();
-            plan.payload.push_back(func);
-            plan.payload.push_back(n);
-            plan.payload.push_back(n_chunks);
-            plan.payload.insert(plan.payload.end(), chunks.begin(), chunks.end());
             std::vector<uint32_t> rd(chunks), wr = {dslot};
             r.w[0] = MK_HASH_CORE;
             r.w[1] = idx;
             r.w[2] = dslot;
-            r.w[3] = r.w[4] = r.w[5] = r.w[6] = NONE;
-            r.w[7] = off;
+            r.w[3] = r.w[4] = r.w[5] = NONE;
+            // descriptor = func, n_bytes, n_chunks, chunk columns.  Up to 37 chunks it rides in the record's coefficient words
+            // (already in shared memory when the micro-op starts: one L2 round trip less on the chain of a hash chain).
+            if (3 + n_chunks <= 40) {
+                uint32_t* d = &r.c[0][0];
+                d[0] = func;
+                d[1] = n;
+                d[2] = n_chunks;
+                for (uint32_t c = 0; c < n_chunks; ++c) d[3 + c] = chunks[c];
+                r.w[6] = 1;
+                r.w[7] = NONE;
+            } else {
+                r.w[6] = 0;
+                r.w[7] = (uint32_t)plan.payload.size();
+                plan.payload.push_back(func);
+                plan.payload.push_back(n);
+                plan.payload.push_back(n_chunks);
+                plan.payload.insert(plan.payload.end(), chunks.begin(), chunks.end());
+            }
             place_heavy(r, rd, wr);
         }
         for (uint32_t s_ : packs) release_pinned(s_, 1);
@@ -1953,7 +2004,12 @@ struct Compiler {
         close_device_segment();
         plan.ring_slots = opt.ring_slots;
         sched.assign_ring(opt.ring_slots, plan.stats.n_operand_reads, plan.stats.n_ring_reads);
-        sched.emit(plan.stream, plan.n_steps, plan.chunk_steps);
+        {
+            // tile width the runtime will pick (runtime.cu pick_T): 32 lanes for circuits with curve calls, else 128 / S
+            uint32_t T = opt.tile_lanes ? opt.tile_lanes : (plan.stats.n_curve ? 32u : std::max(1u, 128u / opt.S));
+            if (T > 32) T = 32;
+            sched.emit(plan.stream, plan.n_steps, plan.chunk_steps, opt.spread_heavy && (32 % T) == 0 ? 32 / T : 1);
+        }
         plan.n_slots = temp_base + opt.temp_pool + extra_slots;
         if (scaled) {
             bool any = false;

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(T* S, (T * S <= 128) ? (CAP ? 896 / (T * S) : 
                       : nullptr;
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t slot = tid / T;
+    const uint32_t slot = tid / T;   // T < 32: a warp holds 32 / T consecutive slots (plan.cpp Scheduler::emit orders them for that)
     const uint32_t lane = tid % T;
     const uint32_t tile = blockIdx.x;
     uint4* cb = a.cols + (size_t)tile * a.n_slots * (2 * T) + lane;

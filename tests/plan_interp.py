@@ -532,7 +532,10 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 writes.append((out, sum((cols[pl[aux + 1 + k_]] & 0xFF) << (8 * k_) for k_ in range(n_))))
             elif kind == MK["HASH_CORE"]:
                 from oracle import hashes as ohashes
-                pl = plan.payload
+                if w2 == 1:   # descriptor in the record's coefficient words
+                    pl, aux = struct.unpack_from("<40I", plan.stream, (step * plan.S + s) * 192 + 32), 0
+                else:
+                    pl = plan.payload
                 func_, n_, nch_ = pl[aux:aux + 3]
                 msg = b"".join(cols[pl[aux + 3 + c_]].to_bytes(32, "little") for c_ in range(nch_))[:n_]
                 dg_ = (ohashes.sha256, ohashes.keccak256, ohashes.blake2s)[func_](msg)

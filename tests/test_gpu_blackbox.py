@@ -64,6 +64,32 @@ def test_hash_circuit_mixed_widths_and_chaining(ctx):
     _check_circuit(ctx, data, [1, 2, 3, 4, 5], batch, inp)
 
 
+@pytest.mark.parametrize("packed", [1, 0])
+def test_hash_calls_over_byte_witnesses_block_edges_and_chaining(packed):
+    """The pack / core / unpack lowering (plan.cpp hash_packed) against the one-micro-op form and the oracle: block edges of the
+    three hash functions, 5-bit and 8-bit inputs, a digest handed to the next call, a message longer than the record-resident
+    descriptor holds (> 37 chunks), narrow tiles with the heavy micro-ops spread over warps or not."""
+    c = acvm_b200.Context(0)
+    c.set_option("packed_hashes", packed)
+    c.set_option("spread_heavy", packed)
+    try:
+        for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 200, 1250)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
+                              ("Blake2s", (1, 32, 63, 64, 65, 128, 129))):
+            b = ab.CircuitBuilder()
+            nxt = 300
+            for n in lengths:
+                b.hash256(name, [(1 + (k * 7 + n) % 200, 8 if k % 3 else 5) for k in range(n)], list(range(nxt, nxt + 32)))
+                nxt += 32
+            b.hash256(name, [(w, 8) for w in range(300, 332)] + [(3, 8)], list(range(nxt, nxt + 32)))
+            batch = 11
+            rnd = random.Random(len(lengths))
+            inp = b"".join(rnd.randrange(256).to_bytes(32, "big") for _ in range(batch * 200))
+            st = _check_circuit(c, b.to_bytes(), list(range(1, 201)), batch, inp)
+            assert all(s.status == "Solved" for s in st)
+    finally:
+        c.close()
+
+
 def test_keccak_variable_length(ctx):
     b = ab.CircuitBuilder()
     b.keccak_var([(w, 8) for w in range(1, 11)], (11, 32), list(range(20, 52)))

@@ -767,6 +767,12 @@ def test_packed_hash_pipeline_plan_vs_oracle(packed):
         ins = list(range(1, 201))
         inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(ins)))
         _interp_vs_oracle(b.to_bytes(), ins, inp, 1, 16, packed_hashes=packed)
+    # more than 37 chunks: the core's descriptor no longer fits the record and goes to the payload
+    b = ab.CircuitBuilder()
+    b.hash256("SHA256", [(1 + (k * 11) % 200, 8) for k in range(1250)], list(range(300, 332)))
+    ins = list(range(1, 201))
+    _interp_vs_oracle(b.to_bytes(), ins, b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(ins))), 1, 16,
+                      packed_hashes=packed)
     b = ab.CircuitBuilder()
     b.arithmetic([], [(1, 2), (ab.P - 1, 13)], 0)                 # w13 := w2: output 3 of the hash is pre-assigned
     b.hash256("SHA256", [(1, 8)], list(range(10, 42)))
@@ -778,3 +784,32 @@ def test_packed_hash_pipeline_plan_vs_oracle(packed):
     st, wm = plan_interp.run_plan(plan_interp.PlanBlob(blob), {1: 5, 2: (good[3] + 1) % 256}, circuit=acir.decode_circuit(data))
     assert st[0] == "Failure" and acvm_b200.solver.ERR_NAMES[st[1]] == "UnsatisfiedConstrain" and st[2] == 1
     assert wm == {1: 5, 2: (good[3] + 1) % 256, 13: good[3]}
+
+
+def test_heavy_micro_ops_of_a_step_sit_in_different_warps():
+    """Scheduler::emit (plan.cpp): with a tile narrower than a warp (S = 16 -> T = 8, four slots per warp) the hash core and the
+    pack / unpack micro-ops beside it take the first slot of different warps; light ops keep consecutive slots."""
+    data, inputs, nw = ab.hash_chain_circuit(6)
+    HEAVY = {25, 26, 27}   # MK_HASH_PACK / MK_HASH_CORE / MK_HASH_UNPACK (plan.hpp)
+    for spread in (True, False):
+        info, blob = acvm_b200.compile_plan_host(data, inputs, 16, spread_heavy=spread)
+        plan = plan_interp.PlanBlob(blob)
+        seen_multi = False
+        for s in range(plan.n_steps):
+            kinds = [plan.record(s * plan.S + j)[0][0] & 0xFF for j in range(plan.S)]
+            pos = [j for j, k in enumerate(kinds) if k in HEAVY]
+            assert all(k in HEAVY or k == 0 for k in kinds)
+            if len(pos) > 1:
+                seen_multi = True
+                warps = [j // 4 for j in pos]
+                if spread:
+                    per_warp = [warps.count(w) for w in range(4)]
+                    assert max(per_warp) - min(per_warp) <= 1            # one per warp before any warp gets a second
+                    if len(pos) <= 4:
+                        assert all(j % 4 == 0 for j in pos)
+                else:
+                    assert pos == list(range(len(pos)))
+        assert seen_multi
+    rng = random.Random(5)
+    inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(inputs)))
+    _interp_vs_oracle(data, inputs, inp, 1, 16, spread_heavy=False)
