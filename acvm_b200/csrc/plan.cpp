@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <stdexcept>
 #include <thread>
 
@@ -76,6 +77,7 @@ class Scheduler {
                kind == MK_JAC_FINAL;
     }
 
+    bool slack_scheduling = true;   // PlanOptions::slack_scheduling
     bool dry = false;   // the inversion-recording pass of compile_plan(): its schedule is thrown away, do not build one
 
     void place(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
@@ -127,7 +129,39 @@ class Scheduler {
                 lvl_w_[s] = d; own_w_[s] = call;
                 lvl_r_[s] = d; own_r_[s] = call;   // readers-since-last-write restarts
             }
-            key[i] = 2 * d + (p.costly ? 0u : 1u);
+            key[i] = 4 * d + (p.costly ? 0u : 2u);
+        }
+        // Slack.  A curve micro-op whose every successor (reader of its outputs, next writer of a slot it reads or writes) sits
+        // two or more levels deeper need not run at its own level: the H1 sums over the fresh inputs of a Pedersen chain have
+        // level 1 and are consumed at level k.  Running them all up front costs full-width steps of their own; moved to the
+        // level just before their first successor -- listed after that level's own curve ops, key 4 d + 1 -- they fill the slots
+        // that the addition trees and finalisers of the chain leave idle (place_now picks steps they do not lengthen).
+        // Backward pass: bound(s) = the deepest level a predecessor through slot s may take, plus one.
+        if (slack_scheduling) {
+            constexpr uint32_t INF = 0xFFFFFFFFu;
+            for (uint32_t s : touched) lvl_w_[s] = lvl_r_[s] = INF;   // reused as: bound by the next writer / by the readers before it
+            for (size_t i = pend_.size(); i-- > 0;) {
+                const Pending& p = pend_[i];
+                const uint32_t* rd = pool_.data() + p.off;
+                const uint32_t* wr = rd + p.nr;
+                uint32_t d = key[i] >> 2, val;
+                if (p.costly) {
+                    uint32_t m = INF;
+                    for (uint32_t k = 0; k < p.nw; ++k) m = std::min(m, std::min(lvl_r_[wr[k]], lvl_w_[wr[k]]));
+                    for (uint32_t k = 0; k < p.nr; ++k) m = std::min(m, lvl_w_[rd[k]]);
+                    if (m != INF && m >= d + 2) {
+                        d = m - 1;
+                        key[i] = 4 * d + 1;
+                        val = d + 1;   // a predecessor may share the level of a slack successor (equal keys keep program order)
+                    } else {
+                        val = d;       // ... but must sort before a regular curve op: one level less
+                    }
+                } else {
+                    val = d + 1;       // cheap ops of level d are listed after every curve op of level d
+                }
+                for (uint32_t k = 0; k < p.nw; ++k) { lvl_w_[wr[k]] = val; lvl_r_[wr[k]] = INF; }
+                for (uint32_t k = 0; k < p.nr; ++k) lvl_r_[rd[k]] = std::min(lvl_r_[rd[k]], val);
+            }
         }
         for (uint32_t s : touched) {
             lvl_w_[s] = lvl_r_[s] = 0;
@@ -137,25 +171,51 @@ class Scheduler {
         std::vector<uint32_t> order(pend_.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-        uint32_t prev = 1;   // ops placed before buffering began are cheap, depth 0
+        uint32_t prev = 2;   // ops placed before buffering began are cheap, depth 0
         for (uint32_t i : order) {
-            if (key[i] != prev) {
+            const uint32_t group = (key[i] & 3u) == 1u ? key[i] - 1 : key[i];   // slack ops share the steps of their level's curve ops
+            if (group != prev) {
                 floor_ = n_steps_;   // curve steps hold curve micro-ops only
-                prev = key[i];
+                prev = group;
             }
             const Pending& p = pend_[i];
             const uint32_t* rd = pool_.data() + p.off;
-            place_now(p.rec, rd, p.nr, rd + p.nr, p.nw);
+            place_now(p.rec, rd, p.nr, rd + p.nr, p.nw, (key[i] & 3u) == 1u);
         }
         pend_.clear();
         pool_.clear();
     }
 
-    void place_now(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw) {
+    // relative run time of a curve micro-op (profiles/r2_pedersen_chain_stalls_v7.txt), in 1/100 of the time of the
+    // mixed additions of a 4-window partial sum: a step lasts as long as its slowest slot
+    static uint32_t op_cost(const OpRec& rec) {
+        switch (rec.w[0] & 0xFF) {
+            case MK_CURVE_PART: return 15 + 48 * (rec.c[0][3] ? rec.c[0][3] - 1 : 0);
+            case MK_JAC_ADD: return 68;
+            case MK_JAC_FINAL: return 355;
+            case MK_FIXED_BASE: case MK_PEDERSEN: case MK_ECDSA: return 2000;
+            default: return 0;
+        }
+    }
+
+    void place_now(const OpRec& rec, const uint32_t* reads, size_t nr, const uint32_t* writes, size_t nw, bool slack = false) {
         uint32_t e = floor_;
         for (size_t i = 0; i < nr; ++i) e = std::max(e, ready_[reads[i]]);
         for (size_t i = 0; i < nw; ++i) e = std::max(e, std::max(ready_[writes[i]], war_[writes[i]]));
         uint32_t s = find(e);
+        const uint32_t cost = op_cost(rec);
+        if (slack && cost) {
+            // among the next steps with a free slot, the first one this op does not lengthen; failing that, the least lengthened
+            uint32_t best = s, best_inc = cost > cost_[s] ? cost - cost_[s] : 0;
+            for (uint32_t cand = s, n = 0; best_inc && n < 64; ++n) {
+                cand = find(cand + 1);
+                if (cand >= n_steps_) break;
+                const uint32_t inc = cost > cost_[cand] ? cost - cost_[cand] : 0;
+                if (inc < best_inc) { best = cand; best_inc = inc; }
+            }
+            s = best;
+        }
+        cost_[s] = std::max(cost_[s], cost);
         if (++fill_[s] == S_) next_[s] = s + 1;
         steps_.push_back(s);
         ops_.push_back(rec);
@@ -358,6 +418,7 @@ class Scheduler {
         while (fill_.size() <= s) {
             next_.push_back((uint32_t)fill_.size());
             fill_.push_back(0);
+            cost_.push_back(0);
         }
     }
     struct Pending {
@@ -373,7 +434,7 @@ class Scheduler {
     bool buffering_ = false;
     uint32_t S_;
     std::vector<uint32_t> ready_, war_;
-    std::vector<uint32_t> fill_, next_;
+    std::vector<uint32_t> fill_, next_, cost_;   // per step: used slots, next step with a free slot, cost of its slowest op
     std::vector<uint32_t> steps_;
     std::vector<OpRec> ops_;
     std::vector<uint32_t> other_writes_at_, other_writes_off_, other_writes_;   // write sets of the ops that bypass the ring
@@ -395,7 +456,9 @@ struct Compiler {
     uint32_t extra_slots_base = 0, extra_slots = 0;   // memory-block columns live after the temporaries
 
     Compiler(const Circuit& circ, const PlanOptions& o, uint32_t nw)
-        : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw), extra_slots_base(nw + o.temp_pool) {}
+        : c(circ), opt(o), known(nw, 0), sched(o.S, nw + o.temp_pool), temp_base(nw), extra_slots_base(nw + o.temp_pool) {
+        sched.slack_scheduling = o.slack_scheduling;
+    }
 
     // Field inversions are the dominant plan-time cost (one or two per solving gate).  The compiler therefore runs twice:
     // a RECORD pass that only collects the values to invert (and gets a non-zero dummy back -- control flow never depends
@@ -1443,6 +1506,20 @@ struct Compiler {
             points.push_back(out);
         }
     }
+    // sum of the 29 table points a CONSTANT scalar selects (mode 1: Pedersen IV table entry `imm`, mode 2: the immediate `imm`):
+    // computed by the first call that needs it, in a slot triple that is never handed out again
+    std::map<uint64_t, uint32_t> const_points_;
+    uint32_t const_curve_point(uint32_t idx, uint32_t mode, uint32_t imm, uint32_t toff) {
+        const uint64_t key = ((uint64_t)mode << 56) | ((uint64_t)toff << 40) | imm;
+        auto it = const_points_.find(key);
+        if (it != const_points_.end()) return it->second;
+        std::vector<uint32_t> pts;
+        curve_parts(idx, mode, NONE, imm, 1, 29, 4, toff, pts);
+        const uint32_t slot = new_pinned(3, 1u << 30);
+        curve_reduce(idx, pts, 1, slot);
+        const_points_[key] = slot;
+        return slot;
+    }
     // pairwise tree of Jacobian additions until at most `keep` points remain
     // `final_dst` (with keep == 1): the slot triple that receives the one remaining point
     void curve_reduce(uint32_t idx, std::vector<uint32_t>& points, size_t keep, uint32_t final_dst = NONE) {
@@ -1809,29 +1886,31 @@ struct Compiler {
                     // of it; a chaining round is then 8 partial sums, a 3-level addition tree and one finaliser.
                     if (known[ox]) flags |= GF_OUT_CHECK;
                     if (known[oy] || oy == ox) flags |= GF_OUT2_CHECK;
+                    // H0(IV) and H1(n) hash plan-time constants: the same point for every instance and every call with that
+                    // domain separator / input count, so each is computed ONCE per plan (const_curve_point) and kept.
                     const uint32_t n_in = (uint32_t)b.inputs.size();
                     std::vector<uint32_t> h1(n_in + 1);
-                    for (uint32_t k = 0; k <= n_in; ++k) {
+                    for (uint32_t k = 0; k < n_in; ++k) {
                         std::vector<uint32_t> pts;
-                        if (k < n_in) curve_parts(idx, 0, b.inputs[k].witness, 0, 1, 29, 4, 29, pts);   // num_bits is ignored (pedersen.rs:18-20)
-                        else curve_parts(idx, 2, NONE, n_in, 1, 29, 4, 29, pts);                          // the length block: an immediate scalar
+                        curve_parts(idx, 0, b.inputs[k].witness, 0, 1, 29, 4, 29, pts);   // num_bits is ignored (pedersen.rs:18-20)
                         h1[k] = new_pinned(3, 1024);   // consumed n_in + 1 - k chaining rounds later: not a pool slot
                         curve_reduce(idx, pts, 1, h1[k]);
                     }
+                    h1[n_in] = const_curve_point(idx, 2, n_in, 29);   // the length block: an immediate scalar
                     uint32_t chain = NONE;   // slot holding r_k (canonical x of the previous round)
                     for (uint32_t k = 0; k <= n_in; ++k) {
                         std::vector<uint32_t> pts;
-                        if (k == 0) curve_parts(idx, 1, NONE, b.domain_separator, 1, 29, 4, 0, pts);
+                        if (k == 0) pts.push_back(const_curve_point(idx, 1, b.domain_separator, 0));
                         else curve_parts(idx, 0, chain, 0, 1, 29, 4, 0, pts);
                         pts.push_back(h1[k]);
                         curve_reduce(idx, pts, 2);
                         if (k < n_in) {
                             chain = new_temp();
                             curve_final(idx, pts, chain, NONE, GF_HEAVY, false, NONE, NONE);
+                            release_pinned(h1[k], 3);   // read for the last time by this round's finaliser
                         } else {
                             curve_final(idx, pts, ox, oy, flags, false, NONE, NONE);
                         }
-                        release_pinned(h1[k], 3);   // read for the last time by this round's finaliser
                     }
                     if (!known[ox]) mark_assigned(ox, idx);
                     if (!known[oy]) mark_assigned(oy, idx);

@@ -186,6 +186,9 @@ struct PlanOptions {
     // tile_lanes = the T the runtime will use (0: the runtime's own rule, 32 with curve calls, else 128 / S).
     bool spread_heavy = true;
     uint32_t tile_lanes = 0;
+    // Curve micro-ops with two or more levels of slack (the H1 sums of a Pedersen chain) run in the idle slots of the level just
+    // before their first successor instead of in steps of their own (Scheduler::flush).
+    bool slack_scheduling = true;
     // Recent-value ring in shared memory (vm_kernel_impl.cuh): the last `ring_slots` values written by gate / logic micro-ops
     // of a tile are kept on chip, and an operand whose producer is that recent is read from there instead of from L2
     // (operand fields get bit 31 set and carry the ring index).  0 disables.

@@ -43,6 +43,7 @@ struct acvmb_ctx {
     uint32_t opt_S = 0;   // 0 = auto: 16, or 8 for circuits with curve calls (see circuit_from_struct)
     uint32_t opt_chunk_steps = 4;   // steps per TMA stage (B200, full size: 4 is 2 % faster than 2 with the one-reduction gate kernel)
     uint32_t opt_split_curve = 1, opt_temp_pool = 0;
+    uint32_t opt_slack_scheduling = 1;   // plan: curve micro-ops with slack fill idle slots of later levels
     uint32_t opt_spread_heavy = 1;   // plan: heavy micro-ops of one step go to different warps (tiles narrower than a warp)
     uint32_t opt_device_brillig = 1;
     uint32_t opt_scaled_columns = 1;
@@ -238,6 +239,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "chunk_steps") ctx->opt_chunk_steps = (uint32_t)value;
     else if (k == "split_curve") ctx->opt_split_curve = (uint32_t)value;
     else if (k == "spread_heavy") ctx->opt_spread_heavy = value != 0;
+    else if (k == "slack_scheduling") ctx->opt_slack_scheduling = value != 0;
     else if (k == "cache_batch") { ctx->opt_cache_batch = (uint32_t)value; if (!value) drop_cached_batch(ctx); }
     else if (k == "temp_pool") ctx->opt_temp_pool = (uint32_t)value;
     else if (k == "pedersen_unpinned") ctx->opt_pedersen_unpinned = value ? 1u : 0u;
@@ -497,6 +499,7 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     opt.scaled_columns = ctx->opt_scaled_columns != 0;
     opt.packed_hashes = ctx->opt_packed_hashes != 0;
     opt.spread_heavy = ctx->opt_spread_heavy != 0;
+    opt.slack_scheduling = ctx->opt_slack_scheduling != 0;
     opt.tile_lanes = ctx->opt_T;
     {
         // the ring is [entries][T lanes][32 B]: size it for the tile width pick_T() will choose for this circuit
@@ -1713,6 +1716,7 @@ extern "C" int acvmb_plan_compile_host_ex(const uint8_t* gz, size_t len, const u
     opt.scaled_columns = (flags & 4u) == 0;
     opt.packed_hashes = (flags & 8u) == 0;
     opt.spread_heavy = (flags & 16u) == 0;
+    opt.slack_scheduling = (flags & 32u) == 0;
     if (const uint32_t rs = (flags >> 8) & 0xFFFFu) opt.ring_slots = rs == 0xFFFFu ? 0u : rs;
     try {
         tmp.plan = compile_plan(circ, std::vector<uint32_t>(input_witnesses, input_witnesses + n_inputs), opt);

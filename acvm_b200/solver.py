@@ -426,7 +426,8 @@ def decompress_witness_map(data: bytes) -> Dict[int, int]:
 
 def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int = 16, temp_pool: int = 0,
                       pedersen_unpinned: bool = False, device_brillig: bool = True, scaled_columns: bool = True,
-                      ring_slots: int = None, packed_hashes: bool = True, spread_heavy: bool = True):
+                      ring_slots: int = None, packed_hashes: bool = True, spread_heavy: bool = True,
+                      slack_scheduling: bool = True):
     """Decode + compile on the host only (no device): returns (info dict, plan blob)."""
     info = _lib.PlanInfo()
     need = C.c_size_t()
@@ -434,6 +435,7 @@ def compile_plan_host(acir_bytes: bytes, input_witnesses: Sequence[int], S: int 
     flags = (1 if pedersen_unpinned else 0) | (0 if device_brillig else 2) | (0 if scaled_columns else 4)
     flags |= 0 if packed_hashes else 8
     flags |= 0 if spread_heavy else 16
+    flags |= 0 if slack_scheduling else 32
     if ring_slots is not None:   # entries of the shared-memory ring of recent values (0 = none)
         flags |= (0xFFFF if ring_slots == 0 else ring_slots) << 8
     _check(lib().acvmb_plan_compile_host_ex(acir_bytes, len(acir_bytes), ids, len(input_witnesses), S, temp_pool, flags,

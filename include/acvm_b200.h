@@ -217,7 +217,8 @@ int acvmb_plan_compile_host(const uint8_t* gz_bincode, size_t len, const uint32_
                             acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
 /* same with plan options: temp_pool (0 = default), flags bit 0 = accept Pedersen (parity unpinned, see "pedersen_unpinned"),
  * bit 1 = keep every Brillig opcode on the host VM (no plan-time lowering to device gates), bit 2 = canonical columns only, bit 3 = one micro-op per
- * hash call (no pack / core / unpack split), bit 4 = no spreading of heavy micro-ops over warps ("spread_heavy" = 0), bits 8..23 = entries of the shared-memory
+ * hash call (no pack / core / unpack split), bit 4 = no spreading of heavy micro-ops over warps ("spread_heavy" = 0),
+ * bit 5 = curve micro-ops with slack keep steps of their own ("slack_scheduling" = 0), bits 8..23 = entries of the shared-memory
  * ring of recent values (0 = default, 0xFFFF = none) */
 int acvmb_plan_compile_host_ex(const uint8_t* gz_bincode, size_t len, const uint32_t* input_witnesses, uint32_t n_inputs, uint32_t S,
                                uint32_t temp_pool, uint32_t flags, acvmb_plan_info* info, uint8_t* blob, size_t cap, size_t* needed);
@@ -252,7 +253,9 @@ int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
  * message byte by byte and scatters its digest itself), "ring_bytes" (shared memory per CTA
  * for the ring of recent values that serves operand reads on chip; 0: every operand comes from L2 / HBM), "spread_heavy" (0: the micro-ops of a
  * step fill its slots in sorted order; default 1 puts the hash / curve / general micro-ops of one step into different warps when
- * the tile is narrower than a warp, so that they do not serialise inside one), "cache_batch" (0: free
+ * the tile is narrower than a warp, so that they do not serialise inside one), "slack_scheduling" (0: curve micro-ops that nothing
+ * needs for two or more dependency levels -- the H1 sums of a Pedersen chain -- run up front in steps of their own; default 1 moves
+ * them into the idle slots of the level before their first use), "cache_batch" (0: free
  * the column buffers at the end of every acvmb_solve_batch; default 1 keeps those of the last call, per context, for an
  * identical next call); plan options apply to circuits created afterwards */
 int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t value);

@@ -604,13 +604,15 @@ def test_curve_ops_monolithic_and_split_plans_vs_oracle(S):
     b.logic("AND", (3, 100), (2, 100), 19)
     b.fixed_base_scalar_mul((18, 128), (19, 128), (20, 21))
     b.arithmetic([(1, 20, 21)], [(1, 16), (ab.P - 1, 24)], 0)
+    b.pedersen([(12, 254), (13, 254)], 0, (30, 31))          # same separator and input count as the first call: its constant
+    b.pedersen([(30, 254), (2, 254)], 0, (32, 33))           # points H0(IV), H1(n) are computed once per plan (const_curve_point)
     b.fixed_base_scalar_mul((1, 254), (19, 128), (22, 23))   # low limb >= 2^128 in the random rows: BlackBoxFunctionFailed
     data = b.to_bytes()
     with pytest.raises(acvm_b200.AcvmError) as e:      # Pedersen is opt-in: parity with barretenberg's tables is unpinned
         acvm_b200.compile_plan_host(data, [1, 2, 3], S)
     assert e.value.rc == -5 and "pedersen_unpinned" in str(e.value)
     info = _interp_vs_oracle(data, [1, 2, 3], ab.synthetic_inputs(3, n_inputs=3, seed_id=9), 3, S=S, pedersen_unpinned=True)
-    assert info["n_curve"] == 6 and (info["n_micro_ops"] > 100) == (S >= 8)
+    assert info["n_curve"] == 8 and (info["n_micro_ops"] > 100) == (S >= 8)
     b = ab.CircuitBuilder()
     b.fixed_base_scalar_mul((1, 128), (2, 128), (4, 3))      # y is pre-assigned: insert_value compares
     b.arithmetic([], [(1, 4), (ab.P - 1, 6)], 1)
