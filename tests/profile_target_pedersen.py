@@ -6,6 +6,9 @@ import acvm_b200
 from acvm_b200 import acir_builder as ab
 ctx = acvm_b200.Context(0)
 ctx.set_option("pedersen_unpinned", 1)   # structure/cost measurement only: values are not barretenberg's
+for kv in filter(None, os.environ.get("ACVMB_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 rng = np.random.default_rng(1)
 data, inputs, nw = ab.pedersen_chain_circuit(int(sys.argv[1]) if len(sys.argv) > 1 else 32)
 batch = 4096
