@@ -97,7 +97,10 @@ struct Reader {
     }
     U256 fe() {  // FieldElement serialises as its hex string (acir_field/src/generic_ark.rs:114-134)
         U256 v;
-        if (!hf::from_hex(str(), v)) throw DecodeError("bad field element hex");
+        uint64_t k = len();
+        need(k);
+        if (!hf::from_hex((const char*)d + o, k, v)) throw DecodeError("bad field element hex");
+        o += k;
         return v;
     }
     std::vector<uint32_t> vec_u32() {

@@ -218,6 +218,15 @@ inline U256 reduce(U256 a) {  // arbitrary 256-bit -> mod p
     return a;
 }
 inline U256 from_be_bytes_reduce(const uint8_t* b, size_t n) {
+    if (n == 32) {   // the common case (every FieldElement of an ACIR circuit): four big-endian words, < 2^256 < 6p
+        U256 v;
+        for (int k = 0; k < 4; ++k) {
+            uint64_t w = 0;
+            for (int j = 0; j < 8; ++j) w = (w << 8) | b[8 * (3 - k) + j];
+            v.l[k] = w;
+        }
+        return reduce(v);
+    }
     // accumulates base-256 digits mod p so inputs longer than 32 bytes reduce correctly
     U256 acc;
     U256 c256;
@@ -255,26 +264,32 @@ inline void to_limbs32(const U256& a, uint32_t out[8]) {
         out[2 * i + 1] = (uint32_t)(a.l[i] >> 32);
     }
 }
-inline bool from_hex(const std::string& s, U256& out) {
-    size_t off = (s.size() >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) ? 2 : 0;
-    size_t n = s.size() - off;
+inline bool from_hex(const char* s, size_t len, U256& out) {
+    size_t off = (len >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) ? 2 : 0;
+    size_t n = len - off;
     if (n % 2) return false;
-    std::string bytes;
-    bytes.resize(n / 2);
     auto hv = [](char c) -> int {
         if (c >= '0' && c <= '9') return c - '0';
         if (c >= 'a' && c <= 'f') return c - 'a' + 10;
         if (c >= 'A' && c <= 'F') return c - 'A' + 10;
         return -1;
     };
+    uint8_t stack[64];
+    std::string heap;
+    uint8_t* bytes = stack;
+    if (n / 2 > sizeof(stack)) {
+        heap.resize(n / 2);
+        bytes = (uint8_t*)&heap[0];
+    }
     for (size_t i = 0; i < n / 2; ++i) {
         int h = hv(s[off + 2 * i]), l = hv(s[off + 2 * i + 1]);
         if (h < 0 || l < 0) return false;
-        bytes[i] = (char)(h * 16 + l);
+        bytes[i] = (uint8_t)(h * 16 + l);
     }
-    out = from_be_bytes_reduce((const uint8_t*)bytes.data(), bytes.size());
+    out = from_be_bytes_reduce(bytes, n / 2);
     return true;
 }
+inline bool from_hex(const std::string& s, U256& out) { return from_hex(s.data(), s.size(), out); }
 
 }  // namespace hf
 }  // namespace acvmb
