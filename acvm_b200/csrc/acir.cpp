@@ -3,6 +3,8 @@
 
 #include <zlib.h>
 
+#include <algorithm>
+
 #include <cstring>
 
 namespace acvmb {
@@ -19,19 +21,25 @@ std::vector<uint8_t> gunzip(const uint8_t* data, size_t len) {
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, 15 + 16) != Z_OK) throw DecodeError("inflateInit2 failed");
     zs.next_in = const_cast<Bytef*>(data);
-    zs.avail_in = (uInt)len;
+    size_t left = len;   // fed in pieces: avail_in is 32 bits wide
     std::vector<uint8_t> out;
-    uint8_t buf[1 << 16];
+    out.reserve(len * 2);
+    std::vector<uint8_t> buf(1 << 20);
     int rc;
     do {
-        zs.next_out = buf;
-        zs.avail_out = sizeof(buf);
+        if (zs.avail_in == 0 && left) {
+            const size_t piece = std::min<size_t>(left, (size_t)1 << 30);
+            zs.avail_in = (uInt)piece;
+            left -= piece;
+        }
+        zs.next_out = buf.data();
+        zs.avail_out = (uInt)buf.size();
         rc = inflate(&zs, Z_NO_FLUSH);
-        if (rc != Z_OK && rc != Z_STREAM_END) {
+        if ((rc != Z_OK && rc != Z_STREAM_END) || (rc == Z_OK && zs.avail_out == buf.size() && zs.avail_in == 0 && left == 0)) {
             inflateEnd(&zs);
             throw DecodeError("gzip stream is corrupt");
         }
-        out.insert(out.end(), buf, buf + (sizeof(buf) - zs.avail_out));
+        out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
     } while (rc != Z_STREAM_END);
     inflateEnd(&zs);
     return out;

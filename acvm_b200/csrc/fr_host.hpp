@@ -264,16 +264,22 @@ inline void to_limbs32(const U256& a, uint32_t out[8]) {
         out[2 * i + 1] = (uint32_t)(a.l[i] >> 32);
     }
 }
+inline const int8_t* hex_table() {
+    static int8_t t[256];
+    static bool init = [] {
+        for (int i = 0; i < 256; ++i) t[i] = -1;
+        for (int i = 0; i < 10; ++i) t['0' + i] = (int8_t)i;
+        for (int i = 0; i < 6; ++i) t['a' + i] = t['A' + i] = (int8_t)(10 + i);
+        return true;
+    }();
+    (void)init;
+    return t;
+}
 inline bool from_hex(const char* s, size_t len, U256& out) {
     size_t off = (len >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) ? 2 : 0;
     size_t n = len - off;
     if (n % 2) return false;
-    auto hv = [](char c) -> int {
-        if (c >= '0' && c <= '9') return c - '0';
-        if (c >= 'a' && c <= 'f') return c - 'a' + 10;
-        if (c >= 'A' && c <= 'F') return c - 'A' + 10;
-        return -1;
-    };
+    const int8_t* hv = hex_table();
     uint8_t stack[64];
     std::string heap;
     uint8_t* bytes = stack;
@@ -281,11 +287,13 @@ inline bool from_hex(const char* s, size_t len, U256& out) {
         heap.resize(n / 2);
         bytes = (uint8_t*)&heap[0];
     }
+    int bad = 0;
     for (size_t i = 0; i < n / 2; ++i) {
-        int h = hv(s[off + 2 * i]), l = hv(s[off + 2 * i + 1]);
-        if (h < 0 || l < 0) return false;
+        const int h = hv[(uint8_t)s[off + 2 * i]], l = hv[(uint8_t)s[off + 2 * i + 1]];
+        bad |= h | l;
         bytes[i] = (uint8_t)(h * 16 + l);
     }
+    if (bad < 0) return false;
     out = from_be_bytes_reduce(bytes, n / 2);
     return true;
 }
