@@ -102,6 +102,11 @@ def test_decoder_rejects_garbage_and_accepts_golden(golden):
     with pytest.raises(acvm_b200.AcvmError) as e:
         acvm_b200.compile_plan_host(b"\x1f\x8b\x08\x00garbage", [], 16)
     assert e.value.rc == -4
+    good = bytes(golden["rust_serialization"]["addition_circuit"])
+    for cut in (len(good) // 2, len(good) - 1, 11):     # a truncated gzip stream is an error, not a hang or a short read
+        with pytest.raises(acvm_b200.AcvmError) as e:
+            acvm_b200.compile_plan_host(good[:cut], [1, 2], 16)
+        assert e.value.rc == -4
     info, _ = acvm_b200.compile_plan_host(bytes(golden["rust_serialization"]["addition_circuit"]), [1, 2], 16)
     assert info["n_opcodes"] == 1 and info["num_witnesses"] == 5 and info["n_gate_assign"] == 1
     # opcodes outside the supported scope decode fine and are refused loudly, never silently skipped
