@@ -37,7 +37,7 @@ struct PanicEx {
     const char* what;
 };
 
-inline void sha256_host(const uint8_t* msg, size_t n, uint8_t out[32]) {
+inline const uint32_t* sha256_k() {
     static const uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
         0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
@@ -45,6 +45,29 @@ inline void sha256_host(const uint8_t* msg, size_t n, uint8_t out[32]) {
         0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
         0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
         0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    return K;
+}
+
+// K[i] + W[i] of the LAST block of a message whose length is a multiple of 64 bytes: that block is padding only
+// (0x80, zeros, the bit length), so its whole message schedule is a plan-time constant (heavy_ops.cuh sha256_compress_kw)
+inline void sha256_pad_block_kw(uint64_t n_bytes, uint32_t kw[64]) {
+    const uint32_t* K = sha256_k();
+    auto rotr = [](uint32_t x, int r) { return (x >> r) | (x << (32 - r)); };
+    uint32_t w[64] = {0};
+    const uint64_t bits = n_bytes * 8;
+    w[0] = 0x80000000u;
+    w[14] = (uint32_t)(bits >> 32);
+    w[15] = (uint32_t)bits;
+    for (int i = 16; i < 64; ++i) {
+        uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    for (int i = 0; i < 64; ++i) kw[i] = K[i] + w[i];
+}
+
+inline void sha256_host(const uint8_t* msg, size_t n, uint8_t out[32]) {
+    const uint32_t* K = sha256_k();
     uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     std::vector<uint8_t> m(msg, msg + n);
     m.push_back(0x80);

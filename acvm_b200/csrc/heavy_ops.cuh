@@ -187,6 +187,29 @@ static __device__ __noinline__ void sha256_compress(uint32_t* h, const uint32_t*
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
+// the compression of a block whose K[i] + W[i] are plan-time constants (the padding-only last block of a message of k * 64
+// bytes, plan.cpp hash_packed): no message schedule, 16 x 128-bit loads of a table every call of that length shares
+static __device__ __noinline__ void sha256_compress_kw(uint32_t* h, const uint32_t* kw) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    const uint4* t = reinterpret_cast<const uint4*>(kw);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const uint4 v = __ldg(t + q);
+        const uint32_t k4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+            uint32_t ch = (e & f) ^ (~e & g);
+            uint32_t t1 = hh + S1 + ch + k4[j];
+            uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+            uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            uint32_t t2 = S0 + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
 // payload: [n_in][check_mask][var_size witness | NONE][0][ (witness, num_bits) * n_in ][ 32 output witnesses ]
 // SHA-256 of a message whose bytes are one witness each (payload flag pl[3]); see fetch_words
 template <int T>
@@ -393,22 +416,26 @@ __device__ __noinline__ void exec_hash_core(const OpRec* r, uint4* cb, const uin
             for (int i = 0; i < 16; ++i) blk[i] = __byte_perm(blk[i], 0, 0x0123);
             sha256_compress(h, blk);
         }
-        load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
-        const uint32_t rem = n_in - base;   // 0..63 message bytes in the last block(s); bytes past the message are zero
+        if (n_in == base && r->w[5] != 0xFFFFFFFFu) {   // whole blocks only: the padding block's K + W table comes with the plan
+            sha256_compress_kw(h, payload + r->w[5]);
+        } else {
+            load_chunks<T, 2>(blk, cb, chunk, base >> 5, n_chunks);
+            const uint32_t rem = n_in - base;   // 0..63 message bytes in the last block(s); bytes past the message are zero
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if ((uint32_t)i == (rem >> 2)) blk[i] |= 0x80u << (8 * (rem & 3));
-            blk[i] = __byte_perm(blk[i], 0, 0x0123);
-        }
-        if (rem >= 56) {
+            for (int i = 0; i < 16; ++i) {
+                if ((uint32_t)i == (rem >> 2)) blk[i] |= 0x80u << (8 * (rem & 3));
+                blk[i] = __byte_perm(blk[i], 0, 0x0123);
+            }
+            if (rem >= 56) {
+                sha256_compress(h, blk);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) blk[i] = 0;
+            }
+            const unsigned long long bits = (unsigned long long)n_in * 8;
+            blk[14] = (uint32_t)(bits >> 32);
+            blk[15] = (uint32_t)bits;
             sha256_compress(h, blk);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) blk[i] = 0;
         }
-        const unsigned long long bits = (unsigned long long)n_in * 8;
-        blk[14] = (uint32_t)(bits >> 32);
-        blk[15] = (uint32_t)bits;
-        sha256_compress(h, blk);
 #pragma unroll
         for (int k = 0; k < 8; ++k) dg.l[k] = __byte_perm(h[k], 0, 0x0123);   // digest byte 4k at the low end of limb k
     } else if (func == 1) {   // Keccak-256, one block (n_in <= 135): 34 words from five chunks

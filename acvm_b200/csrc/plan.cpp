@@ -1575,6 +1575,7 @@ struct Compiler {
         uint32_t slot;
         std::vector<uint32_t> outs;
     };
+    std::map<uint32_t, uint32_t> sha_pad_tables_;   // message length -> payload offset of the pad block's K + W table
     std::vector<std::pair<uint32_t, DigestCol>> digest_cols_;   // (first output, column), searched from the back (recent first)
 
     // returns false when the call does not qualify (the caller then emits the one-micro-op form)
@@ -1631,6 +1632,18 @@ struct Compiler {
             r.w[1] = idx;
             r.w[2] = dslot;
             r.w[3] = r.w[4] = r.w[5] = NONE;
+            if (opt.sha_pad_table && func == 0 && n % 64 == 0) {
+                // SHA-256 over a whole number of blocks: the last block is padding only and its K + W table is a constant
+                auto it = sha_pad_tables_.find(n);
+                if (it == sha_pad_tables_.end()) {
+                    while (plan.payload.size() % 4) plan.payload.push_back(0);   // read with 128-bit loads
+                    uint32_t kw[64];
+                    bvm::sha256_pad_block_kw(n, kw);
+                    it = sha_pad_tables_.emplace(n, (uint32_t)plan.payload.size()).first;
+                    plan.payload.insert(plan.payload.end(), kw, kw + 64);
+                }
+                r.w[5] = it->second;
+            }
             // descriptor = func, n_bytes, n_chunks, chunk columns.  Up to 37 chunks it rides in the record's coefficient words
             // (already in shared memory when the micro-op starts: one L2 round trip less on the chain of a hash chain).
             if (3 + n_chunks <= 40) {

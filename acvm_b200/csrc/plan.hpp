@@ -63,7 +63,8 @@ enum MicroKind : uint32_t {
     MK_HASH_PACK = 25,    // out column := up to 32 message bytes packed (byte i at bit 8i); payload[aux..]: n, witness * n
     MK_HASH_CORE = 26,    // out column := digest (32 bytes packed); payload[aux..]: func (0 SHA256, 1 Keccak256, 2 Blake2s), n_bytes,
                           // n_chunks, chunk column * n_chunks (32 message bytes each: a MK_HASH_PACK column or an earlier digest column);
-                          // w[6] == 1: the same descriptor sits in the record's c[][] words instead (up to 37 chunks)
+                          // w[6] == 1: the same descriptor sits in the record's c[][] words instead (up to 37 chunks);
+                          // w[5] != NONE (SHA256 over k * 64 bytes): payload offset of the padding block's 64 K[i] + W[i] words
     MK_HASH_UNPACK = 27,  // x = digest column; payload[aux..]: check_mask, 32 output witnesses (insert_value each byte)
     MK_INT_OP = 24,       // out := BinaryIntOp(x, y) of a lowered Brillig opcode; w[7] = op | bit_size << 8, 1 <= bit_size <= 128
                           // (brillig_vm/src/arithmetic.rs:23-81; a condition on which the reference panics => EK_REFERENCE_PANIC)
@@ -182,6 +183,7 @@ struct PlanOptions {
     // message and the scatter of the digest run on other slot threads, a digest that is the message of a later call is
     // handed over as one packed column.
     bool packed_hashes = true;
+    bool sha_pad_table = true;   // SHA256 over k * 64 bytes: the padding block's K + W table is a plan constant (MK_HASH_CORE w[5])
     // Tiles narrower than a warp: the heavy micro-ops of one step are spread over different warps (Scheduler::emit).
     // tile_lanes = the T the runtime will use (0: the runtime's own rule, 32 with curve calls, else 128 / S).
     bool spread_heavy = true;

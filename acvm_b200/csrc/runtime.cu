@@ -47,7 +47,7 @@ struct acvmb_ctx {
     uint32_t opt_spread_heavy = 1;   // plan: heavy micro-ops of one step go to different warps (tiles narrower than a warp)
     uint32_t opt_device_brillig = 1;
     uint32_t opt_scaled_columns = 1;
-    uint32_t opt_packed_hashes = 1;
+    uint32_t opt_packed_hashes = 1, opt_sha_pad_table = 1;
     // shared memory per CTA for the ring of recent values; 0 = no ring, the default: measured on B200 at full size the ring
     // is within 1 % of the plain kernel (operand loads hit L2 and four resident CTAs per SM hide that latency already)
     uint32_t opt_ring_bytes = 0;
@@ -246,6 +246,7 @@ extern "C" int acvmb_ctx_set_option(acvmb_ctx* ctx, const char* key, uint64_t va
     else if (k == "device_brillig") ctx->opt_device_brillig = value ? 1u : 0u;
     else if (k == "scaled_columns") ctx->opt_scaled_columns = value ? 1u : 0u;
     else if (k == "packed_hashes") ctx->opt_packed_hashes = value ? 1u : 0u;
+    else if (k == "sha_pad_table") ctx->opt_sha_pad_table = value ? 1u : 0u;
     else if (k == "ring_bytes") ctx->opt_ring_bytes = (uint32_t)value;
     else if (k == "split") ctx->opt_split = (int)value;
     else if (k == "n_stage") ctx->opt_n_stage = (uint32_t)value;
@@ -498,6 +499,7 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
     opt.device_brillig = ctx->opt_device_brillig != 0;
     opt.scaled_columns = ctx->opt_scaled_columns != 0;
     opt.packed_hashes = ctx->opt_packed_hashes != 0;
+    opt.sha_pad_table = ctx->opt_sha_pad_table != 0;
     opt.spread_heavy = ctx->opt_spread_heavy != 0;
     opt.slack_scheduling = ctx->opt_slack_scheduling != 0;
     opt.tile_lanes = ctx->opt_T;

@@ -250,7 +250,8 @@ int acvmb_imad_cc_microbench(acvmb_ctx* ctx, double* out3);
  * BlackBoxFuncCall::Pedersen / acvmb_pedersen although the values are NOT barretenberg's -- refused by default),
  * "device_brillig" (0: every Brillig opcode runs on the host VM), "scaled_columns" (0: every witness column holds the
  * canonical value -- two Montgomery reductions per multiplicative gate instead of one), "packed_hashes" (0: a hash call is ONE micro-op that gathers its
- * message byte by byte and scatters its digest itself), "ring_bytes" (shared memory per CTA
+ * message byte by byte and scatters its digest itself), "sha_pad_table" (0: the padding-only last block of a SHA256 call over k * 64 bytes
+ * recomputes its message schedule instead of reading the plan's constant table), "ring_bytes" (shared memory per CTA
  * for the ring of recent values that serves operand reads on chip; 0: every operand comes from L2 / HBM), "spread_heavy" (0: the micro-ops of a
  * step fill its slots in sorted order; default 1 puts the hash / curve / general micro-ops of one step into different warps when
  * the tile is narrower than a warp, so that they do not serialise inside one), "slack_scheduling" (0: curve micro-ops that nothing

@@ -73,7 +73,7 @@ def test_hash_calls_over_byte_witnesses_block_edges_and_chaining(packed):
     c.set_option("packed_hashes", packed)
     c.set_option("spread_heavy", packed)
     try:
-        for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 200, 1250)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
+        for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 128, 192, 200, 1250)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
                               ("Blake2s", (1, 32, 63, 64, 65, 128, 129))):
             b = ab.CircuitBuilder()
             nxt = 300

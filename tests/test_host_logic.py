@@ -763,7 +763,7 @@ def test_packed_hash_pipeline_plan_vs_oracle(packed):
     assert info["n_hash"] == 6 and (info["n_micro_ops"] > 6) == packed
     if packed:   # 6 cores + 6 unpacks + packs: two for the first call (nothing to hand over), one (the fresh half) afterwards
         assert info["n_micro_ops"] == 6 + 6 + 2 + 5
-    for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 200)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
+    for name, lengths in (("SHA256", (1, 31, 32, 33, 55, 56, 63, 64, 65, 119, 120, 128, 200)), ("Keccak256", (1, 32, 64, 100, 135, 136, 200)),
                           ("Blake2s", (1, 32, 63, 64, 65, 128, 129))):
         b = ab.CircuitBuilder()
         nxt = 300
