@@ -86,6 +86,12 @@ def test_hash_calls_over_byte_witnesses_block_edges_and_chaining(packed):
             inp = b"".join(rnd.randrange(256).to_bytes(32, "big") for _ in range(batch * 200))
             st = _check_circuit(c, b.to_bytes(), list(range(1, 201)), batch, inp)
             assert all(s.status == "Solved" for s in st)
+        # byte-typed inputs holding full-width field values: only the low byte is hashed (fetch_nearest_bytes)
+        b = ab.CircuitBuilder()
+        b.hash256("SHA256", [(1 + k % 7, 8 if k % 2 else 3) for k in range(40)], list(range(300, 332)))
+        b.hash256("Keccak256", [(w, 8) for w in range(300, 332)] + [(2, 8), (2, 8)], list(range(340, 372)))
+        st = _check_circuit(c, b.to_bytes(), list(range(1, 8)), 9, ab.synthetic_inputs(9, n_inputs=7, seed_id=31))
+        assert all(s.status == "Solved" for s in st)
     finally:
         c.close()
 

@@ -774,6 +774,11 @@ def test_packed_hash_pipeline_plan_vs_oracle(packed):
         ins = list(range(1, 201))
         inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(ins)))
         _interp_vs_oracle(b.to_bytes(), ins, inp, 1, 16, packed_hashes=packed)
+    # byte-typed inputs holding full-width field values: only the low byte is hashed (fetch_nearest_bytes, generic_ark.rs:305-317)
+    b = ab.CircuitBuilder()
+    b.hash256("SHA256", [(1 + k % 7, 8 if k % 2 else 3) for k in range(40)], list(range(300, 332)))
+    b.hash256("Keccak256", [(w, 8) for w in range(300, 332)] + [(2, 8), (2, 8)], list(range(340, 372)))
+    _interp_vs_oracle(b.to_bytes(), list(range(1, 8)), ab.synthetic_inputs(2, n_inputs=7, seed_id=31), 2, 16, packed_hashes=packed)
     # more than 37 chunks: the core's descriptor no longer fits the record and goes to the payload
     b = ab.CircuitBuilder()
     b.hash256("SHA256", [(1 + (k * 11) % 200, 8) for k in range(1250)], list(range(300, 332)))
