@@ -657,6 +657,12 @@ struct Compiler {
                 dst = new_temp();
                 ++plan.stats.n_temps;
             }
+            if (inv_record) {
+                // record pass of the batched inversion: only the SEQUENCE of inv() arguments matters, and none of them depends
+                // on a column scale or a stored coefficient (they are circuit constants) -- skip that arithmetic
+                if (!final_gate) acc = dst;
+                continue;
+            }
             // ---- scale of the output column ----
             bool forced = !scaled;
             U256 lo = one, mo = one;   // lambda_out, mu_out

@@ -62,10 +62,31 @@ def test_plan_matches_oracle_synthetic(S, mode, coeffs):
 
 
 def test_plan_batched_inversion_path():
-    # circuits above 2048 opcodes compile in two passes with one batched (Montgomery-trick) inversion in between
+    # circuits above 2048 opcodes compile in two passes with one batched (Montgomery-trick) inversion in between; the record
+    # pass skips the column-scale arithmetic (plan.cpp lower_sum), so the two passes must still ask for the same inverses
     data, inputs, _ = ab.synthetic_arith_circuit(3000, mode="local", coeffs="dense")
     info = _interp_vs_oracle(data, inputs, ab.synthetic_inputs(1), 1, 16)
     assert info["n_opcodes"] == 3000
+    data, inputs, _ = ab.synthetic_arith_circuit(2500, mode="global", coeffs="noir-like")
+    info = _interp_vs_oracle(data, inputs, ab.synthetic_inputs(1), 1, 16)
+    assert info["n_opcodes"] == 2500
+    # wide expressions (partial sums through temporaries), a product whose operands also appear linearly, and at the end a
+    # value-dependent gate: the replay pass meets scaled columns there and the circuit is recompiled with canonical ones
+    for value_dependent in (False, True):
+        rng = ab.SplitMix64(77)
+        b = ab.CircuitBuilder()
+        nxt = 9
+        for i in range(2100):
+            lo = max(1, nxt - 40)
+            ws = [lo + rng.below(nxt - lo) for _ in range(6)]
+            lin = [(rng.nonzero_field(), w) for w in dict.fromkeys(ws)]
+            mul = [(rng.nonzero_field(), ws[0], ws[1])] if i % 3 else []
+            b.arithmetic(mul, lin + [(rng.nonzero_field(), nxt)], rng.field())
+            nxt += 1
+        if value_dependent:
+            b.arithmetic([(1, nxt - 1, nxt)], [(3, nxt - 2)], 5)     # w_last * w_new + 3 w + 5 = 0: solvable only per value
+        info = _interp_vs_oracle(b.to_bytes(), list(range(1, 9)), ab.synthetic_inputs(2, n_inputs=8, seed_id=5), 2, 16)
+        assert info["scaled_columns"] == (0 if value_dependent else 1)
 
 
 def test_plan_failures_and_chains():
