@@ -485,12 +485,21 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
         // measured on B200 (profiles/r1_curve_tile_shapes.txt) T=32,S=8 is ~2x the arithmetic-tuned T=8,S=16 on both the
         // Pedersen chain and the mixed circuit.
         opt.S = 16;
-        for (auto& op : circ.opcodes)
-            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul || op.bb.func == BB_EcdsaSecp256k1 ||
-                                           op.bb.func == BB_EcdsaSecp256r1)) {
+        size_t n_hash = 0;
+        for (auto& op : circ.opcodes) {
+            if (op.kind != OP_BlackBox) continue;
+            if (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul || op.bb.func == BB_EcdsaSecp256k1 ||
+                op.bb.func == BB_EcdsaSecp256r1) {
                 opt.S = 8;
                 break;
             }
+            n_hash += op.bb.func == BB_SHA256 || op.bb.func == BB_Keccak256 || op.bb.func == BB_Blake2s ||
+                      op.bb.func == BB_Keccak256VariableLength || op.bb.func == BB_HashToField128Security;
+        }
+        // Hash-dominated circuits (a hash call is ~5 k instructions of one thread, a gate ~12): wider tiles, fewer CTAs, so that
+        // the warps that run the hash cores do not share a scheduler -- T = 16 / S = 8 is 7 % faster than T = 8 / S = 16 on
+        // the config-3 chain (profiles/r2_hash_packed_ab.txt)
+        if (opt.S == 16 && n_hash * 8 >= circ.opcodes.size() && n_hash) opt.S = 8;
     }
     opt.chunk_steps = ctx->opt_chunk_steps;
     opt.split_curve = ctx->opt_split_curve != 0;
