@@ -406,24 +406,24 @@ void r_opcode(Reader& r, Opcode& op) {
             op.expr = r_expr(r);
             break;
         case OP_BlackBox:
-            op.bb = r_blackbox(r);
+            op.bb() = r_blackbox(r);
             break;
         case OP_Directive:
-            op.dir = r_directive(r);
+            op.dir() = r_directive(r);
             break;
         case OP_Brillig:
-            op.brillig = r_brillig(r);
+            op.brillig() = r_brillig(r);
             break;
         case OP_MemoryOp:
-            op.mem.block_id = r.u32();
-            op.mem.operation = r_expr(r);
-            op.mem.index = r_expr(r);
-            op.mem.value = r_expr(r);
-            op.mem.predicate = r_opt_expr(r);
+            op.mem().block_id = r.u32();
+            op.mem().operation = r_expr(r);
+            op.mem().index = r_expr(r);
+            op.mem().value = r_expr(r);
+            op.mem().predicate = r_opt_expr(r);
             break;
         case OP_MemoryInit:
-            op.block_id = r.u32();
-            op.init = r.vec_u32();
+            op.block_id() = r.u32();
+            op.init() = r.vec_u32();
             break;
         default:
             throw DecodeError("unknown Opcode tag");

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "fr_host.hpp"
@@ -117,15 +118,57 @@ struct MemOp {
 
 enum OpcodeKind : uint32_t { OP_Arithmetic = 0, OP_BlackBox = 1, OP_Directive = 2, OP_Brillig = 3, OP_MemoryOp = 4, OP_MemoryInit = 5 };
 
-struct Opcode {
-    uint32_t kind = 0;
-    Expression expr;              // Arithmetic
+// Everything but an Arithmetic opcode's expression lives out of line: Arithmetic opcodes are the bulk of every circuit, and
+// with the blackbox / directive / Brillig / memory payloads inline one opcode was 1.1 KB (1.2 GB for a 2^20-gate circuit).
+struct OpcodeExtra {
     BlackBoxCall bb;              // BlackBoxFuncCall
     Directive dir;                // Directive
     Brillig brillig;              // Brillig
     MemOp mem;                    // MemoryOp
     uint32_t block_id = 0;        // MemoryInit
     std::vector<uint32_t> init;   // MemoryInit
+};
+
+struct Opcode {
+    uint32_t kind = 0;
+    Expression expr;              // Arithmetic
+
+    BlackBoxCall& bb() { return ext().bb; }
+    const BlackBoxCall& bb() const { return ext().bb; }
+    Directive& dir() { return ext().dir; }
+    const Directive& dir() const { return ext().dir; }
+    Brillig& brillig() { return ext().brillig; }
+    const Brillig& brillig() const { return ext().brillig; }
+    MemOp& mem() { return ext().mem; }
+    const MemOp& mem() const { return ext().mem; }
+    uint32_t& block_id() { return ext().block_id; }
+    uint32_t block_id() const { return ext().block_id; }
+    std::vector<uint32_t>& init() { return ext().init; }
+    const std::vector<uint32_t>& init() const { return ext().init; }
+
+    Opcode() = default;
+    Opcode(Opcode&&) = default;
+    Opcode& operator=(Opcode&&) = default;
+    Opcode(const Opcode& o) : kind(o.kind), expr(o.expr), x_(o.x_ ? new OpcodeExtra(*o.x_) : nullptr) {}
+    Opcode& operator=(const Opcode& o) {
+        if (this != &o) {
+            kind = o.kind;
+            expr = o.expr;
+            x_.reset(o.x_ ? new OpcodeExtra(*o.x_) : nullptr);
+        }
+        return *this;
+    }
+
+   private:
+    OpcodeExtra& ext() {
+        if (!x_) x_.reset(new OpcodeExtra);
+        return *x_;
+    }
+    const OpcodeExtra& ext() const {
+        static const OpcodeExtra empty;
+        return x_ ? *x_ : empty;
+    }
+    std::unique_ptr<OpcodeExtra> x_;
 };
 
 struct AssertMessage {

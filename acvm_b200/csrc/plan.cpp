@@ -2038,22 +2038,22 @@ struct Compiler {
             for (auto& op : c.opcodes) {
                 switch (op.kind) {
                     case OP_BlackBox:
-                        for (auto& in : op.bb.inputs) canon(in.witness);
-                        for (uint32_t w : op.bb.outputs) canon(w);
+                        for (auto& in : op.bb().inputs) canon(in.witness);
+                        for (uint32_t w : op.bb().outputs) canon(w);
                         break;
                     case OP_Directive:
-                        canon(op.dir.q);
-                        canon(op.dir.r);
-                        for (uint32_t w : op.dir.out) canon(w);
+                        canon(op.dir().q);
+                        canon(op.dir().r);
+                        for (uint32_t w : op.dir().out) canon(w);
                         break;
                     case OP_MemoryInit:
-                        for (uint32_t w : op.init) canon(w);
+                        for (uint32_t w : op.init()) canon(w);
                         break;
                     case OP_MemoryOp:   // a read lands in the witness of `value` (memory_op.rs:89-101)
-                        for (auto& t : op.mem.value.linear_combinations) canon(t.w);
+                        for (auto& t : op.mem().value.linear_combinations) canon(t.w);
                         break;
                     case OP_Brillig:
-                        for (auto& out : op.brillig.outputs)
+                        for (auto& out : op.brillig().outputs)
                             for (uint32_t w : out.witnesses) canon(w);
                         break;
                     default:
@@ -2079,19 +2079,19 @@ struct Compiler {
                     ok = arithmetic(i, op.expr);
                     break;
                 case OP_BlackBox:
-                    ok = blackbox(i, op.bb);
+                    ok = blackbox(i, op.bb());
                     break;
                 case OP_Directive:
-                    ok = directive(i, op.dir);
+                    ok = directive(i, op.dir());
                     break;
                 case OP_Brillig:
-                    ok = brillig(i, op.brillig);
+                    ok = brillig(i, op.brillig());
                     break;
                 case OP_MemoryInit:
-                    ok = memory_init(i, op.block_id, op.init);
+                    ok = memory_init(i, op.block_id(), op.init());
                     break;
                 case OP_MemoryOp:
-                    ok = memory_op(i, op.mem);
+                    ok = memory_op(i, op.mem());
                     break;
                 default:
                     throw std::runtime_error("opcode " + std::to_string(i) + ": opcode kind " + std::to_string(op.kind) +
@@ -2142,32 +2142,32 @@ uint32_t witness_span(const Circuit& c, const std::vector<uint32_t>& inputs) {
                 expr(op.expr);
                 break;
             case OP_BlackBox:
-                for (auto& in : op.bb.inputs) upd(in.witness);
-                for (uint32_t w : op.bb.outputs) upd(w);
+                for (auto& in : op.bb().inputs) upd(in.witness);
+                for (uint32_t w : op.bb().outputs) upd(w);
                 break;
             case OP_Directive:
-                expr(op.dir.a);
-                expr(op.dir.b);
-                if (op.dir.predicate.present) expr(op.dir.predicate);
-                upd(op.dir.q);
-                upd(op.dir.r);
-                for (uint32_t w : op.dir.out) upd(w);
+                expr(op.dir().a);
+                expr(op.dir().b);
+                if (op.dir().predicate.present) expr(op.dir().predicate);
+                upd(op.dir().q);
+                upd(op.dir().r);
+                for (uint32_t w : op.dir().out) upd(w);
                 break;
             case OP_MemoryInit:
-                for (uint32_t w : op.init) upd(w);
+                for (uint32_t w : op.init()) upd(w);
                 break;
             case OP_Brillig:
-                for (auto& in : op.brillig.inputs)
+                for (auto& in : op.brillig().inputs)
                     for (auto& e : in.exprs) expr(e);
-                for (auto& out : op.brillig.outputs)
+                for (auto& out : op.brillig().outputs)
                     for (uint32_t w : out.witnesses) upd(w);
-                if (op.brillig.predicate.present) expr(op.brillig.predicate);
+                if (op.brillig().predicate.present) expr(op.brillig().predicate);
                 break;
             case OP_MemoryOp:
-                expr(op.mem.operation);
-                expr(op.mem.index);
-                expr(op.mem.value);
-                if (op.mem.predicate.present) expr(op.mem.predicate);
+                expr(op.mem().operation);
+                expr(op.mem().index);
+                expr(op.mem().value);
+                if (op.mem().predicate.present) expr(op.mem().predicate);
                 break;
             default:
                 break;
@@ -2235,7 +2235,7 @@ Plan compile_plan(const Circuit& c, const std::vector<uint32_t>& input_witnesses
     // round-robin pool keeps slot reuse (a false WAR dependency) from serialising independent curve operations
     if (opt.split_curve && opt.S >= 8)
         for (auto& op : c.opcodes)
-            if (op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul)) {
+            if (op.kind == OP_BlackBox && (op.bb().func == BB_Pedersen || op.bb().func == BB_FixedBaseScalarMul)) {
                 opt.temp_pool = std::max<uint32_t>(opt.temp_pool, 32768);
                 break;
             }

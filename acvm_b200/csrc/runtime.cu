@@ -488,13 +488,13 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
         size_t n_hash = 0;
         for (auto& op : circ.opcodes) {
             if (op.kind != OP_BlackBox) continue;
-            if (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul || op.bb.func == BB_EcdsaSecp256k1 ||
-                op.bb.func == BB_EcdsaSecp256r1) {
+            if (op.bb().func == BB_Pedersen || op.bb().func == BB_FixedBaseScalarMul || op.bb().func == BB_EcdsaSecp256k1 ||
+                op.bb().func == BB_EcdsaSecp256r1) {
                 opt.S = 8;
                 break;
             }
-            n_hash += op.bb.func == BB_SHA256 || op.bb.func == BB_Keccak256 || op.bb.func == BB_Blake2s ||
-                      op.bb.func == BB_Keccak256VariableLength || op.bb.func == BB_HashToField128Security;
+            n_hash += op.bb().func == BB_SHA256 || op.bb().func == BB_Keccak256 || op.bb().func == BB_Blake2s ||
+                      op.bb().func == BB_Keccak256VariableLength || op.bb().func == BB_HashToField128Security;
         }
         // Hash-dominated circuits (a hash call is ~5 k instructions of one thread, a gate ~12): wider tiles, fewer CTAs, so that
         // the warps that run the hash cores do not share a scheduler -- T = 16 / S = 8 is 7 % faster than T = 8 / S = 16 on
@@ -516,8 +516,8 @@ static int circuit_from_struct(acvmb_ctx* ctx, const Circuit& circ, const uint32
         // the ring is [entries][T lanes][32 B]: size it for the tile width pick_T() will choose for this circuit
         bool curve = false;
         for (auto& op : circ.opcodes)
-            curve |= op.kind == OP_BlackBox && (op.bb.func == BB_Pedersen || op.bb.func == BB_FixedBaseScalarMul ||
-                                                op.bb.func == BB_EcdsaSecp256k1 || op.bb.func == BB_EcdsaSecp256r1);
+            curve |= op.kind == OP_BlackBox && (op.bb().func == BB_Pedersen || op.bb().func == BB_FixedBaseScalarMul ||
+                                                op.bb().func == BB_EcdsaSecp256k1 || op.bb().func == BB_EcdsaSecp256r1);
         uint32_t T_guess = ctx->opt_T ? ctx->opt_T : (curve ? 32u : std::max(1u, 128u / opt.S));
         if (T_guess > 32) T_guess = 32;
         opt.ring_slots = std::min<uint32_t>(1024u, ctx->opt_ring_bytes / (T_guess * 32u));
@@ -949,7 +949,7 @@ static int run_host_io(acvmb_batch* b, uint32_t opcode, std::vector<uint32_t> in
 static int run_host_brillig(acvmb_batch* b, const Segment& sg) {
     acvmb_circuit* c = b->c;
     if (!c->has_circuit) return set_err(ACVMB_ERR_STATE, "plan has a host segment but the circuit bytes are not attached");
-    const Brillig& br = c->circuit.opcodes[sg.a].brillig;
+    const Brillig& br = c->circuit.opcodes[sg.a].brillig();
     const uint32_t* d = c->plan.host_desc.data() + sg.b;
     const uint32_t opcode = sg.a;
     // ---- unpack the descriptor ----
@@ -1596,9 +1596,9 @@ extern "C" int acvmb_fixed_base_scalar_mul(acvmb_ctx* ctx, const uint8_t* low, c
     if (!ctx || !low || !high || !out_xy) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     Opcode op;
     op.kind = OP_BlackBox;
-    op.bb.func = BB_FixedBaseScalarMul;
-    op.bb.inputs = {{1, 128}, {2, 128}};
-    op.bb.outputs = {3, 4};
+    op.bb().func = BB_FixedBaseScalarMul;
+    op.bb().inputs = {{1, 128}, {2, 128}};
+    op.bb().outputs = {3, 4};
     std::vector<uint8_t> in((size_t)batch * 64);
     for (uint32_t i = 0; i < batch; ++i) {
         memcpy(&in[(size_t)i * 64], low + (size_t)i * 32, 32);
@@ -1615,15 +1615,15 @@ extern "C" int acvmb_pedersen(acvmb_ctx* ctx, const uint8_t* inputs, uint32_t n_
                                               "fail); set the context option pedersen_unpinned=1 to run the structurally identical kernel");
     Opcode op;
     op.kind = OP_BlackBox;
-    op.bb.func = BB_Pedersen;
+    op.bb().func = BB_Pedersen;
     std::vector<uint32_t> in_ids;
     for (uint32_t i = 0; i < n_inputs; ++i) {
-        op.bb.inputs.push_back({i + 1, 254});
+        op.bb().inputs.push_back({i + 1, 254});
         in_ids.push_back(i + 1);
     }
-    op.bb.n_message_inputs = n_inputs;
-    op.bb.domain_separator = domain_separator;
-    op.bb.outputs = {n_inputs + 1, n_inputs + 2};
+    op.bb().n_message_inputs = n_inputs;
+    op.bb().domain_separator = domain_separator;
+    op.bb().outputs = {n_inputs + 1, n_inputs + 2};
     return run_single_opcode(ctx, op, n_inputs + 3, in_ids, {n_inputs + 1, n_inputs + 2}, inputs, batch, out_xy, st);
 }
 
@@ -1631,15 +1631,15 @@ static int hash_bytes(acvmb_ctx* ctx, uint32_t func, const uint8_t* msgs, uint32
     if (!ctx || (!msgs && msg_len) || !digests) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     Opcode op;
     op.kind = OP_BlackBox;
-    op.bb.func = func;
+    op.bb().func = func;
     std::vector<uint32_t> in_ids, out_ids;
     for (uint32_t i = 0; i < msg_len; ++i) {
-        op.bb.inputs.push_back({i + 1, 8});
+        op.bb().inputs.push_back({i + 1, 8});
         in_ids.push_back(i + 1);
     }
-    op.bb.n_message_inputs = msg_len;
+    op.bb().n_message_inputs = msg_len;
     for (uint32_t i = 0; i < 32; ++i) {
-        op.bb.outputs.push_back(msg_len + 1 + i);
+        op.bb().outputs.push_back(msg_len + 1 + i);
         out_ids.push_back(msg_len + 1 + i);
     }
     // one byte per witness, like the ACIR opcode (hash.rs:51-66)
@@ -1665,15 +1665,15 @@ static int ecdsa_bytes(acvmb_ctx* ctx, uint32_t func, const uint8_t* hashed, con
     if (!ctx || !hashed || !pkx || !pky || !sig || !out_valid || !st) return set_err(ACVMB_ERR_INVALID_ARG, "bad argument");
     Opcode op;
     op.kind = OP_BlackBox;
-    op.bb.func = func;
+    op.bb().func = func;
     std::vector<uint32_t> in_ids;
     for (uint32_t i = 0; i < 160; ++i) {   // get_inputs_vec order: pkx, pky, signature, hashed message
-        op.bb.inputs.push_back({i + 1, 8});
+        op.bb().inputs.push_back({i + 1, 8});
         in_ids.push_back(i + 1);
     }
-    op.bb.seg[0] = op.bb.seg[1] = op.bb.seg[3] = 32;
-    op.bb.seg[2] = 64;
-    op.bb.outputs = {161};
+    op.bb().seg[0] = op.bb().seg[1] = op.bb().seg[3] = 32;
+    op.bb().seg[2] = 64;
+    op.bb().outputs = {161};
     std::vector<uint8_t> in((size_t)batch * 160 * 32, 0);
     for (size_t i = 0; i < batch; ++i) {
         uint8_t* row = &in[i * 160 * 32];
@@ -1825,7 +1825,7 @@ extern "C" int acvmb_brillig_run_host(const uint8_t* gz, size_t len, uint32_t op
     }
     if (opcode_index >= circ.opcodes.size() || circ.opcodes[opcode_index].kind != OP_Brillig)
         return set_err(ACVMB_ERR_INVALID_ARG, "not a Brillig opcode");
-    const Brillig& br = circ.opcodes[opcode_index].brillig;
+    const Brillig& br = circ.opcodes[opcode_index].brillig();
     bvm::VM vm;
     uint32_t pos = 0;
     for (auto& in : br.inputs) {
@@ -1901,7 +1901,7 @@ extern "C" int acvmb_vm_resolve_foreign_call(acvmb_vm* vm, uint32_t n_outputs, c
         for (uint32_t j = 0; j < cnt; ++j, ++k) o.values.push_back(hf::from_be_bytes_reduce(values_be32 + k * 32, 32));
         res.push_back(std::move(o));
     }
-    op.brillig.foreign_call_results.push_back(std::move(res));
+    op.brillig().foreign_call_results.push_back(std::move(res));
     vm->fc_pending = false;
     vm->solved_once = false;
     vm->ip = vm->status.opcode_index;   // the Brillig opcode is attempted again (mod.rs:214-228)
