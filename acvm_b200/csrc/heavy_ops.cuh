@@ -1504,6 +1504,19 @@ __device__ __noinline__ void exec_mem(const OpRec* r, uint32_t kind, uint4* cb, 
         hv_load<T>(p, cb, r->w[5]);
         pred = !fr::is_zero(p);
     }
+    if (r->w[6] != 0xFFFFFFFFu) {   // witness-dependent read/write selector (memory_op.rs:68,81): 0 reads, anything else writes
+        Fe sel;
+        hv_load<T>(sel, cb, r->w[6]);
+        const bool wants_read = fr::is_zero(sel);
+        if (kind == MK_MEM_READ && !wants_read) {       // get_value(value) of the unassigned witness the plan reads into
+            hv_fail(fail, r->w[1], EK_MISSING_ASSIGNMENT, r->c[0][0]);
+            return;
+        }
+        if (kind == MK_MEM_WRITE && wants_read) {       // value.to_witness() is None for an assigned value: the reference panics
+            hv_fail(fail, r->w[1], EK_REFERENCE_PANIC, 0);
+            return;
+        }
+    }
     if (kind == MK_MEM_READ) {
         Fe v;
 #pragma unroll

@@ -1137,23 +1137,42 @@ struct Compiler {
 
     bool memory_op(uint32_t idx, const MemOp& m) {
         Block& b = block_of(m.block_id);
+        // memory_op.rs:68-81 evaluates `operation` per instance.  Noir emits constants; a selector that depends on witnesses is
+        // read from its column (canonical) and decided per lane.  Whether `value` is a readable witness or a writable value is
+        // static, so such an opcode can succeed in one direction only and FAILS the lanes that take the other one exactly as
+        // the reference does: a read lane of a known value panics ("Memory must be read into a specified witness index"), a
+        // write lane of an unassigned witness is MissingAssignment(witness).
         U256 opv;
-        if (!expr_is_const(m.operation, opv))
-            throw std::runtime_error("opcode " + std::to_string(idx) + ": MemoryOp whose read/write selector is not a constant is not supported yet");
+        uint32_t ssel = NONE;
+        const bool const_sel = expr_is_const(m.operation, opv);
+        if (!const_sel && !expr_to_slot(idx, m.operation, ssel)) return false;
         uint32_t si, sp = NONE;
         if (!expr_to_slot(idx, m.index, si)) return false;
-        bool is_read = opv.is_zero();
+        // to_witness(): exactly 1*w + 0 over a witness (after evaluate); anything else panics in the reference
+        // (an already-known witness is folded into the constant by evaluate(), so to_witness() is None there too)
+        std::vector<LinTerm> lin;
+        bool has_mul = false;
+        for (auto& t : m.value.mul_terms) has_mul |= !t.c.is_zero();
+        for (auto& t : m.value.linear_combinations)
+            if (!t.c.is_zero()) lin.push_back(t);
+        const bool readable = !has_mul && lin.size() == 1 && lin[0].c == hf::from_u64(1) && m.value.q_c.is_zero() && !known[lin[0].w];
+        bool is_read;
+        if (const_sel) {
+            is_read = opv.is_zero();
+        } else {
+            bool value_known = true;
+            for (auto& t : m.value.mul_terms) value_known &= t.c.is_zero() || (known[t.a] == W_KNOWN && known[t.b] == W_KNOWN);
+            for (auto& t : lin) value_known &= known[t.w] == W_KNOWN;
+            if (readable && !m.predicate.present) is_read = true;     // write lanes: MissingAssignment(w)
+            else if (value_known) is_read = false;                    // read lanes: the reference panics
+            else
+                throw std::runtime_error("opcode " + std::to_string(idx) + ": MemoryOp with a witness-dependent read/write selector whose "
+                                         "value is neither one unassigned witness (without predicate) nor fully assigned is not supported");
+        }
         // `value` is evaluated (not required) before the predicate (memory_op.rs:75-87)
         uint32_t sv = NONE, out_w = NONE;
         if (is_read) {
-            // to_witness(): exactly 1*w + 0 over a witness (after evaluate); anything else panics in the reference
-            std::vector<LinTerm> lin;
-            bool has_mul = false;
-            for (auto& t : m.value.mul_terms) has_mul |= !t.c.is_zero();
-            for (auto& t : m.value.linear_combinations)
-                if (!t.c.is_zero()) lin.push_back(t);
-            // (an already-known witness is folded into the constant by evaluate(), so to_witness() is None there too)
-            if (has_mul || lin.size() != 1 || !(lin[0].c == hf::from_u64(1)) || !m.value.q_c.is_zero() || known[lin[0].w]) {
+            if (!readable) {
                 if (m.predicate.present && !expr_to_slot(idx, m.predicate, sp)) return false;
                 fail_static(idx, EK_REFERENCE_PANIC, 0, "Memory must be read into a specified witness index, encountered an Expression");
                 return false;
@@ -1172,16 +1191,18 @@ struct Compiler {
         plan.payload.push_back(b.len);
         std::vector<uint32_t> rd = {si}, wr;
         if (sp != NONE) rd.push_back(sp);
+        if (ssel != NONE) rd.push_back(ssel);
         for (uint32_t i = 0; i < b.len; ++i) rd.push_back(b.base + i);
         r.w[1] = idx;
         r.w[3] = si;
         r.w[5] = sp;
-        r.w[6] = NONE;
+        r.w[6] = ssel;   // NONE: the direction is the micro-op kind; else the lanes whose selector disagrees with it fail
         r.w[7] = off;
         if (is_read) {
             r.w[0] = MK_MEM_READ;
             r.w[2] = out_w;
             r.w[4] = NONE;
+            r.c[0][0] = out_w;   // MissingAssignment(witness) of a lane that wanted to write
             wr.push_back(out_w);
             place_heavy(r, rd, wr);
             mark_assigned(out_w, idx);

@@ -514,7 +514,12 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 else:
                     mi = idx_v & 0xFFFFFFFF
                     pred = cols[w1] != 0 if w1 != NONE else True
-                    if kind == MK["MEM_READ"]:
+                    wants_read = cols[w2] == 0 if w2 != NONE else None   # witness-dependent selector (heavy_ops.cuh exec_mem)
+                    if wants_read is False and kind == MK["MEM_READ"]:
+                        record_fail(opcode, EK_MISSING, c[0] & 0xFFFFFFFF)
+                    elif wants_read is True and kind == MK["MEM_WRITE"]:
+                        record_fail(opcode, EK_PANIC)
+                    elif kind == MK["MEM_READ"]:
                         if not pred:
                             writes.append((out, 0))
                         elif mi >= ln:

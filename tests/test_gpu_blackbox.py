@@ -380,3 +380,13 @@ def test_integer_brillig_ops_on_the_device(ctx):
              rnd.randrange(1 << 64), rnd.randrange(1 << 32)) for _ in range(96)]
     inp2 = b"".join((v % F.P).to_bytes(32, "big") for r in many for v in r)
     _check_circuit(ctx, data, [1, 2, 3, 4], len(many), inp2)
+
+
+def test_memory_op_with_witness_dependent_selector(ctx):
+    """memory_op.rs:68-81 evaluates `operation` per instance: lanes whose selector disagrees with the only direction the opcode
+    can take fail exactly like the reference (MissingAssignment of the unread witness / the to_witness() panic)."""
+    from test_host_logic import _dynamic_memory_selector_circuits, _dynamic_memory_selector_inputs
+    rows, inp = _dynamic_memory_selector_inputs()
+    for data in _dynamic_memory_selector_circuits():
+        st = _check_circuit(ctx, data, list(range(1, 9)), len(rows), inp)
+        assert {s.status for s in st} == {"Solved", "Failure"}

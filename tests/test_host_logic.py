@@ -846,3 +846,36 @@ def test_heavy_micro_ops_of_a_step_sit_in_different_warps():
     rng = random.Random(5)
     inp = b"".join(rng.randrange(256).to_bytes(32, "big") for _ in range(len(inputs)))
     _interp_vs_oracle(data, inputs, inp, 1, 16, spread_heavy=False)
+
+
+def _dynamic_memory_selector_circuits():
+    """MemoryOp whose `operation` is a witness (memory_op.rs:68-81 evaluates it per instance)."""
+    a = ab.CircuitBuilder()          # value = one unassigned witness: read lanes succeed, write lanes are MissingAssignment(w10)
+    a.memory_init(0, [4, 5, 6, 7])
+    a.memory_op(0, ab.wexpr(3), ab.wexpr(2), ab.wexpr(10))
+    a.arithmetic([], [(2, 10), (ab.P - 1, 11)], 3)                 # w11 = 2*w10 + 3
+    b = ab.CircuitBuilder()          # value fully assigned: write lanes succeed, read lanes hit the reference's expect() panic
+    b.memory_init(0, [4, 5, 6, 7])
+    b.memory_op(0, ([], [(1, 3)], 0), ab.wexpr(2), ([], [(5, 1)], 1), predicate=ab.wexpr(8))
+    b.memory_op(0, ab.cexpr(0), ab.wexpr(2), ab.wexpr(12))         # observe the write
+    return a.to_bytes(), b.to_bytes()
+
+
+def _dynamic_memory_selector_inputs():
+    #        w1  idx sel  w4..w7 (block)     w8 (predicate)
+    rows = [(9, 0, 0, 40, 50, 60, 70, 1), (9, 3, 1, 40, 50, 60, 70, 1), (9, 2, 2, 40, 50, 60, 70, 0), (9, 7, 0, 40, 50, 60, 70, 1),
+            (9, 7, 1, 40, 50, 60, 70, 1), (9, 1, ab.P - 1, 40, 50, 60, 70, 1), (9, 1 << 70, 1, 40, 50, 60, 70, 1)]
+    return rows, b"".join(int(v).to_bytes(32, "big") for r in rows for v in r)
+
+
+def test_memory_op_with_witness_dependent_selector_plan_vs_oracle():
+    rows, inp = _dynamic_memory_selector_inputs()
+    for data in _dynamic_memory_selector_circuits():
+        _interp_vs_oracle(data, list(range(1, 9)), inp, len(rows))
+    # neither readable nor assigned (and the predicated read, which could leave its witness unassigned): refused loudly
+    c = ab.CircuitBuilder()
+    c.memory_init(0, [4, 5, 6, 7])
+    c.memory_op(0, ab.wexpr(3), ab.wexpr(2), ab.wexpr(10), predicate=ab.wexpr(8))
+    with pytest.raises(acvm_b200.AcvmError) as e:
+        acvm_b200.compile_plan_host(c.to_bytes(), list(range(1, 9)), 16)
+    assert e.value.rc == -5 and "selector" in str(e.value)
