@@ -879,3 +879,20 @@ def test_memory_op_with_witness_dependent_selector_plan_vs_oracle():
     with pytest.raises(acvm_b200.AcvmError) as e:
         acvm_b200.compile_plan_host(c.to_bytes(), list(range(1, 9)), 16)
     assert e.value.rc == -5 and "selector" in str(e.value)
+
+
+@pytest.mark.parametrize("seed_id", [4, 5])
+def test_mixed_circuits_schedule_variants_vs_oracle(seed_id):
+    """BASELINE config-4 shaped circuits (gates, RANGE/AND/XOR, hashes, Pedersen, fixed-base with local operands) through every
+    scheduling variant of the plan compiler -- slack scheduling of curve micro-ops, heavy micro-ops spread over warps, packed
+    hashes -- against the oracle: any order the scheduler picks must compute the same witness map."""
+    data, inputs, nw, counts = ab.mixed_circuit(700, seed_id=seed_id, window=24)
+    assert counts["pedersen"] + counts["fixed_base"] >= 2 and counts["hash"] >= 2
+    inp = ab.synthetic_inputs(1, n_inputs=len(inputs), seed_id=40 + seed_id)
+    for slack, spread, packed in ((True, True, True), (False, True, True), (True, False, False)):
+        _interp_vs_oracle(data, inputs, inp, 1, 8, pedersen_unpinned=True, slack_scheduling=slack, spread_heavy=spread, packed_hashes=packed)
+    if seed_id == 4:   # the config-2 chain: every H1 sum over a fresh input has slack, the constant sums are shared by all calls
+        data, inputs, nw = ab.pedersen_chain_circuit(7, n_fresh=3)
+        inp = ab.synthetic_inputs(1, n_inputs=len(inputs), seed_id=50)
+        infos = [_interp_vs_oracle(data, inputs, inp, 1, 8, pedersen_unpinned=True, slack_scheduling=slack) for slack in (True, False)]
+        assert infos[0]["n_micro_ops"] == infos[1]["n_micro_ops"] and infos[0]["n_steps"] < infos[1]["n_steps"]
