@@ -242,9 +242,24 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
         hooks = default_hooks()
 
     class Cols(dict):
-        """a lane that already failed keeps executing on the device and reads garbage: model that as 0"""
+        """a lane that already failed keeps executing on the device and reads garbage: model that as 0.
+        Inside a step every read is logged with the slot thread that made it (`cur`): the kernel has ONE barrier per step, so
+        no thread may read or write a column that another thread writes in the same step (checked at the end of each step)."""
+        cur = None
+        reads = {}
+
         def __missing__(self, k):
             return 0
+
+        def __getitem__(self, k):
+            if Cols.cur is not None:
+                Cols.reads.setdefault(k, set()).add(Cols.cur)
+            return dict.__getitem__(self, k)
+
+        def get(self, k, default=None):
+            if Cols.cur is not None:
+                Cols.reads.setdefault(k, set()).add(Cols.cur)
+            return dict.get(self, k, default)
     cols = Cols()
     for k_, w in enumerate(plan.input_witnesses):
         cols[w] = inputs[w] % P
@@ -376,7 +391,11 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
         ring_writes = []
         real_cols, cols = cols, cols   # (names kept: the gate code below reads operands through `ops`)
         ops = Operands()
+        Cols.reads = {}
+        owners = []          # slot thread of every entry of `writes`
         for s in range(plan.S):
+            owners += [Cols.cur] * (len(writes) - len(owners))
+            Cols.cur = s
             hdr, c = plan.record(step * plan.S + s)
             kind, flags = hdr[0] & 0xFF, hdr[0] >> 8
             opcode, out, x, y, w1, w2, aux = hdr[1:8]
@@ -577,6 +596,13 @@ def run_plan(plan: PlanBlob, inputs, hooks=None, circuit=None):
                 writes.extend(hooks[kind](cols, hdr, plan.payload, record_fail))
             else:
                 raise NotImplementedError(f"plan_interp: micro-op kind {kind}")
+        owners += [Cols.cur] * (len(writes) - len(owners))
+        Cols.cur = None
+        writer = {}
+        for (slot, _v), own in zip(writes, owners):
+            assert writer.setdefault(slot, own) == own, f"step {step}: column {slot} written by slot threads {writer[slot]} and {own}"
+            others = Cols.reads.get(slot, set()) - {own}
+            assert not others, f"step {step}: column {slot} written by slot thread {own} and read by {sorted(others)} in the same step"
         for (slot, v) in writes:
             cols[slot] = v
         # ring entries are written during the step with no barrier against its reads: no entry may be both

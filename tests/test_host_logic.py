@@ -896,3 +896,25 @@ def test_mixed_circuits_schedule_variants_vs_oracle(seed_id):
         inp = ab.synthetic_inputs(1, n_inputs=len(inputs), seed_id=50)
         infos = [_interp_vs_oracle(data, inputs, inp, 1, 8, pedersen_unpinned=True, slack_scheduling=slack) for slack in (True, False)]
         assert infos[0]["n_micro_ops"] == infos[1]["n_micro_ops"] and infos[0]["n_steps"] < infos[1]["n_steps"]
+
+
+def test_interpreter_detects_a_same_step_race():
+    """The kernel has one barrier per step, so a step must never hold a reader (or a second writer) of a column that another of
+    its slot threads writes.  tests/plan_interp.py asserts that for every step of every plan it runs; this test corrupts a
+    schedule to show the assertion fires."""
+    b = ab.CircuitBuilder()
+    b.arithmetic([], [(1, 1), (ab.P - 1, 3)], 0)      # w3 = w1
+    b.arithmetic([], [(1, 3), (ab.P - 1, 4)], 1)      # w4 = w3 + 1: must sit in a later step
+    data = b.to_bytes()
+    info, blob = acvm_b200.compile_plan_host(data, [1], 4)
+    plan = plan_interp.PlanBlob(blob)
+    assert plan.n_steps >= 2
+    st, wm = plan_interp.run_plan(plan, {1: 5}, circuit=acir.decode_circuit(data))
+    assert st == ("Solved",) and wm == {1: 5, 3: 5, 4: 6}
+    raw = bytearray(plan.stream)
+    S = plan.S
+    raw[192:384] = raw[S * 192:(S + 1) * 192]        # the dependent gate moves into step 0, slot 1
+    raw[S * 192:(S + 1) * 192] = bytes(192)
+    plan.stream = bytes(raw)
+    with pytest.raises(AssertionError, match="in the same step"):
+        plan_interp.run_plan(plan, {1: 5}, circuit=acir.decode_circuit(data))
