@@ -11,7 +11,7 @@ import pytest
 
 import acvm_b200
 from acvm_b200 import acir_builder as ab
-from conftest import ROOT
+from conftest import ROOT, inputs_to_dicts
 from oracle import acir, pwg
 import plan_interp
 
@@ -918,3 +918,16 @@ def test_interpreter_detects_a_same_step_race():
     plan.stream = bytes(raw)
     with pytest.raises(AssertionError, match="in the same step"):
         plan_interp.run_plan(plan, {1: 5}, circuit=acir.decode_circuit(data))
+
+
+def test_medium_mixed_circuit_schedule_is_race_free():
+    """5000 config-4 shaped opcodes (33 Pedersen, 27 fixed-base, 83 hash calls among gates and logic ops) through the plan
+    interpreter: too long for the Python oracle, but the interpreter's per-step race assertion and a Solved status (every
+    gate CHECK of the circuit holds on the computed values) cover the schedule itself."""
+    data, inputs, nw, counts = ab.mixed_circuit(5000, seed_id=7, window=64)
+    assert counts["pedersen"] > 20 and counts["hash"] > 50
+    info, blob = acvm_b200.compile_plan_host(data, inputs, 8, pedersen_unpinned=True)
+    plan = plan_interp.PlanBlob(blob)
+    iw = inputs_to_dicts(ab.synthetic_inputs(1, n_inputs=len(inputs), seed_id=3), 1, inputs)[0]
+    st, wm = plan_interp.run_plan(plan, iw, circuit=acir.decode_circuit(data))
+    assert st == ("Solved",) and len(wm) > 7000
